@@ -1,0 +1,206 @@
+"""numpy restatement of the reference's host-side flow around the hot path
+(readers, SNP QC, -gk, -eigen, null model, -lmm) driving the C oracle.
+
+TEST INFRASTRUCTURE ONLY (see oracle/gemma_oracle.c header).  Each function
+cites the reference file:line it follows.  Eigendecomposition uses LAPACK
+dsyevr through scipy (driver='evr'), the routine the reference calls at
+src/lapack.cpp:205,220.
+"""
+import gzip
+import io
+
+import numpy as np
+import scipy.linalg
+
+from . import oracle as O
+
+
+def _open(path):
+    if str(path).endswith(".gz"):
+        return io.TextIOWrapper(gzip.open(path, "rb"))
+    return open(path, "r")
+
+
+def _tok(line):
+    # strtok(line, " ,\t")  (src/gemma_io.cpp:706 etc.)
+    return line.replace(",", " ").replace("\t", " ").split()
+
+
+def read_pheno(path, p_column=(1,)):
+    """src/gemma_io.cpp:386-444 ReadFile_pheno. Returns (pheno[n,d], indicator[n,d])."""
+    ph, ind = [], []
+    with _open(path) as f:
+        for line in f:
+            t = _tok(line.rstrip("\r\n"))
+            if not t and line.strip() == "":
+                # the reference still pushes a row for an empty line only if strtok fails -> enforce; skip
+                continue
+            row, irow = [], []
+            for c in p_column:
+                s = t[c - 1]
+                if s == "NA":
+                    row.append(-9.0); irow.append(0)
+                else:
+                    row.append(float(s)); irow.append(1)
+            ph.append(row); ind.append(irow)
+    return np.array(ph, dtype=np.float64), np.array(ind, dtype=np.int32)
+
+
+def read_cvt(path):
+    """src/gemma_io.cpp:446-511 ReadFile_cvt. Returns (cvt rows list, indicator_cvt)."""
+    rows, ind = [], []
+    with _open(path) as f:
+        for line in f:
+            t = _tok(line.rstrip("\r\n"))
+            na = any(s == "NA" for s in t)
+            rows.append([(-9.0 if s == "NA" else float(s)) for s in t])
+            ind.append(0 if na else 1)
+    return rows, np.array(ind, dtype=np.int32)
+
+
+def read_anno(path):
+    """src/gemma_io.cpp:280-341 ReadFile_anno: rs, bp, chr[, cM]."""
+    m = {}
+    with _open(path) as f:
+        for line in f:
+            t = _tok(line.rstrip("\r\n"))
+            if not t:
+                continue
+            rs = t[0]
+            bp = -9 if t[1] == "NA" else int(float(t[1]))
+            ch = "-9" if (len(t) < 3 or t[2] == "NA") else t[2]
+            cm = -9.0 if (len(t) < 4 or t[3] == "NA") else float(t[3])
+            m[rs] = (ch, bp, cm)
+    return m
+
+
+def process_cvt_phen(ind_pheno, cvt_rows=None, ind_cvt=None):
+    """src/param.cpp:1993-2098 ProcessCvtPhen + :1937-1990 CheckCvt.
+    Returns (indicator_idv, W_full[n_total, c]) where W rows of excluded individuals are unused."""
+    indicator_idv = np.all(ind_pheno == 1, axis=1).astype(np.int32)
+    if ind_cvt is not None and len(ind_cvt):
+        indicator_idv = indicator_idv * ind_cvt
+    n_total = len(indicator_idv)
+    if cvt_rows is None or ind_cvt is None or len(ind_cvt) == 0:
+        return indicator_idv, np.ones((n_total, 1))
+    sel = [i for i in range(n_total) if indicator_idv[i] == 1 and ind_cvt[i] == 1]
+    W = np.array([cvt_rows[i] for i in sel], dtype=np.float64)
+    const = [j for j in range(W.shape[1]) if W[:, j].min() == W[:, j].max()]
+    if len(const) == W.shape[1]:
+        return indicator_idv, np.ones((n_total, 1))       # covariates dropped, intercept only
+    Wfull = np.zeros((n_total, W.shape[1] + (0 if const else 1)))
+    for k, i in enumerate(sel):
+        Wfull[i, :W.shape[1]] = W[k]
+        if not const:
+            Wfull[i, -1] = 1.0                              # intercept appended as LAST column
+    return indicator_idv, Wfull
+
+
+class Bimbam:
+    """Parsed BIMBAM mean-genotype file: rs ids, alleles, G[p_total, n_total] with NaN = NA."""
+
+    def __init__(self, path):
+        rs, a1, a0, rows = [], [], [], []
+        with _open(path) as f:
+            for line in f:
+                t = _tok(line.rstrip("\r\n"))
+                if not t:
+                    continue
+                rs.append(t[0]); a1.append(t[1]); a0.append(t[2])
+                rows.append(np.array([np.nan if s == "NA" else float(s) for s in t[3:]]))
+        self.rs, self.a1, self.a0 = rs, a1, a0
+        self.G = np.vstack(rows)
+
+
+def qc_bimbam(bb, indicator_idv, W=None, miss_level=0.05, maf_level=0.01, r2_level=0.9999,
+              snps=None):
+    """src/gemma_io.cpp:639-873 ReadFile_geno QC pass. Returns (indicator_snp, n_miss, maf)."""
+    keep = indicator_idv == 1
+    G = bb.G[:, keep]
+    ni_test = int(keep.sum())
+    p = G.shape[0]
+    ind = np.zeros(p, dtype=np.int32)
+    n_miss_a = np.zeros(p, dtype=np.int64)
+    maf_a = np.zeros(p)
+    Wt = None
+    if W is not None and W.shape[1] != 1:
+        Wt = W[keep]
+        WtWi = np.linalg.inv(Wt.T @ Wt)
+    for t in range(p):
+        if snps is not None and bb.rs[t] not in snps:
+            continue
+        g = G[t]
+        miss = np.isnan(g)
+        n_miss = int(miss.sum())
+        gv = g[~miss]
+        maf = float(sum(gv.tolist()))      # sequential sum, as the reference accumulates
+        maf /= 2.0 * (ni_test - n_miss)
+        n_miss_a[t] = n_miss; maf_a[t] = maf
+        if n_miss / ni_test > miss_level:
+            continue
+        if (maf < maf_level or maf > 1.0 - maf_level) and maf_level != -1:
+            continue
+        if gv.size == 0 or np.all(gv == gv[0]):
+            continue
+        if Wt is not None:
+            x = g.copy(); x[miss] = maf * 2.0
+            Wtx = Wt.T @ x
+            v_w = Wtx @ (WtWi @ Wtx); v_x = x @ x
+            if v_w / v_x > r2_level:
+                continue
+        ind[t] = 1
+    return ind, n_miss_a, maf_a
+
+
+def kinship_bimbam(bb, indicator_snp, k_mode=1, batch=20000):
+    """src/gemma_io.cpp:1418-1597 BimbamKin: all ni_total individuals, selected SNPs."""
+    sel = np.nonzero(indicator_snp)[0]
+    n = bb.G.shape[1]
+    K = np.zeros((n, n))
+    for s in range(0, len(sel), batch):
+        Xc = O.kin_transform(bb.G[sel[s:s + batch]], k_mode)
+        K += Xc @ Xc.T            # the dgemm of :1554 (BLAS instead of the oracle's O(n^2 l) loop)
+    K *= 1.0 / len(sel)
+    return K
+
+
+def text_roundtrip(M):
+    """WriteMatrix precision(10) general format (src/param.cpp:1899-1906) then atof."""
+    flat = np.array([float("%.10g" % v) for v in np.asarray(M).ravel()])
+    return flat.reshape(np.shape(M))
+
+
+def eigen_decomp_zeroed(G):
+    """src/lapack.cpp:260-291 (dsyevr 'V','A','L', abstol 1e-7; eval<1e-10 -> 0). Returns U, eval, trace_G."""
+    ev, U = scipy.linalg.eigh(G, lower=True, driver="evr")
+    ev, tr = O.zero_small_eval(ev)
+    return U, ev, tr
+
+
+def lmm_prepare(K_total, indicator_idv, y_total, W_total):
+    """LMM branch of BatchRun up to the null model (src/gemma.cpp:2556-2760)."""
+    keep = indicator_idv == 1
+    G = np.ascontiguousarray(K_total[np.ix_(keep, keep)])
+    G = O.center_matrix(G)
+    U, ev, trace_G = eigen_decomp_zeroed(G)
+    W = np.ascontiguousarray(W_total[keep]); y = np.ascontiguousarray(y_total[keep])
+    UtW = U.T @ W; Uty = U.T @ y
+    l_mle, logl_mle = O.calc_lambda_null("L", ev, UtW, Uty)
+    l_remle, logl_remle = O.calc_lambda_null("R", ev, UtW, Uty)
+    pve, pve_se = O.calc_pve(ev, UtW, Uty, l_remle, trace_G)
+    return dict(U=U, eval=ev, trace_G=trace_G, UtW=UtW, Uty=Uty, W=W, y=y, l_mle_null=l_mle,
+                logl_mle_H0=logl_mle, l_remle_null=l_remle, logl_remle_H0=logl_remle, pve=pve,
+                pve_se=pve_se)
+
+
+def lmm_genotypes_bimbam(bb, indicator_snp, indicator_idv, sel=None):
+    """src/lmm.cpp:1590-1618: analysed individuals only, mean-imputed; returns X n x l."""
+    idx = np.nonzero(indicator_snp)[0] if sel is None else sel
+    keep = indicator_idv == 1
+    return O.lmm_impute(bb.G[np.ix_(idx, keep)])
+
+
+def lmm_analyze(prep, X, a_mode, **kw):
+    UtX = prep["U"].T @ X          # src/lmm.cpp:1521
+    return O.lmm_analyze_utx(prep["eval"], prep["UtW"], prep["Uty"], UtX, a_mode,
+                             l_mle_null=prep["l_mle_null"], logl_mle_H0=prep["logl_mle_H0"], **kw)
