@@ -1,0 +1,641 @@
+// api.cu -- the C ABI of libgemma_b200.so (include/gemma_b200.h).  Host-side orchestration
+// only: every FLOP of the hot path runs in the kernels of lmm_kernel.cu / dgemm.cu /
+// i8gemm_sm100.cu / geno.cu / eigh.cu.  There is NO CPU fallback: without a CUDA device
+// gb200_create fails.
+#include "common.cuh"
+#include <string.h>
+#include <math.h>
+
+using namespace gb;
+
+namespace gb {
+// i8gemm_sm100.cu
+int i8_prepare(gb200_ctx *ctx);                       // slice U into int8 planes (after lmm_setup)
+int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
+                   size_t l, size_t bytes_per_snp, double *UtXt_dev);   // UtXt l x n (ld n)
+bool i8_available(gb200_ctx *ctx);
+}
+
+static bool trans_flag(const char *t, bool *ok) {
+  *ok = t && (t[0] == 'N' || t[0] == 'n' || t[0] == 'T' || t[0] == 't');
+  return t && (t[0] == 'T' || t[0] == 't');
+}
+
+extern "C" {
+
+int gb200_abi_version(void) { return GB200_ABI_VERSION; }
+
+int gb200_create(gb200_ctx **out, int device, void *stream) {
+  if (!out) return GB200_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return GB200_ERR_CUDA;   // fail loudly: no CPU fallback
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return GB200_ERR_CUDA; }
+  if (device >= count) return GB200_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return GB200_ERR_CUDA;
+  gb200_ctx *c = new gb200_ctx();
+  c->device = device;
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GB200_ERR_CUDA; }
+    c->own_stream = true;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return GB200_ERR_CUDA; }
+  c->num_sms = prop.multiProcessorCount;
+  if (c->dTicket.reserve(64) != cudaSuccess) { delete c; return GB200_ERR_CUDA; }
+  *out = c;
+  return GB200_OK;
+}
+
+void gb200_destroy(gb200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &kv : c->profs)
+    for (auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto ev : c->event_pool) cudaEventDestroy(ev);
+  gb::DevBuf *bufs[] = {&c->dK, &c->dU, &c->dEval, &c->dWt, &c->dY, &c->dNull, &c->dX, &c->dUtXt, &c->dOut,
+                        &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale,
+                        &c->i8.geno, &c->i8.miss_mean};
+  for (auto b : bufs) b->release();
+  if (c->i8.tmap_a) free(c->i8.tmap_a);
+  if (c->i8.tmap_b) free(c->i8.tmap_b);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *gb200_last_error(const gb200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+void *gb200_stream(const gb200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int gb200_synchronize(gb200_ctx *c) {
+  if (!c) return GB200_ERR_ARG;
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_profile_enable(gb200_ctx *c, int on) { if (!c) return GB200_ERR_ARG; c->prof = on != 0; return GB200_OK; }
+
+static void prof_drain(gb200_ctx *c, ProfEntry &e) {
+  for (auto &pr : e.pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(pr.second);
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) e.ms += ms;
+    c->event_pool.push_back(pr.first);
+    c->event_pool.push_back(pr.second);
+  }
+  e.pending.clear();
+}
+
+int gb200_profile_reset(gb200_ctx *c) {
+  if (!c) return GB200_ERR_ARG;
+  for (auto &kv : c->profs) { prof_drain(c, kv.second); kv.second.ms = 0.0; kv.second.launches = 0; }
+  return GB200_OK;
+}
+
+int gb200_profile_get(gb200_ctx *c, const char *name, double *ms, long *launches) {
+  if (!c || !name) return GB200_ERR_ARG;
+  auto it = c->profs.find(name);
+  if (it == c->profs.end()) { if (ms) *ms = 0.0; if (launches) *launches = 0; return GB200_OK; }
+  prof_drain(c, it->second);
+  if (ms) *ms = it->second.ms;
+  if (launches) *launches = it->second.launches;
+  return GB200_OK;
+}
+
+int gb200_set_option(gb200_ctx *c, const char *name, long value) {
+  if (!c || !name) return GB200_ERR_ARG;
+  if (!strcmp(name, "utx_path")) {
+    if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "utx_path must be 0,1,2");
+    c->utx_path = value; return GB200_OK;
+  }
+  if (!strcmp(name, "n_slices")) {
+    if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "n_slices must be 0..8");
+    if (value != c->n_slices) c->i8.ready = false;
+    c->n_slices = value; return GB200_OK;
+  }
+  return set_err(c, GB200_ERR_ARG, std::string("unknown option ") + name);
+}
+
+// ---------------------------------------------------------------------------------------
+int gb200_dgemm(gb200_ctx *c, const char *TransA, const char *TransB, double alpha, const double *A,
+                size_t a_rows, size_t a_cols, size_t lda, const double *B, size_t b_rows, size_t b_cols,
+                size_t ldb, double beta, double *C, size_t c_rows, size_t c_cols, size_t ldc) {
+  if (!c) return GB200_ERR_ARG;
+  bool oka, okb;
+  const bool ta = trans_flag(TransA, &oka), tb = trans_flag(TransB, &okb);
+  if (!oka || !okb || !A || !B || !C) return set_err(c, GB200_ERR_ARG, "gb200_dgemm: bad argument");
+  const size_t M = ta ? a_cols : a_rows, K = ta ? a_rows : a_cols;
+  const size_t Kb = tb ? b_cols : b_rows, N = tb ? b_rows : b_cols;
+  // fastblas.cpp:193-195 enforce(M>0, N>0, K>0); :207 "Range error in dgemm"
+  if (M == 0 || N == 0 || K == 0) return set_err(c, GB200_ERR_ARG, "gb200_dgemm: empty dimension");
+  if (K != Kb || c_rows != M || c_cols != N || lda < a_cols || ldb < b_cols || ldc < c_cols)
+    return set_err(c, GB200_ERR_ARG, "Range error in dgemm");
+  cudaStream_t st = c->stream;
+  DevBuf dA, dB, dC;
+  auto fail = [&](cudaError_t e, const char *what) {
+    dA.release(); dB.release(); dC.release();
+    return set_err(c, GB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  if ((e = dA.reserve(a_rows * a_cols * sizeof(double))) != cudaSuccess) return fail(e, "alloc A");
+  if ((e = dB.reserve(b_rows * b_cols * sizeof(double))) != cudaSuccess) return fail(e, "alloc B");
+  if ((e = dC.reserve(M * N * sizeof(double))) != cudaSuccess) return fail(e, "alloc C");
+  if ((e = cudaMemcpy2DAsync(dA.p, a_cols * 8, A, lda * 8, a_cols * 8, a_rows, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e, "copy A");
+  if ((e = cudaMemcpy2DAsync(dB.p, b_cols * 8, B, ldb * 8, b_cols * 8, b_rows, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e, "copy B");
+  if (beta != 0.0)
+    if ((e = cudaMemcpy2DAsync(dC.p, N * 8, C, ldc * 8, N * 8, M, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e, "copy C");
+  {
+    ProfScope ps(c, "dgemm");
+    const size_t sam = ta ? 1 : a_cols, sak = ta ? a_cols : 1;
+    const size_t sbk = tb ? 1 : b_cols, sbn = tb ? b_cols : 1;
+    if ((e = launch_dgemm(M, N, K, alpha, dA.as<double>(), sam, sak, dB.as<double>(), sbk, sbn, beta,
+                          dC.as<double>(), N, false, st)) != cudaSuccess) return fail(e, "dgemm kernel");
+  }
+  if ((e = cudaMemcpy2DAsync(C, ldc * 8, dC.p, N * 8, N * 8, M, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(e, "copy out");
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "sync");
+  dA.release(); dB.release(); dC.release();
+  return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// -gk
+int gb200_kin_begin(gb200_ctx *c, size_t n, int k_mode) {
+  if (!c) return GB200_ERR_ARG;
+  if (n == 0 || (k_mode != 1 && k_mode != 2)) return set_err(c, GB200_ERR_ARG, "gb200_kin_begin: bad argument");
+  GB_CUDA(c, c->dK.reserve(n * n * sizeof(double)));
+  GB_CUDA(c, cudaMemsetAsync(c->dK.p, 0, n * n * sizeof(double), c->stream));   // gsl_matrix_set_zero, param.cpp:1301
+  c->kin_n = n; c->kin_mode = k_mode; c->kin_ns = 0; c->kin_active = true;
+  return GB200_OK;
+}
+
+// K(lower) += Xs^T Xs for an SNP-major centred batch Xs (l x n, ld n) already on the device
+static int kin_accumulate_dev(gb200_ctx *c, const double *Xs, size_t l) {
+  const size_t n = c->kin_n;
+  ProfScope ps(c, "kin");
+  GB_CUDA(c, launch_dgemm(n, n, l, 1.0, Xs, 1, n, Xs, n, 1, 1.0, c->dK.as<double>(), n, true, c->stream));
+  c->kin_ns += l;
+  return GB200_OK;
+}
+
+int gb200_kin_add(gb200_ctx *c, const double *Xb, size_t n, size_t l, size_t ldx) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->kin_active) return set_err(c, GB200_ERR_STATE, "gb200_kin_add before gb200_kin_begin");
+  if (!Xb || n != c->kin_n || ldx < l) return set_err(c, GB200_ERR_ARG, "gb200_kin_add: bad argument");
+  if (l == 0) return GB200_OK;
+  GB_CUDA(c, c->dX.reserve(n * l * sizeof(double)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, l * 8, Xb, ldx * 8, l * 8, n, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "kin");
+    // A(i,s) = X[i*l+s], B(s,j) = X[j*l+s]
+    GB_CUDA(c, launch_dgemm(n, n, l, 1.0, c->dX.as<double>(), l, 1, c->dX.as<double>(), 1, l, 1.0,
+                            c->dK.as<double>(), n, true, c->stream));
+  }
+  c->kin_ns += l;
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_kin_add_geno(gb200_ctx *c, const double *G, size_t l, size_t n, size_t ldg) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->kin_active) return set_err(c, GB200_ERR_STATE, "gb200_kin_add_geno before gb200_kin_begin");
+  if (!G || n != c->kin_n || ldg < n) return set_err(c, GB200_ERR_ARG, "gb200_kin_add_geno: bad argument");
+  if (l == 0) return GB200_OK;
+  GB_CUDA(c, c->dX.reserve(n * l * sizeof(double)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_kin_transform(c->dX.as<double>(), l, n, n, c->kin_mode, c->stream));
+  }
+  int rc = kin_accumulate_dev(c, c->dX.as<double>(), l);
+  if (rc) return rc;
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_kin_add_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, size_t l, size_t bytes_per_snp) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->kin_active) return set_err(c, GB200_ERR_STATE, "gb200_kin_add_bed before gb200_kin_begin");
+  const size_t n = c->kin_n;
+  if (!bed_dev || bytes_per_snp != (n + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_kin_add_bed: bytes_per_snp != ceil(n/4)");
+  // bounded staging: decode + accumulate in chunks of at most ~1 GiB of FP64 genotypes
+  size_t chunk = (size_t(1) << 30) / (n * sizeof(double));
+  if (chunk < 256) chunk = 256;
+  for (size_t s0 = 0; s0 < l; s0 += chunk) {
+    const size_t lc = (l - s0 < chunk) ? (l - s0) : chunk;
+    GB_CUDA(c, c->dX.reserve(n * lc * sizeof(double)));
+    {
+      ProfScope ps(c, "decode");
+      GB_CUDA(c, launch_bed_decode(bed_dev + s0 * bytes_per_snp, lc, bytes_per_snp, nullptr, n,
+                                   c->dX.as<double>(), n, c->stream));
+      GB_CUDA(c, launch_kin_transform(c->dX.as<double>(), lc, n, n, c->kin_mode, c->stream));
+    }
+    int rc = kin_accumulate_dev(c, c->dX.as<double>(), lc);
+    if (rc) return rc;
+  }
+  return GB200_OK;
+}
+
+int gb200_kin_add_bed(gb200_ctx *c, const unsigned char *bed, size_t l, size_t bytes_per_snp) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->kin_active) return set_err(c, GB200_ERR_STATE, "gb200_kin_add_bed before gb200_kin_begin");
+  if (!bed) return set_err(c, GB200_ERR_ARG, "gb200_kin_add_bed: null input");
+  if (l == 0) return GB200_OK;
+  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
+  int rc = gb200_kin_add_bed_dev(c, c->dBed.as<unsigned char>(), l, bytes_per_snp);
+  if (rc) return rc;
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_kin_finish_dev(gb200_ctx *c, double **K_dev, size_t *ns_used) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->kin_active) return set_err(c, GB200_ERR_STATE, "gb200_kin_finish before gb200_kin_begin");
+  const size_t n = c->kin_n;
+  if (c->kin_ns > 0)   // gsl_matrix_scale(matrix_kin, 1.0/ns_test), gemma_io.cpp:1570
+    GB_CUDA(c, launch_scale(c->dK.as<double>(), n * n, 1.0 / (double)c->kin_ns, c->stream));
+  GB_CUDA(c, launch_symmetrize_from_lower(c->dK.as<double>(), n, n, c->stream));
+  if (K_dev) *K_dev = c->dK.as<double>();
+  if (ns_used) *ns_used = c->kin_ns;
+  c->kin_active = false;
+  return GB200_OK;
+}
+
+int gb200_kin_finish(gb200_ctx *c, double *K, size_t ldk, size_t *ns_used) {
+  if (!c) return GB200_ERR_ARG;
+  if (!K || ldk < c->kin_n) return set_err(c, GB200_ERR_ARG, "gb200_kin_finish: bad argument");
+  const size_t n = c->kin_n;
+  int rc = gb200_kin_finish_dev(c, nullptr, ns_used);
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpy2DAsync(K, ldk * 8, c->dK.p, n * 8, n * 8, n, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// -lmm
+static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double *U, size_t ldu,
+                             const double *eval) {
+  if (n == 0 || n_cvt == 0 || !U || !eval || ldu < n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: bad argument");
+  if (n_cvt > GB200_MAX_CVT)
+    return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT (fused kernel register budget)");
+  if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
+  c->lmm_ready = false; c->i8.ready = false;
+  GB_CUDA(c, c->dU.reserve(n * n * sizeof(double)));
+  GB_CUDA(c, c->dEval.reserve(n * sizeof(double)));
+  GB_CUDA(c, c->dWt.reserve(n_cvt * n * sizeof(double)));
+  GB_CUDA(c, c->dY.reserve(n * sizeof(double)));
+  GB_CUDA(c, c->dNull.reserve(sizeof(NullOut)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dU.p, n * 8, U, ldu * 8, n * 8, n, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dEval.p, eval, n * 8, cudaMemcpyHostToDevice, c->stream));
+  c->n = n; c->n_cvt = n_cvt;
+  return GB200_OK;
+}
+
+int gb200_lmm_setup(gb200_ctx *c, size_t n, size_t n_cvt, const double *U, size_t ldu, const double *eval,
+                    const double *W, size_t ldw, const double *y, double *UtW_out, double *Uty_out) {
+  if (!c) return GB200_ERR_ARG;
+  if (!W || !y || ldw < n_cvt) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: bad argument");
+  int rc = lmm_upload_common(c, n, n_cvt, U, ldu, eval);
+  if (rc) return rc;
+  // CalcUtX (mathfunc.cpp:497-510): UtW = U^T W, Uty = U^T y.  Stored transposed (n_cvt x n).
+  GB_CUDA(c, c->dTmp.reserve((n_cvt + 1) * n * sizeof(double)));
+  double *dW = c->dTmp.as<double>(), *dy = dW + n_cvt * n;
+  GB_CUDA(c, cudaMemcpy2DAsync(dW, n_cvt * 8, W, ldw * 8, n_cvt * 8, n, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, c->stream));
+  // Wt[a][i] = sum_j W[j][a] U[j][i]   (M = n_cvt, N = n, K = n)
+  GB_CUDA(c, launch_dgemm(n_cvt, n, n, 1.0, dW, 1, n_cvt, c->dU.as<double>(), n, 1, 0.0, c->dWt.as<double>(), n,
+                          false, c->stream));
+  GB_CUDA(c, launch_dgemm(1, n, n, 1.0, dy, 1, 1, c->dU.as<double>(), n, 1, 0.0, c->dY.as<double>(), n, false,
+                          c->stream));
+  if (UtW_out) {
+    // return as n x n_cvt row-major
+    std::vector<double> t(n_cvt * n);
+    GB_CUDA(c, cudaMemcpyAsync(t.data(), c->dWt.p, n_cvt * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t a = 0; a < n_cvt; ++a)
+      for (size_t i = 0; i < n; ++i) UtW_out[i * n_cvt + a] = t[a * n + i];
+  }
+  if (Uty_out) GB_CUDA(c, cudaMemcpyAsync(Uty_out, c->dY.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->lmm_ready = true;
+  return GB200_OK;
+}
+
+int gb200_lmm_setup_rotated(gb200_ctx *c, size_t n, size_t n_cvt, const double *U, size_t ldu,
+                            const double *eval, const double *UtW, size_t ldw, const double *Uty) {
+  if (!c) return GB200_ERR_ARG;
+  if (!UtW || !Uty || ldw < n_cvt) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated: bad argument");
+  int rc = lmm_upload_common(c, n, n_cvt, U, ldu, eval);
+  if (rc) return rc;
+  std::vector<double> t(n_cvt * n);
+  for (size_t a = 0; a < n_cvt; ++a)
+    for (size_t i = 0; i < n; ++i) t[a * n + i] = UtW[i * ldw + a];
+  GB_CUDA(c, cudaMemcpyAsync(c->dWt.p, t.data(), n_cvt * n * 8, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dY.p, Uty, n * 8, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->lmm_ready = true;
+  return GB200_OK;
+}
+
+static LmmConst make_const(gb200_ctx *c) {
+  LmmConst D;
+  D.n = (int)c->n; D.ldv = (int)c->n;
+  D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
+  return D;
+}
+
+// c x c Gaussian elimination with partial pivoting: beta = A^-1 b, diag of A^-1
+// (LUDecomp/LUSolve/LUInvert at src/lmm.cpp:2246-2250)
+static void solve_small(size_t cN, std::vector<double> A, const std::vector<double> &b, double *x, double *diag_inv) {
+  std::vector<double> M(cN * (cN + 1 + cN));
+  const size_t w = 2 * cN + 1;
+  for (size_t i = 0; i < cN; ++i) {
+    for (size_t j = 0; j < cN; ++j) M[i * w + j] = A[i * cN + j];
+    M[i * w + cN] = b[i];
+    for (size_t j = 0; j < cN; ++j) M[i * w + cN + 1 + j] = (i == j) ? 1.0 : 0.0;
+  }
+  for (size_t k = 0; k < cN; ++k) {
+    size_t pr = k;
+    for (size_t i = k + 1; i < cN; ++i) if (fabs(M[i * w + k]) > fabs(M[pr * w + k])) pr = i;
+    if (pr != k) for (size_t j = 0; j < w; ++j) std::swap(M[k * w + j], M[pr * w + j]);
+    const double piv = M[k * w + k];
+    for (size_t j = 0; j < w; ++j) M[k * w + j] /= piv;
+    for (size_t i = 0; i < cN; ++i) {
+      if (i == k) continue;
+      const double f = M[i * w + k];
+      if (f != 0.0) for (size_t j = 0; j < w; ++j) M[i * w + j] -= f * M[k * w + j];
+    }
+  }
+  for (size_t i = 0; i < cN; ++i) { x[i] = M[i * w + cN]; diag_inv[i] = M[i * w + cN + 1 + i]; }
+}
+
+static double safe_sqrt_host(double d) {   // mathfunc.cpp:122-131
+  double d1 = d;
+  if (d < 0.001) d1 = fabs(d);
+  if (d1 < 0.0) return nan("");
+  return sqrt(d1);
+}
+
+int gb200_lmm_null(gb200_ctx *c, double l_min, double l_max, size_t n_region, double trace_G,
+                   gb200_nullmodel *out, double *beta_mle, double *se_beta_mle, double *beta_remle,
+                   double *se_beta_remle) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, "gb200_lmm_null before gb200_lmm_setup");
+  if (!out || !(l_max > l_min) || n_region == 0) return set_err(c, GB200_ERR_ARG, "gb200_lmm_null: bad argument");
+  LmmConst D = make_const(c);
+  {
+    ProfScope ps(c, "lmm");
+    GB_CUDA(c, launch_lmm_null((int)c->n_cvt, D, l_min, l_max, (int)n_region, c->dNull.as<NullOut>(), c->stream));
+  }
+  NullOut r;
+  GB_CUDA(c, cudaMemcpyAsync(&r, c->dNull.p, sizeof(NullOut), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t n = c->n, cN = c->n_cvt;
+  out->l_mle_null = r.l_mle; out->logl_mle_H0 = r.logl_mle;
+  out->l_remle_null = r.l_remle; out->logl_remle_H0 = r.logl_remle;
+  // CalcPve, src/lmm.cpp:2195-2199
+  const double se = safe_sqrt_host(-1.0 / r.dev2_remle);
+  out->pve_null = trace_G * r.l_remle / (trace_G * r.l_remle + 1.0);
+  out->pve_se_null = trace_G / ((trace_G * r.l_remle + 1.0) * (trace_G * r.l_remle + 1.0)) * se;
+  // CalcLmmVgVeBeta, src/lmm.cpp:2242-2271.  The kernel ran with NC = c-1 and x = last covariate,
+  // so its variable order is w_1..w_{c-1}, x(=w_c), y: NV = c+1 variables.
+  const int NV = (int)cN + 1;
+  for (int which = 0; which < 2; ++which) {
+    const double *S1 = which == 0 ? r.S1_mle : r.S1_remle;
+    const double lam = which == 0 ? r.l_mle : r.l_remle;
+    const double Pyy = which == 0 ? r.Pyy_mle : r.Pyy_remle;
+    std::vector<double> A(cN * cN), b(cN);
+    for (size_t a = 0; a < cN; ++a) {
+      for (size_t bb = 0; bb < cN; ++bb) {
+        const int lo = (int)(a < bb ? a : bb), hi = (int)(a < bb ? bb : a);
+        A[a * cN + bb] = S1[abidx(lo, hi, NV)];
+      }
+      b[a] = S1[abidx((int)a, NV - 1, NV)];
+    }
+    std::vector<double> beta(cN), dinv(cN);
+    solve_small(cN, A, b, beta.data(), dinv.data());
+    const double ve = Pyy / (double)(n - cN), vg = ve * lam;
+    if (which == 0) { out->ve_mle = ve; out->vg_mle = vg; } else { out->ve_remle = ve; out->vg_remle = vg; }
+    double *bo = which == 0 ? beta_mle : beta_remle, *so = which == 0 ? se_beta_mle : se_beta_remle;
+    for (size_t i = 0; i < cN; ++i) {
+      if (bo) bo[i] = beta[i];
+      if (so) so[i] = safe_sqrt_host(dinv[i] * ve);
+    }
+  }
+  return GB200_OK;
+}
+
+int gb200_lmm_params(gb200_ctx *c, int a_mode, double l_min, double l_max, size_t n_region,
+                     double l_mle_null, double logl_mle_H0) {
+  if (!c) return GB200_ERR_ARG;
+  if (!(a_mode == 1 || a_mode == 2 || a_mode == 3 || a_mode == 4 || a_mode == 9))
+    return set_err(c, GB200_ERR_ARG, "gb200_lmm_params: a_mode must be 1,2,3,4 or 9");
+  if (!(l_max > l_min) || !(l_min > 0) || n_region == 0 || n_region > 100000)
+    return set_err(c, GB200_ERR_ARG, "gb200_lmm_params: need 0 < l_min < l_max, n_region >= 1");
+  c->prm.a_mode = a_mode; c->prm.l_min = l_min; c->prm.l_max = l_max; c->prm.n_region = (int)n_region;
+  c->prm.l_mle_null = l_mle_null; c->prm.logl_mle_H0 = logl_mle_H0;
+  c->prm_ready = true;
+  return GB200_OK;
+}
+
+static int lmm_check_ready(gb200_ctx *c, const char *who) {
+  if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, std::string(who) + " before gb200_lmm_setup");
+  if (!c->prm_ready) return set_err(c, GB200_ERR_STATE, std::string(who) + " before gb200_lmm_params");
+  return GB200_OK;
+}
+
+// association kernel on a device-resident rotated batch
+static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev) {
+  LmmConst D = make_const(c);
+  ProfScope ps(c, "lmm");
+  GB_CUDA(c, launch_lmm_assoc((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, c->dTicket.as<unsigned int>(),
+                              c->num_sms, c->stream));
+  return GB200_OK;
+}
+
+// UtXt (l x n) = Xs (l x n, SNP-major, ld n) * U   -- the fast_dgemm("T","N",U,X) of lmm.cpp:1521
+static int project_fp64_snpmajor(gb200_ctx *c, const double *Xs, size_t l, double *UtXt) {
+  const size_t n = c->n;
+  ProfScope ps(c, "utx");
+  GB_CUDA(c, launch_dgemm(l, n, n, 1.0, Xs, n, 1, c->dU.as<double>(), n, 1, 0.0, UtXt, n, false, c->stream));
+  return GB200_OK;
+}
+
+int gb200_lmm_assoc_utx(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = lmm_check_ready(c, "gb200_lmm_assoc_utx");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;
+  if (!UtXt || !out || ldu < c->n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_assoc_utx: bad argument");
+  const size_t n = c->n;
+  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dUtXt.p, n * 8, UtXt, ldu * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, c->dOut.as<gb200_sumstat>());
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_lmm_project(gb200_ctx *c, const double *Xb, size_t l, size_t ldx, double *UtXt) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, "gb200_lmm_project before gb200_lmm_setup");
+  if (l == 0) return GB200_OK;
+  if (!Xb || !UtXt || ldx < l) return set_err(c, GB200_ERR_ARG, "gb200_lmm_project: bad argument");
+  const size_t n = c->n;
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, l * 8, Xb, ldx * 8, l * 8, n, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "utx");
+    // A(s,j) = X[j*l + s]
+    GB_CUDA(c, launch_dgemm(l, n, n, 1.0, c->dX.as<double>(), 1, l, c->dU.as<double>(), n, 1, 0.0,
+                            c->dUtXt.as<double>(), n, false, c->stream));
+  }
+  GB_CUDA(c, cudaMemcpyAsync(UtXt, c->dUtXt.p, l * n * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_lmm_batch(gb200_ctx *c, const double *Xb, size_t l, size_t ldx, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = lmm_check_ready(c, "gb200_lmm_batch");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;     // the reference aborts here (fastblas.cpp:193); a no-op is the sane drop-in
+  if (!Xb || !out || ldx < l) return set_err(c, GB200_ERR_ARG, "gb200_lmm_batch: bad argument");
+  const size_t n = c->n;
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, l * 8, Xb, ldx * 8, l * 8, n, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "utx");
+    GB_CUDA(c, launch_dgemm(l, n, n, 1.0, c->dX.as<double>(), 1, l, c->dU.as<double>(), n, 1, 0.0,
+                            c->dUtXt.as<double>(), n, false, c->stream));
+  }
+  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, c->dOut.as<gb200_sumstat>());
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = lmm_check_ready(c, "gb200_lmm_batch_geno");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;
+  const size_t n = c->n;
+  if (!G || !out || ldg < n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_batch_geno: bad argument");
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  }
+  rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+  if (rc) return rc;
+  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, c->dOut.as<gb200_sumstat>());
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+// rotate + test a device-resident bed batch; idx_dev maps analysed position -> ni_total index (or null)
+static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
+                        size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
+  const size_t n = c->n;
+  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  bool use_i8 = false;
+  if (c->utx_path == 2) {
+    if (!i8_available(c)) return set_err(c, GB200_ERR_UNSUPPORTED, "int8 tensor-core path not available in this build");
+    use_i8 = true;
+  } else if (c->utx_path == 0) {
+    use_i8 = i8_available(c) && n >= 1024;
+  }
+  if (use_i8) {
+    int rc = i8_project_bed(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, c->dUtXt.as<double>());
+    if (rc) return rc;
+  } else {
+    GB_CUDA(c, c->dX.reserve(n * l * 8));
+    {
+      ProfScope ps(c, "decode");
+      GB_CUDA(c, launch_bed_decode(bed_dev, l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
+      GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+    }
+    int rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+    if (rc) return rc;
+  }
+  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, out_dev);
+}
+
+static int upload_idx_from_mask(gb200_ctx *c, const unsigned char *idv_mask, size_t ni_total, const int **idx_dev) {
+  *idx_dev = nullptr;
+  if (!idv_mask) {
+    if (ni_total != c->n) return set_err(c, GB200_ERR_ARG, "idv_mask == NULL requires ni_total == n");
+    return GB200_OK;
+  }
+  if (c->mask_host.size() != ni_total || memcmp(c->mask_host.data(), idv_mask, ni_total) != 0) {
+    c->mask_host.assign(idv_mask, idv_mask + ni_total);
+    c->idx_host.clear();
+    for (size_t i = 0; i < ni_total; ++i) if (idv_mask[i]) c->idx_host.push_back((int)i);
+    if (c->idx_host.size() != c->n) {
+      c->mask_host.clear();
+      return set_err(c, GB200_ERR_ARG, "idv_mask selects a number of individuals different from n");
+    }
+    GB_CUDA(c, c->dIdx.reserve(c->n * sizeof(int)));
+    GB_CUDA(c, cudaMemcpyAsync(c->dIdx.p, c->idx_host.data(), c->n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  *idx_dev = c->dIdx.as<int>();
+  return GB200_OK;
+}
+
+int gb200_lmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
+                        size_t l, size_t bytes_per_snp, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = lmm_check_ready(c, "gb200_lmm_batch_bed");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;
+  if (!bed || !out || bytes_per_snp != (ni_total + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_lmm_batch_bed: bad argument");
+  const int *idx_dev = nullptr;
+  rc = upload_idx_from_mask(c, idv_mask, ni_total, &idx_dev);
+  if (rc) return rc;
+  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
+  rc = lmm_bed_core(c, c->dBed.as<unsigned char>(), idx_dev, ni_total, l, bytes_per_snp, c->dOut.as<gb200_sumstat>());
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_lmm_batch_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const unsigned char *idv_mask_dev,
+                            size_t ni_total, size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = lmm_check_ready(c, "gb200_lmm_batch_bed_dev");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;
+  if (!bed_dev || !out_dev || bytes_per_snp != (ni_total + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_lmm_batch_bed_dev: bad argument");
+  const int *idx_dev = nullptr;
+  if (idv_mask_dev) {
+    // the mask lives on the device: bring it back once (ni_total bytes) to build the gather index
+    std::vector<unsigned char> m(ni_total);
+    GB_CUDA(c, cudaMemcpyAsync(m.data(), idv_mask_dev, ni_total, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    rc = upload_idx_from_mask(c, m.data(), ni_total, &idx_dev);
+    if (rc) return rc;
+  } else if (ni_total != c->n) {
+    return set_err(c, GB200_ERR_ARG, "idv_mask == NULL requires ni_total == n");
+  }
+  return lmm_bed_core(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, out_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// common.cuh -- context object and helpers shared by the translation units of libgemma_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <utility>
+#include "../../include/gemma_b200.h"
+#include "lmm_device.cuh"
+
+namespace gb {
+
+struct ProfEntry {
+  double ms = 0.0;
+  long launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// int8 tensor-core projection state (i8gemm_sm100.cu)
+struct I8State {
+  bool ready = false;
+  int n_slices = 0;
+  size_t n = 0, n_pad = 0;       // individuals, padded to the K tile
+  DevBuf slices;                 // n_slices x [n_pad(i: eigvec) x n_pad(j: individual)] int8, j contiguous
+  DevBuf scale;                  // per-eigenvector power-of-two scale (n doubles)
+  DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
+  DevBuf miss_mean;              // per-SNP mean (for the missing correction)
+  void *tmap_a = nullptr, *tmap_b = nullptr;   // CUtensorMap storage (host)
+};
+
+}  // namespace gb
+
+struct gb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  std::string err;
+  // profiling
+  bool prof = false;
+  std::map<std::string, gb::ProfEntry> profs;
+  std::vector<cudaEvent_t> event_pool;
+  // -gk
+  size_t kin_n = 0;
+  int kin_mode = 0;
+  size_t kin_ns = 0;
+  bool kin_active = false;
+  gb::DevBuf dK;
+  // -lmm
+  size_t n = 0, n_cvt = 0;
+  bool lmm_ready = false, prm_ready = false;
+  gb::DevBuf dU, dEval, dWt, dY;
+  gb::LmmParams prm{};
+  gb::DevBuf dNull;
+  // scratch
+  gb::DevBuf dX, dUtXt, dOut, dBed, dMask, dIdx, dTicket, dTmp;
+  std::vector<int> idx_host;          // analysed-individual index cache for bed batches
+  std::vector<unsigned char> mask_host;
+  // options
+  long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
+  long n_slices = 0;     // 0 = default
+  gb::I8State i8;
+};
+
+namespace gb {
+
+inline int set_err(gb200_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define GB_CUDA(ctx, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      char _b[512];                                                                              \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+               __LINE__);                                                                        \
+      return gb::set_err(ctx, GB200_ERR_CUDA, _b);                                               \
+    }                                                                                            \
+  } while (0)
+
+// RAII-less profiling scope: records start/stop events on the context stream when enabled.
+struct ProfScope {
+  gb200_ctx *c;
+  ProfEntry *e = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get_event(gb200_ctx *c) {
+    if (!c->event_pool.empty()) { cudaEvent_t ev = c->event_pool.back(); c->event_pool.pop_back(); return ev; }
+    cudaEvent_t ev; cudaEventCreate(&ev); return ev;
+  }
+  ProfScope(gb200_ctx *ctx, const char *name) : c(ctx) {
+    if (!c->prof) return;
+    e = &c->profs[name];
+    a = get_event(c); b = get_event(c);
+    cudaEventRecord(a, c->stream);
+  }
+  ~ProfScope() {
+    if (!e) return;
+    cudaEventRecord(b, c->stream);
+    e->pending.emplace_back(a, b);
+    e->launches++;
+  }
+};
+
+// ---- kernels / launchers implemented in the other translation units ----
+cudaError_t launch_lmm_assoc(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt,
+                             size_t ldu, int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,
+                             cudaStream_t st);
+cudaError_t launch_lmm_null(int n_cvt, const LmmConst &D, double l_min, double l_max, int n_region,
+                            NullOut *out, cudaStream_t st);
+
+// C(M x N, row-major ldc) = alpha * A * B + beta * C with arbitrary element strides:
+// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].
+cudaError_t launch_dgemm(size_t M, size_t N, size_t K, double alpha, const double *A, size_t sam, size_t sak,
+                         const double *B, size_t sbk, size_t sbn, double beta, double *C, size_t ldc,
+                         bool lower_only, cudaStream_t st);
+cudaError_t launch_symmetrize_from_lower(double *C, size_t n, size_t ldc, cudaStream_t st);
+cudaError_t launch_scale(double *C, size_t count, double alpha, cudaStream_t st);
+cudaError_t launch_transpose(const double *in, size_t rows, size_t cols, size_t ldi, double *out, size_t ldo,
+                             cudaStream_t st);
+
+// genotype kernels (geno.cu)
+cudaError_t launch_kin_transform(double *G, size_t l, size_t n, size_t ldg, int k_mode, cudaStream_t st);
+cudaError_t launch_lmm_impute(double *G, size_t l, size_t n, size_t ldg, cudaStream_t st);
+cudaError_t launch_bed_decode(const unsigned char *bed, size_t l, size_t bytes_per_snp, const int *idx,
+                              size_t n_out, double *G, size_t ldg, cudaStream_t st);
+cudaError_t launch_center_matrix(double *G, size_t n, size_t ldg, double *row_sums, cudaStream_t st);
+
+}  // namespace gb

@@ -1,0 +1,169 @@
+// dgemm.cu -- FP64 GEMM seam of the reference: fast_dgemm / fast_eigen_dgemm
+// (src/fastblas.cpp:175-236 -> cblas_dgemm).  Exact-FP64 path used for dosage-valued
+// (non-integer) genotypes, for U^T W / U^T y, and as the generic kinship accumulator;
+// integer genotypes take the tensor-core path in i8gemm_sm100.cu.
+//
+// 128x128x16 CTA tile, 256 threads, 8x8 register tile per thread, operands staged in
+// shared memory k-major so the inner product reads 16-byte vectors without bank
+// conflicts.  Element strides are arbitrary (covers N/T on either operand and
+// gsl_matrix sub-views with tda != size2); the global->shared loader picks the thread
+// mapping that makes the unit-stride dimension the fastest varying one (coalesced).
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
+constexpr int PADM = BM + 2, PADN = BN + 2;
+
+template <bool LOWER_ONLY>
+__global__ void __launch_bounds__(256) dgemm_kernel(size_t M, size_t N, size_t K, double alpha,
+                                                    const double *__restrict__ A, size_t sam, size_t sak,
+                                                    const double *__restrict__ B, size_t sbk, size_t sbn,
+                                                    double beta, double *__restrict__ C, size_t ldc) {
+  __shared__ __align__(16) double As[BK][PADM];
+  __shared__ __align__(16) double Bs[BK][PADN];
+  const size_t m0 = (size_t)blockIdx.y * BM, n0 = (size_t)blockIdx.x * BN;
+  if (LOWER_ONLY && n0 > m0 + BM - 1) return;     // tile entirely above the diagonal
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;        // thread tile origin: rows ty*8.., cols tx*8..
+  double acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+
+  const bool a_kfast = (sak == 1);
+  const bool b_nfast = (sbn == 1);
+  for (size_t k0 = 0; k0 < K; k0 += BK) {
+    // ---- stage A tile (BM x BK) -> As[k][m]
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / 256; ++r) {
+      int mm, kk;
+      if (a_kfast) { kk = tid % BK; mm = tid / BK + r * (256 / BK); }
+      else { mm = tid % BM; kk = tid / BM + r * (256 / BM); }
+      const size_t gm = m0 + mm, gk = k0 + kk;
+      double v = 0.0;
+      if (gm < M && gk < K) v = A[gm * sam + gk * sak];
+      As[kk][mm] = v;
+    }
+    // ---- stage B tile (BK x BN) -> Bs[k][n]
+#pragma unroll
+    for (int r = 0; r < (BN * BK) / 256; ++r) {
+      int nn, kk;
+      if (b_nfast) { nn = tid % BN; kk = tid / BN + r * (256 / BN); }
+      else { kk = tid % BK; nn = tid / BK + r * (256 / BK); }
+      const size_t gn = n0 + nn, gk = k0 + kk;
+      double v = 0.0;
+      if (gn < N && gk < K) v = B[gk * sbk + gn * sbn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      double a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 2) {
+        const double2 t = *reinterpret_cast<const double2 *>(&As[kk][ty * TM + i]);
+        a[i] = t.x; a[i + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 2) {
+        const double2 t = *reinterpret_cast<const double2 *>(&Bs[kk][tx * TN + j]);
+        b[j] = t.x; b[j + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const size_t gm = m0 + ty * TM + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const size_t gn = n0 + tx * TN + j;
+      if (gn >= N) continue;
+      if (LOWER_ONLY && gn > gm) continue;
+      double *c = C + gm * ldc + gn;
+      const double prev = (beta == 0.0) ? 0.0 : beta * (*c);
+      *c = fma(alpha, acc[i][j], prev);
+    }
+  }
+}
+
+cudaError_t launch_dgemm(size_t M, size_t N, size_t K, double alpha, const double *A, size_t sam, size_t sak,
+                         const double *B, size_t sbk, size_t sbn, double beta, double *C, size_t ldc,
+                         bool lower_only, cudaStream_t st) {
+  if (M == 0 || N == 0) return cudaSuccess;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+  if (lower_only)
+    dgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  else
+    dgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  return cudaGetLastError();
+}
+
+// mirror the lower triangle into the upper one (PlinkKin symmetrises explicitly,
+// src/gemma_io.cpp:1724-1729; the dgemm of BimbamKin produces both halves)
+__global__ void symmetrize_kernel(double *C, size_t n, size_t ldc) {
+  __shared__ double tile[32][33];
+  const size_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const size_t i = bi * 32 + threadIdx.y, j = bj * 32 + threadIdx.x;
+  // read lower tile (bi,bj), write transposed into (bj,bi)
+  for (int r = 0; r < 32; r += 8) {
+    const size_t ii = i + r;
+    if (ii < n && j < n) tile[threadIdx.y + r][threadIdx.x] = C[ii * ldc + j];
+  }
+  __syncthreads();
+  const size_t oi = bj * 32 + threadIdx.y, oj = bi * 32 + threadIdx.x;
+  for (int r = 0; r < 32; r += 8) {
+    const size_t ii = oi + r;
+    if (ii < n && oj < n && oj > ii) C[ii * ldc + oj] = tile[threadIdx.x][threadIdx.y + r];
+  }
+}
+
+cudaError_t launch_symmetrize_from_lower(double *C, size_t n, size_t ldc, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 8);
+  symmetrize_kernel<<<grid, block, 0, st>>>(C, n, ldc);
+  return cudaGetLastError();
+}
+
+__global__ void scale_kernel(double *C, size_t count, double alpha) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < count; i += stride) C[i] *= alpha;
+}
+cudaError_t launch_scale(double *C, size_t count, double alpha, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  scale_kernel<<<148 * 8, 256, 0, st>>>(C, count, alpha);
+  return cudaGetLastError();
+}
+
+__global__ void transpose_kernel(const double *__restrict__ in, size_t rows, size_t cols, size_t ldi,
+                                 double *__restrict__ out, size_t ldo) {
+  __shared__ double tile[32][33];
+  const size_t r0 = (size_t)blockIdx.y * 32, c0 = (size_t)blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const size_t rr = r0 + r, cc = c0 + threadIdx.x;
+    if (rr < rows && cc < cols) tile[r][threadIdx.x] = in[rr * ldi + cc];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const size_t orow = c0 + r, ocol = r0 + threadIdx.x;   // out is cols x rows
+    if (orow < cols && ocol < rows) out[orow * ldo + ocol] = tile[threadIdx.x][r];
+  }
+}
+cudaError_t launch_transpose(const double *in, size_t rows, size_t cols, size_t ldi, double *out, size_t ldo,
+                             cudaStream_t st) {
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(in, rows, cols, ldi, out, ldo);
+  return cudaGetLastError();
+}
+
+}  // namespace gb

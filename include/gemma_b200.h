@@ -1,0 +1,179 @@
+/*
+ * gemma_b200.h -- C ABI of libgemma_b200.so, the B200-native replacement for the
+ * compute seams of GEMMA's -gk / -eigen / -lmm path.
+ *
+ * The reference (genetics-statistics/GEMMA) has no plugin/FFI layer: it is one C++
+ * binary whose hot path sits behind four internal seams taking gsl_matrix* /
+ * gsl_vector*.  Each entry point below names the seam (reference file:line,
+ * relative to the GEMMA source tree) it replaces.  INTEGRATION.md shows the
+ * binding a GEMMA maintainer would add at each seam.
+ *
+ * Conventions
+ *   - plain C, no exceptions across the boundary; every call returns 0 on success
+ *     or a non-zero gb200_status, and gb200_last_error(ctx) describes the failure;
+ *   - matrices are row-major FP64 with an explicit leading dimension (gsl_matrix's
+ *     `tda`), caller-owned HOST buffers unless the name ends in _dev;
+ *   - one context per GPU and per host thread (the reference is single-threaded
+ *     and non-reentrant; a context is thread-compatible, not thread-safe);
+ *   - all work of a context is issued on ONE CUDA stream (gb200_stream) so that
+ *     callers can bracket it with their own events.
+ */
+#ifndef GEMMA_B200_H
+#define GEMMA_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GB200_API __attribute__((visibility("default")))
+#else
+#define GB200_API
+#endif
+
+typedef enum {
+  GB200_OK = 0,
+  GB200_ERR_ARG = 1,        /* bad argument / shape mismatch ("Range error in dgemm", fastblas.cpp:207) */
+  GB200_ERR_CUDA = 2,       /* CUDA runtime / driver error                                            */
+  GB200_ERR_STATE = 3,      /* call out of order (e.g. lmm_batch before lmm_setup)                    */
+  GB200_ERR_UNSUPPORTED = 4,/* e.g. n_cvt larger than the compiled maximum                            */
+  GB200_ERR_NUMERIC = 5,    /* eigensolver did not converge                                           */
+  GB200_ERR_NOMEM = 6
+} gb200_status;
+
+typedef struct gb200_ctx gb200_ctx;
+
+/* SUMSTAT, src/param.h:54-66: what LMM::Analyze pushes per SNP (src/lmm.cpp:1559-1561). */
+typedef struct {
+  double beta, se, lambda_remle, lambda_mle, p_wald, p_lrt, p_score, logl_H1;
+} gb200_sumstat;
+
+/* Null-model results: what BatchRun computes once per run with CalcLambda('L'/'R'),
+ * CalcLmmVgVeBeta and CalcPve (src/gemma.cpp:2711-2753, src/lmm.cpp:2143-2281). */
+typedef struct {
+  double l_mle_null, logl_mle_H0;
+  double l_remle_null, logl_remle_H0;
+  double pve_null, pve_se_null;
+  double vg_mle, ve_mle, vg_remle, ve_remle;
+} gb200_nullmodel;
+
+#define GB200_MAX_CVT 6      /* covariates incl. intercept supported by the fused per-SNP kernel */
+
+/* ---- context ---------------------------------------------------------------- */
+GB200_API int gb200_abi_version(void);
+/* device < 0: use the current CUDA device.  stream == NULL: the context creates its own
+ * non-blocking stream; otherwise `stream` is a cudaStream_t owned by the caller. */
+GB200_API int gb200_create(gb200_ctx **out, int device, void *stream);
+GB200_API void gb200_destroy(gb200_ctx *ctx);
+GB200_API const char *gb200_last_error(const gb200_ctx *ctx);
+GB200_API void *gb200_stream(const gb200_ctx *ctx);           /* cudaStream_t */
+GB200_API int gb200_synchronize(gb200_ctx *ctx);
+
+/* Per-kernel device timing (CUDA events on the context stream).  Names: "utx", "lmm",
+ * "kin", "decode", "eigh", "dgemm".  Returns accumulated milliseconds and launch count
+ * since the last gb200_profile_reset.  Used by bench.py for the roofline figures. */
+GB200_API int gb200_profile_enable(gb200_ctx *ctx, int on);
+GB200_API int gb200_profile_reset(gb200_ctx *ctx);
+GB200_API int gb200_profile_get(gb200_ctx *ctx, const char *name, double *ms, long *launches);
+
+/* ---- dense GEMM seam -------------------------------------------------------- */
+/* fast_dgemm / fast_eigen_dgemm (src/fastblas.h:36-41, src/fastblas.cpp:175-236):
+ * C = alpha*op(A)*op(B) + beta*C on row-major matrices with leading dimensions.
+ * A is a_rows x a_cols as stored, op selected by TransA/TransB ("N"/"T", first char).
+ * Shape mismatch or an empty dimension returns GB200_ERR_ARG (the reference enforces
+ * M,N,K > 0 at fastblas.cpp:193-195 and aborts on mismatch at :207). */
+GB200_API int gb200_dgemm(gb200_ctx *ctx, const char *TransA, const char *TransB, double alpha,
+                const double *A, size_t a_rows, size_t a_cols, size_t lda,
+                const double *B, size_t b_rows, size_t b_cols, size_t ldb,
+                double beta, double *C, size_t c_rows, size_t c_cols, size_t ldc);
+
+/* ---- -gk : kinship ---------------------------------------------------------- */
+/* PARAM::CalcKin -> BimbamKin / PlinkKin (src/param.cpp:1300-1321,
+ * src/gemma_io.cpp:1418-1597, :1599-1738).  begin zeroes a device-resident n x n
+ * accumulator; each add folds one batch of SNPs (K += Xb Xb^T, the fast_eigen_dgemm
+ * of gemma_io.cpp:1554/:1711); finish scales by 1/ns_used (:1570/:1722) and copies K
+ * (full symmetric matrix) to the host.  k_mode 1 = centred (-gk 1), 2 = standardised. */
+GB200_API int gb200_kin_begin(gb200_ctx *ctx, size_t n, int k_mode);
+/* Xb: n x l row-major, columns ALREADY centred/scaled by the caller (Xlarge as the
+ * reference holds it at gemma_io.cpp:1546-1554). */
+GB200_API int gb200_kin_add(gb200_ctx *ctx, const double *Xb, size_t n, size_t l, size_t ldx);
+/* G: l x n SNP-major raw genotypes/dosages, NaN = missing.  The per-SNP transform of
+ * gemma_io.cpp:1511-1538 (mean over non-missing, variance, mean imputation, centring,
+ * optional 1/sqrt(var)) runs on the device. */
+GB200_API int gb200_kin_add_geno(gb200_ctx *ctx, const double *G, size_t l, size_t n, size_t ldg);
+/* bed: l rows of PLINK SNP-major 2-bit genotypes, bytes_per_snp = ceil(n/4), decoded as
+ * gemma_io.cpp:1665-1682 (00->2, 10->1 [low bit 0, high bit 1], 11->0, 01->missing). */
+GB200_API int gb200_kin_add_bed(gb200_ctx *ctx, const unsigned char *bed, size_t l, size_t bytes_per_snp);
+GB200_API int gb200_kin_add_bed_dev(gb200_ctx *ctx, const unsigned char *bed_dev, size_t l, size_t bytes_per_snp);
+GB200_API int gb200_kin_finish(gb200_ctx *ctx, double *K, size_t ldk, size_t *ns_used);
+/* Same, but leaves K on the device and returns the device pointer (n x n, ld n). */
+GB200_API int gb200_kin_finish_dev(gb200_ctx *ctx, double **K_dev, size_t *ns_used);
+
+/* ---- eigendecomposition ----------------------------------------------------- */
+/* CenterMatrix (src/mathfunc.cpp:147-177, applied when center != 0) followed by
+ * EigenDecomp_Zeroed (src/lapack.cpp:260-291 -> dsyevr): all eigenpairs of the
+ * symmetric G; eigenvalues ascending, those < 1e-10 set to 0; U row-major with
+ * eigenvectors in COLUMNS (lapack.cpp:228); *trace_G = mean(eval).  G is destroyed
+ * (as in the reference).  n_zero / n_negative (optional) feed the reference's warnings
+ * (lapack.cpp:278-289). */
+GB200_API int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int center,
+               double *U, size_t ldu, double *eval, double *trace_G,
+               int *n_zero, int *n_negative);
+
+/* ---- -lmm : per-run setup, null model, per-batch association ---------------- */
+/* Uploads the run-constant state of LMM::Analyze (src/lmm.cpp:1474-1511): U (n x n,
+ * eigenvectors in columns), eval, W (n x n_cvt) and y; computes UtW = U^T W and
+ * Uty = U^T y on the device (CalcUtX, src/mathfunc.cpp:497-510, called at
+ * src/gemma.cpp:2699-2700).  UtW_out (n x n_cvt, ld n_cvt) / Uty_out may be NULL. */
+GB200_API int gb200_lmm_setup(gb200_ctx *ctx, size_t n, size_t n_cvt,
+                    const double *U, size_t ldu, const double *eval,
+                    const double *W, size_t ldw, const double *y,
+                    double *UtW_out, double *Uty_out);
+/* Variant for callers that already hold UtW / Uty (e.g. -d/-u input without W,y). */
+GB200_API int gb200_lmm_setup_rotated(gb200_ctx *ctx, size_t n, size_t n_cvt,
+                            const double *U, size_t ldu, const double *eval,
+                            const double *UtW, size_t ldw, const double *Uty);
+/* Null model on the device with the same fused evaluator (src/gemma.cpp:2711-2753):
+ * also returns beta / se(beta) of the covariates (n_cvt values each) for MLE and REMLE. */
+GB200_API int gb200_lmm_null(gb200_ctx *ctx, double l_min, double l_max, size_t n_region, double trace_G,
+                   gb200_nullmodel *out, double *beta_mle, double *se_beta_mle,
+                   double *beta_remle, double *se_beta_remle);
+/* Parameters of the per-SNP tests: a_mode 1 Wald, 2 LRT, 3 score, 4 all, 9 (src/lmm.cpp:1541-1554). */
+GB200_API int gb200_lmm_params(gb200_ctx *ctx, int a_mode, double l_min, double l_max, size_t n_region,
+                     double l_mle_null, double logl_mle_H0);
+/* batch_compute(l) of src/lmm.cpp:1513-1564.  Xb: n x l row-major (ld ldx) raw genotype
+ * columns of the analysed individuals, missing values already mean-imputed by the caller
+ * (src/lmm.cpp:1611-1618).  l == 0 is a no-op (the reference aborts there, fastblas.cpp:193). */
+GB200_API int gb200_lmm_batch(gb200_ctx *ctx, const double *Xb, size_t l, size_t ldx, gb200_sumstat *out);
+/* G: l x n SNP-major genotypes/dosages of the analysed individuals, NaN = missing; the
+ * mean imputation of src/lmm.cpp:1590-1618 runs on the device. */
+GB200_API int gb200_lmm_batch_geno(gb200_ctx *ctx, const double *G, size_t l, size_t ldg, gb200_sumstat *out);
+/* bed: l PLINK 2-bit rows over ni_total individuals (bytes_per_snp = ceil(ni_total/4));
+ * idv_mask (ni_total bytes, may be NULL = all analysed) is indicator_idv; decode, drop,
+ * mean-impute as src/lmm.cpp:1783-1829 on the device. */
+GB200_API int gb200_lmm_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask,
+                        size_t ni_total, size_t l, size_t bytes_per_snp, gb200_sumstat *out);
+/* Device-resident input and output (bench `value` leg: inputs already in HBM). */
+GB200_API int gb200_lmm_batch_bed_dev(gb200_ctx *ctx, const unsigned char *bed_dev,
+                            const unsigned char *idv_mask_dev, size_t ni_total, size_t l,
+                            size_t bytes_per_snp, gb200_sumstat *out_dev);
+
+/* Only the per-SNP association kernel on an already rotated batch: UtXt is l x n
+ * (SNP-major, U^T x contiguous per SNP, ld ldu).  Exposed for kernel-level parity tests. */
+GB200_API int gb200_lmm_assoc_utx(gb200_ctx *ctx, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out);
+
+/* Projection only: UtXt (l x n, ld n, host) = (U^T Xb)^T for a host batch Xb (n x l). */
+GB200_API int gb200_lmm_project(gb200_ctx *ctx, const double *Xb, size_t l, size_t ldx, double *UtXt);
+
+/* Tuning knobs (0 keeps the default): utx_path 0 auto, 1 FP64 tiled, 2 int8 tensor-core
+ * (error-free U slicing, integer genotypes only); n_slices of the int8 path. */
+GB200_API int gb200_set_option(gb200_ctx *ctx, const char *name, long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMMA_B200_H */

@@ -1,0 +1,312 @@
+"""GPU parity tests: every C-ABI entry point against the CPU oracle on the same seeded
+inputs.  Tolerances follow BASELINE.json's north_star: SNP ids/counts bit-exact, beta / se /
+p-values within 1e-6 relative.  All calls go through the C ABI (gemma_b200.api)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+import gemma_b200
+from gemma_b200 import synth
+from oracle import oracle as O
+from oracle import refpipe as R
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6          # north_star tolerance on beta / se / p-values
+EXP = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "expected.json")))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    nan_ok = np.isnan(a) == np.isnan(b)
+    assert nan_ok.all(), "NaN pattern differs"
+    m = ~np.isnan(b)
+    if not m.any():
+        return 0.0
+    return float(np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-300)))
+
+
+def check_sumstat(got, ref, a_mode, lam_rel=5e-5):
+    fields = {1: ("beta", "se", "p_wald"), 2: ("p_lrt",), 3: ("beta", "se", "p_score"),
+              4: ("beta", "se", "p_wald", "p_lrt", "p_score"), 9: ("beta", "se", "p_lrt", "p_score")}[a_mode]
+    for k in fields:
+        assert rel_err(got[k], ref[k]) < REL, (a_mode, k, rel_err(got[k], ref[k]))
+    # lambda is only reproducible to ~1e-5 across summation orders; logl to 1e-8 relative
+    for k in ("lambda_remle", "lambda_mle"):
+        assert rel_err(got[k], ref[k]) < lam_rel, (a_mode, k, rel_err(got[k], ref[k]))
+    assert rel_err(got["logl_H1"], ref["logl_H1"]) < 1e-8
+    # untouched fields stay exactly 0 like the reference's initialisers (src/lmm.cpp:1536-1538)
+    for k in set(got.dtype.names) - set(fields) - {"lambda_remle", "lambda_mle", "logl_H1"}:
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def random_problem(n, c, l, seed, causal=True):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, 3 * n))
+    K = O.center_matrix(A @ A.T / (3 * n))
+    ev, U = scipy.linalg.eigh(K)
+    ev, _ = O.zero_small_eval(ev)
+    W = np.ones((n, c))
+    if c > 1:
+        W[:, :c - 1] = rng.standard_normal((n, c - 1))
+    f = rng.uniform(0.05, 0.5, l)
+    X = rng.binomial(2, f[None, :], size=(n, l)).astype(np.float64)
+    g = U @ (np.sqrt(ev) * rng.standard_normal(n))
+    y = 0.8 * g + rng.standard_normal(n) + W[:, :1].sum(axis=1) * 0.3
+    if causal:
+        y = y + 0.6 * (X[:, 0] - X[:, 0].mean()) + 0.25 * (X[:, 1] - X[:, 1].mean())
+    return dict(U=U, ev=ev, W=W, y=y, X=X, UtW=U.T @ W, Uty=U.T @ y, trace_G=float(np.mean(ev)))
+
+
+# ----------------------------------------------------------------------------------------
+def test_dgemm_seam_matches_numpy_and_rejects_bad_shapes(ctx):
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((150, 70)); B = rng.standard_normal((70, 90))
+    for ta, tb in (("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")):
+        a = A.T.copy() if ta == "T" else A
+        b = B.T.copy() if tb == "T" else B
+        C0 = rng.standard_normal((150, 90))
+        C = ctx.dgemm(ta, tb, 1.5, a, b, -0.5, C0.copy())
+        assert np.allclose(C, 1.5 * A @ B - 0.5 * C0, rtol=1e-12, atol=1e-12)
+    # the reference's unit test: integer-valued 2000x200 * 200x1000 with known entries
+    # (test/src/unittests-math.cpp:74-178 style): exact in FP64
+    Ai = rng.integers(-5, 6, (300, 129)).astype(float); Bi = rng.integers(-5, 6, (129, 257)).astype(float)
+    C = ctx.dgemm("N", "N", 1.0, Ai, Bi, 0.0, np.zeros((300, 257)))
+    assert np.array_equal(C, Ai @ Bi)
+    with pytest.raises(gemma_b200.GB200Error):       # "Range error in dgemm" (fastblas.cpp:207)
+        ctx.dgemm("N", "N", 1.0, A, B.T.copy(), 0.0, np.zeros((150, 90)))
+    with pytest.raises(gemma_b200.GB200Error):       # enforce(N>0) (fastblas.cpp:193-195)
+        ctx.dgemm("N", "N", 1.0, np.zeros((4, 0)), np.zeros((0, 3)), 0.0, np.zeros((4, 3)))
+
+
+@pytest.mark.parametrize("n,c,seed", [(257, 1, 3), (300, 3, 4), (64, 2, 5)])
+def test_assoc_kernel_all_modes_vs_oracle(ctx, n, c, seed):
+    pb = random_problem(n, c, 96, seed)
+    ctx.lmm_setup_rotated(pb["U"], pb["ev"], pb["UtW"], pb["Uty"])
+    l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"])
+    UtX = pb["U"].T @ pb["X"]
+    for mode in (1, 2, 3, 4, 9):
+        ctx.lmm_params(mode, l_mle_null=l_mle, logl_mle_H0=logl)
+        got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
+        ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, mode, l_mle_null=l_mle, logl_mle_H0=logl)
+        check_sumstat(got, ref, mode)
+
+
+def test_assoc_nondefault_search_grid_and_boundaries(ctx):
+    # narrow / shifted lambda ranges force the "no sign change" and clamp branches (lmm.cpp:1985-2000)
+    pb = random_problem(200, 1, 40, 9, causal=False)
+    ctx.lmm_setup_rotated(pb["U"], pb["ev"], pb["UtW"], pb["Uty"])
+    UtX = pb["U"].T @ pb["X"]
+    for (lo, hi, nr) in ((1e-5, 1e5, 10), (1e-2, 1e-1, 3), (50.0, 5e4, 7), (1e-5, 1e5, 1)):
+        l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"], lo, hi, nr)
+        ctx.lmm_params(4, lo, hi, nr, l_mle, logl)
+        got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
+        ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, 4, lo, hi, nr, l_mle, logl)
+        check_sumstat(got, ref, 4)
+
+
+def test_null_model_vs_oracle(ctx):
+    for n, c, seed in ((257, 1, 11), (180, 3, 12)):
+        pb = random_problem(n, c, 4, seed)
+        UtW, Uty = ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
+        assert np.allclose(UtW, pb["UtW"], atol=1e-11) and np.allclose(Uty, pb["Uty"], atol=1e-11)
+        nm = ctx.lmm_null(pb["trace_G"])
+        l_mle, logl_mle = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"])
+        l_re, logl_re = O.calc_lambda_null("R", pb["ev"], pb["UtW"], pb["Uty"])
+        assert nm["l_mle_null"] == pytest.approx(l_mle, rel=5e-5) and nm["logl_mle_H0"] == pytest.approx(logl_mle, rel=1e-9)
+        assert nm["l_remle_null"] == pytest.approx(l_re, rel=5e-5) and nm["logl_remle_H0"] == pytest.approx(logl_re, rel=1e-9)
+        pve, pve_se = O.calc_pve(pb["ev"], pb["UtW"], pb["Uty"], l_re, pb["trace_G"])
+        assert nm["pve_null"] == pytest.approx(pve, rel=1e-5) and nm["pve_se_null"] == pytest.approx(pve_se, rel=1e-4)
+        for tag, lam in (("mle", l_mle), ("remle", l_re)):
+            vg, ve, beta, se = O.calc_vgvebeta(pb["ev"], pb["UtW"], pb["Uty"], lam)
+            assert nm["vg_" + tag] == pytest.approx(vg, rel=1e-4) and nm["ve_" + tag] == pytest.approx(ve, rel=1e-5)
+            assert np.allclose(nm["beta_" + tag], beta, rtol=1e-5, atol=1e-9)
+            assert np.allclose(nm["se_beta_" + tag], se, rtol=1e-5)
+
+
+def test_eigh_matches_lapack_semantics(ctx):
+    rng = np.random.default_rng(21)
+    n = 193
+    A = rng.standard_normal((n, 2 * n)); K = A @ A.T / (2 * n)
+    U, ev, tr, nz = ctx.eigh(K, center=True)
+    Kc = O.center_matrix(K)
+    ev_ref = scipy.linalg.eigh(Kc, eigvals_only=True)
+    ev_ref, tr_ref = O.zero_small_eval(ev_ref)
+    assert np.allclose(ev, ev_ref, atol=1e-11) and tr == pytest.approx(tr_ref, rel=1e-12)
+    assert nz == 1 and ev[0] == 0.0                     # the centred matrix always has one (lapack.cpp:268)
+    assert np.all(np.diff(ev) >= 0)                     # ascending
+    assert np.allclose(U.T @ U, np.eye(n), atol=1e-11)  # eigenvectors in COLUMNS of row-major U
+    ev_raw = scipy.linalg.eigh(Kc, eigvals_only=True)
+    assert np.allclose((U * ev_raw) @ U.T, Kc, atol=1e-10)
+    U2, ev2, _, _ = ctx.eigh(Kc, center=False)
+    assert np.allclose(ev2, ev, atol=1e-11)
+
+
+@pytest.mark.parametrize("k_mode", [1, 2])
+def test_kinship_geno_bed_and_precentred_paths(ctx, k_mode):
+    n, l = 211, 500
+    bed, G = synth.make_bed(n, l, seed=31, miss_rate=0.03)
+    Gn = np.where(G < 0, np.nan, G)
+    Gd = Gn + np.where(np.isnan(Gn), 0, np.random.default_rng(3).uniform(0, 0.2, Gn.shape))   # dosages
+    for src in ("geno", "bed", "dosage", "precentred"):
+        data = Gd if src == "dosage" else Gn
+        Xc = O.kin_transform(data, k_mode)
+        Kref = Xc @ Xc.T / l
+        ctx.kin_begin(n, k_mode)
+        if src in ("geno", "dosage"):
+            ctx.kin_add_geno(data[:300]); ctx.kin_add_geno(data[300:])     # two batches
+        elif src == "bed":
+            ctx.kin_add_bed(bed[:123]); ctx.kin_add_bed(bed[123:])
+        else:
+            ctx.kin_add(Xc[:, :256]); ctx.kin_add(Xc[:, 256:])
+        K, ns = ctx.kin_finish()
+        assert ns == l
+        assert np.allclose(K, Kref, rtol=1e-11, atol=1e-12), src
+        assert np.array_equal(K, K.T)
+
+
+def test_lmm_batch_entry_points_agree_with_oracle(ctx):
+    n_total, l = 260, 120
+    rng = np.random.default_rng(41)
+    mask = np.ones(n_total, dtype=np.uint8); mask[rng.choice(n_total, 23, replace=False)] = 0
+    n = int(mask.sum())
+    pb = random_problem(n, 2, 4, 42)
+    bed, G = synth.make_bed(n_total, l, seed=43, miss_rate=0.04)
+    Gn = np.where(G < 0, np.nan, G)[:, mask == 1]
+    X = O.lmm_impute(Gn)
+    ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
+    nm = ctx.lmm_null(pb["trace_G"])
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], pb["U"].T @ X, 4, l_mle_null=nm["l_mle_null"],
+                            logl_mle_H0=nm["logl_mle_H0"])
+    check_sumstat(ctx.lmm_batch(X), ref, 4)                                  # Xlarge layout, pre-imputed
+    check_sumstat(ctx.lmm_batch_geno(Gn), ref, 4)                            # SNP-major with NaN
+    check_sumstat(ctx.lmm_batch_bed(bed, n_total, mask), ref, 4)             # PLINK 2-bit + indicator_idv
+    assert np.allclose(ctx.lmm_project(X), (pb["U"].T @ X).T, atol=1e-10)
+    # empty batch is a no-op (the reference aborts: SURVEY appendix C.1)
+    assert len(ctx.lmm_batch(np.zeros((n, 0)))) == 0
+    # out-of-order / bad arguments fail loudly
+    with pytest.raises(gemma_b200.GB200Error):
+        ctx.lmm_batch_bed(bed, n_total, np.ones(n_total, dtype=np.uint8))    # mask selects != n individuals
+
+
+def test_state_errors():
+    c = gemma_b200.Context(0)
+    with pytest.raises(gemma_b200.GB200Error):
+        c.lmm_batch(np.zeros((8, 2)))
+    with pytest.raises(gemma_b200.GB200Error):
+        c.kin_add(np.zeros((8, 2)))
+    with pytest.raises(gemma_b200.GB200Error):
+        c.lmm_setup(np.eye(5), np.ones(5), np.ones((5, 7)), np.ones(5))       # n_cvt > GB200_MAX_CVT
+    c.close()
+
+
+# ---- golden fixtures through the GPU path ------------------------------------------------
+@pytest.fixture(scope="module")
+def mouse(golden_dir):
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    bb = R.Bimbam(os.path.join(d, "mouse_hs1940.geno.txt.gz"))
+    ph, ind = R.read_pheno(os.path.join(d, "mouse_hs1940.pheno.txt"), (1,))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, n_miss, maf = R.qc_bimbam(bb, idv)
+    return dict(bb=bb, ph=ph, idv=idv, W=W, isnp=isnp)
+
+
+def test_mouse_hs1940_gk_then_lmm_matches_demo_txt(ctx, mouse):
+    """BASELINE config 1: -gk then -lmm on example/mouse_hs1940, against example/demo.txt."""
+    bb, idv = mouse["bb"], mouse["idv"]
+    sel = np.nonzero(mouse["isnp"])[0]
+    assert len(sel) == EXP["mouse_counts"]["ns_test"]
+    ctx.kin_begin(bb.G.shape[1], 1)
+    for s in range(0, len(sel), 4000):
+        ctx.kin_add_geno(bb.G[sel[s:s + 4000]])
+    K, ns = ctx.kin_finish()
+    assert ns == len(sel)
+    assert [[float("%.6g" % K[i, j]) for j in range(3)] for i in range(3)] == EXP["mouse_K3"]
+    Kref = R.kinship_bimbam(bb, mouse["isnp"], 1)
+    assert np.allclose(K, Kref, rtol=1e-10, atol=1e-12)
+    keep = idv == 1
+    Kt = R.text_roundtrip(K)[np.ix_(keep, keep)]              # the 10-digit .cXX.txt round trip
+    U, ev, trace_G, _ = ctx.eigh(Kt, center=True)
+    y = mouse["ph"][keep, 0]; W = mouse["W"][keep]
+    ctx.lmm_setup(U, ev, W, y)
+    nm = ctx.lmm_null(trace_G)
+    assert "%.6f" % nm["pve_null"] == "%.6f" % EXP["mouse_pve"]
+    assert "%.6f" % nm["pve_se_null"] == "%.6f" % EXP["mouse_pve_se"]
+    ctx.lmm_params(1, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    Gs = bb.G[np.ix_(sel, keep)]
+    out = ctx.lmm_batch_geno(Gs)
+    for r, e in zip(out[:5], EXP["mouse_lmm1_rows"]):
+        assert "%.6e" % r["beta"] == e["beta"] and "%.6e" % r["se"] == e["se"]
+        assert "%.6e" % r["lambda_remle"] == e["l_remle"] and "%.6e" % r["p_wald"] == e["p_wald"]
+    # all 10768 SNPs against the oracle run on the GPU's own eigendecomposition
+    UtW = U.T @ W; Uty = U.T @ y
+    ref = O.lmm_analyze_utx(ev, UtW, Uty, U.T @ O.lmm_impute(Gs), 1)
+    check_sumstat(out, ref, 1)
+
+
+def test_bxd_covariates_pins(ctx, golden_dir):
+    d = os.path.join(golden_dir, "BXD")
+    bb = R.Bimbam(os.path.join(d, "BXD_geno.txt.gz"))
+    ph, ind = R.read_pheno(os.path.join(d, "BXD_pheno.txt"), (1,))
+    rows, icvt = R.read_cvt(os.path.join(d, "BXD_covariates2.txt"))
+    idv, W = R.process_cvt_phen(ind, rows, icvt)
+    isnp_gk, _, _ = R.qc_bimbam(bb, idv, W)
+    ctx.kin_begin(bb.G.shape[1], 1)
+    ctx.kin_add_geno(bb.G[isnp_gk == 1])
+    K, _ = ctx.kin_finish()
+    keep = idv == 1
+    isnp, _, _ = R.qc_bimbam(bb, idv, W, maf_level=0.1)
+    U, ev, trace_G, _ = ctx.eigh(R.text_roundtrip(K)[np.ix_(keep, keep)], center=True)
+    ctx.lmm_setup(U, ev, W[keep], ph[keep, 0])
+    nm = ctx.lmm_null(trace_G)
+    Gs = bb.G[np.ix_(isnp == 1, keep)]
+    ctx.lmm_params(2, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    o2 = ctx.lmm_batch_geno(Gs)
+    assert o2["p_lrt"][0] == pytest.approx(EXP["bxd_lmm2_row2_p_lrt"], abs=5e-7)
+    assert o2["p_lrt"].max() == pytest.approx(EXP["bxd_max_p_lrt"], abs=5e-7)
+    ctx.lmm_params(9, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    o9 = ctx.lmm_batch_geno(Gs)
+    assert o9["lambda_mle"].max() == pytest.approx(EXP["bxd_lmm9_max_l_mle"], abs=2e-6)
+
+
+# ---- size-independent properties at a larger size ------------------------------------------
+def test_properties_at_scale(ctx):
+    n, l = 4096, 1536
+    rng = np.random.default_rng(77)
+    bed, G = synth.make_bed(n, l, seed=78)
+    # cheap orthogonal U: Householder reflection; kinship-like spectrum
+    v = rng.standard_normal(n); v /= np.linalg.norm(v)
+    U = np.eye(n) - 2.0 * np.outer(v, v)
+    ev = synth.spectrum_like_kinship(n, 79)
+    y = rng.standard_normal(n) + 0.2 * G[5]
+    W = np.ones((n, 1))
+    ctx.lmm_setup(U, ev, W, y)
+    nm = ctx.lmm_null(float(ev.mean()))
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    o4 = ctx.lmm_batch_bed(bed, n)
+    # (1) the combined mode reports exactly what the single-test modes report
+    ctx.lmm_params(1, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    o1 = ctx.lmm_batch_bed(bed, n)
+    for k in ("beta", "se", "p_wald", "lambda_remle"):
+        assert np.array_equal(o1[k], o4[k]), k
+    # (2) SNP order does not matter (warps pull SNPs from a ticket counter)
+    perm = rng.permutation(l)
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    op = ctx.lmm_batch_bed(bed[perm], n)
+    for k in o4.dtype.names:
+        assert np.array_equal(op[k], o4[k][perm]), k
+    # (3) allele flip x -> 2 - x: beta changes sign, se and all p-values are invariant
+    of = ctx.lmm_batch_geno(2.0 - G)
+    assert rel_err(of["beta"], -o4["beta"]) < 1e-6 and rel_err(of["se"], o4["se"]) < 1e-6
+    for k in ("p_wald", "p_lrt", "p_score"):
+        assert rel_err(of[k], o4[k]) < 1e-6
+    # (4) a sub-sample against the oracle at this size
+    idx = np.arange(0, l, 97)
+    UtW = U.T @ W; Uty = U.T @ y
+    ref = O.lmm_analyze_utx(ev, UtW, Uty, U.T @ G[idx].T, 4, l_mle_null=nm["l_mle_null"],
+                            logl_mle_H0=nm["logl_mle_H0"])
+    check_sumstat(o4[idx], ref, 4)

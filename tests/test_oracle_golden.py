@@ -1,0 +1,105 @@
+"""The CPU oracle against the reference's own golden vectors:
+example/demo.txt, test/dev_tests.rb, test/src/unittests-math.cpp.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.special
+import scipy.stats
+
+from oracle import oracle as O
+from oracle import refpipe as R
+
+EXP = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "expected.json")))
+
+
+def test_getab_index_known_answers():
+    # test/src/unittests-math.cpp:17-25
+    assert len(EXP["getab"]) >= 7
+    for a, b, c, r in EXP["getab"]:
+        assert O.getab_index(a, b, c) == r
+    # c = 1 table quoted in SURVEY 8(a10)
+    assert [O.getab_index(a, b, 1) for a, b in [(1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]] == [0, 1, 2, 3, 4, 5]
+
+
+def test_fdist_and_chisq_tails_match_scipy():
+    # gsl_cdf_fdist_Q(x,1,df) / gsl_cdf_chisq_Q(x,1): restated continued fraction vs scipy's incomplete beta
+    for df in (10, 64, 194, 1408, 9998, 49998):
+        for x in (1e-8, 0.01, 0.5, 1.0, 2.9, 3.1, 10.0, 50.0, 300.0, 2000.0, df - 0.5, df + 0.5, 5.0 * df):
+            ref = scipy.special.betaincc(0.5, df / 2.0, x / (df + x))   # 1 - I_u(1/2, df/2), u = x/(df+x)
+            got = O.fdist_Q(x, 1.0, df)
+            assert got == pytest.approx(ref, rel=2e-10), (df, x)
+    for x in (-1.0, 0.0, 1e-12, 0.3, 1.0, 10.0, 100.0, 1400.0):
+        assert O.chisq1_Q(x) == pytest.approx(scipy.stats.chi2.sf(x, 1) if x > 0 else 1.0, rel=1e-12)
+
+
+@pytest.fixture(scope="module")
+def mouse(golden_dir):
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    bb = R.Bimbam(os.path.join(d, "mouse_hs1940.geno.txt.gz"))
+    ph, ind = R.read_pheno(os.path.join(d, "mouse_hs1940.pheno.txt"), (1,))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, n_miss, maf = R.qc_bimbam(bb, idv)
+    return dict(bb=bb, ph=ph, idv=idv, W=W, isnp=isnp, n_miss=n_miss, maf=maf,
+                anno=R.read_anno(os.path.join(d, "mouse_hs1940.anno.txt")))
+
+
+def test_mouse_counts_bit_exact(mouse):
+    c = EXP["mouse_counts"]
+    assert len(mouse["idv"]) == c["ni_total"] and int(mouse["idv"].sum()) == c["ni_test"]
+    assert len(mouse["isnp"]) == c["ns_total"] and int(mouse["isnp"].sum()) == c["ns_test"]
+
+
+def test_mouse_kinship_and_lmm1_rows(mouse):
+    bb = mouse["bb"]
+    K = R.kinship_bimbam(bb, mouse["isnp"], 1)
+    # example/demo.txt:10-12 prints 6 significant digits (padded with a trailing 0)
+    got = [[float("%.6g" % K[i, j]) for j in range(3)] for i in range(3)]
+    assert got == EXP["mouse_K3"]
+    prep = R.lmm_prepare(R.text_roundtrip(K), mouse["idv"], mouse["ph"][:, 0], mouse["W"])
+    assert "%.6f" % prep["pve"] == "%.6f" % EXP["mouse_pve"]          # demo.txt:41
+    assert "%.6f" % prep["pve_se"] == "%.6f" % EXP["mouse_pve_se"]    # demo.txt:42
+    sel = np.nonzero(mouse["isnp"])[0][:5]
+    X = R.lmm_genotypes_bimbam(bb, mouse["isnp"], mouse["idv"], sel)
+    out = R.lmm_analyze(prep, X, 1)
+    for r, s, e in zip(out, sel, EXP["mouse_lmm1_rows"]):            # demo.txt:32-36
+        assert bb.rs[s] == e["rs"]
+        ch, bp, _ = mouse["anno"][bb.rs[s]]
+        assert ch == e["chr"] and str(bp) == e["ps"]
+        assert str(int(mouse["n_miss"][s])) == e["n_miss"] and "%.3f" % mouse["maf"][s] == e["af"]
+        assert (bb.a1[s], bb.a0[s]) == (e["allele1"], e["allele0"])
+        assert "%.6e" % r["beta"] == e["beta"] and "%.6e" % r["se"] == e["se"]
+        assert "%.6e" % r["lambda_remle"] == e["l_remle"] and "%.6e" % r["p_wald"] == e["p_wald"]
+
+
+def test_bxd_lmm2_lmm9_pins(golden_dir):
+    d = os.path.join(golden_dir, "BXD")
+    bb = R.Bimbam(os.path.join(d, "BXD_geno.txt.gz"))
+    ph, ind = R.read_pheno(os.path.join(d, "BXD_pheno.txt"), (1,))
+    rows, icvt = R.read_cvt(os.path.join(d, "BXD_covariates2.txt"))
+    idv, W = R.process_cvt_phen(ind, rows, icvt)
+    assert W.shape[1] == 3                                            # 2 covariates + appended intercept
+    isnp_gk, _, _ = R.qc_bimbam(bb, idv, W)
+    K = R.kinship_bimbam(bb, isnp_gk, 1)
+    isnp, _, _ = R.qc_bimbam(bb, idv, W, maf_level=0.1)
+    assert (int(isnp.sum()) + 1) * 10 == EXP["bxd_lmm2_assoc_words"]  # dev_test_suite.sh:83
+    prep = R.lmm_prepare(R.text_roundtrip(K), idv, ph[:, 0], W)
+    X = R.lmm_genotypes_bimbam(bb, isnp, idv)
+    o2 = R.lmm_analyze(prep, X, 2)
+    assert o2["p_lrt"][0] == pytest.approx(EXP["bxd_lmm2_row2_p_lrt"], abs=5e-7)   # dev_tests.rb:42
+    assert o2["p_lrt"].max() == pytest.approx(EXP["bxd_max_p_lrt"], abs=5e-7)       # dev_tests.rb:43
+    o9 = R.lmm_analyze(prep, X, 9)
+    assert o9["lambda_mle"].max() == pytest.approx(EXP["bxd_lmm9_max_l_mle"], abs=1e-6)  # dev_tests.rb:53
+    assert o9["p_lrt"].max() == pytest.approx(EXP["bxd_max_p_lrt"], abs=5e-7)
+
+
+def test_center_matrix_and_bed_decode_small():
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((7, 7)); G = A + A.T
+    C = O.center_matrix(G)
+    J = np.eye(7) - np.ones((7, 7)) / 7
+    assert np.allclose(C, J @ G @ J, atol=1e-12)
+    # 2-bit decode: byte 0b01_11_10_00 -> samples (00)=2, (10)=1, (11)=0, (01)=missing
+    g = O.bed_decode(bytes([0b01111000]), 4)
+    assert g[0] == 2 and g[1] == 1 and g[2] == 0 and np.isnan(g[3])
