@@ -68,6 +68,7 @@ SIGNATURES = {
     "gb200_lmm_batch_bed_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_lmm_assoc_utx": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_project": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
+    "gb200_lmm_project_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),
 }
 
@@ -257,6 +258,14 @@ class Context:
         UtXt = _f64(UtXt)
         out = np.zeros(UtXt.shape[0], dtype=SUMSTAT_DTYPE)
         self._chk(self.lib.gb200_lmm_assoc_utx(self.h, _ptr(UtXt), UtXt.shape[0], UtXt.shape[1], _ptr(out)))
+        return out
+
+    def lmm_project_bed(self, bed, ni_total, idv_mask=None):
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        m = None if idv_mask is None else np.ascontiguousarray(idv_mask, dtype=np.uint8)
+        out = np.empty((bed.shape[0], self.n))
+        self._chk(self.lib.gb200_lmm_project_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1],
+                                                 _ptr(out)))
         return out
 
     def lmm_project(self, Xb):

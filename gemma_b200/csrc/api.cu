@@ -548,32 +548,34 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
   return GB200_OK;
 }
 
-// rotate + test a device-resident bed batch; idx_dev maps analysed position -> ni_total index (or null)
-static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
-                        size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
+// rotate a device-resident bed batch into UtXt (l x n): int8 tensor-core path for n >= 1024
+// (or when forced), FP64 decode + dgemm otherwise.  idx_dev maps analysed position -> ni_total index.
+static int project_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
+                           size_t l, size_t bytes_per_snp) {
   const size_t n = c->n;
   GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
   bool use_i8 = false;
   if (c->utx_path == 2) {
-    if (!i8_available(c)) return set_err(c, GB200_ERR_UNSUPPORTED, "int8 tensor-core path not available in this build");
+    if (!i8_available(c)) return set_err(c, GB200_ERR_UNSUPPORTED, "int8 tensor-core path not available (no cuTensorMapEncodeTiled)");
     use_i8 = true;
   } else if (c->utx_path == 0) {
     use_i8 = i8_available(c) && n >= 1024;
   }
-  if (use_i8) {
-    int rc = i8_project_bed(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, c->dUtXt.as<double>());
-    if (rc) return rc;
-  } else {
-    GB_CUDA(c, c->dX.reserve(n * l * 8));
-    {
-      ProfScope ps(c, "decode");
-      GB_CUDA(c, launch_bed_decode(bed_dev, l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
-      GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
-    }
-    int rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
-    if (rc) return rc;
+  if (use_i8) return i8_project_bed(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, c->dUtXt.as<double>());
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_bed_decode(bed_dev, l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
   }
-  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, out_dev);
+  return project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+}
+
+static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
+                        size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
+  int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
+  if (rc) return rc;
+  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n, out_dev);
 }
 
 static int upload_idx_from_mask(gb200_ctx *c, const unsigned char *idv_mask, size_t ni_total, const int **idx_dev) {
@@ -636,6 +638,24 @@ int gb200_lmm_batch_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const un
     return set_err(c, GB200_ERR_ARG, "idv_mask == NULL requires ni_total == n");
   }
   return lmm_bed_core(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, out_dev);
+}
+
+int gb200_lmm_project_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
+                          size_t l, size_t bytes_per_snp, double *UtXt) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, "gb200_lmm_project_bed before gb200_lmm_setup");
+  if (l == 0) return GB200_OK;
+  if (!bed || !UtXt || bytes_per_snp != (ni_total + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_lmm_project_bed: bad argument");
+  const int *idx_dev = nullptr;
+  int rc = upload_idx_from_mask(c, idv_mask, ni_total, &idx_dev);
+  if (rc) return rc;
+  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
+  rc = project_bed_dev(c, c->dBed.as<unsigned char>(), idx_dev, ni_total, l, bytes_per_snp);
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(UtXt, c->dUtXt.p, l * c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
 }
 
 }  // extern "C"

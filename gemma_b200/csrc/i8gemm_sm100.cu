@@ -1,9 +1,502 @@
-// i8gemm_sm100.cu -- int8 tensor-core projection (placeholder until the tcgen05 kernel lands)
+// i8gemm_sm100.cu -- eigen-projection (U^T X)^T = G * U on the sm_100a tensor cores.
+//
+// Replaces fast_dgemm("T","N",1.0,U,Xlarge_sub,0.0,UtXlarge_sub) of LMM::Analyze
+// (src/lmm.cpp:1521 / :1847): 2 n^2 flop per SNP, the dominant cost at n = 50 000.
+//
+// Genotypes are small integers (PLINK 2-bit: 0/1/2), so the product is made EXACT on the
+// int8 tensor pipe with an error-free split of U (Ozaki scheme):
+//   U[j][i] = sigma_i * 2^-B * sum_t d_t[j][i] * 256^(T-1-t) + eps,  d_t in int8,
+//   sigma_i = power of two >= max_j |U[j][i]|,  B = 6 + 8 (T-1),  |eps| <= 2^-(B+1) sigma_i
+// (balanced base-256 digits of the fixed-point integer round(U/sigma * 2^B)).  Each digit
+// plane times the int8 genotype tile accumulates exactly in int32 (|sum| <= 128*2*n < 2^31
+// for n < 8e6); the T planes are recombined in FP64 in the epilogue.  T = 6 keeps 46 bits
+// below each eigenvector's largest entry (dot-product error ~1e-14 at n = 50 000, below the
+// rounding error of an FP64 dgemm's n-term sums relative to the statistics that consume it).
+// Mean-imputed missing genotypes are handled exactly as  U^T x = U^T z + mean * U^T q  with
+// z = genotype with 0 at the holes (int8 GEMM) and q = hole indicator (sparse FP64 fix-up).
+//
+// Kernel (one CTA per SM, persistent, warp-specialised, no cluster):
+//   warp 0  : TMA producer  -- cp.async.bulk.tensor 2D, 128B-swizzled K-major tiles,
+//             A = 128 SNPs x 128 B of individuals, B = (T planes x NE eigenvectors) x 128 B
+//   warp 1  : MMA issuer    -- tcgen05.mma.cta_group::1.kind::i8, M=128, N=T*NE (<=256), K=32,
+//             accumulators in TMEM (2 x 256 columns, double buffered against the epilogue)
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue     -- tcgen05.ld 32x32b, FP64 recombination of the T planes, scale,
+//             store of U^T x rows (SNP-major, the layout the per-SNP kernel streams)
+// All T planes of an eigenvector group live in the same N tile, so the genotype tile in
+// shared memory is reused T times per load and no read-modify-write of C is needed.
 #include "common.cuh"
+#include <cuda.h>
+
 namespace gb {
-bool i8_available(gb200_ctx *) { return false; }
-int i8_prepare(gb200_ctx *ctx) { return set_err(ctx, GB200_ERR_UNSUPPORTED, "int8 path not built"); }
-int i8_project_bed(gb200_ctx *ctx, const unsigned char *, const int *, size_t, size_t, size_t, double *) {
-  return set_err(ctx, GB200_ERR_UNSUPPORTED, "int8 path not built");
+
+constexpr int I8_BM = 128;        // SNPs per tile (UMMA M, one TMEM lane per SNP)
+constexpr int I8_BK = 128;        // K bytes per pipeline stage == one 128B swizzle row
+constexpr int I8_UK = 32;         // UMMA K for 8-bit operands
+constexpr int I8_STAGES = 4;
+constexpr int I8_ACC_COLS = 256;  // TMEM columns per accumulator stage
+constexpr int I8_THREADS = 256;
+constexpr int I8_PANEL = 12;      // raster panel width (n-groups) for L2 reuse
+
+struct I8Geom {
+  int T, NE, N;            // planes, eigenvectors per tile, UMMA N = T*NE
+  int n, n_padk;           // individuals, padded K extent in bytes
+  int n_groups;            // ceil(n / NE)
+};
+
+static I8Geom make_geom(size_t n, int T) {
+  I8Geom g;
+  g.T = T;
+  int ne = (256 / T) & ~7;                 // multiple of 8
+  if ((T * ne) % 16 != 0) ne &= ~15;       // UMMA N must be a multiple of 16 for M = 128
+  g.NE = ne; g.N = T * ne;
+  g.n = (int)n; g.n_padk = (int)((n + I8_BK - 1) / I8_BK * I8_BK);
+  g.n_groups = (int)((n + ne - 1) / ne);
+  return g;
 }
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *tmap, uint64_t *bar, void *dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (tcgen05 "smem descriptor", version 1):
+// rows of 128 B, 8-row groups 1024 B apart (SBO), 16-byte units, layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, uint32_t lbo_units) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address  [0,14)
+  d |= (uint64_t)(lbo_units & 0x3FFF) << 16;            // leading byte offset [16,30)
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;          // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell) [46,48)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B [61,64)
+  return d;
+}
+
+// instruction descriptor for kind::i8: D = S32, A = a_fmt (0 u8 / 1 s8), B = s8, both K-major
+__host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N, int a_signed, int b_signed) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | (0u << 15) | (0u << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct I8KernelParams {
+  int T, NE, N;
+  int n, l;                 // eigenvectors (= individuals), SNPs
+  int num_k_blocks;         // n_padk / 128
+  int m_tiles, n_groups;
+  int lbo_units;            // descriptor LBO field (kept runtime for bring-up)
+  const double *scale;      // per eigenvector: sigma_i * 2^-B
+  double *C;                // l x n, ld = ldc
+  size_t ldc;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_groups, int &m_blk, int &n_grp) {
+  // panels of I8_PANEL eigenvector groups; inside a panel SNP tiles vary slowest so that the ~148
+  // concurrently running CTAs cover a ~12 x 12 block of (SNP tile, group) pairs: each A/B K-panel
+  // streamed from HBM is shared by ~12 CTAs through L2.
+  const int panel_tiles = I8_PANEL * m_tiles;
+  const int panel = tile / panel_tiles;
+  const int first = panel * I8_PANEL;
+  const int width = (n_groups - first < I8_PANEL) ? (n_groups - first) : I8_PANEL;
+  const int r = tile - panel * panel_tiles;
+  m_blk = r / width;
+  n_grp = first + r % width;
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const I8KernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: A stages | B stages | barriers | tmem slot
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = I8_BM * I8_BK;
+  const int b_bytes = p.N * I8_BK;
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + I8_STAGES * a_bytes;
+  uint64_t *bars = (uint64_t *)(smem_b + I8_STAGES * b_bytes);
+  uint64_t *full = bars, *empty = bars + I8_STAGES;
+  uint64_t *tfull = bars + 2 * I8_STAGES, *tempty = bars + 2 * I8_STAGES + 2;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * I8_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_groups;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_grp; tile_coords(tile, p.m_tiles, p.n_groups, m_blk, n_grp);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
+          tma_load_2d(&tmap_a, &full[stage], smem_a + stage * a_bytes, kb * I8_BK, m_blk * I8_BM);
+          tma_load_2d(&tmap_b, &full[stage], smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_i8_idesc(I8_BM, p.N, 0, 1);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * I8_ACC_COLS);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * a_bytes), p.lbo_units);
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * b_bytes), p.lbo_units);
+#pragma unroll
+          for (int k = 0; k < I8_BK / I8_UK; ++k) {
+            // advance both start addresses by k*32 bytes inside the 128B swizzle row (16-byte units)
+            tc_mma_i8(tmem_d, adesc + (uint64_t)(k * (I8_UK >> 4)), bdesc + (uint64_t)(k * (I8_UK >> 4)), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
+          if (kb == p.num_k_blocks - 1) tc_commit(&tfull[acc]);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;                         // == warp % 4 : TMEM lane quarter
+    int acc = 0; uint32_t acc_phase = 0;
+    const double w256 = 256.0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_grp; tile_coords(tile, p.m_tiles, p.n_groups, m_blk, n_grp);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int s = m_blk * I8_BM + ew * 32 + lane;                       // SNP row of this thread
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * I8_ACC_COLS);
+      const int i0 = n_grp * p.NE;
+      for (int e0 = 0; e0 < p.NE; e0 += 8) {
+        double v[8];
+        int32_t d[8];
+        tc_ld8(taddr + (uint32_t)e0, d);
+        tc_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (double)d[q];
+        for (int t = 1; t < p.T; ++t) {
+          tc_ld8(taddr + (uint32_t)(t * p.NE + e0), d);
+          tc_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = fma(v[q], w256, (double)d[q]);
+        }
+        if (s < p.l) {
+          double *crow = p.C + (size_t)s * p.ldc;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int i = i0 + e0 + q;
+            if (i < p.n) crow[i] = v[q] * __ldg(p.scale + i);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// U -> int8 digit planes
+__global__ void col_absmax_kernel(const double *__restrict__ U, int n, double *__restrict__ colmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = 0.0;
+  for (int j = 0; j < n; ++j) m = fmax(m, fabs(U[(size_t)j * n + i]));
+  colmax[i] = m;
+}
+
+// scale[i] = sigma_i * 2^-B ; expo[i] = B - e_i  (so that Q = rint(u * 2^expo))
+__global__ void col_scale_kernel(const double *__restrict__ colmax, int n, int B, double *__restrict__ scale,
+                                 int *__restrict__ expo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = colmax[i];
+  int e = 0;
+  if (m > 0.0 && isfinite(m)) { frexp(m, &e); if (ldexp(1.0, e - 1) == m) { /* m is a power of two: |u|/sigma may equal 1 */ } }
+  // frexp: m = f * 2^e, f in [0.5,1)  =>  sigma = 2^e > m, |u|/sigma < 1
+  scale[i] = ldexp(1.0, e - B);
+  expo[i] = B - e;
+}
+
+// one 32x32 tile of U per block: read U[j][i] coalesced in i, write planes coalesced in j
+__global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U, int n, const int *__restrict__ expo,
+                                                    int T, int NE, int n_padk, int8_t *__restrict__ planes) {
+  __shared__ long long q[32][33];
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + tx;
+    long long v = 0;
+    if (j < n && i < n) v = llrint(ldexp(U[(size_t)j * n + i], expo[i]));
+    q[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + tx;      // thread writes eigenvector i, individual j
+    if (i >= n || j >= n) continue;
+    long long Q = q[tx][r];
+    const int g = i / NE, e = i - g * NE;
+    const size_t row0 = (size_t)g * (size_t)(T * NE) + (size_t)e;
+    for (int t = T - 1; t >= 1; --t) {
+      const long long d = ((Q + 128) & 255) - 128;          // balanced digit in [-128,127]
+      Q = (Q - d) >> 8;
+      planes[(row0 + (size_t)t * NE) * (size_t)n_padk + j] = (int8_t)d;
+    }
+    planes[row0 * (size_t)n_padk + j] = (int8_t)Q;           // |Q| <= 2^6 + 1
+  }
+}
+
+// PLINK 2-bit rows -> int8 genotype rows (0 at missing / padding) + per-SNP mean and hole count
+__global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__restrict__ bed, size_t bytes_per_snp,
+                                                        const int *__restrict__ idx, int n, int n_padk, int l,
+                                                        int8_t *__restrict__ G, double *__restrict__ mean,
+                                                        int *__restrict__ nmiss) {
+  __shared__ int sh_sum[8], sh_miss[8];
+  const int s = blockIdx.x;
+  int8_t *g = G + (size_t)s * n_padk;
+  if (s >= l) {                                   // zero padding rows of the last 128-SNP tile
+    for (int p = threadIdx.x; p < n_padk; p += 256) g[p] = 0;
+    return;
+  }
+  const unsigned char *row = bed + (size_t)s * bytes_per_snp;
+  int sum = 0, miss = 0;
+  for (int p = threadIdx.x; p < n_padk; p += 256) {
+    int8_t v = 0;
+    if (p < n) {
+      const size_t j = idx ? (size_t)idx[p] : (size_t)p;
+      const unsigned b = (unsigned)row[j >> 2] >> (2 * (j & 3));
+      const unsigned lo = b & 1u, hi = (b >> 1) & 1u;
+      if (lo == 0) v = hi == 0 ? 2 : 1;
+      else if (hi == 0) { miss++; }
+      sum += v;
+    }
+    g[p] = v;
+  }
+  for (int m = 16; m >= 1; m >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, m); miss += __shfl_xor_sync(0xffffffffu, miss, m); }
+  if ((threadIdx.x & 31) == 0) { sh_sum[threadIdx.x >> 5] = sum; sh_miss[threadIdx.x >> 5] = miss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ts = 0, tm = 0;
+    for (int w = 0; w < 8; ++w) { ts += sh_sum[w]; tm += sh_miss[w]; }
+    nmiss[s] = tm;
+    mean[s] = (double)ts / (double)(n - tm);          // x_mean of src/lmm.cpp:1819
+  }
+}
+
+// U^T x += mean * sum_{j in holes} U[j][:]   for SNPs with missing genotypes
+__global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__restrict__ bed, size_t bytes_per_snp,
+                                                       const int *__restrict__ idx, int n,
+                                                       const double *__restrict__ U, const double *__restrict__ mean,
+                                                       const int *__restrict__ nmiss, double *__restrict__ C, size_t ldc) {
+  constexpr int CAP = 2048;
+  __shared__ int list[CAP];
+  __shared__ int count;
+  const int s = blockIdx.x;
+  if (nmiss[s] == 0) return;
+  const unsigned char *row = bed + (size_t)s * bytes_per_snp;
+  const double m = mean[s];
+  double *c = C + (size_t)s * ldc;
+  for (int base = 0; base < n; base += CAP) {
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const int hi_p = min(n, base + CAP);
+    for (int p = base + threadIdx.x; p < hi_p; p += 256) {
+      const size_t j = idx ? (size_t)idx[p] : (size_t)p;
+      const unsigned b = (unsigned)row[j >> 2] >> (2 * (j & 3));
+      if ((b & 3u) == 1u) list[atomicAdd(&count, 1)] = p;      // low=1, high=0 -> missing
+    }
+    __syncthreads();
+    const int cnt = count;
+    if (cnt > 0) {
+      // deterministic order: sort-free but order-independent result is NOT guaranteed for FP adds,
+      // so order the short list (cnt is small) before summing
+      if (threadIdx.x == 0) {
+        for (int a = 1; a < cnt; ++a) { int key = list[a], b2 = a - 1; while (b2 >= 0 && list[b2] > key) { list[b2 + 1] = list[b2]; --b2; } list[b2 + 1] = key; }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += 256) {
+        double acc = 0.0;
+        for (int q = 0; q < cnt; ++q) acc += U[(size_t)list[q] * n + i];
+        c[i] += m * acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static bool make_tmap(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t row_bytes, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {row_bytes, rows};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)I8_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool i8_available(gb200_ctx *) { return get_encode() != nullptr; }
+
+int i8_prepare(gb200_ctx *c) {
+  if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, "i8_prepare before lmm_setup");
+  const int T = c->n_slices > 0 ? (int)c->n_slices : 6;
+  if (T < 2 || T > 8) return set_err(c, GB200_ERR_ARG, "n_slices must be in 2..8");
+  if (c->i8.ready && c->i8.n_slices == T && c->i8.n == c->n) return GB200_OK;
+  const I8Geom g = make_geom(c->n, T);
+  const size_t rows = (size_t)g.n_groups * (size_t)g.N;
+  const size_t bytes = rows * (size_t)g.n_padk;
+  GB_CUDA(c, c->i8.slices.reserve(bytes));
+  GB_CUDA(c, c->i8.scale.reserve((size_t)g.n * (sizeof(double) + sizeof(int)) + (size_t)g.n * sizeof(double)));
+  GB_CUDA(c, cudaMemsetAsync(c->i8.slices.p, 0, bytes, c->stream));
+  double *scale = c->i8.scale.as<double>();
+  double *colmax = scale + g.n;
+  int *expo = reinterpret_cast<int *>(colmax + g.n);
+  const int B = 6 + 8 * (T - 1);
+  col_absmax_kernel<<<(g.n + 255) / 256, 256, 0, c->stream>>>(c->dU.as<double>(), g.n, colmax);
+  col_scale_kernel<<<(g.n + 255) / 256, 256, 0, c->stream>>>(colmax, g.n, B, scale, expo);
+  dim3 grid((g.n + 31) / 32, (g.n + 31) / 32);
+  slice_kernel<<<grid, 256, 0, c->stream>>>(c->dU.as<double>(), g.n, expo, T, g.NE, g.n_padk, c->i8.slices.as<int8_t>());
+  GB_CUDA(c, cudaGetLastError());
+  if (!c->i8.tmap_a) c->i8.tmap_a = aligned_alloc(64, sizeof(CUtensorMap));
+  if (!c->i8.tmap_b) c->i8.tmap_b = aligned_alloc(64, sizeof(CUtensorMap));
+  if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, rows, (uint64_t)g.n_padk, (uint32_t)g.N))
+    return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes");
+  c->i8.n = c->n; c->i8.n_pad = (size_t)g.n_padk; c->i8.n_slices = T; c->i8.ready = true;
+  return GB200_OK;
+}
+
+int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total, size_t l,
+                   size_t bytes_per_snp, double *UtXt_dev) {
+  (void)ni_total;
+  int rc = i8_prepare(c);
+  if (rc) return rc;
+  const I8Geom g = make_geom(c->n, c->i8.n_slices);
+  const size_t l_pad = (l + I8_BM - 1) / I8_BM * I8_BM;
+  GB_CUDA(c, c->i8.geno.reserve(l_pad * (size_t)g.n_padk));
+  GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int))));
+  double *mean = c->i8.miss_mean.as<double>();
+  int *nmiss = reinterpret_cast<int *>(mean + l_pad);
+  ProfScope ps(c, "utx");
+  bed_to_i8_kernel<<<(unsigned)l_pad, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, g.n_padk, (int)l,
+                                                           c->i8.geno.as<int8_t>(), mean, nmiss);
+  GB_CUDA(c, cudaGetLastError());
+  if (!make_tmap((CUtensorMap *)c->i8.tmap_a, c->i8.geno.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
+    return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the genotype tile");
+  I8KernelParams p;
+  p.T = g.T; p.NE = g.NE; p.N = g.N; p.n = g.n; p.l = (int)l;
+  p.num_k_blocks = g.n_padk / I8_BK;
+  p.m_tiles = (int)(l_pad / I8_BM); p.n_groups = g.n_groups;
+  p.lbo_units = 1;
+  p.scale = c->i8.scale.as<double>();
+  p.C = UtXt_dev; p.ldc = c->n;
+  const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_groups;
+  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  i8_gemm_kernel<<<grid, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+  GB_CUDA(c, cudaGetLastError());
+  miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
+                                                      nmiss, UtXt_dev, c->n);
+  GB_CUDA(c, cudaGetLastError());
+  return GB200_OK;
+}
+
 }  // namespace gb

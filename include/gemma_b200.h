@@ -169,6 +169,11 @@ GB200_API int gb200_lmm_assoc_utx(gb200_ctx *ctx, const double *UtXt, size_t l, 
 /* Projection only: UtXt (l x n, ld n, host) = (U^T Xb)^T for a host batch Xb (n x l). */
 GB200_API int gb200_lmm_project(gb200_ctx *ctx, const double *Xb, size_t l, size_t ldx, double *UtXt);
 
+/* Projection only for a PLINK 2-bit batch (same decode / imputation as gb200_lmm_batch_bed),
+ * through whichever projection path the options select.  UtXt: l x n host buffer. */
+GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask,
+                          size_t ni_total, size_t l, size_t bytes_per_snp, double *UtXt);
+
 /* Tuning knobs (0 keeps the default): utx_path 0 auto, 1 FP64 tiled, 2 int8 tensor-core
  * (error-free U slicing, integer genotypes only); n_slices of the int8 path. */
 GB200_API int gb200_set_option(gb200_ctx *ctx, const char *name, long value);

@@ -310,3 +310,50 @@ def test_properties_at_scale(ctx):
     ref = O.lmm_analyze_utx(ev, UtW, Uty, U.T @ G[idx].T, 4, l_mle_null=nm["l_mle_null"],
                             logl_mle_H0=nm["logl_mle_H0"])
     check_sumstat(o4[idx], ref, 4)
+
+
+# ---- int8 tensor-core projection (tcgen05) vs the FP64 projection ---------------------------
+@pytest.mark.parametrize("n_total,n_drop,l,miss", [(300, 17, 200, 0.02), (1100, 0, 130, 0.0), (2500, 3, 517, 0.01)])
+def test_i8_tensor_core_projection_matches_fp64(n_total, n_drop, l, miss):
+    c = gemma_b200.Context(0)
+    rng = np.random.default_rng(n_total)
+    mask = np.ones(n_total, dtype=np.uint8)
+    if n_drop:
+        mask[rng.choice(n_total, n_drop, replace=False)] = 0
+    n = int(mask.sum())
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = synth.spectrum_like_kinship(n, 5)
+    c.lmm_setup(Q, ev, np.ones((n, 1)), rng.standard_normal(n))
+    bed, G = synth.make_bed(n_total, l, seed=n_total + 1, miss_rate=miss)
+    X = O.lmm_impute(np.where(G < 0, np.nan, G)[:, mask == 1])          # n x l, mean-imputed
+    ref = (Q.T @ X).T
+    c.set_option("utx_path", 1)
+    fp = c.lmm_project_bed(bed, n_total, mask if n_drop else None)
+    assert np.allclose(fp, ref, rtol=0, atol=1e-11)
+    scale = np.abs(ref).max()
+    for T, tol in ((6, 1e-11), (8, 1e-11), (7, 1e-11), (5, 1e-9), (4, 1e-6)):
+        c.set_option("utx_path", 2)
+        c.set_option("n_slices", T)
+        got = c.lmm_project_bed(bed, n_total, mask if n_drop else None)
+        err = np.abs(got - ref).max() / scale
+        assert err < tol, (T, err)
+    c.close()
+
+
+def test_i8_path_end_to_end_parity(ctx):
+    """-lmm 4 through gb200_lmm_batch_bed with the tensor-core projection forced, vs the oracle."""
+    n, l = 1536, 300
+    rng = np.random.default_rng(5)
+    pb = random_problem(n, 1, 4, 91)
+    bed, G = synth.make_bed(n, l, seed=92, miss_rate=0.01)
+    X = O.lmm_impute(np.where(G < 0, np.nan, G))
+    y = pb["y"] + 0.5 * (X[:, 7] - X[:, 7].mean())
+    ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], y)
+    nm = ctx.lmm_null(pb["trace_G"])
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ctx.set_option("utx_path", 2); ctx.set_option("n_slices", 6)
+    got = ctx.lmm_batch_bed(bed, n)
+    ctx.set_option("utx_path", 0); ctx.set_option("n_slices", 0)
+    ref = O.lmm_analyze_utx(pb["ev"], pb["U"].T @ pb["W"], pb["U"].T @ y, pb["U"].T @ X, 4,
+                            l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    check_sumstat(got, ref, 4)
