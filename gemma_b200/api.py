@@ -59,6 +59,7 @@ SIGNATURES = {
                              C.POINTER(C.c_int)]),
     "gb200_lmm_setup": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
     "gb200_lmm_setup_rotated": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "gb200_lmm_setup_rotated_dev": (C.c_int, [_vp, _sz, _sz, _vp, _vp, _vp, _vp]),
     "gb200_lmm_null": (C.c_int, [_vp, C.c_double, C.c_double, _sz, C.c_double, C.POINTER(NullModel), _vp, _vp,
                                  _vp, _vp]),
     "gb200_lmm_params": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _sz, C.c_double, C.c_double]),
@@ -214,6 +215,11 @@ class Context:
         n, c = UtW.shape
         self._chk(self.lib.gb200_lmm_setup_rotated(self.h, n, c, _ptr(U), n, _ptr(eval_), _ptr(UtW), c, _ptr(Uty)))
         self.n, self.n_cvt = n, c
+
+    def lmm_setup_rotated_dev(self, n, n_cvt, U_dev, eval_dev, UtWt_dev, Uty_dev):
+        """Device pointers (ints); U_dev is borrowed."""
+        self._chk(self.lib.gb200_lmm_setup_rotated_dev(self.h, n, n_cvt, U_dev, eval_dev, UtWt_dev, Uty_dev))
+        self.n, self.n_cvt = n, n_cvt
 
     def lmm_null(self, trace_G, l_min=1e-5, l_max=1e5, n_region=10):
         nm = NullModel()

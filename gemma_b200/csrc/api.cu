@@ -96,6 +96,7 @@ int gb200_profile_reset(gb200_ctx *c) {
 
 int gb200_profile_get(gb200_ctx *c, const char *name, double *ms, long *launches) {
   if (!c || !name) return GB200_ERR_ARG;
+  if (!strcmp(name, "__launches")) { if (ms) *ms = 0.0; if (launches) *launches = c->kernel_launches; return GB200_OK; }
   auto it = c->profs.find(name);
   if (it == c->profs.end()) { if (ms) *ms = 0.0; if (launches) *launches = 0; return GB200_OK; }
   prof_drain(c, it->second);
@@ -226,7 +227,7 @@ int gb200_kin_add_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, size_t l, 
     const size_t lc = (l - s0 < chunk) ? (l - s0) : chunk;
     GB_CUDA(c, c->dX.reserve(n * lc * sizeof(double)));
     {
-      ProfScope ps(c, "decode");
+      ProfScope ps(c, "decode", 2);
       GB_CUDA(c, launch_bed_decode(bed_dev + s0 * bytes_per_snp, lc, bytes_per_snp, nullptr, n,
                                    c->dX.as<double>(), n, c->stream));
       GB_CUDA(c, launch_kin_transform(c->dX.as<double>(), lc, n, n, c->kin_mode, c->stream));
@@ -337,6 +338,27 @@ int gb200_lmm_setup_rotated(gb200_ctx *c, size_t n, size_t n_cvt, const double *
   GB_CUDA(c, cudaMemcpyAsync(c->dY.p, Uty, n * 8, cudaMemcpyHostToDevice, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->lmm_ready = true;
+  return GB200_OK;
+}
+
+int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const double *U_dev, const double *eval_dev,
+                                const double *UtWt_dev, const double *Uty_dev) {
+  if (!c) return GB200_ERR_ARG;
+  if (n == 0 || n_cvt == 0 || !U_dev || !eval_dev || !UtWt_dev || !Uty_dev)
+    return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated_dev: bad argument");
+  if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
+  if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
+  c->lmm_ready = false; c->i8.ready = false;
+  c->dU.adopt(const_cast<double *>(U_dev), n * n * 8);          // borrowed: caller keeps it alive
+  GB_CUDA(c, c->dEval.reserve(n * 8));
+  GB_CUDA(c, c->dWt.reserve(n_cvt * n * 8));
+  GB_CUDA(c, c->dY.reserve(n * 8));
+  GB_CUDA(c, c->dNull.reserve(sizeof(NullOut)));
+  GB_CUDA(c, cudaMemcpyAsync(c->dEval.p, eval_dev, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dWt.p, UtWt_dev, n_cvt * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dY.p, Uty_dev, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n = n; c->n_cvt = n_cvt; c->lmm_ready = true;
   return GB200_OK;
 }
 
@@ -564,7 +586,7 @@ static int project_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const int
   if (use_i8) return i8_project_bed(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, c->dUtXt.as<double>());
   GB_CUDA(c, c->dX.reserve(n * l * 8));
   {
-    ProfScope ps(c, "decode");
+    ProfScope ps(c, "decode", 2);
     GB_CUDA(c, launch_bed_decode(bed_dev, l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
     GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
   }

@@ -22,14 +22,16 @@ struct ProfEntry {
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  bool owned = true;
   cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    if (owned && bytes <= cap) return cudaSuccess;
+    release();
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void adopt(void *ptr, size_t bytes) { release(); p = ptr; cap = bytes; owned = false; }   // borrowed, never freed
+  void release() { if (p && owned) cudaFree(p); p = nullptr; cap = 0; owned = true; }
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -73,6 +75,7 @@ struct gb200_ctx {
   gb::DevBuf dX, dUtXt, dOut, dBed, dMask, dIdx, dTicket, dTmp;
   std::vector<int> idx_host;          // analysed-individual index cache for bed batches
   std::vector<unsigned char> mask_host;
+  long kernel_launches = 0;   // kernels of this library launched so far (bench "gpu_launches")
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
   long n_slices = 0;     // 0 = default
@@ -102,17 +105,19 @@ struct ProfScope {
   gb200_ctx *c;
   ProfEntry *e = nullptr;
   cudaEvent_t a = nullptr, b = nullptr;
+  long launches = 1;          // kernels launched inside this scope
   static cudaEvent_t get_event(gb200_ctx *c) {
     if (!c->event_pool.empty()) { cudaEvent_t ev = c->event_pool.back(); c->event_pool.pop_back(); return ev; }
     cudaEvent_t ev; cudaEventCreate(&ev); return ev;
   }
-  ProfScope(gb200_ctx *ctx, const char *name) : c(ctx) {
+  ProfScope(gb200_ctx *ctx, const char *name, long n_launch = 1) : c(ctx), launches(n_launch) {
     if (!c->prof) return;
     e = &c->profs[name];
     a = get_event(c); b = get_event(c);
     cudaEventRecord(a, c->stream);
   }
   ~ProfScope() {
+    c->kernel_launches += launches;
     if (!e) return;
     cudaEventRecord(b, c->stream);
     e->pending.emplace_back(a, b);

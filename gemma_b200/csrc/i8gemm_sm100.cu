@@ -470,10 +470,12 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int))));
   double *mean = c->i8.miss_mean.as<double>();
   int *nmiss = reinterpret_cast<int *>(mean + l_pad);
-  ProfScope ps(c, "utx");
+  {
+  ProfScope ps(c, "decode");
   bed_to_i8_kernel<<<(unsigned)l_pad, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, g.n_padk, (int)l,
                                                            c->i8.geno.as<int8_t>(), mean, nmiss);
   GB_CUDA(c, cudaGetLastError());
+  }
   if (!make_tmap((CUtensorMap *)c->i8.tmap_a, c->i8.geno.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
     return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the genotype tile");
   I8KernelParams p;
@@ -491,8 +493,12 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   }
   const int tiles = p.m_tiles * p.n_groups;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  i8_gemm_kernel<<<grid, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
-  GB_CUDA(c, cudaGetLastError());
+  {
+    ProfScope ps(c, "utx");
+    i8_gemm_kernel<<<grid, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+    GB_CUDA(c, cudaGetLastError());
+  }
+  ProfScope ps2(c, "fix");
   miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
                                                       nmiss, UtXt_dev, c->n);
   GB_CUDA(c, cudaGetLastError());

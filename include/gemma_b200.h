@@ -137,6 +137,10 @@ GB200_API int gb200_lmm_setup(gb200_ctx *ctx, size_t n, size_t n_cvt,
 GB200_API int gb200_lmm_setup_rotated(gb200_ctx *ctx, size_t n, size_t n_cvt,
                             const double *U, size_t ldu, const double *eval,
                             const double *UtW, size_t ldw, const double *Uty);
+/* Same with DEVICE pointers: U_dev (n x n row-major, ld n) is BORROWED (not copied; the caller
+ * keeps it alive while the context uses it), UtWt_dev is U^T W stored TRANSPOSED (n_cvt x n). */
+GB200_API int gb200_lmm_setup_rotated_dev(gb200_ctx *ctx, size_t n, size_t n_cvt, const double *U_dev,
+                                const double *eval_dev, const double *UtWt_dev, const double *Uty_dev);
 /* Null model on the device with the same fused evaluator (src/gemma.cpp:2711-2753):
  * also returns beta / se(beta) of the covariates (n_cvt values each) for MLE and REMLE. */
 GB200_API int gb200_lmm_null(gb200_ctx *ctx, double l_min, double l_max, size_t n_region, double trace_G,
