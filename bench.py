@@ -198,7 +198,9 @@ def run_b200(args):
     if Wm < 3:
         Wm = 3
     bps = (n + 3) // 4
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream shared by torch, NCCL and the library
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = gemma_b200.Context(local, stream=stream.cuda_stream)
     ctx.set_option("utx_path", args.utx_path)
     ctx.set_option("n_slices", args.slices)
