@@ -1,0 +1,69 @@
+"""Host side of the GEMMA-compatible CLI (gemma_b200/host/gemma_cli.cpp): readers + SNP QC must select
+exactly the SNPs / individuals the reference selects (bit-exact ids and counts).  CPU only (-qc-only)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import refpipe as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "gemma_b200", "host", "gemma-b200")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "gemma_b200", "host")])
+
+
+def _qc(args, outdir, name):
+    _build()
+    r = subprocess.run([CLI] + args + ["-qc-only", "-o", name, "-outdir", str(outdir)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [l.rstrip("\n").split("\t") for l in open(os.path.join(outdir, name + ".qc.txt"))]
+    return r.stdout, rows
+
+
+def test_mouse_qc_matches_reference_selection(golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    out, rows = _qc(["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt",
+                     "-a", d + "/mouse_hs1940.anno.txt"], tmp_path, "mouse")
+    assert "## number of analyzed individuals = 1410" in out and "## number of total individuals = 1940" in out
+    assert "## number of analyzed SNPs         =    10768" in out and "## number of total SNPs/var        =    12226" in out
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1,))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, n_miss, maf = R.qc_bimbam(bb, idv)
+    assert [r[0] for r in rows] == bb.rs
+    assert np.array_equal(np.array([int(r[1]) for r in rows]), isnp)
+    assert np.array_equal(np.array([int(r[2]) for r in rows]), n_miss)
+    assert np.allclose(np.array([float(r[3]) for r in rows]), maf, rtol=0, atol=1e-15)
+
+
+def test_bxd_covariates_maf_r2_qc(golden_dir, tmp_path):
+    d = os.path.join(golden_dir, "BXD")
+    out, rows = _qc(["-g", d + "/BXD_geno.txt.gz", "-p", d + "/BXD_pheno.txt", "-c", d + "/BXD_covariates2.txt",
+                     "-a", d + "/BXD_snps.txt", "-maf", "0.1"], tmp_path, "bxd")
+    assert "## number of covariates = 3" in out and "## number of analyzed individuals = 67" in out
+    bb = R.Bimbam(d + "/BXD_geno.txt.gz")
+    ph, ind = R.read_pheno(d + "/BXD_pheno.txt", (1,))
+    rws, icvt = R.read_cvt(d + "/BXD_covariates2.txt")
+    idv, W = R.process_cvt_phen(ind, rws, icvt)
+    isnp, n_miss, maf = R.qc_bimbam(bb, idv, W, maf_level=0.1)
+    assert np.array_equal(np.array([int(r[1]) for r in rows]), isnp)
+    assert int(isnp.sum()) == 7317
+
+
+def test_cli_rejects_unknown_flags_and_missing_inputs():
+    _build()
+    r = subprocess.run([CLI, "-bogus"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unrecognized option" in r.stdout
+    r = subprocess.run([CLI, "-g", "x", "-p", "y", "-lmm", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "missing relatedness file" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/example/mouse_hs1940.bed"), reason="reference examples absent")
+def test_plink_qc_counts_match_bimbam_counts(tmp_path):
+    out, rows = _qc(["-bfile", "/root/reference/example/mouse_hs1940"], tmp_path, "plink")
+    # same cohort through the PLINK reader: .fam phenotype column 1, 2-bit genotypes
+    assert "## number of total individuals = 1940" in out and "## number of total SNPs/var        =    12226" in out

@@ -357,3 +357,39 @@ def test_i8_path_end_to_end_parity(ctx):
     ref = O.lmm_analyze_utx(pb["ev"], pb["U"].T @ pb["W"], pb["U"].T @ y, pb["U"].T @ X, 4,
                             l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
     check_sumstat(got, ref, 4)
+
+
+# ---- the GEMMA-compatible CLI end to end (BASELINE config 1 through the drop-in surface) -------
+def test_cli_mouse_gk_then_lmm_matches_demo_txt(golden_dir, tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+    if not os.path.exists(cli):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt",
+            "-outdir", str(tmp_path)]
+    r = subprocess.run([cli] + base + ["-gk", "-o", "mouse"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    k = open(tmp_path / "mouse.cXX.txt").read().splitlines()
+    assert len(k) == 1940 and len(k[0].split("\t")) == 1940                  # test/test_suite.sh:119-123
+    assert [[float("%.6g" % float(x)) for x in k[i].split("\t")[:3]] for i in range(3)] == EXP["mouse_K3"]
+    r = subprocess.run([cli] + base + ["-n", "1", "-k", str(tmp_path / "mouse.cXX.txt"), "-lmm", "-o", "lmm"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "pve estimate =0.608801" in r.stdout and "se(pve) =0.032774" in r.stdout       # demo.txt:41-42
+    lines = open(tmp_path / "lmm.assoc.txt").read().splitlines()
+    assert len(lines) == 10769                                              # header + 10768 SNPs
+    assert lines[0].split("\t") == ["chr", "rs", "ps", "n_miss", "allele1", "allele0", "af", "beta", "se", "logl_H1",
+                                    "l_remle", "p_wald"]
+    assert sum(len(l.split("\t")) for l in lines) == 129228                 # test/test_suite.sh:138 word count
+    for line, e in zip(lines[1:6], EXP["mouse_lmm1_rows"]):                 # demo.txt:32-36, text for text
+        f = line.split("\t")
+        assert f[:7] == [e["chr"], e["rs"], e["ps"], e["n_miss"], e["allele1"], e["allele0"], e["af"]]
+        assert [f[7], f[8], f[10], f[11]] == [e["beta"], e["se"], e["l_remle"], e["p_wald"]]
+    # -lmm 4 writes the 15-column layout
+    r = subprocess.run([cli] + base + ["-k", str(tmp_path / "mouse.cXX.txt"), "-lmm", "4", "-o", "lmm4", "-snps",
+                                       d + "/../mouse_snps_first200.txt"], capture_output=True, text=True)
+    if r.returncode == 0:
+        h = open(tmp_path / "lmm4.assoc.txt").readline().rstrip("\n").split("\t")
+        assert h[7:] == ["beta", "se", "logl_H1", "l_remle", "l_mle", "p_wald", "p_lrt", "p_score"]
