@@ -16,6 +16,15 @@ int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_
 bool i8_available(gb200_ctx *ctx);
 }
 
+// grow-only buffer whose NEW allocations are zero-filled (row tails of padded buffers stay zero)
+static cudaError_t reserve_zeroed(gb::DevBuf &b, size_t bytes, cudaStream_t st) {
+  if (b.owned && b.p && bytes <= b.cap) return cudaSuccess;
+  cudaError_t e = b.reserve(bytes);
+  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(b.p, 0, bytes, st);
+}
+static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
 static bool trans_flag(const char *t, bool *ok) {
   *ok = t && (t[0] == 'N' || t[0] == 'n' || t[0] == 'T' || t[0] == 't');
   return t && (t[0] == 'T' || t[0] == 't');
@@ -110,6 +119,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
   if (!strcmp(name, "utx_path")) {
     if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "utx_path must be 0,1,2");
     c->utx_path = value; return GB200_OK;
+  }
+  if (!strcmp(name, "lmm_kernel")) {
+    if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2");
+    c->lmm_kernel = value; return GB200_OK;
   }
   if (!strcmp(name, "n_slices")) {
     if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "n_slices must be 0..8");
@@ -284,14 +297,19 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT (fused kernel register budget)");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false;
+  const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
+  c->dUtXt.release();                             // row pitch changes with n: force a fresh zeroed buffer
   GB_CUDA(c, c->dU.reserve(n * n * sizeof(double)));
-  GB_CUDA(c, c->dEval.reserve(n * sizeof(double)));
-  GB_CUDA(c, c->dWt.reserve(n_cvt * n * sizeof(double)));
-  GB_CUDA(c, c->dY.reserve(n * sizeof(double)));
+  GB_CUDA(c, c->dEval.reserve(n_c * sizeof(double)));
+  GB_CUDA(c, c->dWt.reserve(n_cvt * n_c * sizeof(double)));
+  GB_CUDA(c, c->dY.reserve(n_c * sizeof(double)));
   GB_CUDA(c, c->dNull.reserve(sizeof(NullOut)));
+  GB_CUDA(c, cudaMemsetAsync(c->dEval.p, 0, n_c * 8, c->stream));
+  GB_CUDA(c, cudaMemsetAsync(c->dWt.p, 0, n_cvt * n_c * 8, c->stream));
+  GB_CUDA(c, cudaMemsetAsync(c->dY.p, 0, n_c * 8, c->stream));
   GB_CUDA(c, cudaMemcpy2DAsync(c->dU.p, n * 8, U, ldu * 8, n * 8, n, cudaMemcpyHostToDevice, c->stream));
   GB_CUDA(c, cudaMemcpyAsync(c->dEval.p, eval, n * 8, cudaMemcpyHostToDevice, c->stream));
-  c->n = n; c->n_cvt = n_cvt;
+  c->n = n; c->n_cvt = n_cvt; c->n_c = n_c;
   return GB200_OK;
 }
 
@@ -307,17 +325,18 @@ int gb200_lmm_setup(gb200_ctx *c, size_t n, size_t n_cvt, const double *U, size_
   GB_CUDA(c, cudaMemcpy2DAsync(dW, n_cvt * 8, W, ldw * 8, n_cvt * 8, n, cudaMemcpyHostToDevice, c->stream));
   GB_CUDA(c, cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, c->stream));
   // Wt[a][i] = sum_j W[j][a] U[j][i]   (M = n_cvt, N = n, K = n)
-  GB_CUDA(c, launch_dgemm(n_cvt, n, n, 1.0, dW, 1, n_cvt, c->dU.as<double>(), n, 1, 0.0, c->dWt.as<double>(), n,
+  const size_t n_c = c->n_c;
+  GB_CUDA(c, launch_dgemm(n_cvt, n, n, 1.0, dW, 1, n_cvt, c->dU.as<double>(), n, 1, 0.0, c->dWt.as<double>(), n_c,
                           false, c->stream));
-  GB_CUDA(c, launch_dgemm(1, n, n, 1.0, dy, 1, 1, c->dU.as<double>(), n, 1, 0.0, c->dY.as<double>(), n, false,
+  GB_CUDA(c, launch_dgemm(1, n, n, 1.0, dy, 1, 1, c->dU.as<double>(), n, 1, 0.0, c->dY.as<double>(), n_c, false,
                           c->stream));
   if (UtW_out) {
     // return as n x n_cvt row-major
-    std::vector<double> t(n_cvt * n);
-    GB_CUDA(c, cudaMemcpyAsync(t.data(), c->dWt.p, n_cvt * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> t(n_cvt * n_c);
+    GB_CUDA(c, cudaMemcpyAsync(t.data(), c->dWt.p, n_cvt * n_c * 8, cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t a = 0; a < n_cvt; ++a)
-      for (size_t i = 0; i < n; ++i) UtW_out[i * n_cvt + a] = t[a * n + i];
+      for (size_t i = 0; i < n; ++i) UtW_out[i * n_cvt + a] = t[a * n_c + i];
   }
   if (Uty_out) GB_CUDA(c, cudaMemcpyAsync(Uty_out, c->dY.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -331,10 +350,11 @@ int gb200_lmm_setup_rotated(gb200_ctx *c, size_t n, size_t n_cvt, const double *
   if (!UtW || !Uty || ldw < n_cvt) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated: bad argument");
   int rc = lmm_upload_common(c, n, n_cvt, U, ldu, eval);
   if (rc) return rc;
-  std::vector<double> t(n_cvt * n);
+  const size_t n_c = c->n_c;
+  std::vector<double> t(n_cvt * n_c, 0.0);
   for (size_t a = 0; a < n_cvt; ++a)
-    for (size_t i = 0; i < n; ++i) t[a * n + i] = UtW[i * ldw + a];
-  GB_CUDA(c, cudaMemcpyAsync(c->dWt.p, t.data(), n_cvt * n * 8, cudaMemcpyHostToDevice, c->stream));
+    for (size_t i = 0; i < n; ++i) t[a * n_c + i] = UtW[i * ldw + a];
+  GB_CUDA(c, cudaMemcpyAsync(c->dWt.p, t.data(), n_cvt * n_c * 8, cudaMemcpyHostToDevice, c->stream));
   GB_CUDA(c, cudaMemcpyAsync(c->dY.p, Uty, n * 8, cudaMemcpyHostToDevice, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->lmm_ready = true;
@@ -349,22 +369,27 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false;
+  const size_t n_c = round_up(n, 512);
+  c->dUtXt.release();
   c->dU.adopt(const_cast<double *>(U_dev), n * n * 8);          // borrowed: caller keeps it alive
-  GB_CUDA(c, c->dEval.reserve(n * 8));
-  GB_CUDA(c, c->dWt.reserve(n_cvt * n * 8));
-  GB_CUDA(c, c->dY.reserve(n * 8));
+  GB_CUDA(c, c->dEval.reserve(n_c * 8));
+  GB_CUDA(c, c->dWt.reserve(n_cvt * n_c * 8));
+  GB_CUDA(c, c->dY.reserve(n_c * 8));
   GB_CUDA(c, c->dNull.reserve(sizeof(NullOut)));
+  GB_CUDA(c, cudaMemsetAsync(c->dEval.p, 0, n_c * 8, c->stream));
+  GB_CUDA(c, cudaMemsetAsync(c->dWt.p, 0, n_cvt * n_c * 8, c->stream));
+  GB_CUDA(c, cudaMemsetAsync(c->dY.p, 0, n_c * 8, c->stream));
   GB_CUDA(c, cudaMemcpyAsync(c->dEval.p, eval_dev, n * 8, cudaMemcpyDeviceToDevice, c->stream));
-  GB_CUDA(c, cudaMemcpyAsync(c->dWt.p, UtWt_dev, n_cvt * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dWt.p, n_c * 8, UtWt_dev, n * 8, n * 8, n_cvt, cudaMemcpyDeviceToDevice, c->stream));
   GB_CUDA(c, cudaMemcpyAsync(c->dY.p, Uty_dev, n * 8, cudaMemcpyDeviceToDevice, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->n = n; c->n_cvt = n_cvt; c->lmm_ready = true;
+  c->n = n; c->n_cvt = n_cvt; c->n_c = n_c; c->lmm_ready = true;
   return GB200_OK;
 }
 
 static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
-  D.n = (int)c->n; D.ldv = (int)c->n;
+  D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
   return D;
 }
@@ -473,8 +498,14 @@ static int lmm_check_ready(gb200_ctx *c, const char *who) {
 static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev) {
   LmmConst D = make_const(c);
   ProfScope ps(c, "lmm");
-  GB_CUDA(c, launch_lmm_assoc((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, c->dTicket.as<unsigned int>(),
-                              c->num_sms, c->stream));
+  const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
+  if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
+  if (v2_ok && c->lmm_kernel != 1)
+    GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, c->dTicket.as<unsigned int>(),
+                                   c->num_sms, c->stream));
+  else
+    GB_CUDA(c, launch_lmm_assoc((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, c->dTicket.as<unsigned int>(),
+                                c->num_sms, c->stream));
   return GB200_OK;
 }
 
@@ -482,7 +513,7 @@ static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu,
 static int project_fp64_snpmajor(gb200_ctx *c, const double *Xs, size_t l, double *UtXt) {
   const size_t n = c->n;
   ProfScope ps(c, "utx");
-  GB_CUDA(c, launch_dgemm(l, n, n, 1.0, Xs, n, 1, c->dU.as<double>(), n, 1, 0.0, UtXt, n, false, c->stream));
+  GB_CUDA(c, launch_dgemm(l, n, n, 1.0, Xs, n, 1, c->dU.as<double>(), n, 1, 0.0, UtXt, c->n_c, false, c->stream));
   return GB200_OK;
 }
 
@@ -493,10 +524,10 @@ int gb200_lmm_assoc_utx(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, 
   if (l == 0) return GB200_OK;
   if (!UtXt || !out || ldu < c->n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_assoc_utx: bad argument");
   const size_t n = c->n;
-  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
   GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
-  GB_CUDA(c, cudaMemcpy2DAsync(c->dUtXt.p, n * 8, UtXt, ldu * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
-  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, c->dOut.as<gb200_sumstat>());
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dUtXt.p, c->n_c * 8, UtXt, ldu * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, c->dOut.as<gb200_sumstat>());
   if (rc) return rc;
   GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -510,15 +541,15 @@ int gb200_lmm_project(gb200_ctx *c, const double *Xb, size_t l, size_t ldx, doub
   if (!Xb || !UtXt || ldx < l) return set_err(c, GB200_ERR_ARG, "gb200_lmm_project: bad argument");
   const size_t n = c->n;
   GB_CUDA(c, c->dX.reserve(n * l * 8));
-  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
   GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, l * 8, Xb, ldx * 8, l * 8, n, cudaMemcpyHostToDevice, c->stream));
   {
     ProfScope ps(c, "utx");
     // A(s,j) = X[j*l + s]
     GB_CUDA(c, launch_dgemm(l, n, n, 1.0, c->dX.as<double>(), 1, l, c->dU.as<double>(), n, 1, 0.0,
-                            c->dUtXt.as<double>(), n, false, c->stream));
+                            c->dUtXt.as<double>(), c->n_c, false, c->stream));
   }
-  GB_CUDA(c, cudaMemcpyAsync(UtXt, c->dUtXt.p, l * n * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaMemcpy2DAsync(UtXt, n * 8, c->dUtXt.p, c->n_c * 8, n * 8, l, cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   return GB200_OK;
 }
@@ -531,15 +562,15 @@ int gb200_lmm_batch(gb200_ctx *c, const double *Xb, size_t l, size_t ldx, gb200_
   if (!Xb || !out || ldx < l) return set_err(c, GB200_ERR_ARG, "gb200_lmm_batch: bad argument");
   const size_t n = c->n;
   GB_CUDA(c, c->dX.reserve(n * l * 8));
-  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
   GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
   GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, l * 8, Xb, ldx * 8, l * 8, n, cudaMemcpyHostToDevice, c->stream));
   {
     ProfScope ps(c, "utx");
     GB_CUDA(c, launch_dgemm(l, n, n, 1.0, c->dX.as<double>(), 1, l, c->dU.as<double>(), n, 1, 0.0,
-                            c->dUtXt.as<double>(), n, false, c->stream));
+                            c->dUtXt.as<double>(), c->n_c, false, c->stream));
   }
-  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, c->dOut.as<gb200_sumstat>());
+  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, c->dOut.as<gb200_sumstat>());
   if (rc) return rc;
   GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -554,7 +585,7 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
   const size_t n = c->n;
   if (!G || !out || ldg < n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_batch_geno: bad argument");
   GB_CUDA(c, c->dX.reserve(n * l * 8));
-  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
   GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
   GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
   {
@@ -563,7 +594,7 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
   }
   rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
   if (rc) return rc;
-  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, n, c->dOut.as<gb200_sumstat>());
+  rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, c->dOut.as<gb200_sumstat>());
   if (rc) return rc;
   GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -575,7 +606,7 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
 static int project_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                            size_t l, size_t bytes_per_snp) {
   const size_t n = c->n;
-  GB_CUDA(c, c->dUtXt.reserve(l * n * 8));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
   bool use_i8 = false;
   if (c->utx_path == 2) {
     if (!i8_available(c)) return set_err(c, GB200_ERR_UNSUPPORTED, "int8 tensor-core path not available (no cuTensorMapEncodeTiled)");
@@ -597,7 +628,7 @@ static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *i
                         size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
   int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
   if (rc) return rc;
-  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n, out_dev);
+  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, out_dev);
 }
 
 static int upload_idx_from_mask(gb200_ctx *c, const unsigned char *idv_mask, size_t ni_total, const int **idx_dev) {
@@ -675,7 +706,7 @@ int gb200_lmm_project_bed(gb200_ctx *c, const unsigned char *bed, const unsigned
   GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
   rc = project_bed_dev(c, c->dBed.as<unsigned char>(), idx_dev, ni_total, l, bytes_per_snp);
   if (rc) return rc;
-  GB_CUDA(c, cudaMemcpyAsync(UtXt, c->dUtXt.p, l * c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaMemcpy2DAsync(UtXt, c->n * 8, c->dUtXt.p, c->n_c * 8, c->n * 8, l, cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   return GB200_OK;
 }

@@ -79,6 +79,8 @@ struct gb200_ctx {
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
   long n_slices = 0;     // 0 = default
+  long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA
+  size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)
   gb::I8State i8;
 };
 
@@ -129,6 +131,9 @@ struct ProfScope {
 cudaError_t launch_lmm_assoc(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt,
                              size_t ldu, int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,
                              cudaStream_t st);
+bool lmm_v2_supported(int n_cvt, int n_region);
+cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,
+                                int l, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st);
 cudaError_t launch_lmm_null(int n_cvt, const LmmConst &D, double l_min, double l_max, int n_region,
                             NullOut *out, cudaStream_t st);
 

@@ -484,7 +484,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.m_tiles = (int)(l_pad / I8_BM); p.n_groups = g.n_groups;
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
-  p.C = UtXt_dev; p.ldc = c->n;
+  p.C = UtXt_dev; p.ldc = c->n_c;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -500,7 +500,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   }
   ProfScope ps2(c, "fix");
   miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
-                                                      nmiss, UtXt_dev, c->n);
+                                                      nmiss, UtXt_dev, c->n_c);
   GB_CUDA(c, cudaGetLastError());
   return GB200_OK;
 }

@@ -30,7 +30,8 @@ namespace gb {
 
 struct LmmConst {
   int n;                 // analysed individuals
-  int ldv;               // leading dimension of Wt rows
+  int n_c;               // n rounded up to the pipeline chunk (512); every vector is zero-padded to n_c
+  int ldv;               // leading dimension of Wt rows (== n_c)
   const double *delta;   // eigenvalues (n)
   const double *Wt;      // rotated covariates, TRANSPOSED: n_cvt rows of n (coalesced per covariate)
   const double *y;       // rotated phenotype (n)

@@ -8,6 +8,7 @@
 // Replaces the per-SNP loop of LMM::Analyze's batch_compute (src/lmm.cpp:1526-1562).
 #include "common.cuh"
 #include "lmm_device.cuh"
+#include "lmm_v2.cuh"
 
 namespace gb {
 
@@ -25,6 +26,60 @@ __global__ void __launch_bounds__(128) lmm_assoc_kernel(LmmConst D, LmmParams pr
     gb200_sumstat r;
     analyze_snp<NC>(D, prm, UtXt + (size_t)s * ldu, r);
     if (lane == 0) out[s] = r;
+  }
+}
+
+// v2: one CTA = 8 warps = 8 SNPs in lockstep passes over shared-memory stages (lmm_v2.cuh)
+template <int NC>
+__global__ void __launch_bounds__(V2_THREADS, 1) lmm_assoc_v2_kernel(LmmConst D, LmmParams prm,
+                                                                    const double *__restrict__ UtXt, size_t ldu, int l,
+                                                                    gb200_sumstat *__restrict__ out,
+                                                                    unsigned int *__restrict__ ticket) {
+  extern __shared__ __align__(16) double v2_smem[];
+  __shared__ const double *xrows[V2_WARPS];
+  __shared__ unsigned int grp_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nchunks = D.n_c / V2_CHUNK, pad = D.n_c - D.n;
+  for (;;) {
+    if (threadIdx.x == 0) grp_s = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int g = grp_s;
+    if ((size_t)g * V2_WARPS >= (size_t)l) break;
+    const int s = (int)(g * V2_WARPS) + warp;
+    const bool valid = s < l;
+    if (lane == 0) xrows[warp] = valid ? UtXt + (size_t)s * ldu : nullptr;
+    __syncthreads();
+    gb200_sumstat r;
+    v2_analyze_group<NC>(D, prm, xrows, v2_smem, nchunks, pad, valid, r);
+    if (valid && lane == 0) out[s] = r;
+    __syncthreads();
+  }
+}
+
+template <int NC>
+static cudaError_t launch_assoc_v2_nc(const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu, int l,
+                                      gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st) {
+  const size_t smem = v2_smem_bytes(NC);
+  cudaError_t e = cudaFuncSetAttribute(lmm_assoc_v2_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long groups = ((long)l + V2_WARPS - 1) / V2_WARPS;
+  long grid = groups < num_sms ? groups : num_sms;
+  if (grid < 1) grid = 1;
+  e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  lmm_assoc_v2_kernel<NC><<<(unsigned)grid, V2_THREADS, smem, st>>>(D, prm, UtXt, ldu, l, out, ticket);
+  return cudaGetLastError();
+}
+
+bool lmm_v2_supported(int n_cvt, int n_region) { return n_cvt >= 1 && n_cvt <= 3 && n_region <= V2_MAX_REGION; }
+
+cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,
+                                int l, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st) {
+  switch (n_cvt) {
+    case 1: return launch_assoc_v2_nc<1>(D, prm, UtXt, ldu, l, out, ticket, num_sms, st);
+    case 2: return launch_assoc_v2_nc<2>(D, prm, UtXt, ldu, l, out, ticket, num_sms, st);
+    case 3: return launch_assoc_v2_nc<3>(D, prm, UtXt, ldu, l, out, ticket, num_sms, st);
+    default: return cudaErrorInvalidValue;
   }
 }
 

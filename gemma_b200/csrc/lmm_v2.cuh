@@ -1,0 +1,517 @@
+// lmm_v2.cuh -- second-generation fused per-SNP LMM kernel.
+//
+// Same arithmetic and control flow as lmm_device.cuh (one warp owns one SNP; grid scan, GSL Brent,
+// GSL Newton, Wald / score / LRT -- src/lmm.cpp:1526-1562, :1945-2140), re-organised around memory:
+//
+//  * a CTA holds 8 warps = 8 SNPs that walk the n rotated individuals in LOCKSTEP passes.  The
+//    SNP-independent vectors (eigenvalues, rotated covariates, rotated phenotype) are staged once per
+//    CTA and chunk in shared memory by a 3-stage cp.async pipeline and shared by the 8 SNPs; every
+//    warp's own U^T x row streams through its private slice of the same stages.  At n = 50 000 the
+//    v1 kernel re-read 1.6 MB per SNP and pass through L2 with ~2 KB in flight per warp
+//    (latency-bound, 17% of the FP64 pipe); here a pass moves 0.55 MB per SNP with 44 KB x 2 stages in
+//    flight per SM.
+//  * several lambdas per pass ("slots"): the 11 grid lambdas are evaluated 4 at a time, f(l_max) and the
+//    score-test lambda share one pass, and the REML and ML root refinements (independent chains) advance
+//    side by side, so a SNP needs ~16 passes over its row instead of ~35.
+//  * 1/(lambda*delta+1) by MUFU.RCP64H seed + two Newton steps (delta >= 0 after the <1e-10 zeroing of
+//    lapack.cpp:268, so the denominator is >= 1: no special cases).
+//
+// Results are identical to v1 up to summation order (both are checked against the oracle).
+#pragma once
+#include "lmm_device.cuh"
+
+namespace gb {
+
+constexpr int V2_WARPS = 8;
+constexpr int V2_THREADS = V2_WARPS * 32;
+constexpr int V2_CHUNK = 512;          // individuals per pipeline stage
+constexpr int V2_STAGES = 3;
+constexpr int V2_MAX_REGION = 64;
+
+__host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS) * V2_CHUNK; }
+__host__ __device__ constexpr size_t v2_smem_bytes(int nc) { return v2_stage_doubles(nc) * V2_STAGES * sizeof(double) + 64; }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// reciprocal of den >= 1 (finite): hardware seed + two Newton-Raphson steps, ~1 ulp
+__device__ __forceinline__ double rcp_ge1(double den) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  double e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+template <int NC>
+struct V2Ctx {
+  const LmmConst *D;
+  const double *xrow;        // this warp's U^T x row (nullptr for an idle warp)
+  double *smem;              // stage 0 base
+  int nchunks;
+  int pad;                   // n_c - n (zero-padded tail elements: each adds 1 to every sum of h^k)
+};
+
+// all 256 threads: queue the cp.async copies of chunk `c` into stage `st`
+template <int NC>
+__device__ __forceinline__ void v2_issue(const LmmConst &D, const double *const *xrows, double *stage, int c) {
+  constexpr int HALF = V2_CHUNK / 2;
+  const size_t off0 = (size_t)c * V2_CHUNK;
+  for (int op = threadIdx.x; op < (NC + 2) * HALF; op += V2_THREADS) {
+    const int arr = op / HALF, o = (op - arr * HALF) * 2;
+    const double *src = (arr == 0) ? D.delta : (arr == NC + 1) ? D.y : D.Wt + (size_t)(arr - 1) * D.ldv;
+    cp_async16(stage + arr * V2_CHUNK + o, src + off0 + o);
+  }
+  double *xs = stage + (NC + 2) * V2_CHUNK;
+  for (int op = threadIdx.x; op < V2_WARPS * HALF; op += V2_THREADS) {
+    const int w = op / HALF, o = (op - w * HALF) * 2;
+    const double *src = xrows[w];
+    if (src) cp_async16(xs + w * V2_CHUNK + o, src + off0 + o);
+  }
+}
+
+template <int NC, int NS, int KLO, int KHI>
+struct V2Acc {
+  static constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
+  static constexpr int NK = KHI - KLO + 1;
+  double S[NS][NK][NIDX];
+  double tr[NS][NK];
+  double ld[NS];
+};
+
+// One lockstep pass.  Every thread of the CTA must call it (pipeline + barriers); `active` selects
+// whether this warp does arithmetic.  want_ld[s] adds sum log|lambda*delta+1| for slot s.
+template <int NC, int NS, int KLO, int KHI>
+__device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
+                                        int pad, bool active, const double (&lam)[NS], const bool (&want_ld)[NS],
+                                        V2Acc<NC, NS, KLO, KHI> &acc) {
+  constexpr int NV = NC + 2;
+  constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
+  constexpr int NK = KHI - KLO + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t stage_d = v2_stage_doubles(NC);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    acc.ld[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      acc.tr[s][k] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NIDX; ++j) acc.S[s][k][j] = 0.0;
+    }
+  }
+  // prologue: stages 0 .. STAGES-2
+#pragma unroll
+  for (int c = 0; c < V2_STAGES - 1; ++c) {
+    if (c < nchunks) v2_issue<NC>(D, xrows, smem + (size_t)c * stage_d, c);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<V2_STAGES - 2>();                       // this thread's copies of chunk c have landed
+    __syncthreads();                                      // everyone's have; everyone is done with chunk c-1
+    {
+      const int cn = c + V2_STAGES - 1;                   // refill the stage chunk c-1 just vacated
+      if (cn < nchunks) v2_issue<NC>(D, xrows, smem + (size_t)(cn % V2_STAGES) * stage_d, cn);
+      cp_async_commit();
+    }
+    if (active) {
+      const double *st = smem + (size_t)(c % V2_STAGES) * stage_d;
+      const double *xs = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK;
+#pragma unroll 2
+      for (int j = lane; j < V2_CHUNK; j += 32) {
+        double v[NV];
+        const double dl = st[j];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) v[a] = st[(a + 1) * V2_CHUNK + j];
+        v[NC] = xs[j];
+        v[NC + 1] = st[(NC + 1) * V2_CHUNK + j];
+        // products shared by all slots and powers
+        double pr[NIDX];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+          for (int b = a; b < NV; ++b) pr[abidx(a, b, NV)] = v[a] * v[b];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const double den = fma(lam[s], dl, 1.0);
+          const double h = rcp_ge1(den);
+          if (want_ld[s]) acc.ld[s] += log(den);
+          double hk = (KLO == 0) ? 1.0 : h;
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            acc.tr[s][k] += hk;
+#pragma unroll
+            for (int q = 0; q < NIDX; ++q) acc.S[s][k][q] = fma(hk, pr[q], acc.S[s][k][q]);
+            hk *= h;
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                        // stages are free for the next pass
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        acc.tr[s][k] = warp_allsum(acc.tr[s][k]) - (double)pad;     // padded tail: delta=0 -> h=1
+#pragma unroll
+        for (int j = 0; j < NIDX; ++j) acc.S[s][k][j] = warp_allsum(acc.S[s][k][j]);
+      }
+      acc.ld[s] = warp_allsum(acc.ld[s]);
+    }
+  }
+}
+
+// what one slot's sums turn into
+struct V2Eval {
+  double d1R, d1L, d2R, d2L, fR, fL;
+  double P_xx, P_xy, P_yy, Px_yy;       // Wald / score inputs (order-1 tables)
+};
+
+// S1/S2/S3 = order 1..3 tables of one slot (S2/S3 may be dummies), tr1/tr2 = sum h, sum h^2
+template <int NC, int ORD>
+__device__ __forceinline__ void v2_derive(double (&S1)[(NC + 3) * (NC + 2) / 2], double (&S2)[(NC + 3) * (NC + 2) / 2],
+                                          double (&S3)[(NC + 3) * (NC + 2) / 2], double tr1, double tr2, double lam,
+                                          double n, bool want_f, double logdet_h, double logdetI, V2Eval &o) {
+  Derived<NC, ORD> d;
+  sweep_tables<NC, ORD>(S1, S2, S3, d);
+  const double df = n - (double)NC - 1.0;
+  o.P_xx = d.P_xx; o.P_xy = d.P_xy; o.P_yy = d.P_yy; o.Px_yy = d.Px_yy;
+  o.d1R = o.d1L = o.d2R = o.d2L = 0.0; o.fR = o.fL = 0.0;
+  if (ORD >= 2) {
+    const double P_yy = d.Px_yy, PP_yy = d.PPx_yy;
+    const double yPKPy = (P_yy - PP_yy) / lam;
+    const double trace_P = tr1 - d.trace_P_corr;
+    o.d1R = -0.5 * ((df - trace_P) / lam) + 0.5 * df * yPKPy / P_yy;
+    o.d1L = -0.5 * ((n - tr1) / lam) + 0.5 * n * yPKPy / P_yy;
+    if (ORD >= 3) {
+      const double trace_PP = tr2 + d.trace_PP_corr;
+      const double yPKPKPy = (P_yy + d.PPPx_yy - 2.0 * PP_yy) / (lam * lam);
+      const double quad = (2.0 * yPKPKPy * P_yy - yPKPy * yPKPy) / (P_yy * P_yy);
+      o.d2R = 0.5 * ((df + trace_PP - 2.0 * trace_P) / (lam * lam)) - 0.5 * df * quad;
+      o.d2L = 0.5 * ((n + tr2 - 2.0 * tr1) / (lam * lam)) - 0.5 * n * quad;
+    }
+  }
+  if (want_f) {
+    FVals fv = f_from(n, NC, logdet_h, d.logdet_piv, logdetI, d.Px_yy);
+    o.fR = fv.fR; o.fL = fv.fL;
+  }
+}
+
+// ---- resumable CalcLambda state machine for one likelihood (REML or ML) ---------------------------
+enum { V2_SCAN = 0, V2_BRENT_PREP, V2_BRENT_EVAL, V2_NEWTON_INIT, V2_NEWTON_INIT_EVAL, V2_NEWTON_PREP, V2_NEWTON_EVAL,
+       V2_F_EVAL, V2_DONE };
+
+struct V2Fn {
+  int stage, next_g, status;
+  unsigned iter, iter2;
+  double a, b, c, d, e, fa, fb, fc, root, xl, xu;        // Brent state (gsl roots/brent.c)
+  double a_new, fa_new, b_new;
+  double nroot, nf, ndf;                                  // Newton state (gsl roots/newton.c)
+  RootState rs;
+  // f-evaluation cache for the Wald test
+  double cache_lam, cP_xx, cP_xy, cP_yy, cPx_yy;
+};
+
+struct V2Req { bool need; double lam; int K; bool logdet; };
+
+__device__ __forceinline__ void v2fn_init(V2Fn &F) {
+  F.stage = V2_SCAN; F.next_g = 0; F.status = GB_ST_ERR; F.iter = F.iter2 = 0;
+  F.rs.l = F.rs.l_temp = 0.0; F.rs.lambda = nan(""); F.rs.logf = nan("");
+  F.rs.have = F.rs.aborted = F.rs.stopped = false;
+  F.cache_lam = nan("");
+}
+
+// Advance until an evaluation is required (returns req.need) or the interval list is exhausted.
+// `ev_*` carry the result of the evaluation requested by the previous call.
+__device__ __noinline__ void v2fn_advance(V2Fn &F, const double *glam, const double *gd1, int n_region, double l_min,
+                                          double l_max, double ev_d1, double ev_d2, double ev_f, V2Req &req) {
+  req.need = false;
+  const unsigned max_iter = 100;
+  for (;;) {
+    switch (F.stage) {
+      case V2_SCAN: {
+        if (F.rs.aborted || F.rs.stopped) { F.stage = V2_DONE; return; }
+        while (F.next_g < n_region && !(gd1[F.next_g] * gd1[F.next_g + 1] <= 0)) F.next_g++;
+        if (F.next_g >= n_region) { F.stage = V2_DONE; return; }
+        const int g = F.next_g++;
+        const double x_lower = glam[g], x_upper = glam[g + 1], f_lower = gd1[g], f_upper = gd1[g + 1];
+        F.a = x_lower; F.fa = f_lower; F.b = x_upper; F.fb = f_upper; F.c = x_upper; F.fc = f_upper;
+        F.d = x_upper - x_lower; F.e = x_upper - x_lower;
+        F.root = 0.5 * (x_lower + x_upper); F.xl = x_lower; F.xu = x_upper;
+        F.status = GB_ST_ERR; F.iter = 0;
+        F.stage = V2_BRENT_PREP;
+        break;
+      }
+      case V2_BRENT_PREP: {
+        F.iter++;
+        double a = F.a, b = F.b, c = F.c, d = F.d, e = F.e, fa = F.fa, fb = F.fb, fc = F.fc;
+        bool ac_equal = false;
+        if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) { ac_equal = true; c = a; fc = fa; d = b - a; e = b - a; }
+        if (fabs(fc) < fabs(fb)) { ac_equal = true; a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+        const double tol = 0.5 * DBL_EPSILON * fabs(b);
+        const double m = 0.5 * (c - b);
+        bool immediate = false;
+        if (fb == 0) { F.root = b; F.xl = b; F.xu = b; F.status = GB_ST_SUCCESS; immediate = true; }
+        else if (fabs(m) <= tol) {
+          F.root = b;
+          if (b < c) { F.xl = b; F.xu = c; } else { F.xl = c; F.xu = b; }
+          F.status = GB_ST_SUCCESS; immediate = true;
+        }
+        F.a = a; F.b = b; F.c = c; F.d = d; F.e = e; F.fa = fa; F.fb = fb; F.fc = fc;
+        if (immediate) { F.stage = V2_BRENT_EVAL; ev_d1 = nan(""); F.b_new = nan(""); goto brent_post; }
+        if (fabs(e) < tol || fabs(fa) <= fabs(fb)) { d = m; e = m; }
+        else {
+          double p, q, r, s = fb / fa;
+          if (ac_equal) { p = 2 * m * s; q = 1 - s; }
+          else {
+            q = fa / fc; r = fb / fc;
+            p = s * (2 * m * q * (q - r) - (b - a) * (r - 1));
+            q = (q - 1) * (r - 1) * (s - 1);
+          }
+          if (p > 0) q = -q; else p = -p;
+          const double lim1 = 3 * m * q - fabs(tol * q), lim2 = fabs(e * q);
+          if (2 * p < (lim1 < lim2 ? lim1 : lim2)) { e = d; d = p / q; }
+          else { d = m; e = m; }
+        }
+        F.d = d; F.e = e;
+        F.a_new = b; F.fa_new = fb;
+        F.b_new = b + ((fabs(d) > tol) ? d : (m > 0 ? +tol : -tol));
+        F.stage = V2_BRENT_EVAL;
+        req.need = true; req.lam = F.b_new; req.K = 2; req.logdet = false;
+        return;
+      }
+      case V2_BRENT_EVAL: {
+        {
+          const double fb_new = ev_d1;
+          if (!isfinite(fb_new)) F.status = GB_ST_ERR;     // GSL returns before storing the state
+          else {
+            F.a = F.a_new; F.fa = F.fa_new; F.b = F.b_new; F.fb = fb_new;
+            F.root = F.b;
+            double cc = F.c;
+            if ((F.fb < 0 && F.fc < 0) || (F.fb > 0 && F.fc > 0)) cc = F.a;
+            if (F.b < cc) { F.xl = F.b; F.xu = cc; } else { F.xl = cc; F.xu = F.b; }
+            F.status = GB_ST_SUCCESS;
+          }
+        }
+      brent_post:
+        if (F.status != GB_ST_SUCCESS) { F.stage = V2_NEWTON_INIT; break; }       // `break` out of the do-loop (:2040)
+        F.rs.l = F.root;
+        if (F.xl > F.xu) { F.status = GB_ST_ERR; F.stage = V2_NEWTON_INIT; break; }
+        {
+          double min_abs = 0.0;
+          if ((F.xl > 0.0 && F.xu > 0.0) || (F.xl < 0.0 && F.xu < 0.0)) min_abs = fmin(fabs(F.xl), fabs(F.xu));
+          F.status = (fabs(F.xu - F.xl) < 0.1 * min_abs) ? GB_ST_SUCCESS : GB_ST_CONTINUE;
+        }
+        if (F.status == GB_ST_CONTINUE && F.iter < max_iter) { F.stage = V2_BRENT_PREP; break; }
+        if (F.status == GB_ST_CONTINUE) { F.rs.stopped = true; F.stage = V2_DONE; return; }   // :2057-2060
+        F.stage = V2_NEWTON_INIT;
+        break;
+      }
+      case V2_NEWTON_INIT:
+        F.stage = V2_NEWTON_INIT_EVAL;
+        req.need = true; req.lam = F.rs.l; req.K = 3; req.logdet = false;
+        return;
+      case V2_NEWTON_INIT_EVAL:
+        F.nroot = F.rs.l; F.nf = ev_d1; F.ndf = ev_d2; F.iter2 = 0;
+        F.stage = V2_NEWTON_PREP;
+        break;
+      case V2_NEWTON_PREP:
+        F.iter2++;
+        if (F.ndf == 0.0) { F.status = GB_ST_ERR; goto newton_end; }
+        F.nroot = F.nroot - (F.nf / F.ndf);
+        F.stage = V2_NEWTON_EVAL;
+        req.need = true; req.lam = F.nroot; req.K = 3; req.logdet = false;
+        return;
+      case V2_NEWTON_EVAL: {
+        F.nf = ev_d1; F.ndf = ev_d2;
+        if (!isfinite(F.nf) || !isfinite(F.ndf)) { F.status = GB_ST_ERR; goto newton_end; }
+        F.rs.l_temp = F.rs.l;
+        F.rs.l = F.nroot;
+        F.status = (fabs(F.rs.l - F.rs.l_temp) < 1e-5 * fabs(F.rs.l) || F.rs.l == F.rs.l_temp) ? GB_ST_SUCCESS : GB_ST_CONTINUE;
+        if (F.status == GB_ST_CONTINUE && F.iter2 < max_iter && F.rs.l > l_min && F.rs.l < l_max) { F.stage = V2_NEWTON_PREP; break; }
+      newton_end:
+        if (F.status != GB_ST_SUCCESS) {
+          F.rs.aborted = true; F.rs.lambda = nan(""); F.rs.logf = nan("");
+          F.stage = V2_DONE; return;
+        }
+        double l = F.rs.l_temp;                     // the PREVIOUS iterate (src/lmm.cpp:2096)
+        if (l < l_min) l = l_min;
+        if (l > l_max) l = l_max;
+        F.rs.l = l;
+        F.stage = V2_F_EVAL;
+        req.need = true; req.lam = l; req.K = 1; req.logdet = true;
+        return;
+      }
+      case V2_F_EVAL: {
+        const double logf_l = ev_f;
+        if (!F.rs.have) { F.rs.logf = logf_l; F.rs.lambda = F.rs.l; F.rs.have = true; }
+        else if (F.rs.logf < logf_l) { F.rs.logf = logf_l; F.rs.lambda = F.rs.l; }
+        F.stage = V2_SCAN;
+        break;
+      }
+      default:
+        return;
+    }
+  }
+}
+
+__device__ __forceinline__ void v2_finalize(RootState &R, double f_min, double f_max, double l_min, double l_max) {
+  if (R.aborted) return;
+  if (!R.have && !R.stopped) {
+    if (f_min >= f_max) { R.lambda = l_min; R.logf = f_min; } else { R.lambda = l_max; R.logf = f_max; }
+  } else {
+    if (f_min > R.logf) { R.lambda = l_min; R.logf = f_min; }
+    if (f_max > R.logf) { R.lambda = l_max; R.logf = f_max; }
+  }
+}
+
+// One CTA = 8 SNPs.  xrows[w] (shared memory) = U^T x row of warp w or nullptr.
+template <int NC>
+__device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmParams &prm, const double *const *xrows,
+                                                 double *smem, int nchunks, int pad, bool valid, gb200_sumstat &out) {
+  constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
+  const int mode = prm.a_mode;
+  const bool needR = (mode == 1 || mode == 4), needL = (mode == 2 || mode == 4 || mode == 9);
+  const bool needS = (mode == 3 || mode == 4 || mode == 9);
+  const double l_min = prm.l_min, l_max = prm.l_max, n = (double)D.n;
+  const int n_region = prm.n_region;
+  const double lambda_interval = log(l_max / l_min) / (double)n_region;
+  double beta = 0.0, se = 0.0, p_wald = 0.0, p_lrt = 0.0, p_score = 0.0, logl_H1 = 0.0, lambda_remle = 0.0, lambda_mle = 0.0;
+  double glam[V2_MAX_REGION + 1], gd1R[V2_MAX_REGION + 1], gd1L[V2_MAX_REGION + 1];
+  double logdetI = 0.0, fRmin = 0.0, fLmin = 0.0, fRmax = 0.0, fLmax = 0.0;
+  const bool need_search = needR || needL;
+  double dummy[NIDX];
+
+  if (need_search) {
+    // ---- pass A: lambda_0 = l_min (powers 0..2 + logdet): unit-weight pivots, dev1, f(l_min)
+    {
+      V2Acc<NC, 1, 0, 2> acc;
+      const double lam[1] = {l_min * exp(lambda_interval * 0.0)};
+      const bool wl[1] = {true};
+      v2_pass<NC, 1, 0, 2>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+      if (valid) {
+        Derived<NC, 1> dI;
+        sweep_tables<NC, 1>(acc.S[0][0], dummy, dummy, dI);
+        logdetI = dI.logdet_piv;
+        V2Eval ev;
+        v2_derive<NC, 2>(acc.S[0][1], acc.S[0][2], dummy, acc.tr[0][1], acc.tr[0][2], lam[0], n, true, acc.ld[0], logdetI, ev);
+        glam[0] = lam[0]; gd1R[0] = ev.d1R; gd1L[0] = ev.d1L; fRmin = ev.fR; fLmin = ev.fL;
+      }
+    }
+    // ---- grid passes: 4 lambdas at a time
+    for (int g0 = 1; g0 <= n_region; g0 += 4) {
+      V2Acc<NC, 4, 1, 2> acc;
+      double lam[4]; const bool wl[4] = {false, false, false, false};
+#pragma unroll
+      for (int s = 0; s < 4; ++s) lam[s] = (g0 + s <= n_region) ? l_min * exp(lambda_interval * (double)(g0 + s)) : 1.0;
+      v2_pass<NC, 4, 1, 2>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+      if (valid) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (g0 + s <= n_region) {
+            V2Eval ev;
+            v2_derive<NC, 2>(acc.S[s][0], acc.S[s][1], dummy, acc.tr[s][0], acc.tr[s][1], lam[s], n, false, 0.0, 0.0, ev);
+            glam[g0 + s] = lam[s]; gd1R[g0 + s] = ev.d1R; gd1L[g0 + s] = ev.d1L;
+          }
+        }
+      }
+    }
+  }
+  // ---- pass C: f(l_max) and the score test at l_mle_null share one pass
+  if (need_search || needS) {
+    V2Acc<NC, 2, 1, 1> acc;
+    const double lam[2] = {l_max, needS ? prm.l_mle_null : 1.0};
+    const bool wl[2] = {true, false};
+    v2_pass<NC, 2, 1, 1>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+    if (valid) {
+      V2Eval ev;
+      v2_derive<NC, 1>(acc.S[0][0], dummy, dummy, acc.tr[0][0], 0.0, lam[0], n, true, acc.ld[0], logdetI, ev);
+      fRmax = ev.fR; fLmax = ev.fL;
+      if (needS) {
+        Derived<NC, 1> d;
+        sweep_tables<NC, 1>(acc.S[1][0], dummy, dummy, d);
+        wald_score_from<NC>(d, D.n, true, beta, se, p_score);
+      }
+    }
+  }
+  // ---- refinement: REML and ML chains side by side, then (if needed) the Wald pass
+  V2Fn FR, FL;
+  v2fn_init(FR); v2fn_init(FL);
+  if (!needR || !valid) FR.stage = V2_DONE;
+  if (!needL || !valid) FL.stage = V2_DONE;
+  V2Req rq[2]; rq[0].need = rq[1].need = false;
+  if (need_search) {
+    double evR[3] = {0, 0, 0}, evL[3] = {0, 0, 0};     // d1, d2, f delivered to each chain
+    bool finalized = false, wald_pending = false, wald_done = !needR;
+    for (;;) {
+      if (FR.stage != V2_DONE) v2fn_advance(FR, glam, gd1R, n_region, l_min, l_max, evR[0], evR[1], evR[2], rq[0]); else rq[0].need = false;
+      if (FL.stage != V2_DONE) v2fn_advance(FL, glam, gd1L, n_region, l_min, l_max, evL[0], evL[1], evL[2], rq[1]); else rq[1].need = false;
+      if (valid && !finalized && FR.stage == V2_DONE && FL.stage == V2_DONE) {
+        if (needR) v2_finalize(FR.rs, fRmin, fRmax, l_min, l_max);
+        if (needL) v2_finalize(FL.rs, fLmin, fLmax, l_min, l_max);
+        finalized = true;
+        if (needR) {
+          lambda_remle = FR.rs.lambda; logl_H1 = FR.rs.logf;
+          if (lambda_remle == FR.cache_lam) {            // f(lambda_hat) pass already produced the order-1 table
+            Derived<NC, 1> d; d.P_xx = FR.cP_xx; d.P_xy = FR.cP_xy; d.P_yy = FR.cP_yy; d.Px_yy = FR.cPx_yy;
+            wald_score_from<NC>(d, D.n, false, beta, se, p_wald);
+            wald_done = true;
+          } else wald_pending = true;
+        }
+      }
+      const bool want_wald = valid && finalized && wald_pending && !wald_done;
+      if (want_wald) { rq[0].need = true; rq[0].lam = lambda_remle; rq[0].K = 1; rq[0].logdet = false; }
+      const bool active = valid && (rq[0].need || rq[1].need);
+      if (!__syncthreads_or(active ? 1 : 0)) break;
+      const int Kmax = (rq[0].need ? rq[0].K : 0) > (rq[1].need ? rq[1].K : 0) ? (rq[0].need ? rq[0].K : 0) : (rq[1].need ? rq[1].K : 0);
+      const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
+      const bool wl[2] = {rq[0].need && rq[0].logdet, rq[1].need && rq[1].logdet};
+      V2Eval ev[2];
+      if (Kmax >= 3) {
+        V2Acc<NC, 2, 1, 3> acc;
+        v2_pass<NC, 2, 1, 3>(D, xrows, smem, nchunks, pad, active, lam, wl, acc);
+        if (active) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            v2_derive<NC, 3>(acc.S[s][0], acc.S[s][1], acc.S[s][2], acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
+        }
+      } else {
+        V2Acc<NC, 2, 1, 2> acc;
+        v2_pass<NC, 2, 1, 2>(D, xrows, smem, nchunks, pad, active, lam, wl, acc);
+        if (active) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            v2_derive<NC, 2>(acc.S[s][0], acc.S[s][1], dummy, acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
+        }
+      }
+      if (active) {
+        if (want_wald) {
+          Derived<NC, 1> d; d.P_xx = ev[0].P_xx; d.P_xy = ev[0].P_xy; d.P_yy = ev[0].P_yy; d.Px_yy = ev[0].Px_yy;
+          wald_score_from<NC>(d, D.n, false, beta, se, p_wald);
+          wald_done = true; rq[0].need = false;
+        } else if (rq[0].need) {
+          evR[0] = ev[0].d1R; evR[1] = ev[0].d2R; evR[2] = ev[0].fR;
+          if (rq[0].logdet) { FR.cache_lam = lam[0]; FR.cP_xx = ev[0].P_xx; FR.cP_xy = ev[0].P_xy; FR.cP_yy = ev[0].P_yy; FR.cPx_yy = ev[0].Px_yy; }
+        }
+        if (rq[1].need) { evL[0] = ev[1].d1L; evL[1] = ev[1].d2L; evL[2] = ev[1].fL; }
+      }
+    }
+    if (valid && needL) {
+      lambda_mle = FL.rs.lambda; logl_H1 = FL.rs.logf;
+      p_lrt = chisq1_Q_dev(2.0 * (logl_H1 - prm.logl_mle_H0));
+    }
+  }
+  out.beta = beta; out.se = se; out.lambda_remle = lambda_remle; out.lambda_mle = lambda_mle;
+  out.p_wald = p_wald; out.p_lrt = p_lrt; out.p_score = p_score; out.logl_H1 = logl_H1;
+}
+
+}  // namespace gb

@@ -179,7 +179,8 @@ GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, co
                           size_t ni_total, size_t l, size_t bytes_per_snp, double *UtXt);
 
 /* Tuning knobs (0 keeps the default): utx_path 0 auto, 1 FP64 tiled, 2 int8 tensor-core
- * (error-free U slicing, integer genotypes only); n_slices of the int8 path. */
+ * (error-free U slicing, integer genotypes only); n_slices of the int8 path; lmm_kernel 0 auto,
+ * 1 warp-per-SNP kernel, 2 lockstep-CTA pipeline kernel (n_cvt <= 3, n_region <= 64). */
 GB200_API int gb200_set_option(gb200_ctx *ctx, const char *name, long value);
 
 #ifdef __cplusplus

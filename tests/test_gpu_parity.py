@@ -89,10 +89,13 @@ def test_assoc_kernel_all_modes_vs_oracle(ctx, n, c, seed):
     l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"])
     UtX = pb["U"].T @ pb["X"]
     for mode in (1, 2, 3, 4, 9):
-        ctx.lmm_params(mode, l_mle_null=l_mle, logl_mle_H0=logl)
-        got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
         ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, mode, l_mle_null=l_mle, logl_mle_H0=logl)
-        check_sumstat(got, ref, mode)
+        for kern in (1, 2):                   # 1 = warp-per-SNP kernel, 2 = lockstep-CTA pipeline kernel
+            ctx.set_option("lmm_kernel", kern)
+            ctx.lmm_params(mode, l_mle_null=l_mle, logl_mle_H0=logl)
+            got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
+            check_sumstat(got, ref, mode)
+    ctx.set_option("lmm_kernel", 0)
 
 
 def test_assoc_nondefault_search_grid_and_boundaries(ctx):
@@ -100,12 +103,15 @@ def test_assoc_nondefault_search_grid_and_boundaries(ctx):
     pb = random_problem(200, 1, 40, 9, causal=False)
     ctx.lmm_setup_rotated(pb["U"], pb["ev"], pb["UtW"], pb["Uty"])
     UtX = pb["U"].T @ pb["X"]
-    for (lo, hi, nr) in ((1e-5, 1e5, 10), (1e-2, 1e-1, 3), (50.0, 5e4, 7), (1e-5, 1e5, 1)):
+    for (lo, hi, nr) in ((1e-5, 1e5, 10), (1e-2, 1e-1, 3), (50.0, 5e4, 7), (1e-5, 1e5, 1), (1e-5, 1e5, 23)):
         l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"], lo, hi, nr)
-        ctx.lmm_params(4, lo, hi, nr, l_mle, logl)
-        got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
         ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, 4, lo, hi, nr, l_mle, logl)
-        check_sumstat(got, ref, 4)
+        for kern in (1, 2):
+            ctx.set_option("lmm_kernel", kern)
+            ctx.lmm_params(4, lo, hi, nr, l_mle, logl)
+            got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
+            check_sumstat(got, ref, 4)
+    ctx.set_option("lmm_kernel", 0)
 
 
 def test_null_model_vs_oracle(ctx):
