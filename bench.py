@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--mode", type=int, default=4, help="-lmm mode (1 Wald, 2 LRT, 3 score, 4 all)")
     ap.add_argument("--utx-path", type=int, default=0, help="0 auto, 1 FP64 tiled, 2 int8 tensor core")
     ap.add_argument("--slices", type=int, default=0, help="int8 planes of U (0 = default 6)")
+    ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="SNPs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -204,6 +205,7 @@ def run_b200(args):
     ctx = gemma_b200.Context(local, stream=stream.cuda_stream)
     ctx.set_option("utx_path", args.utx_path)
     ctx.set_option("n_slices", args.slices)
+    ctx.set_option("lmm_kernel", args.lmm_kernel)
 
     # ---- run-constant state, generated on the device (identical on every rank) ----------------
     g = torch.Generator(device=dev); g.manual_seed(SEED)
