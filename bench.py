@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--mode", type=int, default=4, help="-lmm mode (1 Wald, 2 LRT, 3 score, 4 all)")
     ap.add_argument("--utx-path", type=int, default=0, help="0 auto, 1 FP64 tiled, 2 int8 tensor core")
     ap.add_argument("--slices", type=int, default=0, help="int8 planes of U (0 = default 6)")
+    ap.add_argument("--workload", default="lmm", choices=["lmm", "gk"], help="lmm: SNPs/s of -lmm (headline); gk: K=XX^T TFLOP/s")
     ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="SNPs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -349,10 +350,60 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_gk(args):
+    """BASELINE config 2: -gk 1 (centred kinship) on synthetic n x p PLINK genotypes, 1 GPU.
+    Reported with the algorithmic flops of ONE triangle, n(n+1)p."""
+    import torch
+    import gemma_b200
+    from gemma_b200 import synth
+    n = args.n if args.n != 50000 else 10000
+    B, K, Wm = max(args.batch, 16384), args.steps, max(3, args.warmup)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
+    ctx = gemma_b200.Context(0, stream=stream.cuda_stream)
+    bps = (n + 3) // 4
+    beds = [synth.make_bed_torch(n, B, dev, seed=SEED, snp_offset=k * B) for k in range(K + Wm)]
+    ctx.kin_begin(n, 1)
+    for k in range(Wm):
+        ctx.kin_add_bed_dev(beds[k].data_ptr(), B, bps)
+    ctx.kin_finish_dev()
+    torch.cuda.synchronize()
+    ctx.profile_enable(True); ctx.profile_reset()
+    sampler = ClockSampler(0); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.kin_begin(n, 1)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for k in range(K):
+        ctx.kin_add_bed_dev(beds[Wm + k].data_ptr(), B, bps)
+    ctx.kin_finish_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    kin_ms, kin_n = ctx.profile_get("kin"); dec_ms, _ = ctx.profile_get("decode")
+    p = K * B
+    flops = float(n) * (n + 1) * p
+    peaks = measured_peaks()
+    line = {"metric": "gk_centered_kinship_tflops", "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s (n(n+1)p, one triangle)",
+            "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8 x int8 -> int32 exact (+FP64 rank-one centring)", "data": "synthetic",
+            "config": {"workload": "-gk 1 centred kinship, n=%d individuals, %d SNPs per step (PLINK 2-bit, no missing)" % (n, B),
+                       "n": n, "snps_per_step": B, "snps_per_sec": p / (ms * 1e-3)},
+            "clocks": clocks,
+            "roofline": {"kernel": "i8_gemm_kernel (mode 1: K += Z Z^T)", "bound": "tensor",
+                         "achieved": (flops / (kin_ms * 1e-3) / 1e12) if kin_n else None, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                         "frac": (flops / (kin_ms * 1e-3) / 1e12 / peaks["bf16"]) if kin_n else None, "traffic": None,
+                         "peak_source": peaks["source"] + ", bf16 sustained", "launches": kin_n, "kernel_ms": kin_ms, "decode_ms": dec_ms}}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "gk":
+        run_gk(args)
     else:
         run_b200(args)
 

@@ -14,6 +14,10 @@ int i8_prepare(gb200_ctx *ctx);                       // slice U into int8 plane
 int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                    size_t l, size_t bytes_per_snp, double *UtXt_dev);   // UtXt l x n (ld n)
 bool i8_available(gb200_ctx *ctx);
+bool kin_i8_eligible(gb200_ctx *ctx);
+int kin_i8_begin(gb200_ctx *ctx);
+int kin_i8_add_chunk(gb200_ctx *ctx, const unsigned char *bed_dev, size_t l, size_t bytes_per_snp, bool *taken);
+int kin_i8_finish(gb200_ctx *ctx, double inv_ns);
 }
 
 // grow-only buffer whose NEW allocations are zero-filled (row tails of padded buffers stay zero)
@@ -67,10 +71,12 @@ void gb200_destroy(gb200_ctx *c) {
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   gb::DevBuf *bufs[] = {&c->dK, &c->dU, &c->dEval, &c->dWt, &c->dY, &c->dNull, &c->dX, &c->dUtXt, &c->dOut,
                         &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale,
-                        &c->i8.geno, &c->i8.miss_mean};
+                        &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles};
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
+  if (c->i8.tmap_ka) free(c->i8.tmap_ka);
+  if (c->i8.tmap_kb) free(c->i8.tmap_kb);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -119,6 +125,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
   if (!strcmp(name, "utx_path")) {
     if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "utx_path must be 0,1,2");
     c->utx_path = value; return GB200_OK;
+  }
+  if (!strcmp(name, "kin_path")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "kin_path must be 0 or 1");
+    c->kin_path = value; return GB200_OK;
   }
   if (!strcmp(name, "lmm_kernel")) {
     if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2");
@@ -181,7 +191,7 @@ int gb200_kin_begin(gb200_ctx *c, size_t n, int k_mode) {
   GB_CUDA(c, c->dK.reserve(n * n * sizeof(double)));
   GB_CUDA(c, cudaMemsetAsync(c->dK.p, 0, n * n * sizeof(double), c->stream));   // gsl_matrix_set_zero, param.cpp:1301
   c->kin_n = n; c->kin_mode = k_mode; c->kin_ns = 0; c->kin_active = true;
-  return GB200_OK;
+  return kin_i8_begin(c);
 }
 
 // K(lower) += Xs^T Xs for an SNP-major centred batch Xs (l x n, ld n) already on the device
@@ -236,8 +246,15 @@ int gb200_kin_add_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, size_t l, 
   // bounded staging: decode + accumulate in chunks of at most ~1 GiB of FP64 genotypes
   size_t chunk = (size_t(1) << 30) / (n * sizeof(double));
   if (chunk < 256) chunk = 256;
+  const bool try_i8 = kin_i8_eligible(c);
   for (size_t s0 = 0; s0 < l; s0 += chunk) {
     const size_t lc = (l - s0 < chunk) ? (l - s0) : chunk;
+    if (try_i8) {            // exact Z Z^T on the int8 tensor pipe when the chunk has no missing genotype
+      bool taken = false;
+      int rc8 = kin_i8_add_chunk(c, bed_dev + s0 * bytes_per_snp, lc, bytes_per_snp, &taken);
+      if (rc8) return rc8;
+      if (taken) continue;
+    }
     GB_CUDA(c, c->dX.reserve(n * lc * sizeof(double)));
     {
       ProfScope ps(c, "decode", 2);
@@ -268,7 +285,10 @@ int gb200_kin_finish_dev(gb200_ctx *c, double **K_dev, size_t *ns_used) {
   if (!c) return GB200_ERR_ARG;
   if (!c->kin_active) return set_err(c, GB200_ERR_STATE, "gb200_kin_finish before gb200_kin_begin");
   const size_t n = c->kin_n;
-  if (c->kin_ns > 0)   // gsl_matrix_scale(matrix_kin, 1.0/ns_test), gemma_io.cpp:1570
+  if (c->i8.kin_used) {  // rank-one centring terms of the int8 batches + the 1/ns_test scaling
+    int rc8 = kin_i8_finish(c, c->kin_ns > 0 ? 1.0 / (double)c->kin_ns : 1.0);
+    if (rc8) return rc8;
+  } else if (c->kin_ns > 0)   // gsl_matrix_scale(matrix_kin, 1.0/ns_test), gemma_io.cpp:1570
     GB_CUDA(c, launch_scale(c->dK.as<double>(), n * n, 1.0 / (double)c->kin_ns, c->stream));
   GB_CUDA(c, launch_symmetrize_from_lower(c->dK.as<double>(), n, n, c->stream));
   if (K_dev) *K_dev = c->dK.as<double>();

@@ -45,6 +45,15 @@ struct I8State {
   DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
   DevBuf miss_mean;              // per-SNP mean (for the missing correction)
   void *tmap_a = nullptr, *tmap_b = nullptr;   // CUtensorMap storage (host)
+  // kinship (K = Z Z^T on the int8 tensor pipe)
+  DevBuf kin_zt;                 // individual-major int8 genotypes: n rows x kin_cap SNP columns
+  DevBuf kin_stats;              // per staged SNP: int sum, int nmiss, double mean
+  DevBuf kin_a;                  // a[i] = sum_s mean_s z_s[i]  (n doubles) + beta + flag
+  DevBuf kin_tiles;              // lower-triangle tile list (int2)
+  size_t kin_cap = 0, kin_fill = 0, kin_n = 0;
+  int kin_num_tiles = 0;
+  bool kin_used = false;
+  void *tmap_ka = nullptr, *tmap_kb = nullptr;
 };
 
 }  // namespace gb
@@ -79,6 +88,7 @@ struct gb200_ctx {
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
   long n_slices = 0;     // 0 = default
+  long kin_path = 0;     // 0 auto (int8 tensor cores for centred K without missing genotypes), 1 = FP64 only
   long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)
   gb::I8State i8;

@@ -127,11 +127,14 @@ struct I8KernelParams {
   int m_tiles, n_groups;
   int lbo_units;            // descriptor LBO field (kept runtime for bring-up)
   const double *scale;      // per eigenvector: sigma_i * 2^-B
-  double *C;                // l x n, ld = ldc
+  double *C;                // l x n, ld = ldc   (mode 0)  |  K accumulator n x n, ld = ldc (mode 1)
   size_t ldc;
+  int mode;                 // 0 = projection (T planes recombined, scaled, stored), 1 = kinship (K[i][j] += Z Z^T, lower triangle)
+  const int2 *tiles;        // mode 1: explicit (m_blk, n_blk) list (lower-triangle tiles only)
+  int num_tiles;
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_groups, int &m_blk, int &n_grp) {
+__device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_groups, int &m_blk, int &n_grp) {
   // panels of I8_PANEL eigenvector groups; inside a panel SNP tiles vary slowest so that the ~148
   // concurrently running CTAs cover a ~12 x 12 block of (SNP tile, group) pairs: each A/B K-panel
   // streamed from HBM is shared by ~12 CTAs through L2.
@@ -142,6 +145,11 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_groups,
   const int r = tile - panel * panel_tiles;
   m_blk = r / width;
   n_grp = first + r % width;
+}
+
+__device__ __forceinline__ void tile_coords(const I8KernelParams &p, int tile, int &m_blk, int &n_grp) {
+  if (p.tiles) { const int2 t = p.tiles[tile]; m_blk = t.x; n_grp = t.y; }
+  else tile_coords_raster(tile, p.m_tiles, p.n_groups, m_blk, n_grp);
 }
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
@@ -160,7 +168,7 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t *tmem_slot = (uint32_t *)(bars + 2 * I8_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_groups;
+  const int num_tiles = p.tiles ? p.num_tiles : p.m_tiles * p.n_groups;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -185,7 +193,7 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m_blk, n_grp; tile_coords(tile, p.m_tiles, p.n_groups, m_blk, n_grp);
+        int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
@@ -229,12 +237,29 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0; uint32_t acc_phase = 0;
     const double w256 = 256.0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int m_blk, n_grp; tile_coords(tile, p.m_tiles, p.n_groups, m_blk, n_grp);
+      int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int s = m_blk * I8_BM + ew * 32 + lane;                       // SNP row of this thread
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * I8_ACC_COLS);
       const int i0 = n_grp * p.NE;
+      if (p.mode == 1) {
+        // kinship: exact integer tile Z Z^T added into the FP64 accumulator (lower triangle only)
+        const int j0 = n_grp * p.N;
+        double *krow = p.C + (size_t)s * p.ldc;
+        for (int e0 = 0; e0 < p.N; e0 += 8) {
+          int32_t d[8];
+          tc_ld8(taddr + (uint32_t)e0, d);
+          tc_ld_wait();
+          if (s < p.l) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = j0 + e0 + q;
+              if (j <= s) krow[j] += (double)d[q];
+            }
+          }
+        }
+      } else
       for (int e0 = 0; e0 < p.NE; e0 += 8) {
         double v[8];
         int32_t d[8];
@@ -484,7 +509,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.m_tiles = (int)(l_pad / I8_BM); p.n_groups = g.n_groups;
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
-  p.C = UtXt_dev; p.ldc = c->n_c;
+  p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -501,6 +526,230 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   ProfScope ps2(c, "fix");
   miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
                                                       nmiss, UtXt_dev, c->n_c);
+  GB_CUDA(c, cudaGetLastError());
+  return GB200_OK;
+}
+
+// ==========================================================================================
+// Kinship on the tensor cores: K_raw = Z Z^T is exact in int32 for 0/1/2 genotypes, and for
+// SNPs without missing calls the centred product of BimbamKin/PlinkKin (gemma_io.cpp:1511-1554)
+// is  sum_s (z_s - m_s 1)(z_s - m_s 1)^T = Z Z^T - a 1^T - 1 a^T + (sum_s m_s^2) 1 1^T,
+// a = sum_s m_s z_s, so one int8 GEMM plus rank-one FP64 terms replaces the FP64 dgemm.
+// Batches that contain a missing genotype (or -gk 2) take the FP64 path.
+
+// .bed (SNP-major 2-bit) -> individual-major int8 tile, plus per-SNP integer sum / missing count
+__global__ void __launch_bounds__(256) bed_transpose_i8_kernel(const unsigned char *__restrict__ bed, size_t bps, int n,
+                                                               int l, int8_t *__restrict__ Zt, size_t pitch, size_t col0,
+                                                               int *__restrict__ sum, int *__restrict__ nmiss) {
+  __shared__ int8_t tile[128][132];
+  const int s0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
+  const int r = threadIdx.x >> 1, half = threadIdx.x & 1;      // SNP row r, individuals half*64 .. +63
+  const int s = s0 + r;
+  int my_sum = 0, my_miss = 0;
+  for (int bq = 0; bq < 16; ++bq) {
+    const int ib = i0 + half * 64 + bq * 4;                    // first individual of this byte
+    unsigned byte = 0xFFu;                                     // 11 11 11 11 -> genotype 0, harmless padding
+    bool inb = false;
+    if (s < l && ib < n) { byte = bed[(size_t)s * bps + (size_t)(ib >> 2)]; inb = true; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int8_t v = 0;
+      if (inb && ib + q < n) {
+        const unsigned b = (byte >> (2 * q)) & 3u;
+        if (b == 0u) v = 2; else if (b == 2u) v = 1; else if (b == 1u) my_miss++;
+        my_sum += v;
+      }
+      tile[half * 64 + bq * 4 + q][r] = v;
+    }
+  }
+  if (s < l) { if (my_sum) atomicAdd(&sum[s], my_sum); if (my_miss) atomicAdd(&nmiss[s], my_miss); }
+  __syncthreads();
+  // write: thread -> individual row (r), 64 SNP columns (half)
+  const int ii = i0 + r;
+  if (ii < n) {
+    int8_t *dst = Zt + (size_t)ii * pitch + col0 + (size_t)s0 + (size_t)half * 64;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int4 w;
+      int8_t *wb = reinterpret_cast<int8_t *>(&w);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) wb[t] = tile[r][half * 64 + q * 16 + t];
+      *reinterpret_cast<int4 *>(dst + q * 16) = w;
+    }
+  }
+}
+
+// mean_s, missing flag, beta += sum mean_s^2
+__global__ void kin_snp_stats_kernel(const int *__restrict__ sum, const int *__restrict__ nmiss, int n, int l,
+                                     double *__restrict__ mean, double *__restrict__ beta_flag /* [0]=beta [1]=flag */) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double m2 = 0.0, fl = 0.0;
+  if (s < l) {
+    const int nm = nmiss[s];
+    const double m = (double)sum[s] / (double)(n - nm);
+    mean[s] = m; m2 = m * m;
+    if (nm > 0) fl = 1.0;
+  }
+  m2 = warp_allsum(m2); fl = warp_allsum(fl);
+  if ((threadIdx.x & 31) == 0) { if (m2 != 0.0) atomicAdd(&beta_flag[2], m2); if (fl != 0.0) atomicAdd(&beta_flag[1], fl); }
+}
+
+// a[i] += sum_s mean_s * Z[s][i] over the staged columns [col0, col0+l)   (one warp per individual)
+__global__ void __launch_bounds__(256) kin_a_kernel(const int8_t *__restrict__ Zt, size_t pitch, size_t col0, int l, int n,
+                                                    const double *__restrict__ mean, double *__restrict__ a_pending) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int8_t *row = Zt + (size_t)i * pitch + col0;
+  double acc = 0.0;
+  for (int s = lane; s < l; s += 32) acc = fma((double)row[s], mean[s], acc);
+  acc = warp_allsum(acc);
+  if (lane == 0) a_pending[i] += acc;
+}
+
+__global__ void kin_commit_kernel(double *a, const double *a_pending, double *beta_flag, int n) {
+  // fold the pending (checked, missing-free) chunk into the running totals
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += a_pending[i];
+  if (i == 0) { beta_flag[0] += beta_flag[2]; }
+}
+
+__global__ void kin_finish_kernel(double *K, size_t n, size_t ld, const double *__restrict__ a, const double *__restrict__ beta_flag,
+                                  double inv_ns) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j > i || i >= n) return;
+  K[i * ld + j] = (K[i * ld + j] - a[i] - a[j] + beta_flag[0]) * inv_ns;
+}
+
+static bool make_tmap_rows(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t inner_bytes, uint64_t pitch_bytes,
+                           uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {inner_bytes, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)I8_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool kin_i8_eligible(gb200_ctx *c) {
+  return c->kin_path != 1 && c->kin_mode == 1 && c->kin_n >= 1024 && get_encode() != nullptr;
+}
+
+static int kin_i8_setup(gb200_ctx *c) {
+  I8State &S = c->i8;
+  const size_t n = c->kin_n;
+  if (S.kin_n == n && S.kin_cap) return GB200_OK;
+  size_t cap = ((size_t)1 << 31) / n;                 // <= 2 GiB of staged int8 genotypes
+  if (cap > 131072) cap = 131072;
+  cap = cap / 128 * 128;
+  if (cap < 1024) cap = 1024;
+  GB_CUDA(c, S.kin_zt.reserve(n * cap));
+  GB_CUDA(c, S.kin_stats.reserve(cap * (2 * sizeof(int) + sizeof(double))));
+  GB_CUDA(c, S.kin_a.reserve((2 * n + 8) * sizeof(double)));
+  // lower-triangle tiles: 128-row x 256-column tiles that intersect j <= i
+  std::vector<int2> tiles;
+  const int m_tiles = (int)((n + 127) / 128);
+  for (int m = 0; m < m_tiles; ++m)
+    for (int nb = 0; nb * 256 <= m * 128 + 127; ++nb) tiles.push_back(make_int2(m, nb));
+  GB_CUDA(c, S.kin_tiles.reserve(tiles.size() * sizeof(int2)));
+  GB_CUDA(c, cudaMemcpyAsync(S.kin_tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  S.kin_num_tiles = (int)tiles.size();
+  if (!S.tmap_ka) S.tmap_ka = aligned_alloc(64, sizeof(CUtensorMap));
+  if (!S.tmap_kb) S.tmap_kb = aligned_alloc(64, sizeof(CUtensorMap));
+  S.kin_cap = cap; S.kin_n = n; S.kin_fill = 0;
+  return GB200_OK;
+}
+
+int kin_i8_begin(gb200_ctx *c) {
+  I8State &S = c->i8;
+  S.kin_used = false; S.kin_fill = 0;
+  if (!kin_i8_eligible(c)) return GB200_OK;
+  int rc = kin_i8_setup(c);
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemsetAsync(S.kin_a.p, 0, (2 * c->kin_n + 8) * sizeof(double), c->stream));
+  return GB200_OK;
+}
+
+int kin_i8_flush(gb200_ctx *c) {
+  I8State &S = c->i8;
+  if (S.kin_fill == 0) return GB200_OK;
+  const size_t n = c->kin_n, kbytes = (S.kin_fill + 127) / 128 * 128;
+  if (!make_tmap_rows((CUtensorMap *)S.tmap_ka, S.kin_zt.p, n, kbytes, S.kin_cap, 128) ||
+      !make_tmap_rows((CUtensorMap *)S.tmap_kb, S.kin_zt.p, n, kbytes, S.kin_cap, 256))
+    return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the kinship genotype matrix");
+  I8KernelParams p;
+  p.T = 1; p.NE = 256; p.N = 256; p.n = (int)n; p.l = (int)n;
+  p.num_k_blocks = (int)(kbytes / I8_BK);
+  p.m_tiles = (int)((n + 127) / 128); p.n_groups = (int)((n + 255) / 256);
+  p.lbo_units = 1; p.scale = nullptr;
+  p.C = c->dK.as<double>(); p.ldc = n; p.mode = 1;
+  p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
+  const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
+  GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int grid = p.num_tiles < c->num_sms ? p.num_tiles : c->num_sms;
+  {
+    ProfScope ps(c, "kin");
+    i8_gemm_kernel<<<grid, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)S.tmap_ka, *(CUtensorMap *)S.tmap_kb, p);
+    GB_CUDA(c, cudaGetLastError());
+  }
+  S.kin_fill = 0;
+  return GB200_OK;
+}
+
+// Try to stage `l` SNPs (device .bed rows) for the int8 kinship GEMM.  *taken = false when the chunk holds a
+// missing genotype (the caller then runs the FP64 path on it); nothing is staged in that case.
+int kin_i8_add_chunk(gb200_ctx *c, const unsigned char *bed_dev, size_t l, size_t bytes_per_snp, bool *taken) {
+  I8State &S = c->i8;
+  *taken = false;
+  const size_t n = c->kin_n;
+  if (l > S.kin_cap) return set_err(c, GB200_ERR_ARG, "kinship chunk larger than the staging capacity");
+  if (S.kin_fill + l > S.kin_cap) { int rc = kin_i8_flush(c); if (rc) return rc; }
+  int *sum = S.kin_stats.as<int>();
+  int *nmiss = sum + S.kin_cap;
+  double *mean = reinterpret_cast<double *>(nmiss + S.kin_cap);
+  double *a = S.kin_a.as<double>(), *a_pending = a + n, *beta_flag = a + 2 * n;   // [0] beta, [1] flag, [2] pending beta
+  const size_t lpad = (l + 127) / 128 * 128;
+  {
+    ProfScope ps(c, "decode", 4);
+    GB_CUDA(c, cudaMemsetAsync(sum, 0, 2 * S.kin_cap * sizeof(int), c->stream));
+    GB_CUDA(c, cudaMemsetAsync(a_pending, 0, n * sizeof(double), c->stream));
+    GB_CUDA(c, cudaMemsetAsync(beta_flag + 1, 0, 2 * sizeof(double), c->stream));
+    dim3 grid((unsigned)(lpad / 128), (unsigned)((n + 127) / 128));
+    bed_transpose_i8_kernel<<<grid, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, (int)n, (int)l, S.kin_zt.as<int8_t>(), S.kin_cap,
+                                                         S.kin_fill, sum, nmiss);
+    kin_snp_stats_kernel<<<(unsigned)((l + 255) / 256), 256, 0, c->stream>>>(sum, nmiss, (int)n, (int)l, mean, beta_flag);
+    kin_a_kernel<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>(S.kin_zt.as<int8_t>(), S.kin_cap, S.kin_fill, (int)l, (int)n, mean, a_pending);
+    GB_CUDA(c, cudaGetLastError());
+  }
+  double flag = 0.0;
+  GB_CUDA(c, cudaMemcpyAsync(&flag, beta_flag + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flag != 0.0) {
+    // missing genotypes in this chunk: un-stage it (zero its columns) and let the FP64 path handle it
+    GB_CUDA(c, cudaMemset2DAsync(S.kin_zt.as<int8_t>() + S.kin_fill, S.kin_cap, 0, lpad, n, c->stream));
+    return GB200_OK;
+  }
+  kin_commit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a, a_pending, beta_flag, (int)n);
+  GB_CUDA(c, cudaGetLastError());
+  S.kin_fill += lpad;                                   // keep the fill pointer 128-aligned (padding columns are zero)
+  S.kin_used = true;
+  c->kin_ns += l;
+  *taken = true;
+  return GB200_OK;
+}
+
+// flush + apply the rank-one centring terms and the 1/ns scaling (replaces launch_scale at finish)
+int kin_i8_finish(gb200_ctx *c, double inv_ns) {
+  I8State &S = c->i8;
+  int rc = kin_i8_flush(c);
+  if (rc) return rc;
+  const size_t n = c->kin_n;
+  double *a = S.kin_a.as<double>();
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  kin_finish_kernel<<<grid, 256, 0, c->stream>>>(c->dK.as<double>(), n, n, a, a + 2 * n, inv_ns);
   GB_CUDA(c, cudaGetLastError());
   return GB200_OK;
 }

@@ -399,3 +399,29 @@ def test_cli_mouse_gk_then_lmm_matches_demo_txt(golden_dir, tmp_path):
     if r.returncode == 0:
         h = open(tmp_path / "lmm4.assoc.txt").readline().rstrip("\n").split("\t")
         assert h[7:] == ["beta", "se", "logl_H1", "l_remle", "l_mle", "p_wald", "p_lrt", "p_score"]
+
+
+# ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
+def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
+    n = 1300
+    bed1, G1 = synth.make_bed(n, 700, seed=61)                       # no missing genotypes -> int8 path
+    bed2, G2 = synth.make_bed(n, 333, seed=62, miss_rate=0.02)       # missing -> FP64 fallback for this call
+    bed3, G3 = synth.make_bed(n, 129, seed=63)                       # int8 again (odd size: padded to 256 columns)
+    G = np.vstack([G1, G2, G3]); Gn = np.where(G < 0, np.nan, G)
+    Xc = O.kin_transform(Gn, 1)
+    Kref = Xc @ Xc.T / G.shape[0]
+    ctx.profile_enable(True); ctx.profile_reset()
+    ctx.kin_begin(n, 1)
+    ctx.kin_add_bed(bed1); ctx.kin_add_bed(bed2); ctx.kin_add_bed(bed3)
+    K, ns = ctx.kin_finish()
+    ctx.profile_enable(False)
+    assert ns == G.shape[0]
+    assert np.allclose(K, Kref, rtol=1e-10, atol=1e-12)
+    assert np.array_equal(K, K.T)
+    # forcing the FP64 path gives the same matrix
+    ctx.set_option("kin_path", 1)
+    ctx.kin_begin(n, 1)
+    ctx.kin_add_bed(np.vstack([bed1, bed2, bed3]))
+    K2, _ = ctx.kin_finish()
+    ctx.set_option("kin_path", 0)
+    assert np.allclose(K2, K, rtol=1e-10, atol=1e-12)
