@@ -320,7 +320,8 @@ def run_b200(args):
         a = by / (lmm_ms / lmm_n * 1e-3) / 1e9
         lmm_roof = {"kernel": "lmm_assoc_kernel (fused per-SNP tests)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "share_of_step": lmm_ms / ms, "avg_launch_ms": lmm_ms / lmm_n,
-                    "note": "algorithmic bytes 8n+64 per SNP; the kernel is FP64-ALU bound (~35 passes x ~40 DFMA per element)"}
+                    "note": "algorithmic bytes 8n+64 per SNP; the kernel is FP64-pipe bound by construction (~16 lockstep passes, ~1000 FP64 "
+                            "instructions per individual and SNP): see DESIGN.md 4.1"}
 
     cpu = None
     if not args.no_cpu_baseline:
