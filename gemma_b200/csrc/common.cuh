@@ -51,7 +51,8 @@ struct I8State {
   DevBuf kin_a;                  // a[i] = sum_s mean_s z_s[i]  (n doubles) + beta + flag
   DevBuf kin_tiles;              // lower-triangle tile list (int2)
   size_t kin_cap = 0, kin_fill = 0, kin_n = 0;
-  int kin_num_tiles = 0;
+  int kin_num_tiles = 0, kin_num_tiles_pair = 0;
+  bool tmap_b_half = false;
   bool kin_used = false;
   void *tmap_ka = nullptr, *tmap_kb = nullptr;
 };
@@ -88,6 +89,7 @@ struct gb200_ctx {
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
   long n_slices = 0;     // 0 = default
+  long cta_pair = 0;     // 1 = run the tensor-core kernels as CTA pairs (tcgen05 cta_group::2)
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K without missing genotypes), 1 = FP64 only
   long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)

@@ -296,6 +296,191 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster form one 256 x N tile.  Each CTA stages
+// its own 128 SNP rows of A and HALF of the B rows; the pair's MMA reads both halves of B, so the
+// shared-memory read traffic per MAC drops from (1/128 + 1/N) to (1/128 + 1/2N) bytes -- the single-CTA
+// kernel above sits at ~97 B/clk of the 128 B/clk shared-memory port (tensor pipe 74-76% active).
+//   - full[] barriers live in the leader (cluster rank 0): both CTAs' TMA loads complete_tx on it;
+//   - the leader's single MMA thread issues tcgen05.mma.cta_group::2 and multicasts its commits to the
+//     empty[] / tfull[] barriers of BOTH CTAs;
+//   - every epilogue warp of both CTAs arrives (remotely for rank 1) on the leader's tempty[] barrier.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *tmap, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const I8KernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int halfN = p.N / 2;
+  const int a_bytes = I8_BM * I8_BK;
+  const int b_bytes = halfN * I8_BK;                       // this CTA's half of the B rows
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + I8_STAGES * a_bytes;
+  uint64_t *bars = (uint64_t *)(smem_b + I8_STAGES * b_bytes);
+  uint64_t *full = bars, *empty = bars + I8_STAGES;
+  uint64_t *tfull = bars + 2 * I8_STAGES, *tempty = bars + 2 * I8_STAGES + 2;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * I8_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.tiles ? p.num_tiles : p.m_tiles * p.n_groups;    // m_tiles counts 256-row tiles here
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }   // 4 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // peer barriers are initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);             // local: released by the leader's multicast commit
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+          if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * (a_bytes + b_bytes)));
+          tma_load_2d_pair(&tmap_a, full_leader, smem_a + stage * a_bytes, kb * I8_BK, m_blk * 256 + (int)rank * I8_BM);
+          tma_load_2d_pair(&tmap_b, full_leader, smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N + (int)rank * halfN);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_i8_idesc(256, p.N, 0, 1);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * I8_ACC_COLS);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * a_bytes), p.lbo_units);
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * b_bytes), p.lbo_units);
+#pragma unroll
+          for (int k = 0; k < I8_BK / I8_UK; ++k)
+            tc_mma_i8_pair(tmem_d, adesc + (uint64_t)(k * (I8_UK >> 4)), bdesc + (uint64_t)(k * (I8_UK >> 4)), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_pair(&empty[stage]);
+          if (kb == p.num_k_blocks - 1) tc_commit_pair(&tfull[acc]);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, each its own 128 rows) =====================
+    const int ew = warp - 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    const double w256 = 256.0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int s = m_blk * 256 + (int)rank * I8_BM + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * I8_ACC_COLS);
+      const int i0 = n_grp * p.NE;
+      if (p.mode == 1) {
+        const int j0 = n_grp * p.N;
+        double *krow = p.C + (size_t)s * p.ldc;
+        for (int e0 = 0; e0 < p.N; e0 += 8) {
+          int32_t d[8];
+          tc_ld8(taddr + (uint32_t)e0, d);
+          tc_ld_wait();
+          if (s < p.l) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = j0 + e0 + q;
+              if (j <= s) krow[j] += (double)d[q];
+            }
+          }
+        }
+      } else {
+        for (int e0 = 0; e0 < p.NE; e0 += 8) {
+          double v[8];
+          int32_t d[8];
+          tc_ld8(taddr + (uint32_t)e0, d);
+          tc_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (double)d[q];
+          for (int t = 1; t < p.T; ++t) {
+            tc_ld8(taddr + (uint32_t)(t * p.NE + e0), d);
+            tc_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fma(v[q], w256, (double)d[q]);
+          }
+          if (s < p.l) {
+            double *crow = p.C + (size_t)s * p.ldc;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int i = i0 + e0 + q;
+              if (i < p.n) crow[i] = v[q] * __ldg(p.scale + i);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // nobody tears TMEM / smem down while the peer still uses it
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // U -> int8 digit planes
 __global__ void col_absmax_kernel(const double *__restrict__ U, int n, double *__restrict__ colmax) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -480,7 +665,7 @@ int i8_prepare(gb200_ctx *c) {
   if (!c->i8.tmap_b) c->i8.tmap_b = aligned_alloc(64, sizeof(CUtensorMap));
   if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, rows, (uint64_t)g.n_padk, (uint32_t)g.N))
     return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes");
-  c->i8.n = c->n; c->i8.n_pad = (size_t)g.n_padk; c->i8.n_slices = T; c->i8.ready = true;
+  c->i8.n = c->n; c->i8.n_pad = (size_t)g.n_padk; c->i8.n_slices = T; c->i8.ready = true; c->i8.tmap_b_half = false;
   return GB200_OK;
 }
 
@@ -490,7 +675,9 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   int rc = i8_prepare(c);
   if (rc) return rc;
   const I8Geom g = make_geom(c->n, c->i8.n_slices);
-  const size_t l_pad = (l + I8_BM - 1) / I8_BM * I8_BM;
+  const bool pair = c->cta_pair != 0 && (g.N % 32 == 0 || g.N == 240);     // half of N must stay a multiple of 8 rows
+  const size_t m_rows = pair ? 256 : I8_BM;
+  const size_t l_pad = (l + m_rows - 1) / m_rows * m_rows;
   GB_CUDA(c, c->i8.geno.reserve(l_pad * (size_t)g.n_padk));
   GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int))));
   double *mean = c->i8.miss_mean.as<double>();
@@ -506,7 +693,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   I8KernelParams p;
   p.T = g.T; p.NE = g.NE; p.N = g.N; p.n = g.n; p.l = (int)l;
   p.num_k_blocks = g.n_padk / I8_BK;
-  p.m_tiles = (int)(l_pad / I8_BM); p.n_groups = g.n_groups;
+  p.m_tiles = (int)(l_pad / m_rows); p.n_groups = g.n_groups;
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
   p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
@@ -517,8 +704,24 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_groups;
-  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  {
+  if (pair) {
+    // B tensor map with a half-N box (each CTA of the pair loads its own half of the plane rows)
+    if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, (uint64_t)g.n_groups * (uint64_t)g.N, (uint64_t)g.n_padk, (uint32_t)(g.N / 2)))
+      return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes (pair)");
+    c->i8.tmap_b_half = true;
+    static bool attr2 = false;
+    if (!attr2) { GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
+    int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
+    ProfScope ps(c, "utx");
+    i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+    GB_CUDA(c, cudaGetLastError());
+  } else {
+    if (c->i8.tmap_b_half) {
+      if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, (uint64_t)g.n_groups * (uint64_t)g.N, (uint64_t)g.n_padk, (uint32_t)g.N))
+        return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes");
+      c->i8.tmap_b_half = false;
+    }
+    const int grid = tiles < c->num_sms ? tiles : c->num_sms;
     ProfScope ps(c, "utx");
     i8_gemm_kernel<<<grid, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
     GB_CUDA(c, cudaGetLastError());
@@ -653,10 +856,14 @@ static int kin_i8_setup(gb200_ctx *c) {
   const int m_tiles = (int)((n + 127) / 128);
   for (int m = 0; m < m_tiles; ++m)
     for (int nb = 0; nb * 256 <= m * 128 + 127; ++nb) tiles.push_back(make_int2(m, nb));
+  S.kin_num_tiles = (int)tiles.size();
+  const int m2_tiles = (int)((n + 255) / 256);            // CTA-pair tiles: 256 x 256, nb <= m
+  for (int m = 0; m < m2_tiles; ++m)
+    for (int nb = 0; nb <= m; ++nb) tiles.push_back(make_int2(m, nb));
+  S.kin_num_tiles_pair = (int)tiles.size() - S.kin_num_tiles;
   GB_CUDA(c, S.kin_tiles.reserve(tiles.size() * sizeof(int2)));
   GB_CUDA(c, cudaMemcpyAsync(S.kin_tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
-  S.kin_num_tiles = (int)tiles.size();
   if (!S.tmap_ka) S.tmap_ka = aligned_alloc(64, sizeof(CUtensorMap));
   if (!S.tmap_kb) S.tmap_kb = aligned_alloc(64, sizeof(CUtensorMap));
   S.kin_cap = cap; S.kin_n = n; S.kin_fill = 0;
@@ -689,8 +896,18 @@ int kin_i8_flush(gb200_ctx *c) {
   p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
   GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  const int grid = p.num_tiles < c->num_sms ? p.num_tiles : c->num_sms;
-  {
+  if (c->cta_pair != 0) {
+    // pair tiles: 256 x 256, lower-triangle tiles nb <= m; B box = 128 rows (half of N)
+    if (!make_tmap_rows((CUtensorMap *)S.tmap_kb, S.kin_zt.p, n, kbytes, S.kin_cap, 128))
+      return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the kinship genotype matrix (pair)");
+    p.tiles = S.kin_tiles.as<int2>() + S.kin_num_tiles; p.num_tiles = S.kin_num_tiles_pair;
+    GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int pairs = c->num_sms / 2; if (pairs > p.num_tiles) pairs = p.num_tiles; if (pairs < 1) pairs = 1;
+    ProfScope ps(c, "kin");
+    i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)S.tmap_ka, *(CUtensorMap *)S.tmap_kb, p);
+    GB_CUDA(c, cudaGetLastError());
+  } else {
+    const int grid = p.num_tiles < c->num_sms ? p.num_tiles : c->num_sms;
     ProfScope ps(c, "kin");
     i8_gemm_kernel<<<grid, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)S.tmap_ka, *(CUtensorMap *)S.tmap_kb, p);
     GB_CUDA(c, cudaGetLastError());

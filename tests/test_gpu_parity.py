@@ -425,3 +425,28 @@ def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     K2, _ = ctx.kin_finish()
     ctx.set_option("kin_path", 0)
     assert np.allclose(K2, K, rtol=1e-10, atol=1e-12)
+
+
+# ---- CTA-pair (tcgen05 cta_group::2) variants of the tensor-core kernels ---------------------------------
+def test_cta_pair_projection_and_kinship_match_single_cta():
+    c = gemma_b200.Context(0)
+    rng = np.random.default_rng(123)
+    n, l = 1500, 700
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    c.lmm_setup(Q, synth.spectrum_like_kinship(n, 5), np.ones((n, 1)), rng.standard_normal(n))
+    bed, G = synth.make_bed(n, l, seed=321, miss_rate=0.01)
+    ref = (Q.T @ O.lmm_impute(np.where(G < 0, np.nan, G))).T
+    c.set_option("utx_path", 2)
+    for T in (6, 8, 4):
+        c.set_option("n_slices", T)
+        c.set_option("cta_pair", 0)
+        single = c.lmm_project_bed(bed, n)
+        c.set_option("cta_pair", 1)
+        pair = c.lmm_project_bed(bed, n)
+        assert np.array_equal(single, pair), T                      # exact integer accumulation: bit-identical
+    assert np.abs(pair - ref).max() / np.abs(ref).max() < 1e-6
+    bedk, Gk = synth.make_bed(n, 900, seed=77)
+    Xc = O.kin_transform(Gk, 1)
+    c.kin_begin(n, 1); c.kin_add_bed(bedk); K, _ = c.kin_finish()
+    assert np.allclose(K, Xc @ Xc.T / 900, rtol=1e-10, atol=1e-12)
+    c.close()
