@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--mode", type=int, default=4, help="-lmm mode (1 Wald, 2 LRT, 3 score, 4 all)")
     ap.add_argument("--utx-path", type=int, default=0, help="0 auto, 1 FP64 tiled, 2 int8 tensor core")
     ap.add_argument("--slices", type=int, default=0, help="int8 planes of U (0 = default 6)")
+    ap.add_argument("--cta-pair", type=int, default=-1, help="tensor-core kernels as CTA pairs (cta_group::2): -1 library default, 0, 1")
     ap.add_argument("--workload", default="lmm", choices=["lmm", "gk"], help="lmm: SNPs/s of -lmm (headline); gk: K=XX^T TFLOP/s")
     ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="SNPs in the CPU baseline sample (0 = auto)")
@@ -208,6 +209,8 @@ def run_b200(args):
     ctx.set_option("utx_path", args.utx_path)
     ctx.set_option("n_slices", args.slices)
     ctx.set_option("lmm_kernel", args.lmm_kernel)
+    if args.cta_pair >= 0:
+        ctx.set_option("cta_pair", args.cta_pair)
 
     # ---- run-constant state, generated on the device (identical on every rank) ----------------
     g = torch.Generator(device=dev); g.manual_seed(SEED)
@@ -363,7 +366,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0):
+def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0, cta_pair=-1):
     """BASELINE config 2: -gk 1 (centred kinship) on synthetic n x p PLINK genotypes, 1 GPU.
     Reported with the algorithmic flops of ONE triangle, n(n+1)p."""
     import torch
@@ -373,6 +376,8 @@ def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0):
     if ctx is None:
         stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
         ctx = gemma_b200.Context(local, stream=stream.cuda_stream)
+    if cta_pair >= 0:
+        ctx.set_option("cta_pair", cta_pair)
     bps = (n + 3) // 4
     beds = [synth.make_bed_torch(n, B, dev, seed=SEED, snp_offset=k * B) for k in range(K + Wm)]
     ctx.kin_begin(n, 1)
@@ -414,7 +419,7 @@ def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0):
 
 def run_gk(args):
     n = args.n if args.n != 50000 else 10000
-    print(json.dumps(measure_gk(n, max(args.batch, 16384), args.steps, max(3, args.warmup))))
+    print(json.dumps(measure_gk(n, max(args.batch, 16384), args.steps, max(3, args.warmup), cta_pair=args.cta_pair)))
 
 
 def main():

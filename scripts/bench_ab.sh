@@ -10,7 +10,8 @@ tag = sys.argv[1]
 try:
     d = json.loads(open("gpurun_out/ab_%s.json" % tag).read().strip().splitlines()[-1])
     km = {k: round(v["ms"] / max(1, v["launches"]), 3) for k, v in d.get("kernel_ms", {}).items()}
-    print(tag, "value=%.0f" % d["value"], "e2e=%s" % (d["e2e"] and round(d["e2e"]["value"])), "ms/step=%.2f" % d["ms_per_step"], km,
+    if "kernel_ms" not in d: km = d.get("roofline")
+    print(tag, "value=%.1f" % d["value"], "e2e=%s" % (d.get("e2e") and round(d["e2e"]["value"])), "ms/step=%.2f" % d["ms_per_step"], km,
           "clk=%s" % d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e:
     print(tag, "FAILED", e); print(open("gpurun_out/ab_%s.err" % tag).read()[-1500:])
