@@ -130,6 +130,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "cta_pair must be 0 or 1");
     c->cta_pair = value; return GB200_OK;
   }
+  if (!strcmp(name, "kin_cta_pair")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "kin_cta_pair must be 0 or 1");
+    c->kin_cta_pair = value; return GB200_OK;
+  }
   if (!strcmp(name, "kin_path")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "kin_path must be 0 or 1");
     c->kin_path = value; return GB200_OK;

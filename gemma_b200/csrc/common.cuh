@@ -89,7 +89,8 @@ struct gb200_ctx {
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
   long n_slices = 0;     // 0 = default
-  long cta_pair = 0;     // 1 = run the tensor-core kernels as CTA pairs (tcgen05 cta_group::2)
+  long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
+  long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K without missing genotypes), 1 = FP64 only
   long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)

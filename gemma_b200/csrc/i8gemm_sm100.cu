@@ -896,7 +896,7 @@ int kin_i8_flush(gb200_ctx *c) {
   p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
   GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  if (c->cta_pair != 0) {
+  if (c->kin_cta_pair != 0) {
     // pair tiles: 256 x 256, lower-triangle tiles nb <= m; B box = 128 rows (half of N)
     if (!make_tmap_rows((CUtensorMap *)S.tmap_kb, S.kin_zt.p, n, kbytes, S.kin_cap, 128))
       return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the kinship genotype matrix (pair)");

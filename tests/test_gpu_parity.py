@@ -447,6 +447,8 @@ def test_cta_pair_projection_and_kinship_match_single_cta():
     assert np.abs(pair - ref).max() / np.abs(ref).max() < 1e-6
     bedk, Gk = synth.make_bed(n, 900, seed=77)
     Xc = O.kin_transform(Gk, 1)
-    c.kin_begin(n, 1); c.kin_add_bed(bedk); K, _ = c.kin_finish()
-    assert np.allclose(K, Xc @ Xc.T / 900, rtol=1e-10, atol=1e-12)
+    for kp in (0, 1):
+        c.set_option("kin_cta_pair", kp)
+        c.kin_begin(n, 1); c.kin_add_bed(bedk); K, _ = c.kin_finish()
+        assert np.allclose(K, Xc @ Xc.T / 900, rtol=1e-10, atol=1e-12), kp
     c.close()
