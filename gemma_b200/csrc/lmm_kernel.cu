@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) lmm_assoc_kernel(LmmConst D, LmmParams pr
 
 // v2: one CTA = 8 warps = 8 SNPs in lockstep passes over shared-memory stages (lmm_v2.cuh)
 template <int NC>
-__global__ void __launch_bounds__(V2_THREADS, 1) lmm_assoc_v2_kernel(LmmConst D, LmmParams prm,
+__global__ void __launch_bounds__(V2_THREADS, 2) lmm_assoc_v2_kernel(LmmConst D, LmmParams prm,
                                                                     const double *__restrict__ UtXt, size_t ldu, int l,
                                                                     gb200_sumstat *__restrict__ out,
                                                                     unsigned int *__restrict__ ticket) {
@@ -63,7 +63,9 @@ static cudaError_t launch_assoc_v2_nc(const LmmConst &D, const LmmParams &prm, c
   cudaError_t e = cudaFuncSetAttribute(lmm_assoc_v2_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long groups = ((long)l + V2_WARPS - 1) / V2_WARPS;
-  long grid = groups < num_sms ? groups : num_sms;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lmm_assoc_v2_kernel<NC>, V2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long grid = groups < (long)num_sms * per_sm ? groups : (long)num_sms * per_sm;
   if (grid < 1) grid = 1;
   e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;

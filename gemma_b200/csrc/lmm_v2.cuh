@@ -24,9 +24,10 @@ namespace gb {
 
 constexpr int V2_WARPS = 8;
 constexpr int V2_THREADS = V2_WARPS * 32;
-constexpr int V2_CHUNK = 512;          // individuals per pipeline stage
+constexpr int V2_CHUNK = 256;          // individuals per pipeline stage
 constexpr int V2_STAGES = 3;
 constexpr int V2_MAX_REGION = 64;
+constexpr int V2_NSG = 2;              // grid lambdas per pass (register budget: 2 CTAs per SM need <= 128 registers)
 
 __host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS) * V2_CHUNK; }
 __host__ __device__ constexpr size_t v2_smem_bytes(int nc) { return v2_stage_doubles(nc) * V2_STAGES * sizeof(double) + 64; }
@@ -407,16 +408,16 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         glam[0] = lam[0]; gd1R[0] = ev.d1R; gd1L[0] = ev.d1L; fRmin = ev.fR; fLmin = ev.fL;
       }
     }
-    // ---- grid passes: 4 lambdas at a time
-    for (int g0 = 1; g0 <= n_region; g0 += 4) {
-      V2Acc<NC, 4, 1, 2> acc;
-      double lam[4]; const bool wl[4] = {false, false, false, false};
+    // ---- grid passes: V2_NSG lambdas at a time
+    for (int g0 = 1; g0 <= n_region; g0 += V2_NSG) {
+      V2Acc<NC, V2_NSG, 1, 2> acc;
+      double lam[V2_NSG]; bool wl[V2_NSG];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) lam[s] = (g0 + s <= n_region) ? l_min * exp(lambda_interval * (double)(g0 + s)) : 1.0;
-      v2_pass<NC, 4, 1, 2>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+      for (int s = 0; s < V2_NSG; ++s) { wl[s] = false; lam[s] = (g0 + s <= n_region) ? l_min * exp(lambda_interval * (double)(g0 + s)) : 1.0; }
+      v2_pass<NC, V2_NSG, 1, 2>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
       if (valid) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < V2_NSG; ++s) {
           if (g0 + s <= n_region) {
             V2Eval ev;
             v2_derive<NC, 2>(acc.S[s][0], acc.S[s][1], dummy, acc.tr[s][0], acc.tr[s][1], lam[s], n, false, 0.0, 0.0, ev);
