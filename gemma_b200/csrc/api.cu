@@ -523,8 +523,10 @@ static int lmm_check_ready(gb200_ctx *c, const char *who) {
 }
 
 // association kernel on a device-resident rotated batch
-static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev) {
+static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev,
+                         bool plink_rule = false) {
   LmmConst D = make_const(c);
+  c->prm.plink_rule = plink_rule ? 1 : 0;
   ProfScope ps(c, "lmm");
   const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
   if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
@@ -656,7 +658,7 @@ static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *i
                         size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
   int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
   if (rc) return rc;
-  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, out_dev);
+  return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, out_dev, /*plink_rule=*/true);   // AnalyzePlink semantics
 }
 
 static int upload_idx_from_mask(gb200_ctx *c, const unsigned char *idv_mask, size_t ni_total, const int **idx_dev) {

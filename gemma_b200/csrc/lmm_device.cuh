@@ -42,6 +42,8 @@ struct LmmParams {
   int n_region;
   double l_min, l_max;
   double l_mle_null, logl_mle_H0;
+  int plink_rule;        // 1: AnalyzePlink semantics (src/lmm.cpp:1866-1884): no Wald when the REML search failed,
+                         //    p_wald = p_lrt = NaN when the reported logl_H1 is NaN; 0: Analyze (BIMBAM) semantics
 };
 
 __host__ __device__ constexpr int abidx(int a, int b, int nv) {
@@ -575,12 +577,13 @@ __device__ __forceinline__ void analyze_snp(const LmmConst &D, const LmmParams &
     calc_lambda_both<NC>(D, x, prm.l_min, prm.l_max, prm.n_region, needR, needL, R, L);
     if (needR) {
       lambda_remle = R.lambda; logl_H1 = R.logf;
-      eval_wald_score<NC>(D, x, lambda_remle, false, beta, se, p_wald);
+      if (!(prm.plink_rule && isnan(logl_H1))) eval_wald_score<NC>(D, x, lambda_remle, false, beta, se, p_wald);
     }
     if (needL) {
       lambda_mle = L.lambda; logl_H1 = L.logf;
       p_lrt = chisq1_Q_dev(2.0 * (logl_H1 - prm.logl_mle_H0));
     }
+    if (prm.plink_rule && isnan(logl_H1)) { p_wald = logl_H1; p_lrt = logl_H1; }
   }
   out.beta = beta; out.se = se; out.lambda_remle = lambda_remle; out.lambda_mle = lambda_mle;
   out.p_wald = p_wald; out.p_lrt = p_lrt; out.p_score = p_score; out.logl_H1 = logl_H1;

@@ -8,11 +8,11 @@
 //    CTA and chunk in shared memory by a 3-stage cp.async pipeline and shared by the 8 SNPs; every
 //    warp's own U^T x row streams through its private slice of the same stages.  At n = 50 000 the
 //    v1 kernel re-read 1.6 MB per SNP and pass through L2 with ~2 KB in flight per warp
-//    (latency-bound, 17% of the FP64 pipe); here a pass moves 0.55 MB per SNP with 44 KB x 2 stages in
-//    flight per SM.
-//  * several lambdas per pass ("slots"): the 11 grid lambdas are evaluated 4 at a time, f(l_max) and the
+//    (latency-bound, 17% of the FP64 pipe); here a pass moves 0.55 MB per SNP with two 22 KB stages in
+//    flight per CTA and two CTAs per SM.
+//  * several lambdas per pass ("slots"): the 11 grid lambdas are evaluated 2 at a time, f(l_max) and the
 //    score-test lambda share one pass, and the REML and ML root refinements (independent chains) advance
-//    side by side, so a SNP needs ~16 passes over its row instead of ~35.
+//    side by side, so a SNP needs ~18 passes over its row instead of ~35.
 //  * 1/(lambda*delta+1) by MUFU.RCP64H seed + two Newton steps (delta >= 0 after the <1e-10 zeroing of
 //    lapack.cpp:268, so the denominator is >= 1: no special cases).
 //
@@ -462,7 +462,9 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         finalized = true;
         if (needR) {
           lambda_remle = FR.rs.lambda; logl_H1 = FR.rs.logf;
-          if (lambda_remle == FR.cache_lam) {            // f(lambda_hat) pass already produced the order-1 table
+          if (prm.plink_rule && isnan(logl_H1)) {          // AnalyzePlink: `if (!isnan(logl_H1)) CalcRLWald(...)` (lmm.cpp:1869-1870)
+            wald_done = true;
+          } else if (lambda_remle == FR.cache_lam) {            // f(lambda_hat) pass already produced the order-1 table
             Derived<NC, 1> d; d.P_xx = FR.cP_xx; d.P_xy = FR.cP_xy; d.P_yy = FR.cP_yy; d.Px_yy = FR.cPx_yy;
             wald_score_from<NC>(d, D.n, false, beta, se, p_wald);
             wald_done = true;
@@ -510,6 +512,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       lambda_mle = FL.rs.lambda; logl_H1 = FL.rs.logf;
       p_lrt = chisq1_Q_dev(2.0 * (logl_H1 - prm.logl_mle_H0));
     }
+    if (valid && prm.plink_rule && isnan(logl_H1)) { p_wald = logl_H1; p_lrt = logl_H1; }   // lmm.cpp:1882-1884
   }
   out.beta = beta; out.se = se; out.lambda_remle = lambda_remle; out.lambda_mle = lambda_mle;
   out.p_wald = p_wald; out.p_lrt = p_lrt; out.p_score = p_score; out.logl_H1 = logl_H1;

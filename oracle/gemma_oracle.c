@@ -686,11 +686,11 @@ typedef struct {
  * UtXlarge).  Results are appended in order.  a_mode in {1,2,3,4,9}.
  * n_eval_out (optional) receives the number of likelihood-function evaluations.
  */
-GO_EXPORT int go_lmm_analyze_utx(size_t n, size_t n_cvt, const double *eval, const double *UtW,
+static int lmm_analyze_impl(size_t n, size_t n_cvt, const double *eval, const double *UtW,
                                  size_t ldw, const double *Uty, const double *UtX, size_t l,
                                  size_t ldx, int a_mode, double l_min, double l_max,
                                  size_t n_region, double l_mle_null, double logl_mle_H0,
-                                 go_sumstat *out, long *n_eval_out) {
+                                 go_sumstat *out, long *n_eval_out, int plink_rule) {
   size_t n_index = n_index_of(n_cvt);
   double *Uab = (double *)calloc(n * n_index, sizeof(double));
   func_param p;
@@ -705,12 +705,14 @@ GO_EXPORT int go_lmm_analyze_utx(size_t n, size_t n_cvt, const double *eval, con
       calc_rl_wald_score(1, l_mle_null, &p, &beta, &se, &p_score);
     if (a_mode == 1 || a_mode == 4) {                           /* :1546-1549 */
       calc_lambda('R', &p, l_min, l_max, n_region, &lambda_remle, &logl_H1);
-      calc_rl_wald_score(0, lambda_remle, &p, &beta, &se, &p_wald);
+      if (!(plink_rule && isnan(logl_H1)))                       /* AnalyzePlink: src/lmm.cpp:1869-1870 */
+        calc_rl_wald_score(0, lambda_remle, &p, &beta, &se, &p_wald);
     }
     if (a_mode == 2 || a_mode == 4 || a_mode == 9) {            /* :1551-1554 */
       calc_lambda('L', &p, l_min, l_max, n_region, &lambda_mle, &logl_H1);
       p_lrt = go_cdf_chisq1_Q(2.0 * (logl_H1 - logl_mle_H0));
     }
+    if (plink_rule && isnan(logl_H1)) { p_wald = logl_H1; p_lrt = logl_H1; }   /* src/lmm.cpp:1882-1884 */
     out[i].beta = beta; out[i].se = se; out[i].lambda_remle = lambda_remle;
     out[i].lambda_mle = lambda_mle; out[i].p_wald = p_wald; out[i].p_lrt = p_lrt;
     out[i].p_score = p_score; out[i].logl_H1 = logl_H1;
@@ -719,6 +721,25 @@ GO_EXPORT int go_lmm_analyze_utx(size_t n, size_t n_cvt, const double *eval, con
   param_free(&p);
   free(Uab);
   return 0;
+}
+
+GO_EXPORT int go_lmm_analyze_utx(size_t n, size_t n_cvt, const double *eval, const double *UtW,
+                                 size_t ldw, const double *Uty, const double *UtX, size_t l,
+                                 size_t ldx, int a_mode, double l_min, double l_max,
+                                 size_t n_region, double l_mle_null, double logl_mle_H0,
+                                 go_sumstat *out, long *n_eval_out) {
+  return lmm_analyze_impl(n, n_cvt, eval, UtW, ldw, Uty, UtX, l, ldx, a_mode, l_min, l_max, n_region, l_mle_null,
+                          logl_mle_H0, out, n_eval_out, 0);
+}
+
+/* Same with the NaN handling of LMM::AnalyzePlink (src/lmm.cpp:1866-1884). */
+GO_EXPORT int go_lmm_analyze_utx_plink(size_t n, size_t n_cvt, const double *eval, const double *UtW,
+                                       size_t ldw, const double *Uty, const double *UtX, size_t l,
+                                       size_t ldx, int a_mode, double l_min, double l_max,
+                                       size_t n_region, double l_mle_null, double logl_mle_H0,
+                                       go_sumstat *out, long *n_eval_out) {
+  return lmm_analyze_impl(n, n_cvt, eval, UtW, ldw, Uty, UtX, l, ldx, a_mode, l_min, l_max, n_region, l_mle_null,
+                          logl_mle_H0, out, n_eval_out, 1);
 }
 
 /* Null model: src/lmm.cpp:2143-2180 CalcLambda(func_name, eval, UtW, Uty, ...) */

@@ -49,6 +49,8 @@ def lib():
                                          c_double_p, c_double_p, C.c_size_t, C.c_size_t, C.c_int,
                                          C.c_double, C.c_double, C.c_size_t, C.c_double, C.c_double,
                                          C.c_void_p, C.POINTER(C.c_long)]
+        L.go_lmm_analyze_utx_plink.restype = C.c_int
+        L.go_lmm_analyze_utx_plink.argtypes = L.go_lmm_analyze_utx.argtypes
         L.go_calc_lambda_null.restype = C.c_int
         L.go_calc_lambda_null.argtypes = [C.c_char, C.c_size_t, C.c_size_t, c_double_p, c_double_p,
                                           C.c_size_t, c_double_p, C.c_double, C.c_double, C.c_size_t,
@@ -102,14 +104,15 @@ def chisq1_Q(x):
 
 
 def lmm_analyze_utx(eval_, UtW, Uty, UtX, a_mode, l_min=1e-5, l_max=1e5, n_region=10,
-                    l_mle_null=0.0, logl_mle_H0=0.0, return_evals=False):
+                    l_mle_null=0.0, logl_mle_H0=0.0, return_evals=False, plink=False):
     """UtX: n x l (SNP per column, like the reference's UtXlarge). Returns SUMSTAT array."""
     eval_, UtW, Uty, UtX = _f64(eval_), _f64(UtW), _f64(Uty), _f64(UtX)
     n, c = UtW.shape
     l = UtX.shape[1]
     out = np.zeros(l, dtype=SUMSTAT_DTYPE)
     nev = C.c_long(0)
-    rc = lib().go_lmm_analyze_utx(n, c, _p(eval_), _p(UtW), c, _p(Uty), _p(UtX), l, UtX.shape[1],
+    fn = lib().go_lmm_analyze_utx_plink if plink else lib().go_lmm_analyze_utx
+    rc = fn(n, c, _p(eval_), _p(UtW), c, _p(Uty), _p(UtX), l, UtX.shape[1],
                                   a_mode, l_min, l_max, n_region, l_mle_null, logl_mle_H0,
                                   out.ctypes.data_as(C.c_void_p), C.byref(nev))
     assert rc == 0

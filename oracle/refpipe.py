@@ -204,3 +204,74 @@ def lmm_analyze(prep, X, a_mode, **kw):
     UtX = prep["U"].T @ X          # src/lmm.cpp:1521
     return O.lmm_analyze_utx(prep["eval"], prep["UtW"], prep["Uty"], UtX, a_mode,
                              l_mle_null=prep["l_mle_null"], logl_mle_H0=prep["logl_mle_H0"], **kw)
+
+
+# ---- PLINK (test infrastructure; src/gemma_io.cpp:514-636, 876-1064, 1599-1738) -------------------------
+class Plink:
+    """.bim/.fam/.bed trio: rs ids, alleles, phenotypes (column 6+, -9/NA missing) and G[p, n] with NaN = missing."""
+
+    def __init__(self, prefix, p_column=(1,)):
+        self.chr, self.rs, self.cM, self.bp, self.a1, self.a0 = [], [], [], [], [], []
+        for line in open(prefix + ".bim"):
+            t = line.split()
+            if not t:
+                continue
+            self.chr.append(t[0]); self.rs.append(t[1]); self.cM.append(float(t[2])); self.bp.append(int(t[3]))
+            self.a1.append(t[4]); self.a0.append(t[5])
+        ph, ind = [], []
+        for line in open(prefix + ".fam"):
+            t = _tok(line.rstrip("\r\n"))
+            if not t:
+                continue
+            row, irow = [], []
+            for c in p_column:
+                s = t[5 + c - 1]
+                if s == "NA" or float(s) == -9:
+                    row.append(-9.0); irow.append(0)
+                else:
+                    row.append(float(s)); irow.append(1)
+            ph.append(row); ind.append(irow)
+        self.pheno = np.array(ph); self.ind_pheno = np.array(ind, dtype=np.int32)
+        n = len(ph)
+        raw = np.fromfile(prefix + ".bed", dtype=np.uint8)[3:]
+        nb = (n + 3) // 4
+        self.bed = raw.reshape(-1, nb)
+        code = np.stack([(self.bed >> (2 * q)) & 3 for q in range(4)], axis=2).reshape(len(self.bed), nb * 4)[:, :n]
+        lut = np.array([2.0, np.nan, 1.0, 0.0])          # bits (hi,lo): 00->2, 01 (lo=1,hi=0)->missing, 10->1, 11->0
+        self.G = lut[code]
+
+
+def qc_plink(pl, indicator_idv, W=None, miss_level=0.05, maf_level=0.01, r2_level=0.9999):
+    """src/gemma_io.cpp:876-1064 ReadFile_bed QC pass."""
+    keep = indicator_idv == 1
+    G = pl.G[:, keep]
+    ni_test = int(keep.sum())
+    miss = np.isnan(G)
+    n_miss = miss.sum(axis=1)
+    s = np.nansum(G, axis=1)
+    maf = s / (2.0 * (ni_test - n_miss))
+    n0 = (G == 0).sum(axis=1); n1 = (G == 1).sum(axis=1); n2 = (G == 2).sum(axis=1)
+    ind = np.ones(len(G), dtype=np.int32)
+    ind[n_miss / ni_test > miss_level] = 0
+    if maf_level != -1:
+        ind[(maf < maf_level) | (maf > 1.0 - maf_level)] = 0
+    ind[((n0 + n1) == 0) | ((n1 + n2) == 0) | ((n2 + n0) == 0)] = 0
+    if W is not None and W.shape[1] != 1:
+        Wt = W[keep]; WtWi = np.linalg.inv(Wt.T @ Wt)
+        for t in np.nonzero(ind)[0]:
+            x = G[t].copy(); x[miss[t]] = maf[t] * 2.0
+            Wtx = Wt.T @ x
+            if (Wtx @ (WtWi @ Wtx)) / (x @ x) > r2_level:
+                ind[t] = 0
+    return ind, n_miss, maf
+
+
+def kinship_plink(pl, indicator_snp, k_mode=1, batch=20000):
+    """src/gemma_io.cpp:1599-1738 PlinkKin (all ni_total individuals)."""
+    sel = np.nonzero(indicator_snp)[0]
+    n = pl.G.shape[1]
+    K = np.zeros((n, n))
+    for s in range(0, len(sel), batch):
+        Xc = O.kin_transform(pl.G[sel[s:s + batch]], k_mode)
+        K += Xc @ Xc.T
+    return K / len(sel)

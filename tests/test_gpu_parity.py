@@ -272,7 +272,7 @@ def test_bxd_covariates_pins(ctx, golden_dir):
     Gs = bb.G[np.ix_(isnp == 1, keep)]
     ctx.lmm_params(2, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
     o2 = ctx.lmm_batch_geno(Gs)
-    assert o2["p_lrt"][0] == pytest.approx(EXP["bxd_lmm2_row2_p_lrt"], abs=5e-7)
+    assert o2["p_lrt"][1] == pytest.approx(EXP["bxd_lmm2_row2_p_lrt"], abs=5e-7)     # lines[2] of the assoc file
     assert o2["p_lrt"].max() == pytest.approx(EXP["bxd_max_p_lrt"], abs=5e-7)
     ctx.lmm_params(9, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
     o9 = ctx.lmm_batch_geno(Gs)
@@ -452,3 +452,29 @@ def test_cta_pair_projection_and_kinship_match_single_cta():
         c.kin_begin(n, 1); c.kin_add_bed(bedk); K, _ = c.kin_finish()
         assert np.allclose(K, Xc @ Xc.T / 900, rtol=1e-10, atol=1e-12), kp
     c.close()
+
+
+def test_plink_entry_point_follows_analyzeplink_nan_rule(ctx):
+    """gb200_lmm_batch_bed mirrors LMM::AnalyzePlink (src/lmm.cpp:1866-1884): when the lambda search fails the Wald
+    test is skipped and p_wald / p_lrt are NaN; the dense / geno entry points mirror LMM::Analyze."""
+    n, l = 300, 64
+    pb = random_problem(n, 1, 4, 17, causal=False)
+    bed, G = synth.make_bed(n, l, seed=18)
+    X = np.ascontiguousarray(G.T)
+    ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
+    UtX = pb["U"].T @ X
+    n_nan = 0
+    for (lo, hi, nr) in ((1e-5, 1e5, 10), (1e-2, 2e-2, 2), (3.0, 3.5, 1), (0.2, 0.25, 3)):
+        l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"], lo, hi, nr)
+        ctx.lmm_params(4, lo, hi, nr, l_mle, logl)
+        for kern in (1, 2):
+            ctx.set_option("lmm_kernel", kern)
+            got_p = ctx.lmm_batch_bed(bed, n)
+            got_b = ctx.lmm_batch(X)
+            ref_p = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, 4, lo, hi, nr, l_mle, logl, plink=True)
+            ref_b = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, 4, lo, hi, nr, l_mle, logl, plink=False)
+            check_sumstat(got_p, ref_p, 4)
+            check_sumstat(got_b, ref_b, 4)
+        n_nan += int(np.isnan(ref_p["p_wald"]).sum())
+    ctx.set_option("lmm_kernel", 0)
+    assert n_nan > 0, "the narrow search ranges were meant to exercise the NaN branch"

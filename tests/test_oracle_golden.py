@@ -87,7 +87,7 @@ def test_bxd_lmm2_lmm9_pins(golden_dir):
     prep = R.lmm_prepare(R.text_roundtrip(K), idv, ph[:, 0], W)
     X = R.lmm_genotypes_bimbam(bb, isnp, idv)
     o2 = R.lmm_analyze(prep, X, 2)
-    assert o2["p_lrt"][0] == pytest.approx(EXP["bxd_lmm2_row2_p_lrt"], abs=5e-7)   # dev_tests.rb:42
+    assert o2["p_lrt"][1] == pytest.approx(EXP["bxd_lmm2_row2_p_lrt"], abs=5e-7)   # dev_tests.rb:42: lines[2] (0-based, header = 0)
     assert o2["p_lrt"].max() == pytest.approx(EXP["bxd_max_p_lrt"], abs=5e-7)       # dev_tests.rb:43
     o9 = R.lmm_analyze(prep, X, 9)
     assert o9["lambda_mle"].max() == pytest.approx(EXP["bxd_lmm9_max_l_mle"], abs=1e-6)  # dev_tests.rb:53
@@ -103,3 +103,24 @@ def test_center_matrix_and_bed_decode_small():
     # 2-bit decode: byte 0b01_11_10_00 -> samples (00)=2, (10)=1, (11)=0, (01)=missing
     g = O.bed_decode(bytes([0b01111000]), 4)
     assert g[0] == 2 and g[1] == 1 and g[2] == 0 and np.isnan(g[3])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/example/HLC.bed"), reason="reference example HLC absent (GPU box)")
+def test_hlc_plink_gk2_lmm1_covariates_pins():
+    """test/dev_tests.rb:81-95: PLINK input, -gk 2 (standardised K), -lmm 1 -maf 0.1 with covariates (c = 3+1...)."""
+    pl = R.Plink("/root/reference/example/HLC")
+    rows, icvt = R.read_cvt("/root/reference/example/HLC_covariates.txt")
+    idv, W = R.process_cvt_phen(pl.ind_pheno, None, None)
+    isnp_gk, _, _ = R.qc_plink(pl, idv)                      # -gk run: no covariates, default maf 0.01
+    K = R.kinship_plink(pl, isnp_gk, 2)
+    idv, W = R.process_cvt_phen(pl.ind_pheno, rows, icvt)
+    isnp, _, _ = R.qc_plink(pl, idv, W, maf_level=0.1)
+    prep = R.lmm_prepare(R.text_roundtrip(K), idv, pl.pheno[:, 0], W)
+    keep = idv == 1
+    X = O.lmm_impute(pl.G[np.ix_(np.nonzero(isnp)[0], keep)])
+    out = O.lmm_analyze_utx(prep["eval"], prep["UtW"], prep["Uty"], prep["U"].T @ X, 1, plink=True)
+    # expect(...,[[100,"p_wald","5.189953e-01"],[:max,"logl_H1","279.2689"],[:max,"l_remle","1.686062"],[:max,"p_wald","0.9999996"]])
+    assert out["p_wald"][99] == pytest.approx(5.189953e-01, abs=1e-3)      # lines[100] of the assoc file (0-based, header = 0)
+    assert np.nanmax(out["logl_H1"]) == pytest.approx(279.2689, abs=1e-3)
+    assert np.nanmax(out["lambda_remle"]) == pytest.approx(1.686062, abs=1e-3)
+    assert np.nanmax(out["p_wald"]) == pytest.approx(0.9999996, abs=1e-3)
