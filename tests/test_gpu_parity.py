@@ -464,7 +464,9 @@ def test_plink_entry_point_follows_analyzeplink_nan_rule(ctx):
     ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
     UtX = pb["U"].T @ X
     n_nan = 0
-    for (lo, hi, nr) in ((1e-5, 1e5, 10), (1e-2, 2e-2, 2), (3.0, 3.5, 1), (0.2, 0.25, 3)):
+    l_re, _ = O.calc_lambda_null("R", pb["ev"], pb["UtW"], pb["Uty"])
+    # a lower bound just under the null REML estimate makes Newton step out of [l_min, l_max] for some SNPs
+    for (lo, hi, nr) in ((1e-5, 1e5, 10), (l_re * 0.9995, 1e5, 9), (l_re * 0.999, 1e5, 5), (0.2, 0.25, 3)):
         l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"], lo, hi, nr)
         ctx.lmm_params(4, lo, hi, nr, l_mle, logl)
         for kern in (1, 2):
