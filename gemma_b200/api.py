@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgemma_b200.so")
+LIB_PATH = os.environ.get("GB200_LIB", os.path.join(_HERE, "csrc", "libgemma_b200.so"))   # override for A/B builds only
 
 SUMSTAT_DTYPE = np.dtype([(k, "<f8") for k in
                           ("beta", "se", "lambda_remle", "lambda_mle", "p_wald", "p_lrt", "p_score", "logl_H1")])

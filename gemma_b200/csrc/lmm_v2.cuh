@@ -22,7 +22,13 @@
 
 namespace gb {
 
-constexpr int V2_WARPS = 8;
+#ifndef GB_V2_WARPS
+#define GB_V2_WARPS 8
+#endif
+#ifndef GB_V2_CTAS
+#define GB_V2_CTAS 2
+#endif
+constexpr int V2_WARPS = GB_V2_WARPS;
 constexpr int V2_THREADS = V2_WARPS * 32;
 constexpr int V2_CHUNK = 256;          // individuals per pipeline stage
 constexpr int V2_STAGES = 3;
@@ -88,10 +94,9 @@ struct V2Acc {
 
 // One lockstep pass.  Every thread of the CTA must call it (pipeline + barriers); `active` selects
 // whether this warp does arithmetic.  want_ld[s] adds sum log|lambda*delta+1| for slot s.
-template <int NC, int NS, int KLO, int KHI>
+template <int NC, int NS, int KLO, int KHI, bool LD>
 __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
-                                        int pad, bool active, const double (&lam)[NS], const bool (&want_ld)[NS],
-                                        V2Acc<NC, NS, KLO, KHI> &acc) {
+                                        int pad, bool active, const double (&lam)[NS], V2Acc<NC, NS, KLO, KHI> &acc) {
   constexpr int NV = NC + 2;
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   constexpr int NK = KHI - KLO + 1;
@@ -124,14 +129,18 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
     if (active) {
       const double *st = smem + (size_t)(c % V2_STAGES) * stage_d;
       const double *xs = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK;
-#pragma unroll 2
-      for (int j = lane; j < V2_CHUNK; j += 32) {
-        double v[NV];
-        const double dl = st[j];
+      const double *sl = st + lane;
+      const double *xl = xs + lane;
 #pragma unroll
-        for (int a = 0; a < NC; ++a) v[a] = st[(a + 1) * V2_CHUNK + j];
-        v[NC] = xs[j];
-        v[NC + 1] = st[(NC + 1) * V2_CHUNK + j];
+      for (int u = 0; u < V2_CHUNK / 32; ++u) {
+        constexpr int dummy_ = 0; (void)dummy_;
+        const int j = u * 32;
+        double v[NV];
+        const double dl = sl[j];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) v[a] = sl[(a + 1) * V2_CHUNK + j];
+        v[NC] = xl[j];
+        v[NC + 1] = sl[(NC + 1) * V2_CHUNK + j];
         // products shared by all slots and powers
         double pr[NIDX];
 #pragma unroll
@@ -142,7 +151,7 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
         for (int s = 0; s < NS; ++s) {
           const double den = fma(lam[s], dl, 1.0);
           const double h = rcp_ge1(den);
-          if (want_ld[s]) acc.ld[s] += log(den);
+          if (LD) acc.ld[s] += log(den);
           double hk = (KLO == 0) ? 1.0 : h;
 #pragma unroll
           for (int k = 0; k < NK; ++k) {
@@ -397,8 +406,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
     {
       V2Acc<NC, 1, 0, 2> acc;
       const double lam[1] = {l_min * exp(lambda_interval * 0.0)};
-      const bool wl[1] = {true};
-      v2_pass<NC, 1, 0, 2>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+      v2_pass<NC, 1, 0, 2, true>(D, xrows, smem, nchunks, pad, valid, lam, acc);
       if (valid) {
         Derived<NC, 1> dI;
         sweep_tables<NC, 1>(acc.S[0][0], dummy, dummy, dI);
@@ -411,10 +419,10 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
     // ---- grid passes: V2_NSG lambdas at a time
     for (int g0 = 1; g0 <= n_region; g0 += V2_NSG) {
       V2Acc<NC, V2_NSG, 1, 2> acc;
-      double lam[V2_NSG]; bool wl[V2_NSG];
+      double lam[V2_NSG];
 #pragma unroll
-      for (int s = 0; s < V2_NSG; ++s) { wl[s] = false; lam[s] = (g0 + s <= n_region) ? l_min * exp(lambda_interval * (double)(g0 + s)) : 1.0; }
-      v2_pass<NC, V2_NSG, 1, 2>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+      for (int s = 0; s < V2_NSG; ++s) lam[s] = (g0 + s <= n_region) ? l_min * exp(lambda_interval * (double)(g0 + s)) : 1.0;
+      v2_pass<NC, V2_NSG, 1, 2, false>(D, xrows, smem, nchunks, pad, valid, lam, acc);
       if (valid) {
 #pragma unroll
         for (int s = 0; s < V2_NSG; ++s) {
@@ -431,8 +439,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   if (need_search || needS) {
     V2Acc<NC, 2, 1, 1> acc;
     const double lam[2] = {l_max, needS ? prm.l_mle_null : 1.0};
-    const bool wl[2] = {true, false};
-    v2_pass<NC, 2, 1, 1>(D, xrows, smem, nchunks, pad, valid, lam, wl, acc);
+    v2_pass<NC, 2, 1, 1, true>(D, xrows, smem, nchunks, pad, valid, lam, acc);
     if (valid) {
       V2Eval ev;
       v2_derive<NC, 1>(acc.S[0][0], dummy, dummy, acc.tr[0][0], 0.0, lam[0], n, true, acc.ld[0], logdetI, ev);
@@ -479,9 +486,11 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
       const bool wl[2] = {rq[0].need && rq[0].logdet, rq[1].need && rq[1].logdet};
       V2Eval ev[2];
+      const bool any_ld = wl[0] || wl[1];
       if (Kmax >= 3) {
         V2Acc<NC, 2, 1, 3> acc;
-        v2_pass<NC, 2, 1, 3>(D, xrows, smem, nchunks, pad, active, lam, wl, acc);
+        if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
+        else v2_pass<NC, 2, 1, 3, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
         if (active) {
 #pragma unroll
           for (int s = 0; s < 2; ++s)
@@ -489,7 +498,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         }
       } else {
         V2Acc<NC, 2, 1, 2> acc;
-        v2_pass<NC, 2, 1, 2>(D, xrows, smem, nchunks, pad, active, lam, wl, acc);
+        if (any_ld) v2_pass<NC, 2, 1, 2, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
+        else v2_pass<NC, 2, 1, 2, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
         if (active) {
 #pragma unroll
           for (int s = 0; s < 2; ++s)

@@ -1,9 +1,11 @@
 #!/bin/bash
-# A/B runs of bench.py on the GPU box; each line: tag + value + per-kernel ms.  usage: bench_ab.sh "<tag>|<bench args>" ...
+# A/B runs of bench.py on the GPU box; each line: tag + value + per-kernel ms.
+# usage: bench_ab.sh "<tag>|<bench args>[|ENV=VAL ...]" ...
 mkdir -p gpurun_out
 for spec in "$@"; do
-  tag="${spec%%|*}"; args="${spec#*|}"
-  timeout 900 python bench.py $args > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  tag="${spec%%|*}"; rest="${spec#*|}"; args="${rest%%|*}"; envs=""
+  if [[ "$rest" == *"|"* ]]; then envs="${rest#*|}"; fi
+  env $envs timeout 900 python bench.py $args > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
   python - "$tag" <<'PY'
 import sys, json
 tag = sys.argv[1]
