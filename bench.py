@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--utx-path", type=int, default=0, help="0 auto, 1 FP64 tiled, 2 int8 tensor core")
     ap.add_argument("--slices", type=int, default=0, help="int8 planes of U (0 = default 6)")
     ap.add_argument("--cta-pair", type=int, default=-1, help="tensor-core kernels as CTA pairs (cta_group::2): -1 library default, 0, 1")
+    ap.add_argument("--overlap", type=int, default=-1, help="sub-batch pipeline (projection || per-SNP tests): -1 default, 0, 1")
     ap.add_argument("--workload", default="lmm", choices=["lmm", "gk"], help="lmm: SNPs/s of -lmm (headline); gk: K=XX^T TFLOP/s")
     ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="SNPs in the CPU baseline sample (0 = auto)")
@@ -211,6 +212,8 @@ def run_b200(args):
     ctx.set_option("lmm_kernel", args.lmm_kernel)
     if args.cta_pair >= 0:
         ctx.set_option("cta_pair", args.cta_pair)
+    if args.overlap >= 0:
+        ctx.set_option("overlap", args.overlap)
 
     # ---- run-constant state, generated on the device (identical on every rank) ----------------
     g = torch.Generator(device=dev); g.manual_seed(SEED)

@@ -77,6 +77,9 @@ void gb200_destroy(gb200_ctx *c) {
   if (c->i8.tmap_b) free(c->i8.tmap_b);
   if (c->i8.tmap_ka) free(c->i8.tmap_ka);
   if (c->i8.tmap_kb) free(c->i8.tmap_kb);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  for (int k = 0; k < 2; ++k) { if (c->evG[k]) cudaEventDestroy(c->evG[k]); if (c->evL[k]) cudaEventDestroy(c->evL[k]); }
+  c->dUtXt2.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -125,6 +128,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
   if (!strcmp(name, "utx_path")) {
     if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "utx_path must be 0,1,2");
     c->utx_path = value; return GB200_OK;
+  }
+  if (!strcmp(name, "overlap")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "overlap must be 0 or 1");
+    c->overlap = value; return GB200_OK;
   }
   if (!strcmp(name, "cta_pair")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "cta_pair must be 0 or 1");
@@ -326,7 +333,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false;
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
-  c->dUtXt.release();                             // row pitch changes with n: force a fresh zeroed buffer
+  c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
   GB_CUDA(c, c->dU.reserve(n * n * sizeof(double)));
   GB_CUDA(c, c->dEval.reserve(n_c * sizeof(double)));
   GB_CUDA(c, c->dWt.reserve(n_cvt * n_c * sizeof(double)));
@@ -398,7 +405,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false;
   const size_t n_c = round_up(n, 512);
-  c->dUtXt.release();
+  c->dUtXt.release(); c->dUtXt2.release();
   c->dU.adopt(const_cast<double *>(U_dev), n * n * 8);          // borrowed: caller keeps it alive
   GB_CUDA(c, c->dEval.reserve(n_c * 8));
   GB_CUDA(c, c->dWt.reserve(n_cvt * n_c * 8));
@@ -524,18 +531,18 @@ static int lmm_check_ready(gb200_ctx *c, const char *who) {
 
 // association kernel on a device-resident rotated batch
 static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev,
-                         bool plink_rule = false) {
+                         bool plink_rule = false, cudaStream_t st = nullptr, unsigned int *ticket = nullptr) {
   LmmConst D = make_const(c);
   c->prm.plink_rule = plink_rule ? 1 : 0;
-  ProfScope ps(c, "lmm");
+  if (!st) st = c->stream;
+  if (!ticket) ticket = c->dTicket.as<unsigned int>();
+  ProfScope ps(c, "lmm", 1, st);
   const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
   if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
   if (v2_ok && c->lmm_kernel != 1)
-    GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, c->dTicket.as<unsigned int>(),
-                                   c->num_sms, c->stream));
+    GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));
   else
-    GB_CUDA(c, launch_lmm_assoc((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, c->dTicket.as<unsigned int>(),
-                                c->num_sms, c->stream));
+    GB_CUDA(c, launch_lmm_assoc((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));
   return GB200_OK;
 }
 
@@ -634,9 +641,9 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
 // rotate a device-resident bed batch into UtXt (l x n): int8 tensor-core path for n >= 1024
 // (or when forced), FP64 decode + dgemm otherwise.  idx_dev maps analysed position -> ni_total index.
 static int project_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
-                           size_t l, size_t bytes_per_snp) {
+                           size_t l, size_t bytes_per_snp, double *dst = nullptr) {
   const size_t n = c->n;
-  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
+  if (!dst) { GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream)); dst = c->dUtXt.as<double>(); }
   bool use_i8 = false;
   if (c->utx_path == 2) {
     if (!i8_available(c)) return set_err(c, GB200_ERR_UNSUPPORTED, "int8 tensor-core path not available (no cuTensorMapEncodeTiled)");
@@ -644,18 +651,51 @@ static int project_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const int
   } else if (c->utx_path == 0) {
     use_i8 = i8_available(c) && n >= 1024;
   }
-  if (use_i8) return i8_project_bed(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, c->dUtXt.as<double>());
+  if (use_i8) return i8_project_bed(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, dst);
   GB_CUDA(c, c->dX.reserve(n * l * 8));
   {
     ProfScope ps(c, "decode", 2);
     GB_CUDA(c, launch_bed_decode(bed_dev, l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
     GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
   }
-  return project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+  return project_fp64_snpmajor(c, c->dX.as<double>(), l, dst);
 }
 
 static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                         size_t l, size_t bytes_per_snp, gb200_sumstat *out_dev) {
+  // Software pipeline over sub-batches: the projection of sub-batch i+1 (tensor pipe, main stream) runs while the
+  // per-SNP tests of sub-batch i (FP64 pipe, side stream) are in flight; U^T X is double buffered.
+  const size_t SUB = 2048;
+  if (c->overlap && l >= 2 * SUB) {
+    if (!c->side) {
+      GB_CUDA(c, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        GB_CUDA(c, cudaEventCreateWithFlags(&c->evG[k], cudaEventDisableTiming));
+        GB_CUDA(c, cudaEventCreateWithFlags(&c->evL[k], cudaEventDisableTiming));
+      }
+    }
+    GB_CUDA(c, reserve_zeroed(c->dUtXt, SUB * c->n_c * 8, c->stream));
+    GB_CUDA(c, reserve_zeroed(c->dUtXt2, SUB * c->n_c * 8, c->stream));
+    double *buf[2] = {c->dUtXt.as<double>(), c->dUtXt2.as<double>()};
+    unsigned int *ticket = c->dTicket.as<unsigned int>() + 4;           // separate ticket word for the side stream
+    size_t i = 0;
+    for (size_t s0 = 0; s0 < l; s0 += SUB, ++i) {
+      const size_t lc = (l - s0 < SUB) ? (l - s0) : SUB;
+      const int b = (int)(i & 1);
+      if (i >= 2) GB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evL[b], 0));     // tests of sub-batch i-2 released the buffer
+      int rc = project_bed_dev(c, bed_dev + s0 * bytes_per_snp, idx_dev, ni_total, lc, bytes_per_snp, buf[b]);
+      if (rc) return rc;
+      GB_CUDA(c, cudaEventRecord(c->evG[b], c->stream));
+      GB_CUDA(c, cudaStreamWaitEvent(c->side, c->evG[b], 0));
+      rc = lmm_assoc_dev(c, buf[b], lc, c->n_c, out_dev + s0, /*plink_rule=*/true, c->side, ticket);
+      if (rc) return rc;
+      GB_CUDA(c, cudaEventRecord(c->evL[b], c->side));
+    }
+    // the caller's stream observes completion of everything
+    GB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evL[0], 0));
+    GB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evL[1], 0));
+    return GB200_OK;
+  }
   int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
   if (rc) return rc;
   return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, out_dev, /*plink_rule=*/true);   // AnalyzePlink semantics

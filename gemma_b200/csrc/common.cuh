@@ -85,6 +85,12 @@ struct gb200_ctx {
   gb::DevBuf dX, dUtXt, dOut, dBed, dMask, dIdx, dTicket, dTmp;
   std::vector<int> idx_host;          // analysed-individual index cache for bed batches
   std::vector<unsigned char> mask_host;
+  // sub-batch software pipeline: projection of sub-batch i+1 (tensor pipe) overlaps the per-SNP tests of
+  // sub-batch i (FP64 pipe) on a second stream; both kernels are sized to co-reside on an SM
+  cudaStream_t side = nullptr;
+  cudaEvent_t evG[2] = {nullptr, nullptr}, evL[2] = {nullptr, nullptr};
+  gb::DevBuf dUtXt2;
+  long overlap = 1;           // 0 = serial (one sub-batch), 1 = pipelined sub-batches when the batch is large enough
   long kernel_launches = 0;   // kernels of this library launched so far (bench "gpu_launches")
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
@@ -125,16 +131,18 @@ struct ProfScope {
     if (!c->event_pool.empty()) { cudaEvent_t ev = c->event_pool.back(); c->event_pool.pop_back(); return ev; }
     cudaEvent_t ev; cudaEventCreate(&ev); return ev;
   }
-  ProfScope(gb200_ctx *ctx, const char *name, long n_launch = 1) : c(ctx), launches(n_launch) {
+  cudaStream_t st;
+  ProfScope(gb200_ctx *ctx, const char *name, long n_launch = 1, cudaStream_t stream = nullptr)
+      : c(ctx), launches(n_launch), st(stream ? stream : ctx->stream) {
     if (!c->prof) return;
     e = &c->profs[name];
     a = get_event(c); b = get_event(c);
-    cudaEventRecord(a, c->stream);
+    cudaEventRecord(a, st);
   }
   ~ProfScope() {
     c->kernel_launches += launches;
     if (!e) return;
-    cudaEventRecord(b, c->stream);
+    cudaEventRecord(b, st);
     e->pending.emplace_back(a, b);
     e->launches++;
   }

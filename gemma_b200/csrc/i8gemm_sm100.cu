@@ -332,7 +332,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 2)     // <= 128 registers: leaves room for a co-resident per-SNP CTA
 i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const I8KernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -712,8 +712,9 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     static bool attr2 = false;
     if (!attr2) { GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
     int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
+    const size_t smem_pair = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK) + 256;   // A + half of B per stage
     ProfScope ps(c, "utx");
-    i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+    i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
     GB_CUDA(c, cudaGetLastError());
   } else {
     if (c->i8.tmap_b_half) {

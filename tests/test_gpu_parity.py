@@ -494,3 +494,25 @@ def test_plink_entry_point_follows_analyzeplink_nan_rule(ctx):
     ctx.set_option("lmm_kernel", 0)
     if len(ranges) > 2:
         assert n_nan > 0          # at least one probed range exercised the NaN branch through both kernels
+
+
+def test_subbatch_pipeline_is_bitwise_identical_to_serial(ctx):
+    """Batches >= 4096 SNPs are software-pipelined (projection of sub-batch i+1 overlaps the tests of sub-batch i on a
+    second stream): same kernels, same inputs -> identical bits, in SNP order."""
+    n, l = 1280, 4500
+    pb = random_problem(n, 1, 4, 33)
+    bed, G = synth.make_bed(n, l, seed=34, miss_rate=0.005)
+    ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
+    nm = ctx.lmm_null(pb["trace_G"])
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ctx.set_option("overlap", 0)
+    serial = ctx.lmm_batch_bed(bed, n)
+    ctx.set_option("overlap", 1)
+    piped = ctx.lmm_batch_bed(bed, n)
+    for k in serial.dtype.names:
+        assert np.array_equal(serial[k], piped[k], equal_nan=True), k
+    idx = np.arange(0, l, 211)
+    X = O.lmm_impute(np.where(G[idx] < 0, np.nan, G[idx]))
+    ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], pb["U"].T @ X, 4, l_mle_null=nm["l_mle_null"],
+                            logl_mle_H0=nm["logl_mle_H0"], plink=True)
+    check_sumstat(piped[idx], ref, 4)
