@@ -90,7 +90,8 @@ struct gb200_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t evG[2] = {nullptr, nullptr}, evL[2] = {nullptr, nullptr};
   gb::DevBuf dUtXt2;
-  long overlap = 1;           // 0 = serial (one sub-batch), 1 = pipelined sub-batches when the batch is large enough
+  long overlap = 0;           // 1 = pipelined sub-batches.  Measured SLOWER on B200 (136 vs 113 ms per 8192 SNPs at n = 50 000:
+                              // the co-resident kernels contend and the power cap bites harder), so off by default
   long kernel_launches = 0;   // kernels of this library launched so far (bench "gpu_launches")
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core

@@ -182,7 +182,8 @@ GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, co
  * (error-free U slicing, integer genotypes only); n_slices of the int8 path; lmm_kernel 0 auto,
  * 1 warp-per-SNP kernel, 2 lockstep-CTA pipeline kernel (n_cvt <= 3, n_region <= 64); cta_pair /
  * kin_cta_pair 0|1 run the projection / kinship tensor-core kernel as CTA pairs (cta_group::2);
- * kin_path 0 auto, 1 FP64 only. */
+ * kin_path 0 auto, 1 FP64 only; overlap 0|1 pipelines 2048-SNP sub-batches of the bed entry points on two streams
+ * (projection of sub-batch i+1 || tests of sub-batch i; measured slower on B200, default 0). */
 GB200_API int gb200_set_option(gb200_ctx *ctx, const char *name, long value);
 
 #ifdef __cplusplus
