@@ -421,8 +421,50 @@ def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0, cta_pair=-1):
 
 
 def run_gk(args):
+    """--workload gk [--gpus N]: every rank accumulates K over its own SNP range, one NCCL all-reduce combines them."""
+    import torch
+    import torch.distributed as dist
+    import gemma_b200
+    from gemma_b200 import synth, shard
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     n = args.n if args.n != 50000 else 10000
-    print(json.dumps(measure_gk(n, max(args.batch, 16384), args.steps, max(3, args.warmup), cta_pair=args.cta_pair)))
+    if world == 1:
+        print(json.dumps(measure_gk(n, max(args.batch, 16384), args.steps, max(3, args.warmup), cta_pair=args.cta_pair)))
+        return
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
+    ctx = gemma_b200.Context(local, stream=stream.cuda_stream)
+    B, K, Wm = max(args.batch, 16384), args.steps, max(3, args.warmup)
+    bps = (n + 3) // 4
+    beds = [synth.make_bed_torch(n, B, dev, seed=SEED, snp_offset=(rank * (K + Wm) + k) * B) for k in range(K + Wm)]
+    def run(lo, hi):
+        ctx.kin_begin(n, 1)
+        for k in range(lo, hi):
+            ctx.kin_add_bed_dev(beds[k].data_ptr(), B, bps)
+        ptr, ns = ctx.kin_finish_dev()
+        Kt = shard.device_tensor(ptr, (n, n))
+        return shard.combine_partial_kinship(Kt, ns)
+    run(0, Wm)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    Kt, ns = run(Wm, Wm + K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        p = world * K * B
+        flops = float(n) * (n + 1) * p
+        print(json.dumps({"metric": "gk_centered_kinship_tflops", "value": flops / (ms.item() * 1e-3) / 1e12,
+                          "unit": "TFLOP/s (n(n+1)p, one triangle)", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms.item() / K,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+                          "dtype": "int8 x int8 -> int32 exact (+FP64 rank-one centring)",
+                          "config": {"workload": "-gk 1, n=%d, %d SNPs per step per GPU, SNP ranges per rank + one NCCL all-reduce of K" % (n, B),
+                                     "ns_total": ns, "trace_over_n": float(torch.diagonal(Kt).mean().item())}}))
+    dist.destroy_process_group()
 
 
 def main():

@@ -32,3 +32,29 @@ def gather_sumstat(local, n_snps, group=None, dst=0):
         return None
     parts = [out[r, :sizes[r]].cpu().numpy() for r in range(world)]
     return np.concatenate(parts, axis=0).reshape(-1).view(SUMSTAT_DTYPE)
+
+
+def combine_partial_kinship(K_local, ns_local, group=None):
+    """-gk across ranks: every rank accumulated K over ITS SNP range and scaled it by its own
+    1/ns (gb200_kin_finish); the global matrix is sum_r ns_r K_r / sum_r ns_r -- one all-reduce of n^2 doubles plus one
+    of the SNP counts.  K_local: torch tensor (CUDA with NCCL, CPU with gloo), modified in place and returned."""
+    import torch
+    import torch.distributed as dist
+    cnt = torch.tensor([float(ns_local)], dtype=torch.float64, device=K_local.device)
+    K_local.mul_(float(ns_local))
+    dist.all_reduce(K_local, group=group)
+    dist.all_reduce(cnt, group=group)
+    K_local.div_(cnt.item())
+    return K_local, int(cnt.item())
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of a device buffer owned by the library (no copy)."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, shape):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, shape), device=torch.device("cuda", torch.cuda.current_device()))

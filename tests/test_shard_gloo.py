@@ -46,3 +46,29 @@ def test_two_rank_gloo_gather_preserves_snp_order(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_two_rank_gloo_partial_kinship_reduce(tmp_path):
+    script = tmp_path / "k.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np, torch, torch.distributed as dist
+        from gemma_b200 import shard
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        rng = np.random.default_rng(5)
+        n, p = 9, 31
+        X = rng.standard_normal((n, p))
+        lo, hi = shard.snp_range(p, rank, world)
+        Kloc = torch.from_numpy(X[:, lo:hi] @ X[:, lo:hi].T / (hi - lo))
+        K, ns = shard.combine_partial_kinship(Kloc, hi - lo)
+        assert ns == p and np.allclose(K.numpy(), X @ X.T / p, atol=1e-13)
+        if rank == 0: print("KIN_OK")
+        dist.destroy_process_group()
+    """ % ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29572", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert "KIN_OK" in r.stdout, r.stdout + r.stderr
