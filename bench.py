@@ -308,6 +308,12 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks = measured_peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")        # per-launch DRAM bytes from the committed ncu capture of this exact config
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("n") == n and tj.get("batch") == B and tj.get("slices") == (args.slices or 6):
+            traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
     utx_ms, utx_n = prof["utx"]
     lmm_ms, lmm_n = prof["lmm"]
     flops_per_launch = 2.0 * n * n * B                    # 2 n^2 per SNP x SNPs per launch
@@ -316,7 +322,8 @@ def run_b200(args):
         ach = flops_per_launch / (utx_ms / utx_n * 1e-3) / 1e12
         roof = {"kernel": "i8_gemm_kernel (U^T X projection)" if (args.utx_path != 1 and n >= 1024) else "dgemm_kernel (FP64 U^T X)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": ach / peaks["bf16"],
-                "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained",
+                "traffic": traffic.get("i8_gemm_pair_kernel") if (args.utx_path != 1 and n >= 1024 and args.cta_pair != 0) else None,
+                "peak_source": peaks["source"] + ", bf16 sustained",
                 "note": "algorithmic FP64-equivalent flops 2*n^2 per SNP; the int8 path executes n_slices x as many "
                         "integer MACs (see DESIGN.md)",
                 "share_of_step": utx_ms / ms, "avg_launch_ms": utx_ms / utx_n}
@@ -326,6 +333,7 @@ def run_b200(args):
         a = by / (lmm_ms / lmm_n * 1e-3) / 1e9
         lmm_roof = {"kernel": "lmm_assoc_kernel (fused per-SNP tests)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "share_of_step": lmm_ms / ms, "avg_launch_ms": lmm_ms / lmm_n,
+                    "traffic": traffic.get("lmm_assoc_v2_kernel") if args.lmm_kernel != 1 else None,
                     "note": "algorithmic bytes 8n+64 per SNP; the kernel is FP64-pipe bound by construction (~16 lockstep passes, ~1000 FP64 "
                             "instructions per individual and SNP): see DESIGN.md 4.1"}
 
