@@ -3,39 +3,47 @@
 // (non-integer) genotypes, for U^T W / U^T y, and as the generic kinship accumulator;
 // integer genotypes take the tensor-core path in i8gemm_sm100.cu.
 //
-// 128x128x16 CTA tile, 256 threads, 8x8 register tile per thread, operands staged in
-// shared memory k-major so the inner product reads 16-byte vectors without bank
-// conflicts.  Element strides are arbitrary (covers N/T on either operand and
-// gsl_matrix sub-views with tda != size2); the global->shared loader picks the thread
-// mapping that makes the unit-stride dimension the fastest varying one (coalesced).
+// 128x128x16 CTA tile, 8 warps x (8x4) DMMA m8n8k4 tiles on the FP64 tensor pipe, operands staged in shared
+// memory k-major.  Element strides are arbitrary (covers N/T on either operand and gsl_matrix sub-views with
+// tda != size2).
 #include "common.cuh"
 
 namespace gb {
 
-constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
-constexpr int PADM = BM + 2, PADN = BN + 2;
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int PITCH = 132;      // doubles per k-row of the staged tiles: 132 = 4 (mod 16) keeps the DMMA fragment loads conflict-free
 
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe.  Fragment layout (PTX mma.m8n8k4.f64):
+// a: row = lane/4, k = lane%4 ; b: k = lane%4, col = lane/4 ; c/d: row = lane/4, cols = 2*(lane%4) + {0,1}
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// 128x128x16 CTA tile, 8 warps in a 2 (m) x 4 (n) grid, each warp 64x32 = 8x4 DMMA tiles (64 accumulators / thread).
+// Operands are staged k-major in shared memory; element strides are arbitrary (N/T, gsl sub-views); the loader picks
+// the thread mapping that makes the unit-stride dimension the fastest varying one (coalesced).
 template <bool LOWER_ONLY>
 __global__ void __launch_bounds__(256) dgemm_kernel(size_t M, size_t N, size_t K, double alpha,
                                                     const double *__restrict__ A, size_t sam, size_t sak,
                                                     const double *__restrict__ B, size_t sbk, size_t sbn,
                                                     double beta, double *__restrict__ C, size_t ldc) {
-  __shared__ __align__(16) double As[BK][PADM];
-  __shared__ __align__(16) double Bs[BK][PADN];
+  __shared__ __align__(16) double As[BK][PITCH];
+  __shared__ __align__(16) double Bs[BK][PITCH];
   const size_t m0 = (size_t)blockIdx.y * BM, n0 = (size_t)blockIdx.x * BN;
   if (LOWER_ONLY && n0 > m0 + BM - 1) return;     // tile entirely above the diagonal
-  const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;        // thread tile origin: rows ty*8.., cols tx*8..
-  double acc[TM][TN];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;     // warp tile origin inside the CTA tile
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[8][4][2];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
   const bool a_kfast = (sak == 1);
   const bool b_nfast = (sbn == 1);
   for (size_t k0 = 0; k0 < K; k0 += BK) {
-    // ---- stage A tile (BM x BK) -> As[k][m]
 #pragma unroll
     for (int r = 0; r < (BM * BK) / 256; ++r) {
       int mm, kk;
@@ -46,7 +54,6 @@ __global__ void __launch_bounds__(256) dgemm_kernel(size_t M, size_t N, size_t K
       if (gm < M && gk < K) v = A[gm * sam + gk * sak];
       As[kk][mm] = v;
     }
-    // ---- stage B tile (BK x BN) -> Bs[k][n]
 #pragma unroll
     for (int r = 0; r < (BN * BK) / 256; ++r) {
       int nn, kk;
@@ -59,37 +66,34 @@ __global__ void __launch_bounds__(256) dgemm_kernel(size_t M, size_t N, size_t K
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      double a[TM], b[TN];
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < TM; i += 2) {
-        const double2 t = *reinterpret_cast<const double2 *>(&As[kk][ty * TM + i]);
-        a[i] = t.x; a[i + 1] = t.y;
-      }
+      for (int i = 0; i < 8; ++i) a[i] = As[kk + fk][wm + i * 8 + fr];
 #pragma unroll
-      for (int j = 0; j < TN; j += 2) {
-        const double2 t = *reinterpret_cast<const double2 *>(&Bs[kk][tx * TN + j]);
-        b[j] = t.x; b[j + 1] = t.y;
-      }
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk + fk][wn + j * 8 + fr];
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const size_t gm = m0 + ty * TM + i;
+  for (int i = 0; i < 8; ++i) {
+    const size_t gm = m0 + wm + i * 8 + fr;
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const size_t gn = n0 + tx * TN + j;
-      if (gn >= N) continue;
-      if (LOWER_ONLY && gn > gm) continue;
-      double *c = C + gm * ldc + gn;
-      const double prev = (beta == 0.0) ? 0.0 : beta * (*c);
-      *c = fma(alpha, acc[i][j], prev);
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const size_t gn = n0 + wn + j * 8 + fk * 2 + q;
+        if (gn >= N) continue;
+        if (LOWER_ONLY && gn > gm) continue;
+        double *c = C + gm * ldc + gn;
+        const double prev = (beta == 0.0) ? 0.0 : beta * (*c);
+        *c = fma(alpha, acc[i][j][q], prev);
+      }
     }
   }
 }
