@@ -516,3 +516,67 @@ def test_subbatch_pipeline_is_bitwise_identical_to_serial(ctx):
     ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], pb["U"].T @ X, 4, l_mle_null=nm["l_mle_null"],
                             logl_mle_H0=nm["logl_mle_H0"], plink=True)
     check_sumstat(piped[idx], ref, 4)
+
+
+# ---- PLINK trio through the CLI (AnalyzePlink / PlinkKin surface) against the oracle's PLINK restatement ---------
+def _write_plink(prefix, bed, y, rs_prefix="snp"):
+    l, nb = bed.shape
+    n = len(y)
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01])); f.write(bed.tobytes())
+    with open(prefix + ".bim", "w") as f:
+        for s in range(l):
+            f.write("%d\t%s%d\t0\t%d\tA\tG\n" % (1 + s % 19, rs_prefix, s, 1000 + 10 * s))
+    with open(prefix + ".fam", "w") as f:
+        for i in range(n):
+            f.write("F%d I%d 0 0 1 %s\n" % (i, i, "NA" if np.isnan(y[i]) else "%.10g" % y[i]))
+
+
+def test_cli_plink_gk_and_lmm4_match_oracle(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+    if not os.path.exists(cli):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    n, l = 1150, 900
+    rng = np.random.default_rng(3)
+    bed, G = synth.make_bed(n, l, seed=444, miss_rate=0.01)
+    bed[5] = 0xFF                                     # a monomorphic SNP (all 0) -> dropped by QC
+    y = rng.standard_normal(n) + 0.4 * np.where(G[7] < 0, 0, G[7])
+    y[rng.choice(n, 37, replace=False)] = np.nan      # individuals without phenotype are excluded from the LMM
+    prefix = str(tmp_path / "syn")
+    _write_plink(prefix, bed, y)
+    out = str(tmp_path / "out")
+    r = subprocess.run([cli, "-bfile", prefix, "-gk", "1", "-o", "k", "-outdir", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([cli, "-bfile", prefix, "-k", out + "/k.cXX.txt", "-lmm", "4", "-o", "a", "-outdir", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # oracle side
+    pl = R.Plink(prefix)
+    idv, W = R.process_cvt_phen(pl.ind_pheno)
+    isnp, n_miss, maf = R.qc_plink(pl, idv)
+    assert "## number of analyzed individuals = %d" % int(idv.sum()) in r.stdout
+    assert "## number of analyzed SNPs         = %8d" % int(isnp.sum()) in r.stdout and isnp[5] == 0
+    K = np.loadtxt(out + "/k.cXX.txt")
+    Kref = R.kinship_plink(pl, isnp, 1)
+    assert np.allclose(K, Kref, rtol=1e-8, atol=1e-9)                      # 10 significant digits in the text file
+    prep = R.lmm_prepare(K, idv, pl.pheno[:, 0], W)
+    keep = idv == 1
+    X = O.lmm_impute(pl.G[np.ix_(np.nonzero(isnp)[0], keep)])
+    ref = O.lmm_analyze_utx(prep["eval"], prep["UtW"], prep["Uty"], prep["U"].T @ X, 4, l_mle_null=prep["l_mle_null"],
+                            logl_mle_H0=prep["logl_mle_H0"], plink=True)
+    lines = open(out + "/a.assoc.txt").read().splitlines()
+    hdr = lines[0].split("\t")
+    assert hdr == ["chr", "rs", "ps", "n_miss", "allele1", "allele0", "af", "beta", "se", "logl_H1", "l_remle", "l_mle",
+                   "p_wald", "p_lrt", "p_score"]
+    assert len(lines) == 1 + int(isnp.sum())
+    sel = np.nonzero(isnp)[0]
+    got = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:]])
+    for ln, s in zip(lines[1:], sel):
+        f = ln.split("\t")
+        assert f[1] == "snp%d" % s and int(f[3]) == int(n_miss[s]) and f[6] == "%.3f" % maf[s]
+    # text carries 7 significant digits; the eigendecomposition differs (cuSOLVER vs LAPACK) only in rounding
+    for col, key in zip(range(8), ("beta", "se", "logl_H1", "lambda_remle", "lambda_mle", "p_wald", "p_lrt", "p_score")):
+        tol = 2e-4 if key.startswith("lambda") else 2e-6
+        assert np.allclose(got[:, col], ref[key], rtol=tol, atol=1e-12), key
