@@ -29,6 +29,15 @@ class NullModel(C.Structure):
                  "vg_mle", "ve_mle", "vg_remle", "ve_remle")]
 
 
+class SnpQC(C.Structure):
+    _fields_ = [("n_miss", C.c_int), ("n_0", C.c_int), ("n_1", C.c_int), ("n_2", C.c_int),
+                ("maf", C.c_double), ("v_x", C.c_double), ("v_w", C.c_double)]
+
+
+SNPQC_DTYPE = np.dtype([("n_miss", "<i4"), ("n_0", "<i4"), ("n_1", "<i4"), ("n_2", "<i4"), ("maf", "<f8"), ("v_x", "<f8"),
+                        ("v_w", "<f8")])
+
+
 class GB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("%s: %s" % (STATUS.get(code, code), msg))
@@ -57,6 +66,7 @@ SIGNATURES = {
     "gb200_kin_finish_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "gb200_eigh": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _vp, _sz, _vp, _dp, C.POINTER(C.c_int),
                              C.POINTER(C.c_int)]),
+    "gb200_qc_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp]),
     "gb200_lmm_setup": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
     "gb200_lmm_setup_rotated": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gb200_lmm_setup_rotated_dev": (C.c_int, [_vp, _sz, _sz, _vp, _vp, _vp, _vp]),
@@ -199,6 +209,18 @@ class Context:
         self._chk(self.lib.gb200_eigh(self.h, _ptr(G), n, n, int(center), _ptr(U), n, _ptr(ev), C.byref(tr),
                                       C.byref(nz), C.byref(nn)))
         return U, ev, tr.value, nz.value
+
+    # ---- SNP QC statistics (PLINK)
+    def qc_bed(self, bed, ni_total, idv_mask=None, W=None):
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        m = None if idv_mask is None else np.ascontiguousarray(idv_mask, dtype=np.uint8)
+        out = np.zeros(bed.shape[0], dtype=SNPQC_DTYPE)
+        Wc = WtWi = None; c = 0
+        if W is not None:
+            Wc = _f64(W); c = Wc.shape[1]; WtWi = _f64(np.linalg.inv(Wc.T @ Wc))
+        self._chk(self.lib.gb200_qc_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1], _ptr(Wc), _ptr(WtWi),
+                                        c, _ptr(out)))
+        return out
 
     # ---- -lmm
     def lmm_setup(self, U, eval_, W, y):

@@ -781,4 +781,50 @@ int gb200_lmm_project_bed(gb200_ctx *c, const unsigned char *bed, const unsigned
   return GB200_OK;
 }
 
+int gb200_qc_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l,
+                 size_t bytes_per_snp, const double *W, const double *WtWi, size_t n_cvt, gb200_snpqc *out) {
+  if (!c) return GB200_ERR_ARG;
+  if (l == 0) return GB200_OK;
+  if (!bed || !out || bytes_per_snp != (ni_total + 3) / 4 || (W && (!WtWi || n_cvt == 0 || n_cvt > GB200_MAX_CVT)))
+    return set_err(c, GB200_ERR_ARG, "gb200_qc_bed: bad argument");
+  // analysed-individual gather index (independent of any lmm_setup state)
+  std::vector<int> idx;
+  size_t n_test = ni_total;
+  if (idv_mask) { for (size_t i = 0; i < ni_total; ++i) if (idv_mask[i]) idx.push_back((int)i); n_test = idx.size(); }
+  if (n_test == 0) return set_err(c, GB200_ERR_ARG, "gb200_qc_bed: no analysed individuals");
+  DevBuf dIdx, dW, dOutQ;
+  auto fail = [&](cudaError_t e, const char *what) {
+    dIdx.release(); dW.release(); dOutQ.release();
+    return set_err(c, GB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  if (idv_mask) {
+    if ((e = dIdx.reserve(n_test * sizeof(int))) != cudaSuccess) return fail(e, "alloc idx");
+    if ((e = cudaMemcpyAsync(dIdx.p, idx.data(), n_test * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "copy idx");
+  }
+  const double *dWp = nullptr, *dWi = nullptr;
+  if (W) {
+    if ((e = dW.reserve((n_test * n_cvt + n_cvt * n_cvt) * sizeof(double))) != cudaSuccess) return fail(e, "alloc W");
+    if ((e = cudaMemcpyAsync(dW.p, W, n_test * n_cvt * 8, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "copy W");
+    if ((e = cudaMemcpyAsync(dW.as<double>() + n_test * n_cvt, WtWi, n_cvt * n_cvt * 8, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "copy WtWi");
+    dWp = dW.as<double>(); dWi = dWp + n_test * n_cvt;
+  }
+  const size_t chunk = 1 << 16;
+  if ((e = dOutQ.reserve(chunk * sizeof(gb200_snpqc))) != cudaSuccess) return fail(e, "alloc out");
+  for (size_t s0 = 0; s0 < l; s0 += chunk) {
+    const size_t lc = (l - s0 < chunk) ? (l - s0) : chunk;
+    if ((e = c->dBed.reserve(lc * bytes_per_snp)) != cudaSuccess) return fail(e, "alloc bed");
+    if ((e = cudaMemcpyAsync(c->dBed.p, bed + s0 * bytes_per_snp, lc * bytes_per_snp, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return fail(e, "copy bed");
+    {
+      ProfScope ps(c, "decode");
+      if ((e = launch_qc_bed(c->dBed.as<unsigned char>(), lc, bytes_per_snp, idv_mask ? dIdx.as<int>() : nullptr, (int)n_test, dWp, dWi,
+                             (int)n_cvt, dOutQ.as<gb200_snpqc>(), c->stream)) != cudaSuccess) return fail(e, "qc kernel");
+    }
+    if ((e = cudaMemcpyAsync(out + s0, dOutQ.p, lc * sizeof(gb200_snpqc), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return fail(e, "copy out");
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return fail(e, "sync");
+  }
+  dIdx.release(); dW.release(); dOutQ.release();
+  return GB200_OK;
+}
+
 }  // extern "C"

@@ -174,6 +174,8 @@ cudaError_t launch_kin_transform(double *G, size_t l, size_t n, size_t ldg, int 
 cudaError_t launch_lmm_impute(double *G, size_t l, size_t n, size_t ldg, cudaStream_t st);
 cudaError_t launch_bed_decode(const unsigned char *bed, size_t l, size_t bytes_per_snp, const int *idx,
                               size_t n_out, double *G, size_t ldg, cudaStream_t st);
+cudaError_t launch_qc_bed(const unsigned char *bed, size_t l, size_t bytes_per_snp, const int *idx, int n_test,
+                          const double *W, const double *WtWi, int n_cvt, gb200_snpqc *out, cudaStream_t st);
 cudaError_t launch_center_matrix(double *G, size_t n, size_t ldg, double *row_sums, cudaStream_t st);
 
 }  // namespace gb

@@ -101,6 +101,76 @@ cudaError_t launch_bed_decode(const unsigned char *bed, size_t l, size_t bytes_p
   return cudaGetLastError();
 }
 
+// SNP QC statistics from PLINK rows (ReadFile_bed counting pass + r2 terms, src/gemma_io.cpp:951-1046)
+__global__ void __launch_bounds__(128) qc_bed_kernel(const unsigned char *__restrict__ bed, size_t bytes_per_snp,
+                                                     const int *__restrict__ idx, int n_test, const double *__restrict__ W,
+                                                     const double *__restrict__ WtWi, int n_cvt, gb200_snpqc *__restrict__ out) {
+  __shared__ int sh_i[4][4];
+  __shared__ double sh_d[4][GB200_MAX_CVT + 1];
+  const unsigned char *row = bed + (size_t)blockIdx.x * bytes_per_snp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cnt[4] = {0, 0, 0, 0};                  // n_miss, n_0, n_1, n_2
+  for (int p = threadIdx.x; p < n_test; p += 128) {
+    const size_t j = idx ? (size_t)idx[p] : (size_t)p;
+    const unsigned b = ((unsigned)row[j >> 2] >> (2 * (j & 3))) & 3u;
+    // bits (hi,lo): 00 -> 2 copies, 10 -> 1, 11 -> 0, 01 -> missing
+    cnt[b == 1u ? 0 : b == 3u ? 1 : b == 2u ? 2 : 3]++;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int v = cnt[q];
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) sh_i[warp][q] = v;
+  }
+  __syncthreads();
+  int tot[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tot[q] = sh_i[0][q] + sh_i[1][q] + sh_i[2][q] + sh_i[3][q];
+  const double maf = (double)(tot[2] + 2 * tot[3]) / (2.0 * (double)(n_test - tot[0]));
+  double v_x = 0.0, v_w = 0.0;
+  if (W) {
+    double acc[GB200_MAX_CVT + 1];
+#pragma unroll
+    for (int a = 0; a <= GB200_MAX_CVT; ++a) acc[a] = 0.0;
+    for (int p = threadIdx.x; p < n_test; p += 128) {
+      const size_t j = idx ? (size_t)idx[p] : (size_t)p;
+      const unsigned b = ((unsigned)row[j >> 2] >> (2 * (j & 3))) & 3u;
+      const double x = b == 0u ? 2.0 : b == 2u ? 1.0 : b == 3u ? 0.0 : maf * 2.0;
+      acc[GB200_MAX_CVT] += x * x;
+      for (int a = 0; a < n_cvt; ++a) acc[a] += W[(size_t)p * n_cvt + a] * x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a <= GB200_MAX_CVT; ++a) {
+      const double v = warp_allsum(acc[a]);
+      if (lane == 0) sh_d[warp][a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double wtx[GB200_MAX_CVT];
+      for (int a = 0; a < n_cvt; ++a) wtx[a] = sh_d[0][a] + sh_d[1][a] + sh_d[2][a] + sh_d[3][a];
+      v_x = sh_d[0][GB200_MAX_CVT] + sh_d[1][GB200_MAX_CVT] + sh_d[2][GB200_MAX_CVT] + sh_d[3][GB200_MAX_CVT];
+      for (int a = 0; a < n_cvt; ++a) {
+        double t = 0.0;
+        for (int b2 = 0; b2 < n_cvt; ++b2) t += WtWi[a * n_cvt + b2] * wtx[b2];
+        v_w += wtx[a] * t;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    gb200_snpqc r;
+    r.n_miss = tot[0]; r.n_0 = tot[1]; r.n_1 = tot[2]; r.n_2 = tot[3]; r.maf = maf; r.v_x = v_x; r.v_w = v_w;
+    out[blockIdx.x] = r;
+  }
+}
+
+cudaError_t launch_qc_bed(const unsigned char *bed, size_t l, size_t bytes_per_snp, const int *idx, int n_test,
+                          const double *W, const double *WtWi, int n_cvt, gb200_snpqc *out, cudaStream_t st) {
+  if (l == 0) return cudaSuccess;
+  qc_bed_kernel<<<(unsigned)l, 128, 0, st>>>(bed, bytes_per_snp, idx, n_test, W, WtWi, n_cvt, out);
+  return cudaGetLastError();
+}
+
 // CenterMatrix: G <- G - (Gw 1^T + 1 Gw^T)/n + (1^T G 1 / n^2) 11^T, evaluated from the
 // upper triangle and mirrored (the reference updates the upper triangle with dsyr2/dsyr
 // and copies it to the lower one, src/mathfunc.cpp:157-171).

@@ -363,8 +363,9 @@ static void qc_bimbam(Run &R) {
 static vector<unsigned char> g_bed;      // whole .bed payload (without the 3 magic bytes)
 static size_t g_nbit = 0;
 
-// QC pass over a PLINK .bed: ReadFile_bed, src/gemma_io.cpp:876-1064
-static void qc_plink(Run &R) {
+// QC pass over a PLINK .bed: ReadFile_bed, src/gemma_io.cpp:876-1064.  With a context the per-SNP counting and the
+// r2 terms run on the device (gb200_qc_bed); the thresholds are applied here in the reference's order.
+static void qc_plink(Run &R, gb200_ctx *ctx) {
   std::ifstream in(R.P.file_bfile + ".bed", std::ios::binary);
   if (!in) die("error reading bed file:" + R.P.file_bfile + ".bed");
   g_nbit = (R.ni_total + 3) / 4;
@@ -373,6 +374,30 @@ static void qc_plink(Run &R) {
   in.seekg(3);
   in.read(reinterpret_cast<char *>(g_bed.data()), (std::streamsize)g_bed.size());
   R2Filter r2; r2.init(R);
+  if (ctx) {
+    vector<unsigned char> mask(R.ni_total); for (size_t i = 0; i < R.ni_total; ++i) mask[i] = (unsigned char)R.indicator_idv[i];
+    vector<gb200_snpqc> st(R.ns_total);
+    const bool with_w = r2.c != 1;
+    if (gb200_qc_bed(ctx, g_bed.data(), mask.data(), R.ni_total, R.ns_total, g_nbit, with_w ? r2.W.data() : nullptr,
+                     with_w ? r2.WtWi.data() : nullptr, with_w ? r2.c : 0, st.data()) != 0)
+      die(string("gb200_qc_bed: ") + gb200_last_error(ctx));
+    for (size_t t = 0; t < R.ns_total; ++t) {
+      SnpInfo &s = R.snpInfo[t];
+      if (!R.setSnps.empty() && !R.setSnps.count(s.rs)) { s.n_miss = -9; s.missingness = -9; s.maf = -9; R.indicator_snp.push_back(0); continue; }
+      const gb200_snpqc &q = st[t];
+      const size_t n_miss = (size_t)q.n_miss, n_0 = (size_t)q.n_0, n_1 = (size_t)q.n_1, n_2 = (size_t)q.n_2;
+      const double maf = q.maf;
+      s.n_miss = (long)n_miss; s.missingness = (double)n_miss / (double)R.ni_test; s.maf = maf; s.n_idv = (long)(R.ni_test - n_miss);
+      int keep = 1;
+      if ((double)n_miss / (double)R.ni_test > R.P.miss_level) keep = 0;
+      else if ((maf < R.P.maf_level || maf > (1.0 - R.P.maf_level)) && R.P.maf_level != -1) keep = 0;
+      else if ((n_0 + n_1) == 0 || (n_1 + n_2) == 0 || (n_2 + n_0) == 0) keep = 0;
+      else if (R.P.hwe_level != 0 && R.P.maf_level != -1 && hwe_exact(n_0, n_2, n_1) < R.P.hwe_level) keep = 0;
+      else if (with_w && q.v_w / q.v_x > R.P.r2_level) keep = 0;
+      R.indicator_snp.push_back(keep); R.ns_test += keep;
+    }
+    return;
+  }
   vector<double> geno(R.ni_test); vector<char> miss(R.ni_test);
   for (size_t t = 0; t < R.ns_total; ++t) {
     SnpInfo &s = R.snpInfo[t];
@@ -744,7 +769,9 @@ int main(int argc, char **argv) {
   else read_pheno(R);
   if (!P.file_cvt.empty()) read_cvt(R);
   process_cvt_phen(R);
-  if (!P.file_bfile.empty()) qc_plink(R); else qc_bimbam(R);
+  gb200_ctx *ctx = nullptr;
+  if (!P.qc_only && gb200_create(&ctx, P.device, nullptr) != GB200_OK) die("no CUDA device: gemma-b200 has no CPU fallback");
+  if (!P.file_bfile.empty()) qc_plink(R, ctx); else qc_bimbam(R);
   print_counts(R);
   if (P.qc_only) {
     std::ofstream out(out_path(R, "qc"));
@@ -755,8 +782,6 @@ int main(int argc, char **argv) {
   }
   if (R.ns_test == 0) die("number of analyzed SNPs equals 0");
 
-  gb200_ctx *ctx = nullptr;
-  if (gb200_create(&ctx, P.device, nullptr) != GB200_OK) die("no CUDA device: gemma-b200 has no CPU fallback");
   if (P.a_mode == 21 || P.a_mode == 22) run_kinship(R, ctx); else run_lmm(R, ctx);
   R.t_total = now_s() - t_start;
   write_log(R);

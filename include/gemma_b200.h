@@ -124,6 +124,17 @@ GB200_API int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int ce
                double *U, size_t ldu, double *eval, double *trace_G,
                int *n_zero, int *n_negative);
 
+/* ---- SNP QC statistics for PLINK input ------------------------------------- */
+/* The per-SNP counting pass of ReadFile_bed (src/gemma_io.cpp:951-1005) and the covariate-correlation terms of its
+ * -r2 filter (:1031-1046) on the device: for each of the l SNP rows, over the analysed individuals (idv_mask),
+ * n_miss / genotype class counts / maf = sum/(2(n - n_miss)); when W != NULL also v_x = x'x and
+ * v_w = (W'x)' WtWi (W'x) with missing genotypes imputed as 2*maf.  The caller applies the thresholds in the
+ * reference's order (miss, maf, polymorphism, hwe, r2).  W: n_test x n_cvt row-major; WtWi: n_cvt x n_cvt. */
+typedef struct { int n_miss, n_0, n_1, n_2; double maf, v_x, v_w; } gb200_snpqc;
+GB200_API int gb200_qc_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
+                 size_t l, size_t bytes_per_snp, const double *W, const double *WtWi, size_t n_cvt,
+                 gb200_snpqc *out);
+
 /* ---- -lmm : per-run setup, null model, per-batch association ---------------- */
 /* Uploads the run-constant state of LMM::Analyze (src/lmm.cpp:1474-1511): U (n x n,
  * eigenvectors in columns), eval, W (n x n_cvt) and y; computes UtW = U^T W and

@@ -580,3 +580,27 @@ def test_cli_plink_gk_and_lmm4_match_oracle(tmp_path):
     for col, key in zip(range(8), ("beta", "se", "logl_H1", "lambda_remle", "lambda_mle", "p_wald", "p_lrt", "p_score")):
         tol = 2e-4 if key.startswith("lambda") else 2e-6
         assert np.allclose(got[:, col], ref[key], rtol=tol, atol=1e-12), key
+
+
+def test_qc_bed_statistics_match_host_restatement(ctx):
+    """gb200_qc_bed (device counting pass of ReadFile_bed + r2 terms) vs the oracle's numpy restatement."""
+    n_total, l = 777, 300
+    rng = np.random.default_rng(8)
+    bed, G = synth.make_bed(n_total, l, seed=9, miss_rate=0.03)
+    mask = np.ones(n_total, dtype=np.uint8); mask[rng.choice(n_total, 40, replace=False)] = 0
+    Gk = np.where(G < 0, np.nan, G)[:, mask == 1]
+    W = np.column_stack([rng.standard_normal(int(mask.sum())), np.ones(int(mask.sum()))])
+    st = ctx.qc_bed(bed, n_total, mask, W)
+    miss = np.isnan(Gk)
+    assert np.array_equal(st["n_miss"], miss.sum(axis=1))
+    assert np.array_equal(st["n_0"], (Gk == 0).sum(axis=1)) and np.array_equal(st["n_1"], (Gk == 1).sum(axis=1))
+    assert np.array_equal(st["n_2"], (Gk == 2).sum(axis=1))
+    maf = np.nansum(Gk, axis=1) / (2.0 * (Gk.shape[1] - miss.sum(axis=1)))
+    assert np.array_equal(st["maf"], maf)                                   # integer sums: bit-exact
+    X = np.where(miss, (2.0 * maf)[:, None], Gk)
+    WtWi = np.linalg.inv(W.T @ W)
+    Wtx = X @ W
+    assert np.allclose(st["v_x"], (X * X).sum(axis=1), rtol=1e-13)
+    assert np.allclose(st["v_w"], np.einsum("sa,ab,sb->s", Wtx, WtWi, Wtx), rtol=1e-10)
+    st2 = ctx.qc_bed(bed, n_total)                                           # no mask, no covariates
+    assert np.array_equal(st2["n_miss"], (G < 0).sum(axis=1)) and np.all(st2["v_w"] == 0)
