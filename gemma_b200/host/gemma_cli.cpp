@@ -47,7 +47,7 @@ struct SnpInfo {   // SNPINFO, src/param.h:37-51
 };
 
 struct Params {
-  string file_geno, file_pheno, file_anno, file_cvt, file_bfile, file_kin, file_ku, file_kd, file_snps, file_ksnps;
+  string file_geno, file_pheno, file_anno, file_cvt, file_bfile, file_kin, file_ku, file_kd, file_snps, file_ksnps, file_gwasnps, loco;
   string path_out = "./output/", file_out = "result";
   vector<size_t> p_column;
   int a_mode = 0;            // 21/22 -gk, 31 -eigen, 1/2/3/4/9 -lmm
@@ -134,7 +134,7 @@ struct Run {
   vector<vector<double>> cvt; vector<int> ind_cvt; size_t n_cvt = 1;
   vector<int> indicator_idv; size_t ni_total = 0, ni_test = 0;
   std::map<string, std::tuple<string, long, double>> anno;
-  std::set<string> setSnps, setKSnps;
+  std::set<string> setSnps, setKSnps, setGWASnps;
   vector<SnpInfo> snpInfo; vector<int> indicator_snp; size_t ns_total = 0, ns_test = 0;
   std::map<string, int> mapID2num;
   // results
@@ -245,9 +245,6 @@ static void read_fam(Run &R) {                         // ReadFile_fam, src/gemm
 
 static void process_cvt_phen(Run &R) {                 // ProcessCvtPhen + CheckCvt, src/param.cpp:1993-2098, 1937-1990
   R.ni_total = R.ind_pheno.size();
-  if (R.P.nind >= 0 && (size_t)R.P.nind < R.ni_total) {    // -nind: keep the first nind individuals (src/param.cpp:263-272)
-    for (size_t i = (size_t)R.P.nind; i < R.ni_total; ++i) for (auto &v : R.ind_pheno[i]) v = 0;
-  }
   R.indicator_idv.assign(R.ni_total, 1);
   for (size_t i = 0; i < R.ni_total; ++i) for (int v : R.ind_pheno[i]) if (!v) R.indicator_idv[i] = 0;
   if (!R.ind_cvt.empty()) {
@@ -272,6 +269,19 @@ static void process_cvt_phen(Run &R) {                 // ProcessCvtPhen + Check
     }
   }
   if (R.ind_cvt.empty()) { R.cvt.assign(R.ni_total, vector<double>(1, 1.0)); R.ind_cvt.assign(R.ni_total, 1); R.n_cvt = 1; }
+}
+
+// -nind (BIMBAM only; the PLINK branch rebuilds indicator_idv afterwards, src/param.cpp:247-274): trim_individuals,
+// src/param.cpp:74-90, applied after ProcessCvtPhen (:315-316).  The vector is cut to the NUMBER of set flags seen
+// when the scan stops, i.e. the first min(#set, nind) individuals of the file, and ni_total / ni_test follow
+// (CheckData, src/param.cpp:1033-1041).
+static void trim_individuals(Run &R) {
+  if (R.P.nind <= 0 || !R.P.file_bfile.empty()) return;
+  size_t count = 0;
+  for (int v : R.indicator_idv) { if (v) count++; if (count >= (size_t)R.P.nind) break; }
+  if (count == R.indicator_idv.size()) return;
+  R.indicator_idv.resize(count); R.ni_total = count;
+  R.ni_test = 0; for (int v : R.indicator_idv) R.ni_test += v;
 }
 
 // W (ni_test x n_cvt) and y (ni_test) of the analysed individuals: CopyCvtPhen, src/param.cpp:2146-2198
@@ -484,7 +494,7 @@ static void run_kinship(Run &R, gb200_ctx *ctx) {
       if (cur >= R.indicator_snp.size()) break;
       if (!R.indicator_snp[cur]) continue;
       char *p = tok(&line[0]); if (!p) continue;
-      if (!R.setKSnps.empty() && !R.setKSnps.count(p)) continue;       // -ksnps, src/gemma_io.cpp:1479
+      if (!R.setKSnps.empty() && !R.setKSnps.count(p)) continue;       // -ksnps / -loco, src/gemma_io.cpp:1479
       p = tok(nullptr); p = tok(nullptr);
       double *g = G.data() + l * R.ni_total;
       for (size_t i = 0; i < R.ni_total; ++i) {
@@ -572,6 +582,7 @@ static void write_assoc(const Run &R) {                // LMM::WriteFiles, src/l
   size_t t = 0;
   for (size_t i = 0; i < R.snpInfo.size(); ++i) {
     if (!R.indicator_snp[i]) continue;
+    if (!R.setGWASnps.empty() && !R.setGWASnps.count(R.snpInfo[i].rs)) continue;     // src/lmm.cpp:209-210
     const SnpInfo &s = R.snpInfo[i]; const gb200_sumstat &st = R.sumStat[t++];
     out << s.chr << "\t" << s.rs << "\t" << s.bp << "\t" << s.n_miss << "\t" << s.a_minor << "\t" << s.a_major << "\t"
         << std::fixed << std::setprecision(3) << s.maf << "\t";
@@ -651,7 +662,9 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
       const size_t cur = t++;
       if (cur >= R.indicator_snp.size()) break;
       if (!R.indicator_snp[cur]) continue;
-      char *p = tok(&line[0]); p = tok(nullptr); p = tok(nullptr);
+      char *p = tok(&line[0]);
+      if (!R.setGWASnps.empty() && (!p || !R.setGWASnps.count(p))) continue;       // -gwasnps / -loco, src/lmm.cpp:1585-1587
+      p = tok(nullptr); p = tok(nullptr);
       double *g = G.data() + l * n; size_t pos = 0;
       for (size_t i = 0; i < R.ni_total; ++i) {
         p = tok(nullptr);
@@ -725,6 +738,8 @@ int main(int argc, char **argv) {
     else if (a == "-u") P.file_ku = need(i);
     else if (a == "-snps") P.file_snps = need(i);
     else if (a == "-ksnps") P.file_ksnps = need(i);
+    else if (a == "-gwasnps") P.file_gwasnps = need(i);
+    else if (a == "-loco") P.loco = need(i);
     else if (a == "-o") P.file_out = need(i);
     else if (a == "-outdir") P.path_out = need(i);
     else if (a == "-n") { while (i + 1 < argc && argv[i + 1][0] != '-') P.p_column.push_back((size_t)atoi(argv[++i])); }
@@ -764,11 +779,20 @@ int main(int argc, char **argv) {
   std::cout << "Reading Files ... " << std::endl;
   if (!P.file_snps.empty()) read_snp_set(P.file_snps, R.setSnps);
   if (!P.file_ksnps.empty()) read_snp_set(P.file_ksnps, R.setKSnps);
+  if (!P.file_gwasnps.empty()) read_snp_set(P.file_gwasnps, R.setGWASnps);
   if (!P.file_anno.empty()) read_anno(R);
+  if (!P.loco.empty()) {                                                           // src/param.cpp:923-933, 52-66, 497-500
+    if (P.file_anno.empty()) die("LOCO requires annotation file (-a switch)");
+    if (!P.file_ksnps.empty()) die("LOCO does not allow -ksnps switch");
+    if (!P.file_gwasnps.empty()) die("LOCO does not allow -gwasnps switch");
+    if (!P.file_bfile.empty()) die("LOCO with PLINK input mis-aligns rows in the reference (its own tests are disabled); use BIMBAM input");
+    for (const auto &kv : R.anno) (std::get<0>(kv.second) != P.loco ? R.setKSnps : R.setGWASnps).insert(kv.first);
+  }
   if (!P.file_bfile.empty()) { read_bim(R); read_fam(R); if (!P.file_pheno.empty()) { R.pheno.clear(); R.ind_pheno.clear(); read_pheno(R); } }
   else read_pheno(R);
   if (!P.file_cvt.empty()) read_cvt(R);
   process_cvt_phen(R);
+  trim_individuals(R);
   gb200_ctx *ctx = nullptr;
   if (!P.qc_only && gb200_create(&ctx, P.device, nullptr) != GB200_OK) die("no CUDA device: gemma-b200 has no CPU fallback");
   if (!P.file_bfile.empty()) qc_plink(R, ctx); else qc_bimbam(R);

@@ -116,7 +116,7 @@ def qc_bimbam(bb, indicator_idv, W=None, miss_level=0.05, maf_level=0.01, r2_lev
               snps=None):
     """src/gemma_io.cpp:639-873 ReadFile_geno QC pass. Returns (indicator_snp, n_miss, maf)."""
     keep = indicator_idv == 1
-    G = bb.G[:, keep]
+    G = bb.G[:, :len(keep)][:, keep]          # only the first len(indicator) columns are parsed (:702)
     ni_test = int(keep.sum())
     p = G.shape[0]
     ind = np.zeros(p, dtype=np.int32)
@@ -152,13 +152,37 @@ def qc_bimbam(bb, indicator_idv, W=None, miss_level=0.05, maf_level=0.01, r2_lev
     return ind, n_miss_a, maf_a
 
 
-def kinship_bimbam(bb, indicator_snp, k_mode=1, batch=20000):
-    """src/gemma_io.cpp:1418-1597 BimbamKin: all ni_total individuals, selected SNPs."""
+def trim_individuals(indicator, ni_max):
+    """src/param.cpp:74-90 (-nind, a test-speed switch): the vector is resized to the NUMBER of set flags
+    seen before the scan stops (i.e. min(#set, ni_max)), not to the position of the ni_max-th set flag."""
+    if not ni_max:
+        return indicator
+    count = 0
+    for v in indicator:
+        if v:
+            count += 1
+        if count >= ni_max:
+            break
+    return indicator[:count] if count != len(indicator) else indicator
+
+
+def loco_sets(anno, loco):
+    """src/param.cpp:52-66 LOCO_set_Snps: (ksnps, gwasnps) = annotated SNPs off / on chromosome `loco`."""
+    ks = {rs for rs, v in anno.items() if v[0] != loco}
+    gw = {rs for rs, v in anno.items() if v[0] == loco}
+    return ks, gw
+
+
+def kinship_bimbam(bb, indicator_snp, k_mode=1, batch=20000, ni_total=None, ksnps=None):
+    """src/gemma_io.cpp:1418-1597 BimbamKin: all ni_total individuals (the first ni_total columns under -nind),
+    SNPs with indicator 1 that are also in ksnps when that set is non-empty (:1478-1480)."""
     sel = np.nonzero(indicator_snp)[0]
-    n = bb.G.shape[1]
+    if ksnps:
+        sel = np.array([t for t in sel if bb.rs[t] in ksnps], dtype=np.int64)
+    n = bb.G.shape[1] if ni_total is None else ni_total
     K = np.zeros((n, n))
     for s in range(0, len(sel), batch):
-        Xc = O.kin_transform(bb.G[sel[s:s + batch]], k_mode)
+        Xc = O.kin_transform(bb.G[sel[s:s + batch], :n], k_mode)
         K += Xc @ Xc.T            # the dgemm of :1554 (BLAS instead of the oracle's O(n^2 l) loop)
     K *= 1.0 / len(sel)
     return K
@@ -196,7 +220,7 @@ def lmm_prepare(K_total, indicator_idv, y_total, W_total):
 def lmm_genotypes_bimbam(bb, indicator_snp, indicator_idv, sel=None):
     """src/lmm.cpp:1590-1618: analysed individuals only, mean-imputed; returns X n x l."""
     idx = np.nonzero(indicator_snp)[0] if sel is None else sel
-    keep = indicator_idv == 1
+    keep = np.nonzero(indicator_idv == 1)[0]
     return O.lmm_impute(bb.G[np.ix_(idx, keep)])
 
 

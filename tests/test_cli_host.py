@@ -54,6 +54,23 @@ def test_bxd_covariates_maf_r2_qc(golden_dir, tmp_path):
     assert int(isnp.sum()) == 7317
 
 
+def test_mouse_nind_snps_selection(golden_dir, tmp_path):
+    """-nind 400 -snps list (the LOCO test's inputs, test/dev_tests.rb:57-63): same individuals / SNPs as the oracle."""
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    out, rows = _qc(["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt",
+                     "-a", d + "/mouse_hs1940.anno.txt", "-snps", d + "/mouse_hs1940_snps.txt", "-nind", "400",
+                     "-loco", "1"], tmp_path, "loco")
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1,))
+    idv, W = R.process_cvt_phen(ind)
+    idv = R.trim_individuals(idv, 400)
+    snps = {ln.split()[0] for ln in open(d + "/mouse_hs1940_snps.txt") if ln.strip()}
+    isnp, n_miss, maf = R.qc_bimbam(bb, idv, snps=snps)
+    assert "## number of total individuals = 400" in out
+    assert "## number of analyzed individuals = %d" % int(idv.sum()) in out
+    assert np.array_equal(np.array([int(r[1]) for r in rows]), isnp)
+
+
 def test_cli_rejects_unknown_flags_and_missing_inputs():
     _build()
     r = subprocess.run([CLI, "-bogus"], capture_output=True, text=True)

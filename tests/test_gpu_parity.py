@@ -401,6 +401,32 @@ def test_cli_mouse_gk_then_lmm_matches_demo_txt(golden_dir, tmp_path):
         assert h[7:] == ["beta", "se", "logl_H1", "l_remle", "l_mle", "p_wald", "p_lrt", "p_score"]
 
 
+def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
+    """test/dev_tests.rb:57-77 and test/dev_test_suite.sh:121-153, text for text."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+    if not os.path.exists(cli):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    e = EXP["mouse_loco"]
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt",
+            "-snps", d + "/mouse_hs1940_snps.txt", "-nind", "400", "-loco", "1", "-outdir", str(tmp_path)]
+    r = subprocess.run([cli] + base + ["-gk", "-o", "loco"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    txt = open(tmp_path / "loco.cXX.txt").read()
+    assert len(txt.splitlines()) == e["cxx_lines"] and txt[:5] == e["cxx_head5"]
+    assert "%.2f" % sum(float("%.2f" % float(w[:6])) for w in txt.split()) == e["cxx_sum2"]
+    r = subprocess.run([cli] + base + ["-n", "1", "-k", str(tmp_path / "loco.cXX.txt"), "-lmm", "-no-check", "-o", "loco"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(tmp_path / "loco.assoc.txt").read().splitlines()
+    assert len(lines) == e["assoc_lines"]
+    assert lines[2].split("\t")[9] == e["row2_logl_H1"]
+    assert "%.6e" % max(float(l.split("\t")[11]) for l in lines[1:]) == e["max_p_wald"]
+    assert all(l.split("\t")[0] == "1" for l in lines[1:])            # only chromosome-1 SNPs are tested
+
+
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
 def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     n = 1300

@@ -73,6 +73,29 @@ def test_mouse_kinship_and_lmm1_rows(mouse):
         assert "%.6e" % r["lambda_remle"] == e["l_remle"] and "%.6e" % r["p_wald"] == e["p_wald"]
 
 
+def test_mouse_loco_nind_pins(mouse, golden_dir):
+    """test/dev_tests.rb:57-77 + test/dev_test_suite.sh:121-153: -snps list, -nind 400, -loco 1."""
+    e = EXP["mouse_loco"]
+    bb = mouse["bb"]
+    with open(os.path.join(golden_dir, "mouse_hs1940", "mouse_hs1940_snps.txt")) as f:
+        snps = {ln.split()[0] for ln in f if ln.strip()}
+    idv = R.trim_individuals(mouse["idv"], 400)
+    assert len(idv) == 400
+    isnp, _, _ = R.qc_bimbam(bb, idv, snps=snps)
+    ks, gw = R.loco_sets(mouse["anno"], "1")
+    K = R.kinship_bimbam(bb, isnp, 1, ni_total=400, ksnps=ks)
+    txt = "\n".join("\t".join("%.10g" % v for v in row) for row in K)       # WriteMatrix, src/param.cpp:1899-1906
+    assert K.shape[0] == e["cxx_lines"] and txt[:5] == e["cxx_head5"]
+    tot = sum(float("%.2f" % float(w[:6])) for w in txt.split())               # the perl one-liner of dev_test_suite.sh:132
+    assert "%.2f" % tot == e["cxx_sum2"]
+    prep = R.lmm_prepare(R.text_roundtrip(K), idv, mouse["ph"][:400, 0], mouse["W"][:400])
+    sel = np.array([t for t in np.nonzero(isnp)[0] if bb.rs[t] in gw])
+    assert len(sel) + 1 == e["assoc_lines"]
+    out = R.lmm_analyze(prep, R.lmm_genotypes_bimbam(bb, isnp, idv, sel), 1)
+    assert "%.6e" % out["logl_H1"][1] == e["row2_logl_H1"]
+    assert "%.6e" % out["p_wald"].max() == e["max_p_wald"]
+
+
 def test_bxd_lmm2_lmm9_pins(golden_dir):
     d = os.path.join(golden_dir, "BXD")
     bb = R.Bimbam(os.path.join(d, "BXD_geno.txt.gz"))
