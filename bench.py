@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cta-pair", type=int, default=-1, help="tensor-core kernels as CTA pairs (cta_group::2): -1 library default, 0, 1")
     ap.add_argument("--overlap", type=int, default=-1, help="sub-batch pipeline (projection || per-SNP tests): -1 default, 0, 1")
     ap.add_argument("--workload", default="lmm", choices=["lmm", "gk"], help="lmm: SNPs/s of -lmm (headline); gk: K=XX^T TFLOP/s")
+    ap.add_argument("--gk-miss", type=float, default=0.0, help="--workload gk: fraction of missing genotypes in the synthetic data")
     ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="SNPs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -327,6 +328,11 @@ def run_b200(args):
                 "note": "algorithmic FP64-equivalent flops 2*n^2 per SNP; the int8 path executes n_slices x as many "
                         "integer MACs (see DESIGN.md)",
                 "share_of_step": utx_ms / ms, "avg_launch_ms": utx_ms / utx_n}
+        if args.utx_path != 1 and n >= 1024:
+            T = args.slices or 6
+            roof["executed"] = {"tops_int8": ach * T, "digit_planes": T, "frac_of_2x_bf16_peak": ach * T / (2.0 * peaks["bf16"]),
+                                "note": "integer MACs actually issued on the tensor pipe (T exact int8 digit planes of U per "
+                                        "FP64-equivalent product); the dense int8 rate of sm_100a is 2x the bf16 rate"}
     lmm_roof = None
     if lmm_n:
         by = (8.0 * n + 64.0) * B
@@ -377,7 +383,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0, cta_pair=-1):
+def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0, cta_pair=-1, miss=0.0):
     """BASELINE config 2: -gk 1 (centred kinship) on synthetic n x p PLINK genotypes, 1 GPU.
     Reported with the algorithmic flops of ONE triangle, n(n+1)p."""
     import torch
@@ -390,7 +396,7 @@ def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0, cta_pair=-1):
     if cta_pair >= 0:
         ctx.set_option("cta_pair", cta_pair)
     bps = (n + 3) // 4
-    beds = [synth.make_bed_torch(n, B, dev, seed=SEED, snp_offset=k * B) for k in range(K + Wm)]
+    beds = [synth.make_bed_torch(n, B, dev, seed=SEED, snp_offset=k * B, miss_rate=miss) for k in range(K + Wm)]
     ctx.kin_begin(n, 1)
     for k in range(Wm):
         ctx.kin_add_bed_dev(beds[k].data_ptr(), B, bps)
@@ -409,15 +415,17 @@ def measure_gk(n, B, K, Wm, ctx=None, stream=None, local=0, cta_pair=-1):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    kin_ms, kin_n = ctx.profile_get("kin"); dec_ms, _ = ctx.profile_get("decode")
+    kin_ms, kin_n = ctx.profile_get("kin"); dec_ms, _ = ctx.profile_get("decode"); fix_ms, fix_n = ctx.profile_get("fix")
     p = K * B
     flops = float(n) * (n + 1) * p
     peaks = measured_peaks()
     line = {"metric": "gk_centered_kinship_tflops", "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s (n(n+1)p, one triangle)",
             "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8 x int8 -> int32 exact (+FP64 rank-one centring)", "data": "synthetic",
-            "config": {"workload": "-gk 1 centred kinship, n=%d individuals, %d SNPs per step (PLINK 2-bit, no missing)" % (n, B),
-                       "n": n, "snps_per_step": B, "snps_per_sec": p / (ms * 1e-3)},
+            "config": {"workload": "-gk 1 centred kinship, n=%d individuals, %d SNPs per step (PLINK 2-bit, %s)"
+                                   % (n, B, ("%.3g%% missing genotypes" % (100 * miss)) if miss else "no missing"),
+                       "n": n, "snps_per_step": B, "snps_per_sec": p / (ms * 1e-3), "missing_rate": miss,
+                       "sparse_missing_terms_ms": fix_ms, "sparse_missing_launches": fix_n},
             "clocks": clocks,
             "roofline": {"kernel": "i8_gemm_kernel (mode 1: K += Z Z^T)", "bound": "tensor",
                          "achieved": (flops / (kin_ms * 1e-3) / 1e12) if kin_n else None, "peak": peaks["bf16"], "unit": "TFLOP/s",
@@ -437,7 +445,7 @@ def run_gk(args):
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     n = args.n if args.n != 50000 else 10000
     if world == 1:
-        print(json.dumps(measure_gk(n, max(args.batch, 16384), args.steps, max(3, args.warmup), cta_pair=args.cta_pair)))
+        print(json.dumps(measure_gk(n, max(args.batch, 16384), args.steps, max(3, args.warmup), cta_pair=args.cta_pair, miss=args.gk_miss)))
         return
     torch.cuda.set_device(local); dev = torch.device("cuda", local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -141,6 +141,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "kin_cta_pair must be 0 or 1");
     c->kin_cta_pair = value; return GB200_OK;
   }
+  if (!strcmp(name, "kin_miss_max_permille")) {
+    if (value < 0 || value > 1000) return set_err(c, GB200_ERR_ARG, "kin_miss_max_permille must be in 0..1000");
+    c->kin_miss_max = (double)value / 1000.0; return GB200_OK;
+  }
   if (!strcmp(name, "kin_path")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "kin_path must be 0 or 1");
     c->kin_path = value; return GB200_OK;

@@ -50,6 +50,9 @@ struct I8State {
   DevBuf kin_stats;              // per staged SNP: int sum, int nmiss, double mean
   DevBuf kin_a;                  // a[i] = sum_s mean_s z_s[i]  (n doubles) + beta + flag
   DevBuf kin_tiles;              // lower-triangle tile list (int2)
+  DevBuf kin_qbits;              // missing-genotype bit rows: n x (kin_cap / 64) 64-bit words
+  DevBuf kin_y;                  // Y (n x n) + b (n): sparse missing-genotype corrections, allocated on first use
+  bool kin_y_used = false;
   size_t kin_cap = 0, kin_fill = 0, kin_n = 0;
   int kin_num_tiles = 0, kin_num_tiles_pair = 0;
   bool tmap_b_half = false;
@@ -98,7 +101,8 @@ struct gb200_ctx {
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
   long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)
-  long kin_path = 0;     // 0 auto (int8 tensor cores for centred K without missing genotypes), 1 = FP64 only
+  long kin_path = 0;     // 0 auto (int8 tensor cores for centred K; sparse FP64 terms for missing genotypes), 1 = FP64 only
+  double kin_miss_max = 0.2;   // chunks with a larger fraction of missing genotypes take the dense FP64 path
   long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)
   gb::I8State i8;

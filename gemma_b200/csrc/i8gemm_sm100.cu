@@ -744,7 +744,8 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
 // .bed (SNP-major 2-bit) -> individual-major int8 tile, plus per-SNP integer sum / missing count
 __global__ void __launch_bounds__(256) bed_transpose_i8_kernel(const unsigned char *__restrict__ bed, size_t bps, int n,
                                                                int l, int8_t *__restrict__ Zt, size_t pitch, size_t col0,
-                                                               int *__restrict__ sum, int *__restrict__ nmiss) {
+                                                               int *__restrict__ sum, int *__restrict__ nmiss,
+                                                               unsigned long long *__restrict__ qbits, size_t qpitch) {
   __shared__ int8_t tile[128][132];
   const int s0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
   const int r = threadIdx.x >> 1, half = threadIdx.x & 1;      // SNP row r, individuals half*64 .. +63
@@ -760,8 +761,8 @@ __global__ void __launch_bounds__(256) bed_transpose_i8_kernel(const unsigned ch
       int8_t v = 0;
       if (inb && ib + q < n) {
         const unsigned b = (byte >> (2 * q)) & 3u;
-        if (b == 0u) v = 2; else if (b == 2u) v = 1; else if (b == 1u) my_miss++;
-        my_sum += v;
+        if (b == 0u) v = 2; else if (b == 2u) v = 1; else if (b == 1u) { my_miss++; v = -1; }   // -1 marks "missing" inside the tile only
+        my_sum += (v > 0) ? v : 0;
       }
       tile[half * 64 + bq * 4 + q][r] = v;
     }
@@ -772,14 +773,20 @@ __global__ void __launch_bounds__(256) bed_transpose_i8_kernel(const unsigned ch
   const int ii = i0 + r;
   if (ii < n) {
     int8_t *dst = Zt + (size_t)ii * pitch + col0 + (size_t)s0 + (size_t)half * 64;
+    unsigned long long mask = 0ull;                      // bit t: individual ii is missing at SNP s0 + half*64 + t
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int4 w;
       int8_t *wb = reinterpret_cast<int8_t *>(&w);
 #pragma unroll
-      for (int t = 0; t < 16; ++t) wb[t] = tile[r][half * 64 + q * 16 + t];
+      for (int t = 0; t < 16; ++t) {
+        int8_t v = tile[r][half * 64 + q * 16 + t];
+        if (v < 0) { mask |= 1ull << (q * 16 + t); v = 0; }
+        wb[t] = v;
+      }
       *reinterpret_cast<int4 *>(dst + q * 16) = w;
     }
+    if (qbits) qbits[(size_t)ii * qpitch + ((col0 + (size_t)s0) >> 6) + (size_t)half] = mask;
   }
 }
 
@@ -792,7 +799,7 @@ __global__ void kin_snp_stats_kernel(const int *__restrict__ sum, const int *__r
     const int nm = nmiss[s];
     const double m = (double)sum[s] / (double)(n - nm);
     mean[s] = m; m2 = m * m;
-    if (nm > 0) fl = 1.0;
+    fl = (double)nm;                                    // total number of missing genotypes in the chunk
   }
   m2 = warp_allsum(m2); fl = warp_allsum(fl);
   if ((threadIdx.x & 31) == 0) { if (m2 != 0.0) atomicAdd(&beta_flag[2], m2); if (fl != 0.0) atomicAdd(&beta_flag[1], fl); }
@@ -810,6 +817,119 @@ __global__ void __launch_bounds__(256) kin_a_kernel(const int8_t *__restrict__ Z
   if (lane == 0) a_pending[i] += acc;
 }
 
+// Missing genotypes on the int8 path.  The reference imputes a missing entry to the SNP mean, i.e. its centred value is
+// 0 (src/gemma_io.cpp:1688-1706): with z = 0 at missing entries and q the missing indicator,
+//   sum_s (z_si - m_s (1-q_si)) (z_sj - m_s (1-q_sj))
+//     = [Z Z^T]_ij - a_i - a_j + beta  +  X_ij + X_ji + G3_ij - b_i - b_j,
+//   X_ij = sum_s m_s z_si q_sj,  G3_ij = sum_s m_s^2 q_si q_sj,  b_i = sum_s m_s^2 q_si.
+// X and G3 are sparse in q: for each individual j this kernel walks the SNPs where j is missing (bit rows written by the
+// transposer) and adds  m_s z_s[i] + (m_s^2 / 2) q_s[i]  into row j of Y (so that Y + Y^T = X + X^T + G3), reading the
+// 2-bit SNP rows straight from the .bed chunk.  Work = (#missing entries) x n instead of a dense FP64 GEMM.
+constexpr int KFIX_CAP = 512;      // SNPs staged per pass: index + 4-entry value table (2 m, m^2/2, m, 0) indexed by the .bed code
+__global__ void __launch_bounds__(256) kin_miss_fix_kernel(const unsigned char *__restrict__ bed, size_t bps, int n, int l,
+                                                           const unsigned long long *__restrict__ qbits, size_t qpitch, size_t word0,
+                                                           const double *__restrict__ mean, double *__restrict__ Y,
+                                                           double *__restrict__ b) {
+  __shared__ int list_s[KFIX_CAP];
+  __shared__ __align__(16) double lut[KFIX_CAP][4];
+  __shared__ int warp_cnt[8];
+  __shared__ double warp_b[8];
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i_base = (blockIdx.y * 256 + tid) * 16;
+  const unsigned long long *qrow = qbits + (size_t)j * qpitch + word0;
+  const int nwords = (l + 63) >> 6;
+  const size_t byte0 = (size_t)(i_base >> 2);
+  const bool active = i_base < n;
+  const bool whole = active && byte0 + 4 <= bps;
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  double bsum = 0.0;
+  bool any = false;
+  for (int w0 = 0; w0 < nwords; w0 += 256) {
+    // every thread owns one 64-SNP word of the bit row; positions in the staged list follow the SNP order (deterministic sums)
+    const int w = w0 + tid;
+    unsigned long long bits = (w < nwords) ? __ldg(qrow + w) : 0ull;
+    const int cnt = __popcll(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_cnt[wid] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int c = warp_cnt[q]; if (q < wid) base += c; total += c; }
+    const int first = base + incl - cnt;                  // list position of this thread's first set bit
+    __syncthreads();
+    if (total == 0) continue;
+    any = true;
+    for (int seg0 = 0; seg0 < total; seg0 += KFIX_CAP) {
+      // stage the SNPs [seg0, seg0 + KFIX_CAP) of this pass
+      {
+        unsigned long long bb = bits; int pos = first;
+        while (bb) {
+          const int k = __ffsll((long long)bb) - 1;
+          bb &= bb - 1;
+          if (pos >= seg0 && pos < seg0 + KFIX_CAP) {
+            const int sidx = w * 64 + k;
+            const double m = __ldg(mean + sidx);
+            list_s[pos - seg0] = sidx;
+            lut[pos - seg0][0] = m + m; lut[pos - seg0][1] = 0.5 * m * m; lut[pos - seg0][2] = m; lut[pos - seg0][3] = 0.0;
+            if (blockIdx.y == 0) bsum += m * m;
+          }
+          ++pos;
+        }
+      }
+      __syncthreads();
+      const int cntseg = (total - seg0 < KFIX_CAP) ? (total - seg0) : KFIX_CAP;
+      if (active) {
+        int e = 0;
+        for (; e + 4 <= cntseg; e += 4) {
+          unsigned g[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned char *row = bed + (size_t)list_s[e + u] * bps + byte0;
+            if (whole) g[u] = (unsigned)row[0] | ((unsigned)row[1] << 8) | ((unsigned)row[2] << 16) | ((unsigned)row[3] << 24);
+            else {
+              g[u] = 0xFFFFFFFFu;
+              for (int q = 0; q < 4; ++q) if (byte0 + (size_t)q < bps) g[u] = (g[u] & ~(0xFFu << (8 * q))) | ((unsigned)row[q] << (8 * q));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double *L = lut[e + u];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc[t] += L[(g[u] >> (2 * t)) & 3u];
+          }
+        }
+        for (; e < cntseg; ++e) {
+          const unsigned char *row = bed + (size_t)list_s[e] * bps + byte0;
+          unsigned g = 0xFFFFFFFFu;
+          for (int q = 0; q < 4; ++q) if (byte0 + (size_t)q < bps) g = (g & ~(0xFFu << (8 * q))) | ((unsigned)row[q] << (8 * q));
+          const double *L = lut[e];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) acc[t] += L[(g >> (2 * t)) & 3u];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!any) return;                                        // uniform over the CTA
+  if (active) {
+    double *yrow = Y + (size_t)j * (size_t)n;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (i_base + t < n) yrow[i_base + t] += acc[t];
+  }
+  if (blockIdx.y == 0) {                                   // b[j] += sum of m_s^2 over the SNPs where j is missing (fixed reduction order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    if (lane == 0) warp_b[wid] = bsum;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int q = 0; q < 8; ++q) t += warp_b[q]; b[j] += t; }
+  }
+}
+
 __global__ void kin_commit_kernel(double *a, const double *a_pending, double *beta_flag, int n) {
   // fold the pending (checked, missing-free) chunk into the running totals
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -818,10 +938,12 @@ __global__ void kin_commit_kernel(double *a, const double *a_pending, double *be
 }
 
 __global__ void kin_finish_kernel(double *K, size_t n, size_t ld, const double *__restrict__ a, const double *__restrict__ beta_flag,
-                                  double inv_ns) {
+                                  const double *__restrict__ Y, const double *__restrict__ b, double inv_ns) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j > i || i >= n) return;
-  K[i * ld + j] = (K[i * ld + j] - a[i] - a[j] + beta_flag[0]) * inv_ns;
+  double v = K[i * ld + j] - a[i] - a[j] + beta_flag[0];
+  if (Y) v += (Y[i * n + j] + Y[j * n + i]) - b[i] - b[j];      // missing-genotype terms (kin_miss_fix_kernel)
+  K[i * ld + j] = v * inv_ns;
 }
 
 static bool make_tmap_rows(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t inner_bytes, uint64_t pitch_bytes,
@@ -852,6 +974,7 @@ static int kin_i8_setup(gb200_ctx *c) {
   GB_CUDA(c, S.kin_zt.reserve(n * cap));
   GB_CUDA(c, S.kin_stats.reserve(cap * (2 * sizeof(int) + sizeof(double))));
   GB_CUDA(c, S.kin_a.reserve((2 * n + 8) * sizeof(double)));
+  GB_CUDA(c, S.kin_qbits.reserve(n * (cap / 64) * sizeof(unsigned long long)));
   // lower-triangle tiles: 128-row x 256-column tiles that intersect j <= i
   std::vector<int2> tiles;
   const int m_tiles = (int)((n + 127) / 128);
@@ -873,7 +996,7 @@ static int kin_i8_setup(gb200_ctx *c) {
 
 int kin_i8_begin(gb200_ctx *c) {
   I8State &S = c->i8;
-  S.kin_used = false; S.kin_fill = 0;
+  S.kin_used = false; S.kin_fill = 0; S.kin_y_used = false;
   if (!kin_i8_eligible(c)) return GB200_OK;
   int rc = kin_i8_setup(c);
   if (rc) return rc;
@@ -937,7 +1060,8 @@ int kin_i8_add_chunk(gb200_ctx *c, const unsigned char *bed_dev, size_t l, size_
     GB_CUDA(c, cudaMemsetAsync(beta_flag + 1, 0, 2 * sizeof(double), c->stream));
     dim3 grid((unsigned)(lpad / 128), (unsigned)((n + 127) / 128));
     bed_transpose_i8_kernel<<<grid, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, (int)n, (int)l, S.kin_zt.as<int8_t>(), S.kin_cap,
-                                                         S.kin_fill, sum, nmiss);
+                                                         S.kin_fill, sum, nmiss, S.kin_qbits.as<unsigned long long>(),
+                                                         S.kin_cap / 64);
     kin_snp_stats_kernel<<<(unsigned)((l + 255) / 256), 256, 0, c->stream>>>(sum, nmiss, (int)n, (int)l, mean, beta_flag);
     kin_a_kernel<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>(S.kin_zt.as<int8_t>(), S.kin_cap, S.kin_fill, (int)l, (int)n, mean, a_pending);
     GB_CUDA(c, cudaGetLastError());
@@ -945,10 +1069,24 @@ int kin_i8_add_chunk(gb200_ctx *c, const unsigned char *bed_dev, size_t l, size_
   double flag = 0.0;
   GB_CUDA(c, cudaMemcpyAsync(&flag, beta_flag + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (flag != 0.0) {
-    // missing genotypes in this chunk: un-stage it (zero its columns) and let the FP64 path handle it
+  if (flag > c->kin_miss_max * (double)n * (double)l) {
+    // too many missing genotypes for the sparse correction to pay: un-stage the chunk (zero its columns), FP64 path
     GB_CUDA(c, cudaMemset2DAsync(S.kin_zt.as<int8_t>() + S.kin_fill, S.kin_cap, 0, lpad, n, c->stream));
     return GB200_OK;
+  }
+  if (flag != 0.0) {
+    // sparse missing-genotype terms of this chunk (the integer GEMM sees z = 0 at those entries)
+    if (!S.kin_y_used) {
+      GB_CUDA(c, S.kin_y.reserve((n * n + n) * sizeof(double)));
+      GB_CUDA(c, cudaMemsetAsync(S.kin_y.p, 0, (n * n + n) * sizeof(double), c->stream));
+      S.kin_y_used = true;
+    }
+    ProfScope ps(c, "fix", 1);
+    dim3 grid((unsigned)n, (unsigned)((n + 4095) / 4096));
+    kin_miss_fix_kernel<<<grid, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, (int)n, (int)l, S.kin_qbits.as<unsigned long long>(),
+                                                     S.kin_cap / 64, S.kin_fill / 64, mean, S.kin_y.as<double>(),
+                                                     S.kin_y.as<double>() + n * n);
+    GB_CUDA(c, cudaGetLastError());
   }
   kin_commit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a, a_pending, beta_flag, (int)n);
   GB_CUDA(c, cudaGetLastError());
@@ -967,7 +1105,8 @@ int kin_i8_finish(gb200_ctx *c, double inv_ns) {
   const size_t n = c->kin_n;
   double *a = S.kin_a.as<double>();
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
-  kin_finish_kernel<<<grid, 256, 0, c->stream>>>(c->dK.as<double>(), n, n, a, a + 2 * n, inv_ns);
+  const double *Y = S.kin_y_used ? S.kin_y.as<double>() : nullptr;
+  kin_finish_kernel<<<grid, 256, 0, c->stream>>>(c->dK.as<double>(), n, n, a, a + 2 * n, Y, Y ? Y + n * n : nullptr, inv_ns);
   GB_CUDA(c, cudaGetLastError());
   return GB200_OK;
 }

@@ -431,7 +431,7 @@ def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
 def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     n = 1300
     bed1, G1 = synth.make_bed(n, 700, seed=61)                       # no missing genotypes -> int8 path
-    bed2, G2 = synth.make_bed(n, 333, seed=62, miss_rate=0.02)       # missing -> FP64 fallback for this call
+    bed2, G2 = synth.make_bed(n, 333, seed=62, miss_rate=0.02)       # missing -> int8 GEMM + sparse FP64 correction terms
     bed3, G3 = synth.make_bed(n, 129, seed=63)                       # int8 again (odd size: padded to 256 columns)
     G = np.vstack([G1, G2, G3]); Gn = np.where(G < 0, np.nan, G)
     Xc = O.kin_transform(Gn, 1)
@@ -450,6 +450,42 @@ def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     ctx.kin_add_bed(np.vstack([bed1, bed2, bed3]))
     K2, _ = ctx.kin_finish()
     ctx.set_option("kin_path", 0)
+    assert np.allclose(K2, K, rtol=1e-10, atol=1e-12)
+
+
+def test_kinship_missing_genotypes_sparse_terms_and_dense_fallback(ctx):
+    """Missing genotypes (imputed to the SNP mean by the reference, src/gemma_io.cpp:1688-1706): the int8 GEMM sees 0 there and
+    the per-individual sparse kernel adds the X + X^T + G3 - b terms; chunks above the missing-rate limit take the dense FP64
+    path.  Both must reproduce the oracle, also with a whole individual / a whole-SNP-but-one missing and n not a multiple of 16."""
+    n = 1237
+    bed1, G1 = synth.make_bed(n, 517, seed=71, miss_rate=0.004)
+    bed2, G2 = synth.make_bed(n, 300, seed=72, miss_rate=0.08)
+    bed3, G3 = synth.make_bed(n, 260, seed=73, miss_rate=0.35)       # above the default 20% limit -> dense FP64 for this call
+    # individual 5 missing everywhere in batch 1; SNP 9 of batch 2 observed in only 3 individuals
+    def set_missing(bed, G, s, i):
+        byte, sh = i >> 2, 2 * (i & 3)
+        bed[s, byte] = (int(bed[s, byte]) & (0xFF ^ (3 << sh))) | (1 << sh)
+        G[s, i] = -9
+    for s_ in range(G1.shape[0]): set_missing(bed1, G1, s_, 5)
+    for i_ in range(3, n): set_missing(bed2, G2, 9, i_)
+    G = np.vstack([G1, G2, G3]); Gn = np.where(G < 0, np.nan, G)
+    Xc = O.kin_transform(Gn, 1)
+    Kref = Xc @ Xc.T / G.shape[0]
+    ctx.profile_enable(True); ctx.profile_reset()
+    ctx.kin_begin(n, 1)
+    ctx.kin_add_bed(bed1); ctx.kin_add_bed(bed2); ctx.kin_add_bed(bed3)
+    K, ns = ctx.kin_finish()
+    prof = {k: ctx.profile_get(k) for k in ("kin", "fix")}
+    ctx.profile_enable(False)
+    assert ns == G.shape[0]
+    assert prof["kin"][1] >= 2 and prof["fix"][1] == 2, prof          # int8 GEMM + dense FP64 chunk; 2 sparse passes
+    assert np.allclose(K, Kref, rtol=1e-10, atol=1e-12)
+    assert np.array_equal(K, K.T)
+    ctx.set_option("kin_miss_max_permille", 0)                       # every chunk with a hole -> dense FP64
+    ctx.kin_begin(n, 1)
+    ctx.kin_add_bed(bed1); ctx.kin_add_bed(bed2); ctx.kin_add_bed(bed3)
+    K2, _ = ctx.kin_finish()
+    ctx.set_option("kin_miss_max_permille", 200)
     assert np.allclose(K2, K, rtol=1e-10, atol=1e-12)
 
 
