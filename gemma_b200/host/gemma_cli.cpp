@@ -35,6 +35,7 @@
 #include <chrono>
 
 #include "../../include/gemma_b200.h"
+#include "line_pipeline.h"
 
 using std::string;
 using std::vector;
@@ -315,55 +316,67 @@ struct R2Filter {            // the -r2 filter state (src/gemma_io.cpp:672-688, 
   }
 };
 
-// QC pass over a BIMBAM mean-genotype file: ReadFile_geno, src/gemma_io.cpp:639-873
+// QC pass over a BIMBAM mean-genotype file: ReadFile_geno, src/gemma_io.cpp:639-873.  Lines are tokenised and tested on the
+// host worker pool (line_pipeline.h); the consumer appends the per-SNP records in file order.
+struct RowBlock { size_t rows = 0, ncol = 0; vector<double> v; };     // parsed genotype rows of one block of lines (SNP-major)
+struct QcBlock { vector<SnpInfo> info; vector<int> keep; double min_g = 1e300, max_g = -1e300; };
+
 static void qc_bimbam(Run &R) {
-  LineReader in(R.P.file_geno);
-  if (!in.ok()) die("error reading genotype file:" + R.P.file_geno);
   R2Filter r2; r2.init(R);
-  vector<double> geno(R.ni_test); vector<char> miss(R.ni_test);
-  string line; double min_g = 1e300, max_g = -1e300;
-  while (in.next(line)) {
-    char *p = tok(&line[0]); if (!p) continue;
-    SnpInfo s{}; s.rs = p;
-    p = tok(nullptr); if (!p) die("Parsing input file '" + R.P.file_geno + "' failed"); s.a_minor = p;
-    p = tok(nullptr); if (!p) die("Parsing input file '" + R.P.file_geno + "' failed"); s.a_major = p;
-    if (!R.setSnps.empty() && !R.setSnps.count(s.rs)) {
-      s.chr = "-9"; s.bp = -9; s.cM = -9; s.n_miss = 0; s.missingness = -9; s.maf = -9; s.n_idv = 0;
-      R.snpInfo.push_back(s); R.indicator_snp.push_back(0); continue;
+  const Run *Rc = &R; const R2Filter *r2c = &r2;
+  LinePipeline<QcBlock> pipe(R.P.file_geno, [Rc, r2c](LineBlock &blk, QcBlock &out) {
+    const Run &R = *Rc;
+    vector<double> geno(R.ni_test); vector<char> miss(R.ni_test);
+    for (char *line : blk.lines) {
+      char *cur = line;
+      char *p = next_token(cur); if (!p) continue;
+      SnpInfo s{}; s.rs = p;
+      p = next_token(cur); if (!p) die("Parsing input file '" + R.P.file_geno + "' failed"); s.a_minor = p;
+      p = next_token(cur); if (!p) die("Parsing input file '" + R.P.file_geno + "' failed"); s.a_major = p;
+      if (!R.setSnps.empty() && !R.setSnps.count(s.rs)) {
+        s.chr = "-9"; s.bp = -9; s.cM = -9; s.n_miss = 0; s.missingness = -9; s.maf = -9; s.n_idv = 0;
+        out.info.push_back(s); out.keep.push_back(0); continue;
+      }
+      auto it = R.anno.find(s.rs);
+      if (it == R.anno.end()) { s.chr = "-9"; s.bp = -9; s.cM = -9; } else { s.chr = std::get<0>(it->second); s.bp = std::get<1>(it->second); s.cM = std::get<2>(it->second); }
+      double maf = 0.0; size_t n_miss = 0, n_0 = 0, n_1 = 0, n_2 = 0, c_idv = 0; int flag_poly = 0; double geno_old = -9;
+      std::fill(miss.begin(), miss.end(), 0);
+      for (size_t i = 0; i < R.ni_total; ++i) {
+        p = next_token(cur);
+        if (!p) die("Problem reading geno file (not enough genotypes in line)");
+        if (!R.indicator_idv[i]) continue;
+        if (p[0] == 'N' && p[1] == 'A' && p[2] == 0) { miss[c_idv] = 1; n_miss++; c_idv++; continue; }
+        const double g = token_to_double(p);
+        if (g >= 0 && g <= 0.5) n_0++;
+        if (g > 0.5 && g < 1.5) n_1++;
+        if (g >= 1.5 && g <= 2.0) n_2++;
+        geno[c_idv] = g;
+        if (g < out.min_g) out.min_g = g;
+        if (g > out.max_g) out.max_g = g;
+        if (flag_poly == 0) { geno_old = g; flag_poly = 2; }
+        if (flag_poly == 2 && g != geno_old) flag_poly = 1;
+        maf += g; c_idv++;
+      }
+      maf /= 2.0 * (double)(R.ni_test - n_miss);
+      s.n_miss = (long)n_miss; s.missingness = (double)n_miss / (double)R.ni_test; s.maf = maf; s.n_idv = (long)(R.ni_test - n_miss);
+      int keep = 1;
+      if ((double)n_miss / (double)R.ni_test > R.P.miss_level) keep = 0;
+      else if ((maf < R.P.maf_level || maf > (1.0 - R.P.maf_level)) && R.P.maf_level != -1) keep = 0;
+      else if (flag_poly != 1) keep = 0;
+      else if (R.P.hwe_level != 0 && R.P.maf_level != -1 && hwe_exact(n_0, n_2, n_1) < R.P.hwe_level) keep = 0;
+      else {
+        for (size_t i = 0; i < R.ni_test; ++i) if (miss[i]) geno[i] = maf * 2.0;
+        if (r2c->correlated(geno, R.P.r2_level)) keep = 0;
+      }
+      out.info.push_back(std::move(s)); out.keep.push_back(keep);
     }
-    auto it = R.anno.find(s.rs);
-    if (it == R.anno.end()) { s.chr = "-9"; s.bp = -9; s.cM = -9; } else { s.chr = std::get<0>(it->second); s.bp = std::get<1>(it->second); s.cM = std::get<2>(it->second); }
-    double maf = 0.0; size_t n_miss = 0, n_0 = 0, n_1 = 0, n_2 = 0, c_idv = 0; int flag_poly = 0; double geno_old = -9;
-    std::fill(miss.begin(), miss.end(), 0);
-    for (size_t i = 0; i < R.ni_total; ++i) {
-      p = tok(nullptr);
-      if (!p) die("Problem reading geno file (not enough genotypes in line)");
-      if (!R.indicator_idv[i]) continue;
-      if (strcmp(p, "NA") == 0) { miss[c_idv] = 1; n_miss++; c_idv++; continue; }
-      const double g = atof(p);
-      if (g >= 0 && g <= 0.5) n_0++;
-      if (g > 0.5 && g < 1.5) n_1++;
-      if (g >= 1.5 && g <= 2.0) n_2++;
-      geno[c_idv] = g;
-      if (g < min_g) min_g = g;
-      if (g > max_g) max_g = g;
-      if (flag_poly == 0) { geno_old = g; flag_poly = 2; }
-      if (flag_poly == 2 && g != geno_old) flag_poly = 1;
-      maf += g; c_idv++;
-    }
-    maf /= 2.0 * (double)(R.ni_test - n_miss);
-    s.n_miss = (long)n_miss; s.missingness = (double)n_miss / (double)R.ni_test; s.maf = maf; s.n_idv = (long)(R.ni_test - n_miss);
-    R.snpInfo.push_back(s);
-    int keep = 1;
-    if ((double)n_miss / (double)R.ni_test > R.P.miss_level) keep = 0;
-    else if ((maf < R.P.maf_level || maf > (1.0 - R.P.maf_level)) && R.P.maf_level != -1) keep = 0;
-    else if (flag_poly != 1) keep = 0;
-    else if (R.P.hwe_level != 0 && R.P.maf_level != -1 && hwe_exact(n_0, n_2, n_1) < R.P.hwe_level) keep = 0;
-    else {
-      for (size_t i = 0; i < R.ni_test; ++i) if (miss[i]) geno[i] = maf * 2.0;
-      if (r2.correlated(geno, R.P.r2_level)) keep = 0;
-    }
-    R.indicator_snp.push_back(keep); R.ns_test += keep;
+  });
+  if (!pipe.ok()) die("error reading genotype file:" + R.P.file_geno);
+  double min_g = 1e300, max_g = -1e300;
+  QcBlock blk;
+  while (pipe.next(blk)) {
+    for (size_t k = 0; k < blk.info.size(); ++k) { R.snpInfo.push_back(std::move(blk.info[k])); R.indicator_snp.push_back(blk.keep[k]); R.ns_test += blk.keep[k]; }
+    min_g = std::min(min_g, blk.min_g); max_g = std::max(max_g, blk.max_g);
   }
   R.ns_total = R.indicator_snp.size();
   if (min_g != 0.0) std::cout << "**** WARNING: The minimum genotype value is not 0.0 - this is not the BIMBAM standard and will skew l_lme and effect sizes" << std::endl;
@@ -484,25 +497,39 @@ static void run_kinship(Run &R, gb200_ctx *ctx) {
     }
     if (l) GB(gb200_kin_add_bed(ctx, rows.data(), l, g_nbit));
   } else {
-    LineReader in(R.P.file_geno);
-    if (!in.ok()) die("error reading genotype file:" + R.P.file_geno);
+    // BimbamKin, src/gemma_io.cpp:1418-1597: rows of all ni_total individuals, "NA" -> NaN; parsed on the worker pool
+    const Run *Rc = &R;
+    LinePipeline<RowBlock> pipe(R.P.file_geno, [Rc](LineBlock &blk, RowBlock &out) {
+      const Run &R = *Rc;
+      out.ncol = R.ni_total;
+      for (size_t k = 0; k < blk.lines.size(); ++k) {
+        const size_t cur_line = blk.first_line + k;
+        if (cur_line >= R.indicator_snp.size() || !R.indicator_snp[cur_line]) continue;
+        char *cur = blk.lines[k];
+        char *p = next_token(cur); if (!p) continue;
+        if (!R.setKSnps.empty() && !R.setKSnps.count(p)) continue;       // -ksnps / -loco, src/gemma_io.cpp:1479
+        p = next_token(cur); p = next_token(cur);
+        const size_t off = out.v.size();
+        out.v.resize(off + R.ni_total);
+        double *g = out.v.data() + off;
+        for (size_t i = 0; i < R.ni_total; ++i) {
+          p = next_token(cur);
+          if (!p) die("line " + std::to_string(cur_line + 1) + " of " + R.P.file_geno + ": number of fields");
+          g[i] = (p[0] == 'N' && p[1] == 'A') ? NAN : token_to_double(p);
+        }
+        out.rows++;
+      }
+    });
+    if (!pipe.ok()) die("error reading genotype file:" + R.P.file_geno);
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(BATCH, (size_t(1) << 28) / R.ni_total));
     vector<double> G(chunk * R.ni_total);
-    string line; size_t t = 0, l = 0;
-    while (in.next(line)) {
-      const size_t cur = t++;
-      if (cur >= R.indicator_snp.size()) break;
-      if (!R.indicator_snp[cur]) continue;
-      char *p = tok(&line[0]); if (!p) continue;
-      if (!R.setKSnps.empty() && !R.setKSnps.count(p)) continue;       // -ksnps / -loco, src/gemma_io.cpp:1479
-      p = tok(nullptr); p = tok(nullptr);
-      double *g = G.data() + l * R.ni_total;
-      for (size_t i = 0; i < R.ni_total; ++i) {
-        p = tok(nullptr);
-        if (!p) die(line + " number of fields");
-        g[i] = (strncmp(p, "NA", 2) == 0) ? NAN : atof(p);
+    size_t l = 0;
+    RowBlock blk;
+    while (pipe.next(blk)) {
+      for (size_t r = 0; r < blk.rows; ++r) {
+        std::memcpy(G.data() + l * R.ni_total, blk.v.data() + r * R.ni_total, R.ni_total * sizeof(double));
+        if (++l == chunk) { GB(gb200_kin_add_geno(ctx, G.data(), l, R.ni_total, R.ni_total)); l = 0; }
       }
-      if (++l == chunk) { GB(gb200_kin_add_geno(ctx, G.data(), l, R.ni_total, R.ni_total)); l = 0; }
     }
     if (l) GB(gb200_kin_add_geno(ctx, G.data(), l, R.ni_total, R.ni_total));
   }
@@ -646,11 +673,34 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
     }
     flush();
   } else {                                             // AnalyzeBimbam, src/lmm.cpp:1660-1706 + Analyze :1474-1658
-    LineReader in(R.P.file_geno);
-    if (!in.ok()) die("error reading genotype file:" + R.P.file_geno);
+    // analysed individuals only, "NA" -> NaN (src/lmm.cpp:1675-1700); parsed on the worker pool, tested in file order
+    const Run *Rc = &R;
+    LinePipeline<RowBlock> pipe(R.P.file_geno, [Rc, n](LineBlock &blk, RowBlock &out) {
+      const Run &R = *Rc;
+      out.ncol = n;
+      for (size_t k = 0; k < blk.lines.size(); ++k) {
+        const size_t cur_line = blk.first_line + k;
+        if (cur_line >= R.indicator_snp.size() || !R.indicator_snp[cur_line]) continue;
+        char *cur = blk.lines[k];
+        char *p = next_token(cur);
+        if (!R.setGWASnps.empty() && (!p || !R.setGWASnps.count(p))) continue;       // -gwasnps / -loco, src/lmm.cpp:1585-1587
+        p = next_token(cur); p = next_token(cur);
+        const size_t off = out.v.size();
+        out.v.resize(off + n);
+        double *g = out.v.data() + off; size_t pos = 0;
+        for (size_t i = 0; i < R.ni_total; ++i) {
+          p = next_token(cur);
+          if (!p) die("Problem reading geno file (not enough genotypes in line)");
+          if (!R.indicator_idv[i]) continue;
+          g[pos++] = (p[0] == 'N' && p[1] == 'A' && p[2] == 0) ? NAN : token_to_double(p);      // "NA" -> NaN, src/lmm.cpp:1690-1694
+        }
+        out.rows++;
+      }
+    });
+    if (!pipe.ok()) die("error reading genotype file:" + R.P.file_geno);
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(BATCH, (size_t(1) << 28) / n));
     vector<double> G(chunk * n);
-    string line; size_t t = 0, l = 0;
+    size_t l = 0;
     auto flush = [&]() {
       if (!l) return;
       out.resize(l);
@@ -658,21 +708,12 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
       R.sumStat.insert(R.sumStat.end(), out.begin(), out.end());
       l = 0;
     };
-    while (in.next(line)) {
-      const size_t cur = t++;
-      if (cur >= R.indicator_snp.size()) break;
-      if (!R.indicator_snp[cur]) continue;
-      char *p = tok(&line[0]);
-      if (!R.setGWASnps.empty() && (!p || !R.setGWASnps.count(p))) continue;       // -gwasnps / -loco, src/lmm.cpp:1585-1587
-      p = tok(nullptr); p = tok(nullptr);
-      double *g = G.data() + l * n; size_t pos = 0;
-      for (size_t i = 0; i < R.ni_total; ++i) {
-        p = tok(nullptr);
-        if (!p) die("Problem reading geno file (not enough genotypes in line)");
-        if (!R.indicator_idv[i]) continue;
-        g[pos++] = (strcmp(p, "NA") == 0) ? NAN : atof(p);      // "NA" -> NaN, src/lmm.cpp:1690-1694
+    RowBlock blk;
+    while (pipe.next(blk)) {
+      for (size_t r = 0; r < blk.rows; ++r) {
+        std::memcpy(G.data() + l * n, blk.v.data() + r * n, n * sizeof(double));
+        if (++l == chunk) flush();
       }
-      if (++l == chunk) flush();
     }
     flush();
   }
