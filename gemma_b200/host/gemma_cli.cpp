@@ -56,7 +56,7 @@ struct Params {
   double miss_level = 0.05, maf_level = 0.01, hwe_level = 0.0, r2_level = 0.9999;
   double l_min = 1e-5, l_max = 1e5; size_t n_region = 10;
   long nind = -1;
-  bool silence = false, qc_only = false;
+  bool silence = false, qc_only = false, bin = false;
   int device = -1;
 };
 
@@ -464,13 +464,38 @@ static void print_counts(const Run &R) {               // CheckData, src/param.c
 
 static string out_path(const Run &R, const string &suffix) { return R.P.path_out + "/" + R.P.file_out + "." + suffix + ".txt"; }
 
+// Binary side channel for K / U / D (the reference's own design notes ask for a new kinship format,
+// doc/developers/design.org): the 10-digit text of a 50k x 50k matrix is ~35 GB and its rounding is visible in the results.
+// With -bin the writers add "<file>.bin" next to the text file; every matrix reader accepts a path ending in ".bin".
+// Layout: 8-byte magic "GB2MAT01", uint64 rows, uint64 cols, rows*cols little-endian doubles (row-major).
+static bool is_bin(const string &path) { return path.size() > 4 && path.compare(path.size() - 4, 4, ".bin") == 0; }
+static void write_bin(const string &path, const double *M, size_t rows, size_t cols) {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) { std::cout << "error writing file: " << path << std::endl; return; }
+  const uint64_t hdr[2] = {rows, cols};
+  fwrite("GB2MAT01", 1, 8, f); fwrite(hdr, sizeof(uint64_t), 2, f); fwrite(M, sizeof(double), rows * cols, f);
+  fclose(f);
+}
+static void read_bin(const string &path, vector<double> &M, size_t &rows, size_t &cols) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) die("fail to open binary matrix file: " + path);
+  char magic[8]; uint64_t hdr[2];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "GB2MAT01", 8) != 0 || fread(hdr, sizeof(uint64_t), 2, f) != 2) die("not a gemma-b200 binary matrix: " + path);
+  rows = hdr[0]; cols = hdr[1];
+  M.resize(rows * cols);
+  if (fread(M.data(), sizeof(double), rows * cols, f) != rows * cols) die("truncated binary matrix: " + path);
+  fclose(f);
+}
+
 static void write_matrix(const Run &R, const double *M, size_t rows, size_t cols, const string &suffix) {   // WriteMatrix, src/param.cpp:1886-1910
+  if (R.P.bin) write_bin(out_path(R, suffix) + ".bin", M, rows, cols);
   std::ofstream out(out_path(R, suffix));
   if (!out) { std::cout << "error writing file: " << out_path(R, suffix) << std::endl; return; }
   out.precision(10);
   for (size_t i = 0; i < rows; ++i) { for (size_t j = 0; j < cols; ++j) out << (j ? "\t" : "") << M[i * cols + j]; out << std::endl; }
 }
 static void write_vector(const Run &R, const double *v, size_t n, const string &suffix) {                    // WriteVector, src/param.cpp:1912-1935
+  if (R.P.bin) write_bin(out_path(R, suffix) + ".bin", v, n, 1);
   std::ofstream out(out_path(R, suffix));
   if (!out) { std::cout << "error writing file: " << out_path(R, suffix) << std::endl; return; }
   out.precision(10);
@@ -541,9 +566,23 @@ static void run_kinship(Run &R, gb200_ctx *ctx) {
 }
 
 static void read_kin(Run &R, vector<double> &G) {      // ReadFile_kin -km 1/2, src/gemma_io.cpp:1186-1294
+  const size_t n = R.ni_test;
+  if (is_bin(R.P.file_kin)) {
+    vector<double> full; size_t rows = 0, cols = 0;
+    read_bin(R.P.file_kin, full, rows, cols);
+    if (rows != R.ni_total || cols != R.ni_total) die("number of rows in the kinship file does not match the number of individuals.");
+    G.assign(n * n, 0.0);
+    size_t it = 0;
+    for (size_t i = 0; i < R.ni_total; ++i) {
+      if (!R.indicator_idv[i]) continue;
+      size_t jt = 0;
+      for (size_t j = 0; j < R.ni_total; ++j) if (R.indicator_idv[j]) G[it * n + jt++] = full[i * R.ni_total + j];
+      ++it;
+    }
+    return;
+  }
   LineReader in(R.P.file_kin);
   if (!in.ok()) die("fail to open kinship file: " + R.P.file_kin);
-  const size_t n = R.ni_test;
   G.assign(n * n, 0.0);
   string line;
   if (R.P.k_mode == 1) {
@@ -580,6 +619,13 @@ static void read_kin(Run &R, vector<double> &G) {      // ReadFile_kin -km 1/2, 
 }
 
 static void read_dense_rows(const string &file, double *dst, size_t rows, size_t cols, const char *what) {   // ReadFile_eigenU/D, src/gemma_io.cpp:1323-1415
+  if (is_bin(file)) {
+    vector<double> M; size_t r = 0, c = 0;
+    read_bin(file, M, r, c);
+    if (r != rows || c != cols) die(string("shape of the binary ") + what + " file does not match the analysed individuals");
+    std::copy(M.begin(), M.end(), dst);
+    return;
+  }
   LineReader in(file);
   if (!in.ok()) die(string("fail to open the ") + what + " file: " + file);
   std::fill(dst, dst + rows * cols, 0.0);
@@ -756,7 +802,8 @@ static void usage() {
   std::cout << "gemma-b200: GEMMA-compatible -gk / -eigen / -lmm on a B200\n"
                " -g/-p/-a/-c files (BIMBAM)  |  -bfile prefix (PLINK)   -n col...   -o prefix  -outdir dir\n"
                " -gk [1|2]   -eigen   -lmm [1|2|3|4|9]   -k K.txt [-km 1|2]   -d D.txt -u U.txt\n"
-               " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -lmin x -lmax x -region n -nind n -silence\n";
+               " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -gwasnps file -loco chr -lmin x -lmax x -region n -nind n -silence\n"
+               " -bin  also write K / U / D as <file>.bin (exact doubles); -k/-u/-d accept such .bin files\n";
 }
 
 int main(int argc, char **argv) {
@@ -799,6 +846,7 @@ int main(int argc, char **argv) {
     else if (a == "-lmm") { P.a_mode = optnum(i, 1); n_modes++; }                 // src/gemma.cpp:1299-1314
     else if (a == "-silence") P.silence = true;
     else if (a == "-qc-only") P.qc_only = true;
+    else if (a == "-bin") P.bin = true;
     else if (a == "-no-check" || a == "-check" || a == "-debug" || a == "-strict" || a == "-legacy" || a == "-nocheck") {}
     else if (a == "-h" || a == "-help") { usage(); return 0; }
     else die("unrecognized option " + a);                                          // src/gemma.cpp:1626-1629

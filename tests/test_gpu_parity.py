@@ -425,6 +425,19 @@ def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
     assert lines[2].split("\t")[9] == e["row2_logl_H1"]
     assert "%.6e" % max(float(l.split("\t")[11]) for l in lines[1:]) == e["max_p_wald"]
     assert all(l.split("\t")[0] == "1" for l in lines[1:])            # only chromosome-1 SNPs are tested
+    # binary side channel: -bin writes <file>.bin next to the text; feeding the exact K changes results only at the
+    # level of the 10-digit rounding of the text file
+    r = subprocess.run([cli] + base + ["-gk", "-bin", "-o", "locob"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(tmp_path / "locob.cXX.txt").read() == txt
+    r = subprocess.run([cli] + base + ["-n", "1", "-k", str(tmp_path / "locob.cXX.txt.bin"), "-lmm", "-o", "locob"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lb = open(tmp_path / "locob.assoc.txt").read().splitlines()
+    assert len(lb) == len(lines)
+    a = np.array([[float(x) for x in l.split("\t")[7:]] for l in lines[1:]])
+    b = np.array([[float(x) for x in l.split("\t")[7:]] for l in lb[1:]])
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-8) and [l.split("\t")[:7] for l in lb] == [l.split("\t")[:7] for l in lines]
 
 
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
