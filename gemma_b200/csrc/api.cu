@@ -150,7 +150,7 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     c->kin_path = value; return GB200_OK;
   }
   if (!strcmp(name, "lmm_kernel")) {
-    if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2");
+    if (value < 0 || value > 3) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2,3");
     c->lmm_kernel = value; return GB200_OK;
   }
   if (!strcmp(name, "n_slices")) {
@@ -333,7 +333,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
                              const double *eval) {
   if (n == 0 || n_cvt == 0 || !U || !eval || ldu < n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: bad argument");
   if (n_cvt > GB200_MAX_CVT)
-    return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT (fused kernel register budget)");
+    return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false;
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
@@ -430,6 +430,8 @@ static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
+  D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
+  D.gen_stride = 0;
   return D;
 }
 
@@ -543,7 +545,7 @@ static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu,
   ProfScope ps(c, "lmm", 1, st);
   const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
   if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
-  if (v2_ok && c->lmm_kernel != 1)
+  if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3)
     GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));
   else
     GB_CUDA(c, launch_lmm_assoc((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));

@@ -35,6 +35,8 @@ struct LmmConst {
   const double *delta;   // eigenvalues (n)
   const double *Wt;      // rotated covariates, TRANSPOSED: n_cvt rows of n (coalesced per covariate)
   const double *y;       // rotated phenotype (n)
+  int nc_gen;            // generic-covariate path (NC < 0 instantiations): number of swept covariates
+  int gen_stride;        // doubles of shared-memory scratch per warp on that path (3 tables of (nc_gen+3)(nc_gen+2)/2)
 };
 
 struct LmmParams {
@@ -286,6 +288,139 @@ __device__ __forceinline__ void sweep_tables(double (&P)[(NC + 3) * (NC + 2) / 2
   d.PPPx_yy = (ORD >= 3) ? PPP[abidx(NC + 1, NC + 1, NV)] : 0.0;
 }
 
+// ---------------------------------------------------------------------------------
+// Any number of covariates (instantiations with NC < 0; the count is D.nc_gen at run time).  The register-resident
+// tables above grow as (c+2)(c+3)/2 per power of h and stop fitting at c = 6; here the weighted sums are accumulated in
+// 4 x 4 register blocks of (a, b) pairs -- one pass over the individuals per block, the columns re-read from L1/L2 --
+// and the totals live in a per-warp shared-memory table that is swept lane-parallel (one (a, b) entry per lane and
+// step).  Every sum is accumulated in the same order and with the same fma sequence as lmm_pass, so for c <= 6 this
+// path is bit-identical to the templated one (tests force it to check exactly that).
+__device__ __forceinline__ double *gen_tables(const LmmConst &D) {
+  extern __shared__ __align__(16) double gb_gen_smem[];
+  return gb_gen_smem + (size_t)(threadIdx.x >> 5) * (size_t)D.gen_stride;
+}
+__device__ __forceinline__ int gen_nidx(int nc) { return (nc + 3) * (nc + 2) / 2; }
+
+template <int KLO, int KHI, bool LOGDET>
+__device__ __noinline__ void gen_pass(const LmmConst &D, const double *__restrict__ x, double lam, double *__restrict__ S,
+                                      double (&tr)[KHI - KLO + 1], double &logdet) {
+  constexpr int NK = KHI - KLO + 1;
+  const int nc = D.nc_gen, NV = nc + 2, NIDX = gen_nidx(nc);
+  const int lane = threadIdx.x & 31, n = D.n;
+  const double *__restrict__ dl = D.delta;
+#pragma unroll
+  for (int k = 0; k < NK; ++k) tr[k] = 0.0;
+  logdet = 0.0;
+  for (int a0 = 0; a0 < NV; a0 += 4) {
+    const double *ca[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { const int a = a0 + r; ca[r] = (a < nc) ? D.Wt + (size_t)a * D.ldv : (a == nc ? x : D.y); }
+    for (int b0 = a0; b0 < NV; b0 += 4) {
+      const double *cb[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const int b = b0 + r; cb[r] = (b < nc) ? D.Wt + (size_t)b * D.ldv : (b == nc ? x : D.y); }
+      const bool first = (a0 == 0 && b0 == 0);
+      double acc[NK][4][4];
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[k][r][q] = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        double va[4], vb[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { va[r] = __ldg(ca[r] + i); vb[r] = __ldg(cb[r] + i); }
+        const double den = fma(lam, __ldg(dl + i), 1.0);
+        const double h = 1.0 / den;
+        if (LOGDET && first) logdet += log(fabs(den));
+        double hk = (KLO == 0) ? 1.0 : h;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          if (first) tr[k] += hk;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double t = hk * va[r];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[k][r][q] = fma(t, vb[q], acc[k][r][q]);
+          }
+          hk *= h;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double tot = warp_allsum(acc[k][r][q]);
+            const int a = a0 + r, b = b0 + q;
+            if (a < NV && b < NV && a <= b && lane == 0) S[k * NIDX + abidx(a, b, NV)] = tot;
+          }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k) tr[k] = warp_allsum(tr[k]);
+  if (LOGDET) logdet = warp_allsum(logdet);
+  __syncwarp();
+}
+
+// lane-parallel form of sweep_tables on shared-memory tables (same per-entry arithmetic)
+template <int ORD>
+__device__ __noinline__ void gen_sweep(double *__restrict__ P, double *__restrict__ PP, double *__restrict__ PPP, int nc,
+                                       Derived<-1, ORD> &d) {
+  const int NV = nc + 2, lane = threadIdx.x & 31;
+  d.trace_P_corr = 0.0; d.trace_PP_corr = 0.0; d.logdet_piv = 0.0;
+  d.P_xx = d.P_xy = d.P_yy = 0.0;
+  for (int p = 0; p <= nc; ++p) {
+    if (p == nc) {
+      d.P_xx = P[abidx(nc, nc, NV)];
+      d.P_xy = P[abidx(nc, nc + 1, NV)];
+      d.P_yy = P[abidx(nc + 1, nc + 1, NV)];
+    }
+    const double ww = P[abidx(p, p, NV)];
+    const double ww2 = (ORD >= 2) ? PP[abidx(p, p, NV)] : 0.0;
+    const double ww3 = (ORD >= 3) ? PPP[abidx(p, p, NV)] : 0.0;
+    d.logdet_piv += log(ww);
+    if (ORD >= 2) {
+      const double r = ww2 / ww;
+      d.trace_P_corr += r;
+      if (ORD >= 3) d.trace_PP_corr += r * r - 2.0 * ww3 / ww;
+    }
+    if (ww != 0) {
+      const double iw = 1.0 / ww;
+      for (int a = p + 1; a < NV; ++a) {
+        const double aw = P[abidx(p, a, NV)];
+        const double aw2 = (ORD >= 2) ? PP[abidx(p, a, NV)] : 0.0;
+        const double aw3 = (ORD >= 3) ? PPP[abidx(p, a, NV)] : 0.0;
+        for (int b = a + lane; b < NV; b += 32) {
+          const double bw = P[abidx(p, b, NV)];
+          const double bw2 = (ORD >= 2) ? PP[abidx(p, b, NV)] : 0.0;
+          const double bw3 = (ORD >= 3) ? PPP[abidx(p, b, NV)] : 0.0;
+          const int ab = abidx(a, b, NV);
+          if (ORD >= 3) {
+            double p3 = PPP[ab] - aw * bw * ww2 * ww2 * (iw * iw * iw);
+            p3 -= (aw * bw3 + bw * aw3 + aw2 * bw2) * iw;
+            p3 += (aw * bw2 * ww2 + bw * aw2 * ww2 + aw * bw * ww3) * (iw * iw);
+            PPP[ab] = p3;
+          }
+          if (ORD >= 2) {
+            double p2 = PP[ab] + aw * bw * ww2 * (iw * iw);
+            p2 -= (aw * bw2 + bw * aw2) * iw;
+            PP[ab] = p2;
+          }
+          P[ab] = P[ab] - aw * bw * iw;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  d.Px_yy = P[abidx(nc + 1, nc + 1, NV)];
+  d.PPx_yy = (ORD >= 2) ? PP[abidx(nc + 1, nc + 1, NV)] : 0.0;
+  d.PPPx_yy = (ORD >= 3) ? PPP[abidx(nc + 1, nc + 1, NV)] : 0.0;
+  __syncwarp();
+}
+
 struct DevVals { double d1R, d2R, d1L, d2L; };
 
 // dev1 (and dev2 when ORD==3) of the REML and ML log-likelihoods from one pass.
@@ -293,24 +428,37 @@ struct DevVals { double d1R, d2R, d1L, d2L; };
 template <int NC, int KHI>
 __device__ __forceinline__ DevVals eval_devs(const LmmConst &D, const double *x, double lam) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
-  PassOut<NC, 1, KHI, false> o;
-  lmm_pass<NC, 1, KHI, false>(D, x, lam, o);
   Derived<NC, KHI> d;
-  double dummy[NIDX];
-  if constexpr (KHI == 3) sweep_tables<NC, KHI>(o.S[0], o.S[1], o.S[2], d);
-  else sweep_tables<NC, KHI>(o.S[0], o.S[1], dummy, d);
+  double tr0, tr1 = 0.0;
+  int ncv = NC;
+  if constexpr (NC < 0) {
+    ncv = D.nc_gen;
+    double *T = gen_tables(D);
+    const int gi = gen_nidx(ncv);
+    double tr[KHI], ld;
+    gen_pass<1, KHI, false>(D, x, lam, T, tr, ld);
+    gen_sweep<KHI>(T, T + gi, T + 2 * gi, ncv, d);
+    tr0 = tr[0]; if (KHI >= 2) tr1 = tr[KHI >= 2 ? 1 : 0];
+  } else {
+    PassOut<NC, 1, KHI, false> o;
+    lmm_pass<NC, 1, KHI, false>(D, x, lam, o);
+    double dummy[NIDX];
+    if constexpr (KHI == 3) sweep_tables<NC, KHI>(o.S[0], o.S[1], o.S[2], d);
+    else sweep_tables<NC, KHI>(o.S[0], o.S[1], dummy, d);
+    tr0 = o.tr[0]; if (KHI >= 2) tr1 = o.tr[KHI >= 2 ? 1 : 0];
+  }
   const double n = (double)D.n;
-  const double df = n - (double)NC - 1.0;
+  const double df = n - (double)ncv - 1.0;
   const double P_yy = d.Px_yy, PP_yy = d.PPx_yy;
   const double yPKPy = (P_yy - PP_yy) / lam;
-  const double trace_Hi = o.tr[0];
+  const double trace_Hi = tr0;
   const double trace_P = trace_Hi - d.trace_P_corr;
   DevVals r;
   r.d1R = -0.5 * ((df - trace_P) / lam) + 0.5 * df * yPKPy / P_yy;
   r.d1L = -0.5 * ((n - trace_Hi) / lam) + 0.5 * n * yPKPy / P_yy;
   r.d2R = 0.0; r.d2L = 0.0;
   if (KHI == 3) {
-    const double trace_HiHi = o.tr[1];
+    const double trace_HiHi = tr1;
     const double trace_PP = trace_HiHi + d.trace_PP_corr;
     const double PPP_yy = d.PPPx_yy;
     const double yPKPKPy = (P_yy + PPP_yy - 2.0 * PP_yy) / (lam * lam);
@@ -341,20 +489,29 @@ template <int NC>
 __device__ __forceinline__ FVals eval_f(const LmmConst &D, const double *x, double lam, double logdetI,
                                         Derived<NC, 1> *dout = nullptr) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
-  PassOut<NC, 1, 1, true> o;
-  lmm_pass<NC, 1, 1, true>(D, x, lam, o);
   Derived<NC, 1> d;
-  double dm1[NIDX], dm2[NIDX];
-  sweep_tables<NC, 1>(o.S[0], dm1, dm2, d);
-  if (dout) *dout = d;
-  return f_from((double)D.n, NC, o.logdet, d.logdet_piv, logdetI, d.Px_yy);
+  if constexpr (NC < 0) {
+    double *T = gen_tables(D);
+    double tr[1], ld;
+    gen_pass<1, 1, true>(D, x, lam, T, tr, ld);
+    gen_sweep<1>(T, T, T, D.nc_gen, d);
+    if (dout) *dout = d;
+    return f_from((double)D.n, D.nc_gen, ld, d.logdet_piv, logdetI, d.Px_yy);
+  } else {
+    PassOut<NC, 1, 1, true> o;
+    lmm_pass<NC, 1, 1, true>(D, x, lam, o);
+    double dm1[NIDX], dm2[NIDX];
+    sweep_tables<NC, 1>(o.S[0], dm1, dm2, d);
+    if (dout) *dout = d;
+    return f_from((double)D.n, NC, o.logdet, d.logdet_piv, logdetI, d.Px_yy);
+  }
 }
 
 // CalcRLWald src/lmm.cpp:1127-1167 / CalcRLScore :1170-1211 from a swept order-1 table.
 template <int NC>
 __device__ __forceinline__ void wald_score_from(const Derived<NC, 1> &d, int n, bool score,
-                                                double &beta, double &se, double &pval) {
-  const int df = n - NC - 1;
+                                                double &beta, double &se, double &pval, int nc_run = NC) {
+  const int df = n - nc_run - 1;
   beta = d.P_xy / d.P_xx;
   const double tau = (double)df / d.Px_yy;
   se = safe_sqrt_dev(1.0 / (tau * d.P_xx));
@@ -366,12 +523,20 @@ template <int NC>
 __device__ __forceinline__ void eval_wald_score(const LmmConst &D, const double *x, double lam, bool score,
                                                 double &beta, double &se, double &pval) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
-  PassOut<NC, 1, 1, false> o;
-  lmm_pass<NC, 1, 1, false>(D, x, lam, o);
   Derived<NC, 1> d;
-  double dm1[NIDX], dm2[NIDX];
-  sweep_tables<NC, 1>(o.S[0], dm1, dm2, d);
-  wald_score_from<NC>(d, D.n, score, beta, se, pval);
+  if constexpr (NC < 0) {
+    double *T = gen_tables(D);
+    double tr[1], ld;
+    gen_pass<1, 1, false>(D, x, lam, T, tr, ld);
+    gen_sweep<1>(T, T, T, D.nc_gen, d);
+    wald_score_from<NC>(d, D.n, score, beta, se, pval, D.nc_gen);
+  } else {
+    PassOut<NC, 1, 1, false> o;
+    lmm_pass<NC, 1, 1, false>(D, x, lam, o);
+    double dm1[NIDX], dm2[NIDX];
+    sweep_tables<NC, 1>(o.S[0], dm1, dm2, d);
+    wald_score_from<NC>(d, D.n, score, beta, se, pval);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -511,23 +676,39 @@ __device__ __forceinline__ void calc_lambda_both(const LmmConst &D, const double
   double logdetI, fRmin, fLmin, dR_prev, dL_prev;
   double lam_l = l_min * exp(lambda_interval * 0.0);
   {
-    PassOut<NC, 0, 2, true> o;
-    lmm_pass<NC, 0, 2, true>(D, x, lam_l, o);
-    {
-      Derived<NC, 1> dI;
-      double dm1[NIDX], dm2[NIDX];
-      sweep_tables<NC, 1>(o.S[0], dm1, dm2, dI);
-      logdetI = dI.logdet_piv;
-    }
     Derived<NC, 2> d;
-    double dm3[NIDX];
-    sweep_tables<NC, 2>(o.S[1], o.S[2], dm3, d);
-    const double n = (double)D.n, df = n - (double)NC - 1.0;
+    double tr1v, logdet_h;
+    int ncv = NC;
+    if constexpr (NC < 0) {
+      ncv = D.nc_gen;
+      double *T = gen_tables(D);
+      const int gi = gen_nidx(ncv);
+      double tr[3];
+      gen_pass<0, 2, true>(D, x, lam_l, T, tr, logdet_h);
+      Derived<NC, 1> dI;
+      gen_sweep<1>(T, T, T, ncv, dI);
+      logdetI = dI.logdet_piv;
+      gen_sweep<2>(T + gi, T + 2 * gi, T, ncv, d);
+      tr1v = tr[1];
+    } else {
+      PassOut<NC, 0, 2, true> o;
+      lmm_pass<NC, 0, 2, true>(D, x, lam_l, o);
+      {
+        Derived<NC, 1> dI;
+        double dm1[NIDX], dm2[NIDX];
+        sweep_tables<NC, 1>(o.S[0], dm1, dm2, dI);
+        logdetI = dI.logdet_piv;
+      }
+      double dm3[NIDX];
+      sweep_tables<NC, 2>(o.S[1], o.S[2], dm3, d);
+      tr1v = o.tr[1]; logdet_h = o.logdet;
+    }
+    const double n = (double)D.n, df = n - (double)ncv - 1.0;
     const double yPKPy = (d.Px_yy - d.PPx_yy) / lam_l;
-    const double trace_P = o.tr[1] - d.trace_P_corr;
+    const double trace_P = tr1v - d.trace_P_corr;
     dR_prev = -0.5 * ((df - trace_P) / lam_l) + 0.5 * df * yPKPy / d.Px_yy;
-    dL_prev = -0.5 * ((n - o.tr[1]) / lam_l) + 0.5 * n * yPKPy / d.Px_yy;
-    FVals fv = f_from(n, NC, o.logdet, d.logdet_piv, logdetI, d.Px_yy);
+    dL_prev = -0.5 * ((n - tr1v) / lam_l) + 0.5 * n * yPKPy / d.Px_yy;
+    FVals fv = f_from(n, ncv, logdet_h, d.logdet_piv, logdetI, d.Px_yy);
     fRmin = fv.fR; fLmin = fv.fL;
   }
   for (int i = 0; i < n_region; ++i) {
@@ -614,14 +795,24 @@ __device__ __forceinline__ void null_model(const LmmConst &D, const double *x, d
   out.dev2_remle = dv.d2R;
   for (int which = 0; which < 2; ++which) {
     const double lam = which == 0 ? L.lambda : R.lambda;
-    PassOut<NC, 1, 1, false> o;
-    lmm_pass<NC, 1, 1, false>(D, x, lam, o);
     double *dst = which == 0 ? out.S1_mle : out.S1_remle;
-#pragma unroll
-    for (int j = 0; j < NIDX; ++j) dst[j] = o.S[0][j];
     Derived<NC, 1> d;
-    double dm1[NIDX], dm2[NIDX];
-    sweep_tables<NC, 1>(o.S[0], dm1, dm2, d);
+    if constexpr (NC < 0) {
+      double *T = gen_tables(D);
+      double tr[1], ld;
+      gen_pass<1, 1, false>(D, x, lam, T, tr, ld);
+      const int gi = gen_nidx(D.nc_gen);
+      for (int j = 0; j < gi; ++j) dst[j] = T[j];
+      __syncwarp();
+      gen_sweep<1>(T, T, T, D.nc_gen, d);
+    } else {
+      PassOut<NC, 1, 1, false> o;
+      lmm_pass<NC, 1, 1, false>(D, x, lam, o);
+#pragma unroll
+      for (int j = 0; j < NIDX; ++j) dst[j] = o.S[0][j];
+      double dm1[NIDX], dm2[NIDX];
+      sweep_tables<NC, 1>(o.S[0], dm1, dm2, d);
+    }
     if (which == 0) out.Pyy_mle = d.Px_yy; else out.Pyy_remle = d.Px_yy;
   }
 }

@@ -89,8 +89,32 @@ template <int NC>
 __global__ void __launch_bounds__(32) lmm_null_kernel(LmmConst D, double l_min, double l_max,
                                                       int n_region, NullOut *out) {
   NullOut r;
-  null_model<NC>(D, D.Wt + (size_t)NC * D.ldv, l_min, l_max, n_region, r);
+  const int nc = NC < 0 ? D.nc_gen : NC;
+  null_model<NC>(D, D.Wt + (size_t)nc * D.ldv, l_min, l_max, n_region, r);
   if ((threadIdx.x & 31) == 0) *out = r;
+}
+
+// any number of covariates: NC = -1 instantiations (lmm_device.cuh, "generic" section); shared memory holds the
+// per-warp sum tables
+static size_t gen_smem_bytes(int nc, int warps) { return (size_t)warps * 3 * (size_t)((nc + 3) * (nc + 2) / 2) * sizeof(double); }
+
+static cudaError_t launch_assoc_generic(int n_cvt, LmmConst D, const LmmParams &prm, const double *UtXt, size_t ldu, int l,
+                                        gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st) {
+  D.nc_gen = n_cvt; D.gen_stride = 3 * ((n_cvt + 3) * (n_cvt + 2) / 2);
+  const size_t smem = gen_smem_bytes(n_cvt, 4);
+  cudaError_t e = cudaFuncSetAttribute(lmm_assoc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lmm_assoc_kernel<-1>, 128, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long want = ((long)l + 3) / 4, grid = (long)num_sms * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  lmm_assoc_kernel<-1><<<(unsigned)grid, 128, smem, st>>>(D, prm, UtXt, ldu, l, out, ticket);
+  return cudaGetLastError();
 }
 
 template <int NC>
@@ -114,6 +138,7 @@ static cudaError_t launch_assoc_nc(const LmmConst &D, const LmmParams &prm, cons
 cudaError_t launch_lmm_assoc(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt,
                              size_t ldu, int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,
                              cudaStream_t st) {
+  if (n_cvt > 6 || D.nc_gen > 0) return launch_assoc_generic(n_cvt, D, prm, UtXt, ldu, l, out, ticket, num_sms, st);
   switch (n_cvt) {
     case 1: return launch_assoc_nc<1>(D, prm, UtXt, ldu, l, out, ticket, num_sms, st);
     case 2: return launch_assoc_nc<2>(D, prm, UtXt, ldu, l, out, ticket, num_sms, st);
@@ -128,6 +153,15 @@ cudaError_t launch_lmm_assoc(int n_cvt, const LmmConst &D, const LmmParams &prm,
 cudaError_t launch_lmm_null(int n_cvt, const LmmConst &D, double l_min, double l_max, int n_region,
                             NullOut *out, cudaStream_t st) {
   // null model with c covariates == alternative model with c-1 covariates and x = last covariate
+  if (n_cvt > 6 || D.nc_gen > 0) {
+    LmmConst G = D;
+    G.nc_gen = n_cvt - 1; G.gen_stride = 3 * ((n_cvt + 2) * (n_cvt + 1) / 2);
+    const size_t smem = gen_smem_bytes(n_cvt - 1, 1);
+    cudaError_t e = cudaFuncSetAttribute(lmm_null_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lmm_null_kernel<-1><<<1, 32, smem, st>>>(G, l_min, l_max, n_region, out);
+    return cudaGetLastError();
+  }
   switch (n_cvt) {
     case 1: lmm_null_kernel<0><<<1, 32, 0, st>>>(D, l_min, l_max, n_region, out); break;
     case 2: lmm_null_kernel<1><<<1, 32, 0, st>>>(D, l_min, l_max, n_region, out); break;

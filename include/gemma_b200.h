@@ -61,7 +61,7 @@ typedef struct {
   double vg_mle, ve_mle, vg_remle, ve_remle;
 } gb200_nullmodel;
 
-#define GB200_MAX_CVT 6      /* covariates incl. intercept supported by the fused per-SNP kernel */
+#define GB200_MAX_CVT 32     /* covariates incl. intercept (1..3 lockstep pipeline kernel, 4..6 register kernel, 7..32 shared-memory-table kernel) */
 
 /* ---- context ---------------------------------------------------------------- */
 GB200_API int gb200_abi_version(void);

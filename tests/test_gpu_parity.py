@@ -98,6 +98,45 @@ def test_assoc_kernel_all_modes_vs_oracle(ctx, n, c, seed):
     ctx.set_option("lmm_kernel", 0)
 
 
+@pytest.mark.parametrize("n,c,seed", [(310, 4, 21), (280, 6, 22), (333, 7, 23), (401, 12, 24), (520, 20, 25), (700, 32, 26)])
+def test_assoc_many_covariates_vs_oracle(ctx, n, c, seed):
+    """c = 4..6: register-table kernel; c >= 7: the shared-memory-table kernel (GWAS runs carry age / sex / 10-20 PCs)."""
+    pb = random_problem(n, c, 48, seed)
+    UtW, Uty = ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
+    nm = ctx.lmm_null(pb["trace_G"])
+    l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"])
+    l_re, logl_re = O.calc_lambda_null("R", pb["ev"], pb["UtW"], pb["Uty"])
+    assert nm["l_mle_null"] == pytest.approx(l_mle, rel=5e-5) and nm["logl_mle_H0"] == pytest.approx(logl, rel=1e-9)
+    assert nm["l_remle_null"] == pytest.approx(l_re, rel=5e-5) and nm["logl_remle_H0"] == pytest.approx(logl_re, rel=1e-9)
+    pve, pve_se = O.calc_pve(pb["ev"], pb["UtW"], pb["Uty"], l_re, pb["trace_G"])
+    assert nm["pve_null"] == pytest.approx(pve, rel=1e-5) and nm["pve_se_null"] == pytest.approx(pve_se, rel=1e-4)
+    vg, ve, beta, se = O.calc_vgvebeta(pb["ev"], pb["UtW"], pb["Uty"], l_re)
+    assert np.allclose(nm["beta_remle"], beta, rtol=1e-5, atol=1e-9) and np.allclose(nm["se_beta_remle"], se, rtol=1e-5)
+    UtX = pb["U"].T @ pb["X"]
+    for mode in (1, 4, 9):
+        ref = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, mode, l_mle_null=l_mle, logl_mle_H0=logl)
+        ctx.lmm_params(mode, l_mle_null=l_mle, logl_mle_H0=logl)
+        got = ctx.lmm_assoc_utx(np.ascontiguousarray(UtX.T))
+        check_sumstat(got, ref, mode)
+
+
+def test_generic_covariate_kernel_is_bitwise_equal_to_register_kernel(ctx):
+    """lmm_kernel = 3 forces the any-c kernel: same sums in the same order -> identical bits for c <= 6."""
+    for n, c, seed in ((257, 1, 31), (300, 3, 32), (290, 5, 33)):
+        pb = random_problem(n, c, 64, seed)
+        ctx.lmm_setup_rotated(pb["U"], pb["ev"], pb["UtW"], pb["Uty"])
+        l_mle, logl = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"])
+        UtXt = np.ascontiguousarray((pb["U"].T @ pb["X"]).T)
+        ctx.lmm_params(4, l_mle_null=l_mle, logl_mle_H0=logl)
+        ctx.set_option("lmm_kernel", 1); a = ctx.lmm_assoc_utx(UtXt); nm1 = ctx.lmm_null(pb["trace_G"])
+        ctx.set_option("lmm_kernel", 3); b = ctx.lmm_assoc_utx(UtXt); nm3 = ctx.lmm_null(pb["trace_G"])
+        ctx.set_option("lmm_kernel", 0)
+        for k in a.dtype.names:
+            assert np.array_equal(a[k], b[k], equal_nan=True), (c, k)
+        for k in ("l_mle_null", "l_remle_null", "logl_mle_H0", "logl_remle_H0", "pve_null", "pve_se_null"):
+            assert nm1[k] == nm3[k], (c, k)
+
+
 def test_assoc_nondefault_search_grid_and_boundaries(ctx):
     # narrow / shifted lambda ranges force the "no sign change" and clamp branches (lmm.cpp:1985-2000)
     pb = random_problem(200, 1, 40, 9, causal=False)
@@ -206,7 +245,7 @@ def test_state_errors():
     with pytest.raises(gemma_b200.GB200Error):
         c.kin_add(np.zeros((8, 2)))
     with pytest.raises(gemma_b200.GB200Error):
-        c.lmm_setup(np.eye(5), np.ones(5), np.ones((5, 7)), np.ones(5))       # n_cvt > GB200_MAX_CVT
+        c.lmm_setup(np.eye(40), np.ones(40), np.ones((40, 33)), np.ones(40))  # n_cvt > GB200_MAX_CVT
     c.close()
 
 
