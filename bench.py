@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cta-pair", type=int, default=-1, help="tensor-core kernels as CTA pairs (cta_group::2): -1 library default, 0, 1")
     ap.add_argument("--overlap", type=int, default=-1, help="sub-batch pipeline (projection || per-SNP tests): -1 default, 0, 1")
     ap.add_argument("--workload", default="lmm", choices=["lmm", "gk"], help="lmm: SNPs/s of -lmm (headline); gk: K=XX^T TFLOP/s")
+    ap.add_argument("--cvt", type=int, default=1, help="covariates incl. intercept (headline config: 1); extra columns are synthetic N(0,1)")
     ap.add_argument("--gk-miss", type=float, default=0.0, help="--workload gk: fraction of missing genotypes in the synthetic data")
     ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="SNPs in the CPU baseline sample (0 = auto)")
@@ -235,9 +236,12 @@ def run_b200(args):
     gc = torch.from_numpy(synth.genotypes(n, 64, seed=SEED, snp_offset=10 ** 9).astype(np.float64))
     y_h = synth.phenotype(n, gc.numpy(), SEED)
     y = torch.from_numpy(y_h).to(dev)
-    UtWt = (torch.ones((1, n), dtype=torch.float64, device=dev) @ U).contiguous()      # (U^T 1)^T, 1 x n
+    Wt = torch.ones((args.cvt, n), dtype=torch.float64, device=dev)
+    if args.cvt > 1:
+        Wt[:args.cvt - 1] = torch.randn((args.cvt - 1, n), dtype=torch.float64, device=dev, generator=g)   # intercept stays LAST
+    UtWt = (Wt @ U).contiguous()                                                       # (U^T W)^T, c x n
     Uty = (y @ U).contiguous()
-    ctx.lmm_setup_rotated_dev(n, 1, U.data_ptr(), ev.data_ptr(), UtWt.data_ptr(), Uty.data_ptr())
+    ctx.lmm_setup_rotated_dev(n, args.cvt, U.data_ptr(), ev.data_ptr(), UtWt.data_ptr(), Uty.data_ptr())
     nm = ctx.lmm_null(float(ev_h.mean()))
     ctx.lmm_params(args.mode, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
 
@@ -370,8 +374,8 @@ def run_b200(args):
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "-lmm %d (Wald+LRT+score), n=%d individuals, %d SNPs per step per GPU from PLINK 2-bit rows, "
-                                   "c=1 covariate, precomputed eigendecomposition (BASELINE config 4: 5M SNPs sharded by SNP)"
-                                   % (args.mode, n, B),
+                                   "c=%d covariate(s), precomputed eigendecomposition (BASELINE config 4: 5M SNPs sharded by SNP)"
+                                   % (args.mode, n, B, args.cvt),
                        "n": n, "snps_per_step_per_gpu": B, "parallelism": "snp-shard x%d, 1 NCCL all-gather of SUMSTAT rows" % world,
                        "l2": "every step reads a different %.0f MB .bed batch and streams %.1f GB of U planes (inputs >> L2)"
                              % (B * bps / 1e6, (args.slices or 6) * n * n / 1e9)},

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) lmm_assoc_kernel(LmmConst D, LmmParams pr
 
 // v2: one CTA = 8 warps = 8 SNPs in lockstep passes over shared-memory stages (lmm_v2.cuh)
 template <int NC>
-__global__ void __launch_bounds__(V2_THREADS, GB_V2_CTAS) lmm_assoc_v2_kernel(LmmConst D, LmmParams prm,
+__global__ void __launch_bounds__(V2_THREADS, (NC <= GB_V2_CTAS2_MAXNC) ? GB_V2_CTAS : 1) lmm_assoc_v2_kernel(LmmConst D, LmmParams prm,
                                                                     const double *__restrict__ UtXt, size_t ldu, int l,
                                                                     gb200_sumstat *__restrict__ out,
                                                                     unsigned int *__restrict__ ticket) {

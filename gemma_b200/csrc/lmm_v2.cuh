@@ -25,6 +25,9 @@ namespace gb {
 #ifndef GB_V2_WARPS
 #define GB_V2_WARPS 8
 #endif
+#ifndef GB_V2_CTAS2_MAXNC
+#define GB_V2_CTAS2_MAXNC 1     // covariate counts up to this run 2 CTAs per SM (<= 128 registers); larger tables get the full register file
+#endif
 #ifndef GB_V2_CTAS
 #define GB_V2_CTAS 2
 #endif
