@@ -40,6 +40,9 @@ __global__ void __launch_bounds__(V2_THREADS, (NC <= GB_V2_CTAS2_MAXNC) ? GB_V2_
   __shared__ unsigned int grp_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = D.n_c / V2_CHUNK, pad = D.n_c - D.n;
+#if GB_V2_TMA
+  v2_pipeline_init(v2_smem, NC);
+#endif
   for (;;) {
     if (threadIdx.x == 0) grp_s = atomicAdd(ticket, 1u);
     __syncthreads();

@@ -5,7 +5,9 @@
 //
 //  * a CTA holds 8 warps = 8 SNPs that walk the n rotated individuals in LOCKSTEP passes.  The
 //    SNP-independent vectors (eigenvalues, rotated covariates, rotated phenotype) are staged once per
-//    CTA and chunk in shared memory by a 3-stage cp.async pipeline and shared by the 8 SNPs; every
+//    CTA and chunk in shared memory by a 3-stage TMA bulk-copy pipeline (one elected thread issues the 2 KB row copies,
+//    completion counted in bytes on an mbarrier per stage; GB_V2_TMA=0 selects the older per-thread cp.async
+//    variant) and shared by the 8 SNPs; every
 //    warp's own U^T x row streams through its private slice of the same stages.  At n = 50 000 the
 //    v1 kernel re-read 1.6 MB per SNP and pass through L2 with ~2 KB in flight per warp
 //    (latency-bound, 17% of the FP64 pipe); here a pass moves 0.55 MB per SNP with two 22 KB stages in
@@ -48,6 +50,44 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA (bulk async copy) producer: one elected thread queues the 2 KB rows of a stage, completion is counted in bytes
+// on the stage's mbarrier; the other 255 threads issue nothing (the per-thread cp.async variant spent ~15% of the kernel's
+// instructions on copy addressing).  Barriers + the pass counter live in the 64 spare bytes behind the stages.
+#ifndef GB_V2_TMA
+#define GB_V2_TMA 1
+#endif
+__device__ __forceinline__ uint32_t v2_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void v2_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = v2_smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void v2_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(v2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(v2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t *v2_bars(double *smem, int nc) { return reinterpret_cast<uint64_t *>(smem + v2_stage_doubles(nc) * V2_STAGES); }
+
+// once per kernel, before the first pass
+__device__ __forceinline__ void v2_pipeline_init(double *smem, int nc) {
+  if (threadIdx.x == 0) {
+    uint64_t *bars = v2_bars(smem, nc);
+    for (int s = 0; s < V2_STAGES; ++s) v2_mbar_init(&bars[s], 1);
+    *reinterpret_cast<unsigned int *>(&bars[V2_STAGES]) = 0u;        // passes completed so far
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
 // reciprocal of den >= 1 (finite): hardware seed + two Newton-Raphson steps, ~1 ulp
 __device__ __forceinline__ double rcp_ge1(double den) {
   double r;
@@ -86,6 +126,25 @@ __device__ __forceinline__ void v2_issue(const LmmConst &D, const double *const 
   }
 }
 
+// thread 0 only: queue chunk `c` into `stage` with bulk copies that complete on `bar`
+template <int NC>
+__device__ __forceinline__ void v2_issue_tma(const LmmConst &D, const double *const *xrows, double *stage, int c, uint64_t *bar) {
+  constexpr uint32_t ROW = V2_CHUNK * sizeof(double);
+  const size_t off0 = (size_t)c * V2_CHUNK;
+  uint32_t rows = NC + 2;
+#pragma unroll
+  for (int w = 0; w < V2_WARPS; ++w) rows += (xrows[w] != nullptr) ? 1u : 0u;
+  v2_mbar_expect_tx(bar, rows * ROW);
+  v2_bulk_load(stage, D.delta + off0, ROW, bar);
+#pragma unroll
+  for (int a = 0; a < NC; ++a) v2_bulk_load(stage + (a + 1) * V2_CHUNK, D.Wt + (size_t)a * D.ldv + off0, ROW, bar);
+  v2_bulk_load(stage + (NC + 1) * V2_CHUNK, D.y + off0, ROW, bar);
+  double *xs = stage + (NC + 2) * V2_CHUNK;
+#pragma unroll
+  for (int w = 0; w < V2_WARPS; ++w)
+    if (xrows[w]) v2_bulk_load(xs + w * V2_CHUNK, xrows[w] + off0, ROW, bar);
+}
+
 template <int NC, int NS, int KLO, int KHI>
 struct V2Acc {
   static constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
@@ -95,12 +154,52 @@ struct V2Acc {
   double ld[NS];
 };
 
+// arithmetic of one staged chunk for this warp's SNP: 8 individuals per lane, all slots and powers
+template <int NC, int NS, int KLO, int KHI, bool LD>
+__device__ __forceinline__ void v2_chunk(const double *__restrict__ st, int warp, int lane, const double (&lam)[NS],
+                                         V2Acc<NC, NS, KLO, KHI> &acc) {
+  constexpr int NV = NC + 2;
+  constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
+  constexpr int NK = KHI - KLO + 1;
+  const double *sl = st + lane;
+  const double *xl = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK + lane;
+#pragma unroll
+  for (int u = 0; u < V2_CHUNK / 32; ++u) {
+    const int j = u * 32;
+    double v[NV];
+    const double dl = sl[j];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) v[a] = sl[(a + 1) * V2_CHUNK + j];
+    v[NC] = xl[j];
+    v[NC + 1] = sl[(NC + 1) * V2_CHUNK + j];
+    // products shared by all slots and powers
+    double pr[NIDX];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int b = a; b < NV; ++b) pr[abidx(a, b, NV)] = v[a] * v[b];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const double den = fma(lam[s], dl, 1.0);
+      const double h = rcp_ge1(den);
+      if (LD) acc.ld[s] += log(den);
+      double hk = (KLO == 0) ? 1.0 : h;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        acc.tr[s][k] += hk;
+#pragma unroll
+        for (int q = 0; q < NIDX; ++q) acc.S[s][k][q] = fma(hk, pr[q], acc.S[s][k][q]);
+        hk *= h;
+      }
+    }
+  }
+}
+
 // One lockstep pass.  Every thread of the CTA must call it (pipeline + barriers); `active` selects
 // whether this warp does arithmetic.  want_ld[s] adds sum log|lambda*delta+1| for slot s.
 template <int NC, int NS, int KLO, int KHI, bool LD>
 __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
                                         int pad, bool active, const double (&lam)[NS], V2Acc<NC, NS, KLO, KHI> &acc) {
-  constexpr int NV = NC + 2;
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   constexpr int NK = KHI - KLO + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -115,6 +214,37 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
       for (int j = 0; j < NIDX; ++j) acc.S[s][k][j] = 0.0;
     }
   }
+#if GB_V2_TMA
+  uint64_t *bars = v2_bars(smem, NC);
+  const unsigned int npass = *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]);     // identical in every thread
+  // fills of stage s per pass (every pass walks the same nchunks): phase parity = (passes * fills + fill index) & 1
+  unsigned int base_par[V2_STAGES];
+#pragma unroll
+  for (int s = 0; s < V2_STAGES; ++s) {
+    const unsigned int fills = (s < nchunks) ? (unsigned int)((nchunks - s + V2_STAGES - 1) / V2_STAGES) : 0u;
+    base_par[s] = npass * fills;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < V2_STAGES - 1; ++c)
+      if (c < nchunks) v2_issue_tma<NC>(D, xrows, smem + (size_t)c * stage_d, c, &bars[c]);
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    __syncthreads();                                      // everyone is done with chunk c-1: its stage may be refilled
+    if (threadIdx.x == 0) {
+      const int cn = c + V2_STAGES - 1;
+      if (cn < nchunks) v2_issue_tma<NC>(D, xrows, smem + (size_t)(cn % V2_STAGES) * stage_d, cn, &bars[cn % V2_STAGES]);
+    }
+    {
+      const int sidx = c % V2_STAGES;
+      const unsigned int par = (sidx == 0 ? base_par[0] : sidx == 1 ? base_par[1] : base_par[V2_STAGES - 1]) + (unsigned int)(c / V2_STAGES);
+      v2_mbar_wait(&bars[sidx], par & 1u);                // chunk c has landed
+    }
+    if (active) v2_chunk<NC, NS, KLO, KHI, LD>(smem + (size_t)(c % V2_STAGES) * stage_d, warp, lane, lam, acc);
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]) = npass + 1u;
+  __syncthreads();                                        // stages are free for the next pass; the counter is visible
+#else
   // prologue: stages 0 .. STAGES-2
 #pragma unroll
   for (int c = 0; c < V2_STAGES - 1; ++c) {
@@ -129,46 +259,11 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
       if (cn < nchunks) v2_issue<NC>(D, xrows, smem + (size_t)(cn % V2_STAGES) * stage_d, cn);
       cp_async_commit();
     }
-    if (active) {
-      const double *st = smem + (size_t)(c % V2_STAGES) * stage_d;
-      const double *xs = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK;
-      const double *sl = st + lane;
-      const double *xl = xs + lane;
-#pragma unroll
-      for (int u = 0; u < V2_CHUNK / 32; ++u) {
-        constexpr int dummy_ = 0; (void)dummy_;
-        const int j = u * 32;
-        double v[NV];
-        const double dl = sl[j];
-#pragma unroll
-        for (int a = 0; a < NC; ++a) v[a] = sl[(a + 1) * V2_CHUNK + j];
-        v[NC] = xl[j];
-        v[NC + 1] = sl[(NC + 1) * V2_CHUNK + j];
-        // products shared by all slots and powers
-        double pr[NIDX];
-#pragma unroll
-        for (int a = 0; a < NV; ++a)
-#pragma unroll
-          for (int b = a; b < NV; ++b) pr[abidx(a, b, NV)] = v[a] * v[b];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const double den = fma(lam[s], dl, 1.0);
-          const double h = rcp_ge1(den);
-          if (LD) acc.ld[s] += log(den);
-          double hk = (KLO == 0) ? 1.0 : h;
-#pragma unroll
-          for (int k = 0; k < NK; ++k) {
-            acc.tr[s][k] += hk;
-#pragma unroll
-            for (int q = 0; q < NIDX; ++q) acc.S[s][k][q] = fma(hk, pr[q], acc.S[s][k][q]);
-            hk *= h;
-          }
-        }
-      }
-    }
+    if (active) v2_chunk<NC, NS, KLO, KHI, LD>(smem + (size_t)(c % V2_STAGES) * stage_d, warp, lane, lam, acc);
   }
   cp_async_wait<0>();
   __syncthreads();                                        // stages are free for the next pass
+#endif
   if (active) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
