@@ -317,7 +317,7 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")        # per-launch DRAM bytes from the committed ncu capture of this exact config
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        if tj.get("n") == n and tj.get("batch") == B and tj.get("slices") == (args.slices or 6):
+        if tj.get("n") == n and tj.get("batch") == B and tj.get("slices") == ctx.get_option("n_slices"):
             traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
     utx_ms, utx_n = prof["utx"]
     lmm_ms, lmm_n = prof["lmm"]
@@ -333,7 +333,7 @@ def run_b200(args):
                         "integer MACs (see DESIGN.md)",
                 "share_of_step": utx_ms / ms, "avg_launch_ms": utx_ms / utx_n}
         if args.utx_path != 1 and n >= 1024:
-            T = args.slices or 6
+            T = ctx.get_option("n_slices")
             roof["executed"] = {"tops_int8": ach * T, "digit_planes": T, "frac_of_2x_bf16_peak": ach * T / (2.0 * peaks["bf16"]),
                                 "note": "integer MACs actually issued on the tensor pipe (T exact int8 digit planes of U per "
                                         "FP64-equivalent product); the dense int8 rate of sm_100a is 2x the bf16 rate"}
@@ -378,7 +378,7 @@ def run_b200(args):
                                    % (args.mode, n, B, args.cvt),
                        "n": n, "snps_per_step_per_gpu": B, "parallelism": "snp-shard x%d, 1 NCCL all-gather of SUMSTAT rows" % world,
                        "l2": "every step reads a different %.0f MB .bed batch and streams %.1f GB of U planes (inputs >> L2)"
-                             % (B * bps / 1e6, (args.slices or 6) * n * n / 1e9)},
+                             % (B * bps / 1e6, ctx.get_option("n_slices") * n * n / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roof, "roofline_lmm": lmm_roof, "cpu_baseline": cpu, "gk": gk,
             "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in prof.items()}}

@@ -81,6 +81,7 @@ SIGNATURES = {
     "gb200_lmm_project": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_project_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),
+    "gb200_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_long)]),
 }
 
 _LIB = None
@@ -147,6 +148,11 @@ class Context:
 
     def set_option(self, name, value):
         self._chk(self.lib.gb200_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_long()
+        self._chk(self.lib.gb200_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
 
     def profile_enable(self, on=True):
         self._chk(self.lib.gb200_profile_enable(self.h, int(on)))

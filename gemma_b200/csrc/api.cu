@@ -14,6 +14,7 @@ int i8_prepare(gb200_ctx *ctx);                       // slice U into int8 plane
 int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                    size_t l, size_t bytes_per_snp, double *UtXt_dev);   // UtXt l x n (ld n)
 bool i8_available(gb200_ctx *ctx);
+int i8_default_planes(size_t n);
 bool kin_i8_eligible(gb200_ctx *ctx);
 int kin_i8_begin(gb200_ctx *ctx);
 int kin_i8_add_chunk(gb200_ctx *ctx, const unsigned char *bed_dev, size_t l, size_t bytes_per_snp, bool *taken);
@@ -158,6 +159,20 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value != c->n_slices) c->i8.ready = false;
     c->n_slices = value; return GB200_OK;
   }
+  return set_err(c, GB200_ERR_ARG, std::string("unknown option ") + name);
+}
+
+int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
+  if (!c) return GB200_ERR_ARG;
+  if (!name || !value) return set_err(c, GB200_ERR_ARG, "gb200_get_option: null argument");
+  if (!strcmp(name, "n_slices")) { *value = c->n_slices > 0 ? c->n_slices : (c->n ? i8_default_planes(c->n) : 0); return GB200_OK; }   // effective
+  if (!strcmp(name, "utx_path")) { *value = c->utx_path; return GB200_OK; }
+  if (!strcmp(name, "overlap")) { *value = c->overlap; return GB200_OK; }
+  if (!strcmp(name, "cta_pair")) { *value = c->cta_pair; return GB200_OK; }
+  if (!strcmp(name, "kin_cta_pair")) { *value = c->kin_cta_pair; return GB200_OK; }
+  if (!strcmp(name, "kin_path")) { *value = c->kin_path; return GB200_OK; }
+  if (!strcmp(name, "kin_miss_max_permille")) { *value = (long)(c->kin_miss_max * 1000.0 + 0.5); return GB200_OK; }
+  if (!strcmp(name, "lmm_kernel")) { *value = c->lmm_kernel; return GB200_OK; }
   return set_err(c, GB200_ERR_ARG, std::string("unknown option ") + name);
 }
 

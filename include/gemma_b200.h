@@ -190,12 +190,17 @@ GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, co
                           size_t ni_total, size_t l, size_t bytes_per_snp, double *UtXt);
 
 /* Tuning knobs (0 keeps the default): utx_path 0 auto, 1 FP64 tiled, 2 int8 tensor-core
- * (error-free U slicing, integer genotypes only); n_slices of the int8 path; lmm_kernel 0 auto,
- * 1 warp-per-SNP kernel, 2 lockstep-CTA pipeline kernel (n_cvt <= 3, n_region <= 64); cta_pair /
+ * (exact int8 digit planes of U, integer genotypes only); n_slices = digit planes of that path (0 = smallest count whose
+ * truncation noise sqrt(n) 2^-(6+8(T-1)) stays below 2^-30: 5 up to n = 65 536, else 6); lmm_kernel 0 auto,
+ * 1 warp-per-SNP register kernel (n_cvt <= 6), 2 lockstep-CTA pipeline kernel (n_cvt <= 3, n_region <= 64), 3 the
+ * any-covariate-count kernel (default for n_cvt >= 7); kin_miss_max_permille: chunks with a larger share of missing
+ * genotypes take the dense FP64 kinship path (default 200); cta_pair /
  * kin_cta_pair 0|1 run the projection / kinship tensor-core kernel as CTA pairs (cta_group::2);
  * kin_path 0 auto, 1 FP64 only; overlap 0|1 pipelines 2048-SNP sub-batches of the bed entry points on two streams
  * (projection of sub-batch i+1 || tests of sub-batch i; measured slower on B200, default 0). */
 GB200_API int gb200_set_option(gb200_ctx *ctx, const char *name, long value);
+/* Current value of a knob; "n_slices" returns the EFFECTIVE plane count for the individuals of the last gb200_lmm_setup*. */
+GB200_API int gb200_get_option(gb200_ctx *ctx, const char *name, long *value);
 
 #ifdef __cplusplus
 }
