@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cta-pair", type=int, default=-1, help="tensor-core kernels as CTA pairs (cta_group::2): -1 library default, 0, 1")
     ap.add_argument("--overlap", type=int, default=-1, help="sub-batch pipeline (projection || per-SNP tests): -1 default, 0, 1")
     ap.add_argument("--workload", default="lmm", choices=["lmm", "gk"], help="lmm: SNPs/s of -lmm (headline); gk: K=XX^T TFLOP/s")
+    ap.add_argument("--lmm-hoist", type=int, default=-1, help="lockstep kernel: hoisted common-lambda passes: -1 default, 0, 1")
     ap.add_argument("--cvt", type=int, default=1, help="covariates incl. intercept (headline config: 1); extra columns are synthetic N(0,1)")
     ap.add_argument("--gk-miss", type=float, default=0.0, help="--workload gk: fraction of missing genotypes in the synthetic data")
     ap.add_argument("--lmm-kernel", type=int, default=0, help="0 auto, 1 warp-per-SNP, 2 lockstep-CTA pipeline")
@@ -211,6 +212,8 @@ def run_b200(args):
     ctx = gemma_b200.Context(local, stream=stream.cuda_stream)
     ctx.set_option("utx_path", args.utx_path)
     ctx.set_option("n_slices", args.slices)
+    if args.lmm_hoist >= 0:
+        ctx.set_option("lmm_hoist", args.lmm_hoist)
     ctx.set_option("lmm_kernel", args.lmm_kernel)
     if args.cta_pair >= 0:
         ctx.set_option("cta_pair", args.cta_pair)
@@ -318,7 +321,7 @@ def run_b200(args):
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("n") == n and tj.get("batch") == B and tj.get("slices") == ctx.get_option("n_slices"):
-            traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
+            traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict) and "dram_read_bytes" in v}
     utx_ms, utx_n = prof["utx"]
     lmm_ms, lmm_n = prof["lmm"]
     flops_per_launch = 2.0 * n * n * B                    # 2 n^2 per SNP x SNPs per launch

@@ -154,6 +154,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 3) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2,3");
     c->lmm_kernel = value; return GB200_OK;
   }
+  if (!strcmp(name, "lmm_hoist")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "lmm_hoist must be 0 or 1");
+    c->lmm_hoist = value; return GB200_OK;
+  }
   if (!strcmp(name, "n_slices")) {
     if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "n_slices must be 0..8");
     if (value != c->n_slices) c->i8.ready = false;
@@ -173,6 +177,7 @@ int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
   if (!strcmp(name, "kin_path")) { *value = c->kin_path; return GB200_OK; }
   if (!strcmp(name, "kin_miss_max_permille")) { *value = (long)(c->kin_miss_max * 1000.0 + 0.5); return GB200_OK; }
   if (!strcmp(name, "lmm_kernel")) { *value = c->lmm_kernel; return GB200_OK; }
+  if (!strcmp(name, "lmm_hoist")) { *value = c->lmm_hoist; return GB200_OK; }
   return set_err(c, GB200_ERR_ARG, std::string("unknown option ") + name);
 }
 
@@ -350,7 +355,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
   if (n_cvt > GB200_MAX_CVT)
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false;
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
   c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
   GB_CUDA(c, c->dU.reserve(n * n * sizeof(double)));
@@ -422,7 +427,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
     return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated_dev: bad argument");
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false;
   const size_t n_c = round_up(n, 512);
   c->dUtXt.release(); c->dUtXt2.release();
   c->dU.adopt(const_cast<double *>(U_dev), n * n * 8);          // borrowed: caller keeps it alive
@@ -445,6 +450,7 @@ static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
+  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0;
   D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
   D.gen_stride = 0;
   return D;
@@ -540,6 +546,7 @@ int gb200_lmm_params(gb200_ctx *c, int a_mode, double l_min, double l_max, size_
     return set_err(c, GB200_ERR_ARG, "gb200_lmm_params: need 0 < l_min < l_max, n_region >= 1");
   c->prm.a_mode = a_mode; c->prm.l_min = l_min; c->prm.l_max = l_max; c->prm.n_region = (int)n_region;
   c->prm.l_mle_null = l_mle_null; c->prm.logl_mle_H0 = logl_mle_H0;
+  c->common_ready = false;
   c->prm_ready = true;
   return GB200_OK;
 }
@@ -560,6 +567,18 @@ static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu,
   ProfScope ps(c, "lmm", 1, st);
   const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
   if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
+  if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3 && c->lmm_hoist) {
+    // SNP-independent sums at the lambdas shared by every SNP (once per setup/params pair)
+    const size_t J = (size_t)c->prm.n_region + 3, rec = lmm_common_record_doubles((int)c->n_cvt);
+    if (!c->common_ready) {
+      GB_CUDA(c, c->dHrows.reserve(J * c->n_c * sizeof(double)));
+      GB_CUDA(c, c->dCtab.reserve(J * rec * sizeof(double)));
+      GB_CUDA(c, launch_lmm_common((int)c->n_cvt, D, c->prm, c->dHrows.as<double>(), c->dCtab.as<double>(), c->stream));
+      GB_CUDA(c, cudaStreamSynchronize(c->stream));       // the tests may run on a side stream
+      c->common_ready = true;
+    }
+    D.Hrows = c->dHrows.as<double>(); D.ctab = c->dCtab.as<double>(); D.n_common = (int)J;
+  }
   if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3)
     GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));
   else

@@ -84,6 +84,8 @@ struct gb200_ctx {
   gb::DevBuf dU, dEval, dWt, dY;
   gb::LmmParams prm{};
   gb::DevBuf dNull;
+  gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
+  bool common_ready = false;
   // scratch
   gb::DevBuf dX, dUtXt, dOut, dBed, dMask, dIdx, dTicket, dTmp;
   std::vector<int> idx_host;          // analysed-individual index cache for bed batches
@@ -103,7 +105,8 @@ struct gb200_ctx {
   long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K; sparse FP64 terms for missing genotypes), 1 = FP64 only
   double kin_miss_max = 0.2;   // chunks with a larger fraction of missing genotypes take the dense FP64 path
-  long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA
+  long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA, 3 = any-covariate-count kernel
+  long lmm_hoist = 1;    // lockstep kernel: SNP-independent sums at the shared lambdas computed once per run
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)
   gb::I8State i8;
 };
@@ -158,6 +161,8 @@ cudaError_t launch_lmm_assoc(int n_cvt, const LmmConst &D, const LmmParams &prm,
                              size_t ldu, int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,
                              cudaStream_t st);
 bool lmm_v2_supported(int n_cvt, int n_region);
+cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st);
+size_t lmm_common_record_doubles(int n_cvt);
 cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,
                                 int l, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st);
 cudaError_t launch_lmm_null(int n_cvt, const LmmConst &D, double l_min, double l_max, int n_region,

@@ -35,6 +35,10 @@ struct LmmConst {
   const double *delta;   // eigenvalues (n)
   const double *Wt;      // rotated covariates, TRANSPOSED: n_cvt rows of n (coalesced per covariate)
   const double *y;       // rotated phenotype (n)
+  // common-lambda tables of the lockstep kernel (lmm_v2.cuh "hoisted" passes); null = not available
+  const double *Hrows;   // n_common rows of n_c doubles: h_i = 1/(lambda_j delta_i + 1)
+  const double *ctab;    // n_common records: SNP-independent sums at lambda_j (v2c_stride doubles each)
+  int n_common;
   int nc_gen;            // generic-covariate path (NC < 0 instantiations): number of swept covariates
   int gen_stride;        // doubles of shared-memory scratch per warp on that path (3 tables of (nc_gen+3)(nc_gen+2)/2)
 };

@@ -76,6 +76,68 @@ static cudaError_t launch_assoc_v2_nc(const LmmConst &D, const LmmParams &prm, c
   return cudaGetLastError();
 }
 
+// SNP-independent quantities at the lambdas every SNP visits (grid 0..n_region, exactly l_max, l_mle_null): one CTA per
+// lambda writes the h row and the record read by the hoisted passes of lmm_v2.cuh.  Once per (setup, params) pair.
+template <int NC>
+__global__ void __launch_bounds__(256) lmm_common_kernel(LmmConst D, LmmParams prm, double *__restrict__ H, double *__restrict__ ctab) {
+  constexpr int CN = v2c_nidx(NC), CS = v2c_stride(NC), NVC = NC + 1, NVAL = 3 * CN + 3;
+  __shared__ double part[8][NVAL];
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_region = prm.n_region;
+  const double lambda_interval = log(prm.l_max / prm.l_min) / (double)n_region;
+  const double lam = (j <= n_region) ? prm.l_min * exp(lambda_interval * (double)j) : (j == n_region + 1 ? prm.l_max : prm.l_mle_null);
+  double acc[NVAL];
+#pragma unroll
+  for (int q = 0; q < NVAL; ++q) acc[q] = 0.0;
+  double *hrow = H + (size_t)j * D.n_c;
+  for (int i = tid; i < D.n_c; i += 256) {
+    double h = 1.0;                                     // zero-padded tail: delta = 0
+    if (i < D.n) {
+      const double den = fma(lam, __ldg(D.delta + i), 1.0);
+      h = 1.0 / den;
+      const double h2 = h * h;
+      double v[NVC];
+#pragma unroll
+      for (int a = 0; a < NC; ++a) v[a] = __ldg(D.Wt + (size_t)a * D.ldv + i);
+      v[NC] = __ldg(D.y + i);
+#pragma unroll
+      for (int a = 0; a < NVC; ++a)
+#pragma unroll
+        for (int b = a; b < NVC; ++b) {
+          const double pr = v[a] * v[b];
+          const int q = abidx(a, b, NVC);
+          acc[q] += pr; acc[CN + q] = fma(h, pr, acc[CN + q]); acc[2 * CN + q] = fma(h2, pr, acc[2 * CN + q]);
+        }
+      acc[3 * CN] += h; acc[3 * CN + 1] += h2; acc[3 * CN + 2] += log(fabs(den));
+    }
+    hrow[i] = h;
+  }
+#pragma unroll
+  for (int q = 0; q < NVAL; ++q) {
+    const double t = warp_allsum(acc[q]);
+    if (lane == 0) part[wid][q] = t;
+  }
+  __syncthreads();
+  if (tid < NVAL) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += part[w][tid];
+    ctab[(size_t)j * CS + tid] = t;
+  }
+  if (tid == 0) ctab[(size_t)j * CS + 3 * CN + 3] = lam;
+}
+
+cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st) {
+  const int J = prm.n_region + 3;
+  switch (n_cvt) {
+    case 1: lmm_common_kernel<1><<<J, 256, 0, st>>>(D, prm, H, ctab); break;
+    case 2: lmm_common_kernel<2><<<J, 256, 0, st>>>(D, prm, H, ctab); break;
+    case 3: lmm_common_kernel<3><<<J, 256, 0, st>>>(D, prm, H, ctab); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+size_t lmm_common_record_doubles(int n_cvt) { return (size_t)v2c_stride(n_cvt); }
+
 bool lmm_v2_supported(int n_cvt, int n_region) { return n_cvt >= 1 && n_cvt <= 3 && n_region <= V2_MAX_REGION; }
 
 cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,

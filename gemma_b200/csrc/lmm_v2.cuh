@@ -39,8 +39,12 @@ constexpr int V2_CHUNK = 256;          // individuals per pipeline stage
 constexpr int V2_STAGES = 3;
 constexpr int V2_MAX_REGION = 64;
 constexpr int V2_NSG = 2;              // grid lambdas per pass (register budget: 2 CTAs per SM need <= 128 registers)
+constexpr int V2_NSC = 5;              // common-lambda slots per hoisted pass (h rows staged next to the data rows)
 
-__host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS) * V2_CHUNK; }
+__host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS + V2_NSC) * V2_CHUNK; }
+// SNP-independent sums at one common lambda: S^k_ab over (w_1..w_c, y) for k = 0,1,2, then sum h, sum h^2, sum log(l d+1), lambda
+__host__ __device__ constexpr int v2c_nidx(int nc) { return (nc + 2) * (nc + 1) / 2; }
+__host__ __device__ constexpr int v2c_stride(int nc) { return 3 * v2c_nidx(nc) + 4; }
 __host__ __device__ constexpr size_t v2_smem_bytes(int nc) { return v2_stage_doubles(nc) * V2_STAGES * sizeof(double) + 64; }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -278,6 +282,135 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
   }
 }
 
+// ---- hoisted passes ---------------------------------------------------------------------------------------------
+// The lambdas of the grid scan, the two end points and the score test are the same for every SNP of a run, so everything
+// that does not involve x is computed ONCE (lmm_common_kernel): h rows, S^k_ab over (w, y), sum h^k, sum log(l d + 1).
+// A hoisted pass then only accumulates the c+2 sums per power that involve this SNP's x, for V2_NSC lambdas at a time,
+// with h read from the staged rows instead of being recomputed (no reciprocal, no log): 7 FP64 operations per
+// (individual, lambda) for c = 1 instead of 21-54, and 3 passes instead of 7 for the default 10-interval grid.
+template <int NC>
+struct V2CAcc {
+  double X[V2_NSC][2][NC + 2];     // sum h^k v_q x  for q over (w_1..w_c, x, y), k = 1, 2
+  double I[NC + 2];                // unit-weight sums (the Iab table of LogRL_f)
+};
+
+template <int NC>
+__device__ __forceinline__ void v2_issue_common(const LmmConst &D, const double *const *xrows, double *stage, int c,
+                                                uint64_t *bar, const int (&jrow)[V2_NSC]) {
+  constexpr uint32_t ROW = V2_CHUNK * sizeof(double);
+  const size_t off0 = (size_t)c * V2_CHUNK;
+  uint32_t rows = NC + 1 + V2_NSC;
+#pragma unroll
+  for (int w = 0; w < V2_WARPS; ++w) rows += (xrows[w] != nullptr) ? 1u : 0u;
+  v2_mbar_expect_tx(bar, rows * ROW);
+#pragma unroll
+  for (int a = 0; a < NC; ++a) v2_bulk_load(stage + (a + 1) * V2_CHUNK, D.Wt + (size_t)a * D.ldv + off0, ROW, bar);
+  v2_bulk_load(stage + (NC + 1) * V2_CHUNK, D.y + off0, ROW, bar);
+  double *xs = stage + (NC + 2) * V2_CHUNK;
+#pragma unroll
+  for (int w = 0; w < V2_WARPS; ++w)
+    if (xrows[w]) v2_bulk_load(xs + w * V2_CHUNK, xrows[w] + off0, ROW, bar);
+  double *hs = stage + (NC + 2 + V2_WARPS) * V2_CHUNK;
+#pragma unroll
+  for (int s = 0; s < V2_NSC; ++s) v2_bulk_load(hs + s * V2_CHUNK, D.Hrows + (size_t)jrow[s] * D.n_c + off0, ROW, bar);
+}
+
+template <int NC, bool WITH_I>
+__device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
+                                               bool active, const int (&jrow)[V2_NSC], V2CAcc<NC> &acc) {
+  constexpr int NQ = NC + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t stage_d = v2_stage_doubles(NC);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    acc.I[q] = 0.0;
+#pragma unroll
+    for (int s = 0; s < V2_NSC; ++s) { acc.X[s][0][q] = 0.0; acc.X[s][1][q] = 0.0; }
+  }
+  uint64_t *bars = v2_bars(smem, NC);
+  const unsigned int npass = *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]);
+  unsigned int base_par[V2_STAGES];
+#pragma unroll
+  for (int s = 0; s < V2_STAGES; ++s) {
+    const unsigned int fills = (s < nchunks) ? (unsigned int)((nchunks - s + V2_STAGES - 1) / V2_STAGES) : 0u;
+    base_par[s] = npass * fills;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < V2_STAGES - 1; ++c)
+      if (c < nchunks) v2_issue_common<NC>(D, xrows, smem + (size_t)c * stage_d, c, &bars[c], jrow);
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int cn = c + V2_STAGES - 1;
+      if (cn < nchunks) v2_issue_common<NC>(D, xrows, smem + (size_t)(cn % V2_STAGES) * stage_d, cn, &bars[cn % V2_STAGES], jrow);
+    }
+    {
+      const int sidx = c % V2_STAGES;
+      const unsigned int par = (sidx == 0 ? base_par[0] : sidx == 1 ? base_par[1] : base_par[V2_STAGES - 1]) + (unsigned int)(c / V2_STAGES);
+      v2_mbar_wait(&bars[sidx], par & 1u);
+    }
+    if (active) {
+      const double *st = smem + (size_t)(c % V2_STAGES) * stage_d;
+      const double *sl = st + lane;
+      const double *xl = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK + lane;
+      const double *hl = st + (NC + 2 + V2_WARPS) * V2_CHUNK + lane;
+#pragma unroll
+      for (int u = 0; u < V2_CHUNK / 32; ++u) {
+        const int j = u * 32;
+        const double x = xl[j];
+        double px[NQ];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) px[a] = sl[(a + 1) * V2_CHUNK + j] * x;
+        px[NC] = x * x;
+        px[NC + 1] = x * sl[(NC + 1) * V2_CHUNK + j];
+        if (WITH_I) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc.I[q] += px[q];
+        }
+#pragma unroll
+        for (int s = 0; s < V2_NSC; ++s) {
+          const double h = hl[s * V2_CHUNK + j];
+          const double h2 = h * h;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            acc.X[s][0][q] = fma(h, px[q], acc.X[s][0][q]);
+            acc.X[s][1][q] = fma(h2, px[q], acc.X[s][1][q]);
+          }
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]) = npass + 1u;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (WITH_I) acc.I[q] = warp_allsum(acc.I[q]);
+#pragma unroll
+      for (int s = 0; s < V2_NSC; ++s) { acc.X[s][0][q] = warp_allsum(acc.X[s][0][q]); acc.X[s][1][q] = warp_allsum(acc.X[s][1][q]); }
+    }
+  }
+}
+
+// full (w, x, y) table of one power from the common record (pairs without x) and this SNP's x sums
+template <int NC>
+__device__ __forceinline__ void v2_assemble(const double *__restrict__ ct_k, const double (&Xq)[NC + 2],
+                                            double (&S)[(NC + 3) * (NC + 2) / 2]) {
+  constexpr int NV = NC + 2;
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int b = a; b < NV; ++b) {
+      double v;
+      if (a == NC) v = (b == NC) ? Xq[NC] : Xq[NC + 1];                 // xx, xy
+      else if (b == NC) v = Xq[a];                                       // w_a x
+      else v = __ldg(ct_k + abidx(a > NC ? NC : a, b > NC ? NC : b, NC + 1));   // pair over (w, y): y sits at index NC there
+      S[abidx(a, b, NV)] = v;
+    }
+}
+
 // what one slot's sums turn into
 struct V2Eval {
   double d1R, d1L, d2R, d2L, fR, fL;
@@ -499,6 +632,65 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   const bool need_search = needR || needL;
   double dummy[NIDX];
 
+#if GB_V2_TMA
+  const bool hoist = (D.ctab != nullptr);
+#else
+  const bool hoist = false;
+#endif
+  if (hoist) {
+#if GB_V2_TMA
+    // ---- hoisted passes: every lambda shared by all SNPs (grid 0..n_region, exactly l_max, l_mle_null), V2_NSC at a time
+    constexpr int CS = v2c_stride(NC), CN = v2c_nidx(NC);
+    const int n_grid = need_search ? n_region + 2 : 0;
+    const int nslots = n_grid + (needS ? 1 : 0);
+    const int j_score = n_region + 2;
+    double S1[NIDX], S2[NIDX];
+    for (int s0 = 0; s0 < nslots; s0 += V2_NSC) {
+      int jrow[V2_NSC];
+#pragma unroll
+      for (int s = 0; s < V2_NSC; ++s) {
+        const int slot = s0 + s;
+        jrow[s] = (slot < nslots) ? (slot < n_grid ? slot : j_score) : 0;
+      }
+      V2CAcc<NC> acc;
+      const bool with_I = (s0 == 0) && need_search;
+      if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc);
+      else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc);
+      if (valid) {
+        if (with_I) {
+          v2_assemble<NC>(D.ctab, acc.I, S1);
+          Derived<NC, 1> dI;
+          sweep_tables<NC, 1>(S1, dummy, dummy, dI);
+          logdetI = dI.logdet_piv;
+        }
+#pragma unroll
+        for (int s = 0; s < V2_NSC; ++s) {
+          const int slot = s0 + s;
+          if (slot < nslots) {
+            const double *ct = D.ctab + (size_t)jrow[s] * CS;
+            const double tr1 = __ldg(ct + 3 * CN), tr2 = __ldg(ct + 3 * CN + 1), ldj = __ldg(ct + 3 * CN + 2), lamj = __ldg(ct + 3 * CN + 3);
+            v2_assemble<NC>(ct + CN, acc.X[s][0], S1);
+            if (slot < n_grid && slot <= n_region) {               // grid point: dev1 of both likelihoods (+ f at l_min)
+              v2_assemble<NC>(ct + 2 * CN, acc.X[s][1], S2);
+              V2Eval ev;
+              v2_derive<NC, 2>(S1, S2, dummy, tr1, tr2, lamj, n, slot == 0, ldj, logdetI, ev);
+              glam[slot] = lamj; gd1R[slot] = ev.d1R; gd1L[slot] = ev.d1L;
+              if (slot == 0) { fRmin = ev.fR; fLmin = ev.fL; }
+            } else if (slot < n_grid) {                            // exactly l_max: f only
+              V2Eval ev;
+              v2_derive<NC, 1>(S1, dummy, dummy, tr1, 0.0, lamj, n, true, ldj, logdetI, ev);
+              fRmax = ev.fR; fLmax = ev.fL;
+            } else {                                               // score test at l_mle_null ("3 is before 1")
+              Derived<NC, 1> d;
+              sweep_tables<NC, 1>(S1, dummy, dummy, d);
+              wald_score_from<NC>(d, D.n, true, beta, se, p_score);
+            }
+          }
+        }
+      }
+    }
+#endif
+  } else {
   if (need_search) {
     // ---- pass A: lambda_0 = l_min (powers 0..2 + logdet): unit-weight pivots, dev1, f(l_min)
     {
@@ -548,6 +740,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         wald_score_from<NC>(d, D.n, true, beta, se, p_score);
       }
     }
+  }
   }
   // ---- refinement: REML and ML chains side by side, then (if needed) the Wald pass
   V2Fn FR, FL;
