@@ -33,6 +33,7 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <thread>
 
 #include "../../include/gemma_b200.h"
 #include "line_pipeline.h"
@@ -489,10 +490,32 @@ static void read_bin(const string &path, vector<double> &M, size_t &rows, size_t
 
 static void write_matrix(const Run &R, const double *M, size_t rows, size_t cols, const string &suffix) {   // WriteMatrix, src/param.cpp:1886-1910
   if (R.P.bin) write_bin(out_path(R, suffix) + ".bin", M, rows, cols);
-  std::ofstream out(out_path(R, suffix));
-  if (!out) { std::cout << "error writing file: " << out_path(R, suffix) << std::endl; return; }
-  out.precision(10);
-  for (size_t i = 0; i < rows; ++i) { for (size_t j = 0; j < cols; ++j) out << (j ? "\t" : "") << M[i * cols + j]; out << std::endl; }
+  // precision(10) with the default float field == "%.10g"; rows are formatted on the host worker threads, written in order
+  FILE *f = fopen(out_path(R, suffix).c_str(), "w");
+  if (!f) { std::cout << "error writing file: " << out_path(R, suffix) << std::endl; return; }
+  const int nt = host_threads();
+  const size_t group = std::max<size_t>(1, std::min<size_t>(rows, (size_t(1) << 22) / std::max<size_t>(cols, 1) + 1)) * (size_t)nt;
+  vector<string> text(std::min(group, rows));
+  for (size_t r0 = 0; r0 < rows; r0 += group) {
+    const size_t r1 = std::min(rows, r0 + group);
+    vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        char buf[40];
+        for (size_t i = r0 + (size_t)t; i < r1; i += (size_t)nt) {
+          string &line = text[i - r0];
+          line.clear(); line.reserve(cols * 14);
+          for (size_t j = 0; j < cols; ++j) {
+            if (j) line.push_back('\t');
+            line.append(buf, (size_t)snprintf(buf, sizeof buf, "%.10g", M[i * cols + j]));
+          }
+          line.push_back('\n');
+        }
+      });
+    for (auto &x : th) x.join();
+    for (size_t i = r0; i < r1; ++i) fwrite(text[i - r0].data(), 1, text[i - r0].size(), f);
+  }
+  fclose(f);
 }
 static void write_vector(const Run &R, const double *v, size_t n, const string &suffix) {                    // WriteVector, src/param.cpp:1912-1935
   if (R.P.bin) write_bin(out_path(R, suffix) + ".bin", v, n, 1);
@@ -586,18 +609,34 @@ static void read_kin(Run &R, vector<double> &G) {      // ReadFile_kin -km 1/2, 
   G.assign(n * n, 0.0);
   string line;
   if (R.P.k_mode == 1) {
-    size_t i_test = 0, i_total = 0;
-    while (in.next(line)) {
-      if (i_total == R.ni_total) die("number of rows in the kinship file is larger than the number of phenotypes");
-      if (!R.indicator_idv[i_total]) { i_total++; continue; }
-      size_t j_total = 0, j_test = 0;
-      for (char *p = tok(&line[0]); p; p = tok(nullptr)) {
-        if (j_total == R.ni_total) die("number of columns in the kinship file is larger than the number of individuals for row = " + std::to_string(i_total));
-        if (R.indicator_idv[j_total]) { G[i_test * n + j_test] = atof(p); j_test++; }
-        j_total++;
+    // n x n text (ReadFile_kin, -km 1): rows parsed on the worker pool, kept rows / columns copied in file order
+    struct KinBlock { size_t first = 0, nlines = 0; vector<double> v; };
+    const Run *Rc = &R;
+    LinePipeline<KinBlock> pipe(R.P.file_kin, [Rc, n](LineBlock &blk, KinBlock &out) {
+      const Run &R = *Rc;
+      out.first = blk.first_line; out.nlines = blk.lines.size();
+      for (size_t k = 0; k < blk.lines.size(); ++k) {
+        const size_t i_total = blk.first_line + k;
+        if (i_total >= R.ni_total) die("number of rows in the kinship file is larger than the number of phenotypes");
+        if (!R.indicator_idv[i_total]) continue;
+        const size_t off = out.v.size();
+        out.v.resize(off + n);
+        size_t j_total = 0, j_test = 0;
+        char *cur = blk.lines[k];
+        for (char *p = next_token(cur); p; p = next_token(cur)) {
+          if (j_total == R.ni_total) die("number of columns in the kinship file is larger than the number of individuals for row = " + std::to_string(i_total));
+          if (R.indicator_idv[j_total]) { out.v[off + j_test] = token_to_double(p); j_test++; }
+          j_total++;
+        }
+        if (j_total != R.ni_total) die("number of columns in the kinship file does not match the number of individuals for row = " + std::to_string(i_total));
       }
-      if (j_total != R.ni_total) die("number of columns in the kinship file does not match the number of individuals for row = " + std::to_string(i_total));
-      i_total++; i_test++;
+    });
+    if (!pipe.ok()) die("fail to open kinship file: " + R.P.file_kin);
+    size_t i_test = 0, i_total = 0;
+    KinBlock blk;
+    while (pipe.next(blk)) {
+      std::memcpy(G.data() + i_test * n, blk.v.data(), blk.v.size() * sizeof(double));
+      i_test += blk.v.size() / n; i_total += blk.nlines;
     }
     if (i_total != R.ni_total) die("number of rows in the kinship file does not match the number of individuals.");
   } else {
