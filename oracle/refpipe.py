@@ -133,7 +133,8 @@ def qc_bimbam(bb, indicator_idv, W=None, miss_level=0.05, maf_level=0.01, r2_lev
         miss = np.isnan(g)
         n_miss = int(miss.sum())
         gv = g[~miss]
-        maf = float(sum(gv.tolist()))      # sequential sum, as the reference accumulates
+        maf = float(np.cumsum(gv)[-1]) if gv.size else 0.0   # strictly sequential left fold, as the reference accumulates
+        # (Python >= 3.12 sum() is Neumaier-compensated and differs from the plain loop by an ulp)
         maf /= 2.0 * (ni_test - n_miss)
         n_miss_a[t] = n_miss; maf_a[t] = maf
         if n_miss / ni_test > miss_level:

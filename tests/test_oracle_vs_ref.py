@@ -1,0 +1,108 @@
+"""The restated oracle (oracle/gemma_oracle.c, oracle/refpipe.py) against the REFERENCE's own code: src/lmm.cpp, mathfunc.cpp,
+gemma_io.cpp ... compiled in place against the GSL API shim into oracle/_ref/libgemma_ref.so (`make -C oracle ref`).
+CPU only.  Skipped when neither the prebuilt library nor /root/reference is available."""
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import oracle as O
+from oracle import ref as REF
+from oracle import refpipe as R
+
+pytestmark = pytest.mark.skipif(not REF.available(), reason="oracle/_ref not built and /root/reference absent")
+
+
+def problem(n, c, l, seed, miss=0.0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, 3 * n))
+    K = O.center_matrix(A @ A.T / (3 * n))
+    ev, U = scipy.linalg.eigh(K)
+    ev, _ = O.zero_small_eval(ev)
+    W = np.ones((n, c))
+    if c > 1:
+        W[:, :c - 1] = rng.standard_normal((n, c - 1))
+    f = rng.uniform(0.05, 0.5, l)
+    G = rng.binomial(2, f[:, None], size=(l, n)).astype(np.float64)
+    y = 0.7 * (U @ (np.sqrt(ev) * rng.standard_normal(n))) + rng.standard_normal(n) + 0.5 * (G[0] - G[0].mean())
+    if miss:
+        G[rng.random(G.shape) < miss] = np.nan
+    return dict(U=U, ev=ev, W=W, y=y, G=G, UtW=U.T @ W, Uty=U.T @ y, trace_G=float(np.mean(ev)))
+
+
+def test_getab_index_table_from_the_reference_binary():
+    for c in (1, 2, 5):
+        for a in range(1, c + 3):
+            for b in range(1, c + 3):
+                assert REF.getab_index(a, b, c) == O.getab_index(a, b, c)
+
+
+@pytest.mark.parametrize("n,c,seed", [(150, 1, 1), (211, 3, 2), (97, 5, 3)])
+def test_likelihood_functions_match_reference_code(n, c, seed):
+    pb = problem(n, c, 3, seed)
+    Utx = pb["U"].T @ pb["G"][1]
+    for fn in "LR":
+        for which in (0, 1, 2):
+            for lam in (1e-5, 3.3e-3, 0.7, 1.0, 42.0, 1e5):
+                for calc_null, x in ((0, Utx), (1, None)):
+                    a = O.eval_fn(fn, which, calc_null, lam, pb["ev"], pb["UtW"], pb["Uty"], x)
+                    b = REF.eval_fn(fn, which, calc_null, lam, pb["ev"], pb["UtW"], pb["Uty"], x)
+                    assert a == pytest.approx(b, rel=1e-11, abs=1e-12), (fn, which, lam, calc_null)
+
+
+@pytest.mark.parametrize("n,c,seed", [(180, 1, 4), (230, 4, 5)])
+def test_null_model_matches_reference_code(n, c, seed):
+    pb = problem(n, c, 2, seed)
+    r = REF.null_model(pb["ev"], pb["UtW"], pb["Uty"], pb["trace_G"])
+    l_mle, logl_mle = O.calc_lambda_null("L", pb["ev"], pb["UtW"], pb["Uty"])
+    l_re, logl_re = O.calc_lambda_null("R", pb["ev"], pb["UtW"], pb["Uty"])
+    assert l_mle == pytest.approx(r["l_mle_null"], rel=1e-10) and logl_mle == pytest.approx(r["logl_mle_H0"], rel=1e-12)
+    assert l_re == pytest.approx(r["l_remle_null"], rel=1e-10) and logl_re == pytest.approx(r["logl_remle_H0"], rel=1e-12)
+    pve, pve_se = O.calc_pve(pb["ev"], pb["UtW"], pb["Uty"], l_re, pb["trace_G"])
+    assert pve == pytest.approx(r["pve_null"], rel=1e-9) and pve_se == pytest.approx(r["pve_se_null"], rel=1e-8)
+    vg, ve, beta, se = O.calc_vgvebeta(pb["ev"], pb["UtW"], pb["Uty"], l_re)
+    assert vg == pytest.approx(r["vg_remle"], rel=1e-9) and ve == pytest.approx(r["ve_remle"], rel=1e-9)
+    assert np.allclose(beta, r["beta_remle"], rtol=1e-9, atol=1e-12) and np.allclose(se, r["se_beta_remle"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,c,seed,miss", [(160, 1, 6, 0.0), (201, 2, 7, 0.03), (140, 4, 8, 0.01)])
+def test_lmm_analyze_all_modes_match_reference_code(n, c, seed, miss):
+    """LMM::Analyze itself (imputation, U^T X, CalcUab, CalcLambda, Wald / LRT / score) vs the oracle's restatement."""
+    pb = problem(n, c, 40, seed, miss)
+    nm = REF.null_model(pb["ev"], pb["UtW"], pb["Uty"], pb["trace_G"])
+    idv = np.ones(n, dtype=np.int32)
+    UtX = pb["U"].T @ O.lmm_impute(pb["G"])
+    for mode in (1, 2, 3, 4, 9):
+        ref = REF.lmm_analyze(idv, pb["U"], pb["ev"], pb["UtW"], pb["Uty"], pb["W"], pb["y"], pb["G"], mode,
+                              l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+        got = O.lmm_analyze_utx(pb["ev"], pb["UtW"], pb["Uty"], UtX, mode, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+        for k in REF.SUMSTAT:
+            a, b = got[k], ref[k]
+            ok = np.isfinite(b)
+            assert np.array_equal(np.isfinite(a), ok), (mode, k)
+            tol = 1e-6 if k.startswith("lambda") else 1e-8        # lambda: Newton stops at 1e-5, so last-bit input changes move it by ~1e-7
+            assert np.allclose(a[ok], b[ok], rtol=tol, atol=1e-300), (mode, k, np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-300)))
+
+
+def test_mouse_qc_and_kinship_match_reference_readers(golden_dir):
+    """ReadFile_geno's QC and BimbamKin of the reference itself on the mouse example: bit-exact SNP selection, K to rounding."""
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    geno = os.path.join(d, "mouse_hs1940.geno.txt.gz")
+    bb = R.Bimbam(geno)
+    ph, ind = R.read_pheno(os.path.join(d, "mouse_hs1940.pheno.txt"), (1,))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, n_miss, maf = R.qc_bimbam(bb, idv)
+    r_isnp, r_miss, r_maf, r_ns = REF.qc_bimbam(geno, idv, W)
+    assert r_ns == int(isnp.sum()) == 10768 and len(r_isnp) == 12226
+    assert np.array_equal(r_isnp, isnp) and np.array_equal(r_miss, n_miss)
+    assert np.array_equal(r_maf, maf)                                  # same sequential sums -> same bits
+    sub = np.zeros_like(isnp); sub[np.nonzero(isnp)[0][:600]] = 1      # 600 SNPs keep the reference's triple-loop dgemm shim fast
+    Kr = REF.bimbam_kin(geno, sub, 1, bb.G.shape[1])
+    Ko = R.kinship_bimbam(bb, sub, 1)
+    assert np.allclose(Kr, Ko, rtol=1e-12, atol=1e-14)
+    Kr2 = REF.bimbam_kin(geno, sub, 2, bb.G.shape[1])
+    Ko2 = R.kinship_bimbam(bb, sub, 2)
+    assert np.allclose(Kr2, Ko2, rtol=1e-11, atol=1e-13)
+    Kc = Ko[:300, :300].copy()
+    assert np.allclose(REF.center_matrix(Kc), O.center_matrix(Kc), rtol=1e-12, atol=1e-15)
