@@ -49,6 +49,14 @@ def lib():
         L.ref_qc_bimbam.restype = C.c_long
         L.ref_qc_bimbam.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_size_t, _dp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_double,
                                     C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_long), _dp, C.c_size_t, C.POINTER(C.c_long)]
+        L.ref_qc_plink.restype = C.c_long
+        L.ref_qc_plink.argtypes = L.ref_qc_bimbam.argtypes
+        L.ref_plink_kin.restype = C.c_int
+        L.ref_plink_kin.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_size_t, C.c_int, C.c_size_t, _dp]
+        L.ref_lmm_analyze_plink.restype = C.c_int
+        L.ref_lmm_analyze_plink.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_size_t, C.c_size_t, C.c_size_t,
+                                            _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_size_t, C.c_double, C.c_double,
+                                            _dp, C.c_size_t]
         L.ref_bimbam_kin.restype = C.c_int
         L.ref_bimbam_kin.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_size_t, C.c_int, C.c_size_t, _dp]
         L.ref_center_matrix.restype = None
@@ -126,6 +134,41 @@ def qc_bimbam(path, indicator_idv, W, maf_level=0.01, miss_level=0.05, hwe_level
                               C.byref(ns_test))
     assert tot >= 0
     return isnp[:tot].copy(), n_miss[:tot].copy(), maf[:tot].copy(), ns_test.value
+
+
+def qc_plink(prefix, indicator_idv, W, maf_level=0.01, miss_level=0.05, hwe_level=0.0, r2_level=0.9999, cap=1 << 22):
+    idv = np.ascontiguousarray(indicator_idv, dtype=np.int32)
+    Wt = _f(W[idv == 1])
+    isnp = np.zeros(cap, dtype=np.int32); n_miss = np.zeros(cap, dtype=np.int64); maf = np.zeros(cap); ns_test = C.c_long()
+    tot = lib().ref_qc_plink(prefix.encode(), idv.ctypes.data_as(C.POINTER(C.c_int)), len(idv), _p(Wt), Wt.shape[0], Wt.shape[1], maf_level, miss_level,
+                             hwe_level, r2_level, isnp.ctypes.data_as(C.POINTER(C.c_int)), n_miss.ctypes.data_as(C.POINTER(C.c_long)), _p(maf), cap,
+                             C.byref(ns_test))
+    assert tot >= 0
+    return isnp[:tot].copy(), n_miss[:tot].copy(), maf[:tot].copy(), ns_test.value
+
+
+def plink_kin(prefix, indicator_snp, k_mode, ni_total):
+    isnp = np.ascontiguousarray(indicator_snp, dtype=np.int32)
+    K = np.zeros((ni_total, ni_total))
+    assert lib().ref_plink_kin(prefix.encode(), isnp.ctypes.data_as(C.POINTER(C.c_int)), len(isnp), k_mode, ni_total, _p(K)) == 0
+    return K
+
+
+def lmm_analyze_plink(prefix, indicator_idv, indicator_snp, U, eval_, UtW, Uty, W, y, a_mode, l_min=1e-5, l_max=1e5, n_region=10, l_mle_null=0.0,
+                      logl_mle_H0=0.0):
+    idv = np.ascontiguousarray(indicator_idv, dtype=np.int32); isnp = np.ascontiguousarray(indicator_snp, dtype=np.int32)
+    U, eval_, UtW, Uty, W, y = _f(U), _f(eval_), _f(UtW), _f(Uty), _f(W), _f(y)
+    n, c = UtW.shape
+    cap = int(isnp.sum())
+    out = np.zeros((cap, 8))
+    got = lib().ref_lmm_analyze_plink(prefix.encode(), len(idv), idv.ctypes.data_as(C.POINTER(C.c_int)), isnp.ctypes.data_as(C.POINTER(C.c_int)), len(isnp),
+                                      n, c, _p(U), _p(eval_), _p(UtW), _p(Uty), _p(W), _p(y), a_mode, l_min, l_max, n_region, l_mle_null, logl_mle_H0,
+                                      _p(out), cap)
+    assert got == cap, (got, cap)
+    r = np.zeros(cap, dtype=[(k, "<f8") for k in SUMSTAT])
+    for i, k in enumerate(SUMSTAT):
+        r[k] = out[:, i]
+    return r
 
 
 def bimbam_kin(path, indicator_snp, k_mode, ni_total):

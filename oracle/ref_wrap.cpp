@@ -177,6 +177,57 @@ int ref_bimbam_kin(const char *file_geno, const int *indicator_snp, size_t ns_to
   return ok ? 0 : -1;
 }
 
+// ---- PLINK: ReadFile_bim + ReadFile_bed QC (src/gemma_io.cpp:514-556, 876-1064), PlinkKin (:1599-1738), LMM::AnalyzePlink (src/lmm.cpp:1710-1903)
+long ref_qc_plink(const char *prefix, const int *indicator_idv, size_t ni_total, const double *W, size_t ni_test, size_t n_cvt, double maf_level,
+                  double miss_level, double hwe_level, double r2_level, int *indicator_snp, long *n_miss, double *maf, size_t cap, long *ns_test_out) {
+  Quiet q;
+  vector<SNPINFO> info;
+  if (!ReadFile_bim(string(prefix) + ".bim", info)) return -1;
+  set<string> setSnps; vector<int> idv(indicator_idv, indicator_idv + ni_total), isnp; size_t ns_test = 0;
+  gsl_matrix *mW = mat_from(W, ni_test, n_cvt, n_cvt);
+  if (!ReadFile_bed(string(prefix) + ".bed", setSnps, mW, idv, isnp, info, maf_level, miss_level, hwe_level, r2_level, ns_test)) return -1;
+  gsl_matrix_free(mW);
+  for (size_t t = 0; t < isnp.size() && t < cap; ++t) { indicator_snp[t] = isnp[t]; n_miss[t] = (long)info[t].n_miss; maf[t] = info[t].maf; }
+  *ns_test_out = (long)ns_test;
+  return (long)isnp.size();
+}
+
+int ref_plink_kin(const char *prefix, const int *indicator_snp, size_t ns_total, int k_mode, size_t ni_total, double *K) {
+  Quiet q;
+  vector<int> isnp(indicator_snp, indicator_snp + ns_total);
+  gsl_matrix *mK = gsl_matrix_alloc(ni_total, ni_total);
+  gsl_matrix_set_zero(mK);
+  const bool ok = PlinkKin(string(prefix) + ".bed", isnp, k_mode, 100000, mK);
+  for (size_t i = 0; i < ni_total; ++i) for (size_t j = 0; j < ni_total; ++j) K[i * ni_total + j] = gsl_matrix_get(mK, i, j);
+  gsl_matrix_free(mK);
+  return ok ? 0 : -1;
+}
+
+int ref_lmm_analyze_plink(const char *prefix, size_t ni_total, const int *indicator_idv, const int *indicator_snp, size_t ns_total, size_t n,
+                          size_t n_cvt, const double *U, const double *eval, const double *UtW, const double *Uty, const double *W, const double *y,
+                          int a_mode, double l_min, double l_max, size_t n_region, double l_mle_null, double logl_mle_H0, double *out, size_t cap) {
+  Quiet q;
+  LMM c;
+  c.a_mode = a_mode; c.d_pace = 100000; c.l_min = l_min; c.l_max = l_max; c.n_region = n_region; c.l_mle_null = l_mle_null;
+  c.logl_mle_H0 = logl_mle_H0; c.ni_total = ni_total; c.ni_test = n; c.ns_total = ns_total; c.n_cvt = n_cvt; c.time_UtX = 0; c.time_opt = 0;
+  c.file_bfile = prefix;
+  c.indicator_idv.assign(indicator_idv, indicator_idv + ni_total);
+  c.indicator_snp.assign(indicator_snp, indicator_snp + ns_total);
+  if (!ReadFile_bim(string(prefix) + ".bim", c.snpInfo)) return -1;
+  c.ns_test = 0; for (size_t t = 0; t < ns_total; ++t) c.ns_test += indicator_snp[t];
+  gsl_matrix *mU = mat_from(U, n, n, n), *mUtW = mat_from(UtW, n, n_cvt, n_cvt), *mW = mat_from(W, n, n_cvt, n_cvt);
+  gsl_vector *vev = vec_from(eval, n), *vUty = vec_from(Uty, n), *vy = vec_from(y, n);
+  c.AnalyzePlink(mU, vev, mUtW, vUty, mW, vy, std::set<std::string>());
+  const size_t got = c.sumStat.size();
+  for (size_t t = 0; t < got && t < cap; ++t) {
+    const SUMSTAT &s = c.sumStat[t];
+    double *o = out + 8 * t;
+    o[0] = s.beta; o[1] = s.se; o[2] = s.lambda_remle; o[3] = s.lambda_mle; o[4] = s.p_wald; o[5] = s.p_lrt; o[6] = s.p_score; o[7] = s.logl_H1;
+  }
+  gsl_matrix_free(mU); gsl_matrix_free(mUtW); gsl_matrix_free(mW); gsl_vector_free(vev); gsl_vector_free(vUty); gsl_vector_free(vy);
+  return (int)got;
+}
+
 // CenterMatrix (src/mathfunc.cpp:147-177), in place
 void ref_center_matrix(double *G, size_t n) {
   gsl_matrix_view v = gsl_matrix_view_array(G, n, n);

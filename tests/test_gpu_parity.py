@@ -137,6 +137,33 @@ def test_generic_covariate_kernel_is_bitwise_equal_to_register_kernel(ctx):
             assert nm1[k] == nm3[k], (c, k)
 
 
+def test_cuda_path_against_the_compiled_reference_itself(ctx):
+    """The CUDA path vs the REFERENCE's own LMM::Analyze / null-model code (oracle/_ref/libgemma_ref.so: src/lmm.cpp compiled in
+    place against the GSL API shim; prebuilt in the authoring container, shipped with the snapshot)."""
+    from oracle import ref as REF
+    if not REF.available():
+        pytest.skip("oracle/_ref not shipped")
+    rng = np.random.default_rng(17)
+    for n, c, seed in ((260, 1, 41), (311, 3, 42), (290, 8, 43)):
+        pb = random_problem(n, c, 72, seed)
+        G = pb["X"].T.copy()
+        G[rng.random(G.shape) < 0.02] = np.nan
+        ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], pb["y"])
+        nm = ctx.lmm_null(pb["trace_G"])
+        rnm = REF.null_model(pb["ev"], pb["UtW"], pb["Uty"], pb["trace_G"])
+        for k in ("l_mle_null", "l_remle_null"):
+            assert nm[k] == pytest.approx(rnm[k], rel=5e-5)
+        for k in ("logl_mle_H0", "logl_remle_H0", "pve_null"):
+            assert nm[k] == pytest.approx(rnm[k], rel=1e-6)
+        assert np.allclose(nm["beta_remle"], rnm["beta_remle"], rtol=1e-5, atol=1e-9)
+        for mode in (1, 2, 3, 4, 9):
+            ref = REF.lmm_analyze(np.ones(n, dtype=np.int32), pb["U"], pb["ev"], pb["UtW"], pb["Uty"], pb["W"], pb["y"], G, mode,
+                                  l_mle_null=rnm["l_mle_null"], logl_mle_H0=rnm["logl_mle_H0"])
+            ctx.lmm_params(mode, l_mle_null=rnm["l_mle_null"], logl_mle_H0=rnm["logl_mle_H0"])
+            got = ctx.lmm_batch_geno(G)
+            check_sumstat(got, ref, mode)
+
+
 def test_assoc_nondefault_search_grid_and_boundaries(ctx):
     # narrow / shifted lambda ranges force the "no sign change" and clamp branches (lmm.cpp:1985-2000)
     pb = random_problem(200, 1, 40, 9, causal=False)

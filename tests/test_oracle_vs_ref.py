@@ -106,3 +106,57 @@ def test_mouse_qc_and_kinship_match_reference_readers(golden_dir):
     assert np.allclose(Kr2, Ko2, rtol=1e-11, atol=1e-13)
     Kc = Ko[:300, :300].copy()
     assert np.allclose(REF.center_matrix(Kc), O.center_matrix(Kc), rtol=1e-12, atol=1e-15)
+
+
+def _write_plink(prefix, bed, y):
+    l, nb = bed.shape
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01])); f.write(bed.tobytes())
+    with open(prefix + ".bim", "w") as f:
+        for s in range(l):
+            f.write("%d\tsnp%d\t0\t%d\tA\tG\n" % (1 + s % 19, s, 1000 + 10 * s))
+    with open(prefix + ".fam", "w") as f:
+        for i in range(len(y)):
+            f.write("F%d I%d 0 0 1 %s\n" % (i, i, "NA" if np.isnan(y[i]) else "%.10g" % y[i]))
+
+
+def test_plink_readers_kinship_and_analyzeplink_match_reference_code(tmp_path):
+    """ReadFile_bim/bed QC, PlinkKin (-gk 1/2) and LMM::AnalyzePlink (incl. its NaN rule, src/lmm.cpp:1866-1884) of the reference
+    itself on a synthetic PLINK file set with missing genotypes and phenotypes."""
+    from gemma_b200 import synth
+    n, l = 300, 260
+    rng = np.random.default_rng(5)
+    bed, G = synth.make_bed(n, l, seed=91, miss_rate=0.02)
+    bed[7] = 0xFF                                                  # monomorphic SNP -> dropped
+    y = rng.standard_normal(n) + 0.5 * np.where(G[3] < 0, 0, G[3])
+    y[rng.choice(n, 23, replace=False)] = np.nan
+    prefix = str(tmp_path / "syn")
+    _write_plink(prefix, bed, y)
+    pl = R.Plink(prefix)
+    idv, W = R.process_cvt_phen(pl.ind_pheno)
+    isnp, n_miss, maf = R.qc_plink(pl, idv)
+    r_isnp, r_miss, r_maf, r_ns = REF.qc_plink(prefix, idv, W)
+    assert np.array_equal(r_isnp, isnp) and isnp[7] == 0 and r_ns == int(isnp.sum())
+    assert np.array_equal(r_miss[isnp == 1], n_miss[isnp == 1]) and np.allclose(r_maf[isnp == 1], maf[isnp == 1], rtol=0, atol=1e-15)
+    for k_mode in (1, 2):
+        Kr = REF.plink_kin(prefix, isnp, k_mode, n)
+        Ko = R.kinship_plink(pl, isnp, k_mode)
+        assert np.allclose(Kr, Ko, rtol=1e-11, atol=1e-13), k_mode
+    keep = idv == 1
+    K = R.kinship_plink(pl, isnp, 1)
+    prep = R.lmm_prepare(K, idv, pl.pheno[:, 0], W)
+    X = O.lmm_impute(pl.G[np.ix_(np.nonzero(isnp)[0], keep)])
+    UtX = prep["U"].T @ X
+    # a lambda range that makes Newton leave it for some SNPs exercises the NaN rule of AnalyzePlink
+    for (lo, hi) in ((1e-5, 1e5), (0.5, 2.0)):
+        l_mle, logl = O.calc_lambda_null("L", prep["eval"], prep["UtW"], prep["Uty"], lo, hi)
+        for mode in (1, 4):
+            ref = REF.lmm_analyze_plink(prefix, idv, isnp, prep["U"], prep["eval"], prep["UtW"], prep["Uty"], prep["W"], prep["y"], mode,
+                                        l_min=lo, l_max=hi, l_mle_null=l_mle, logl_mle_H0=logl)
+            got = O.lmm_analyze_utx(prep["eval"], prep["UtW"], prep["Uty"], UtX, mode, lo, hi, 10, l_mle, logl, plink=True)
+            for k in REF.SUMSTAT:
+                a, b = got[k], ref[k]
+                assert np.array_equal(np.isnan(a), np.isnan(b)), (mode, k, lo)
+                ok = np.isfinite(b)
+                tol = 1e-6 if k.startswith("lambda") else 1e-8
+                assert np.allclose(a[ok], b[ok], rtol=tol, atol=1e-300), (mode, k, lo)
