@@ -22,6 +22,7 @@ enum { GSL_SUCCESS = 0, GSL_FAILURE = -1, GSL_CONTINUE = -2, GSL_EDOM = 1, GSL_E
        GSL_EFACTOR = 6, GSL_ESANITY = 7, GSL_ENOMEM = 8, GSL_EBADFUNC = 9, GSL_ERUNAWAY = 10, GSL_EMAXITER = 11, GSL_EZERODIV = 12,
        GSL_EBADTOL = 13, GSL_ETOL = 14, GSL_EUNDRFLW = 15, GSL_EOVRFLW = 16, GSL_ELOSS = 17, GSL_EROUND = 18, GSL_EBADLEN = 19,
        GSL_ENOTSQR = 20, GSL_ESING = 21, GSL_EDIVERGE = 22 };
+#define GSL_VERSION "2.x API shim (oracle/gsl_shim)"
 #define GSL_DBL_EPSILON 2.2204460492503131e-16
 #define GSL_NAN (NAN)
 #define GSL_POSINF (INFINITY)
@@ -106,6 +107,17 @@ int gsl_matrix_get_col(gsl_vector *v, const gsl_matrix *m, const size_t j);
 int gsl_matrix_set_row(gsl_matrix *m, const size_t i, const gsl_vector *v);
 int gsl_matrix_set_col(gsl_matrix *m, const size_t j, const gsl_vector *v);
 
+typedef struct { size_t size; size_t stride; int *data; void *block; int owner; } gsl_vector_int;
+typedef struct { size_t size1; size_t size2; size_t tda; int *data; void *block; int owner; } gsl_matrix_int;
+gsl_vector_int *gsl_vector_int_alloc(size_t n);
+void gsl_vector_int_free(gsl_vector_int *v);
+static inline int gsl_vector_int_get(const gsl_vector_int *v, const size_t i) { return v->data[i * v->stride]; }
+static inline void gsl_vector_int_set(gsl_vector_int *v, const size_t i, int x) { v->data[i * v->stride] = x; }
+gsl_matrix_int *gsl_matrix_int_alloc(size_t n1, size_t n2);
+void gsl_matrix_int_free(gsl_matrix_int *m);
+static inline int gsl_matrix_int_get(const gsl_matrix_int *m, const size_t i, const size_t j) { return m->data[i * m->tda + j]; }
+static inline void gsl_matrix_int_set(gsl_matrix_int *m, const size_t i, const size_t j, int x) { m->data[i * m->tda + j] = x; }
+
 gsl_permutation *gsl_permutation_alloc(size_t n);
 gsl_permutation *gsl_permutation_calloc(size_t n);
 void gsl_permutation_init(gsl_permutation *p);
@@ -136,6 +148,7 @@ int gsl_blas_dsyr2(CBLAS_UPLO_t Uplo, double alpha, const gsl_vector *x, const g
 int gsl_blas_dger(double alpha, const gsl_vector *x, const gsl_vector *y, gsl_matrix *A);
 int gsl_blas_dgemm(CBLAS_TRANSPOSE_t TransA, CBLAS_TRANSPOSE_t TransB, double alpha, const gsl_matrix *A, const gsl_matrix *B, double beta,
                    gsl_matrix *C);
+int gsl_blas_dtrsv(CBLAS_UPLO_t Uplo, CBLAS_TRANSPOSE_t TransA, CBLAS_DIAG_t Diag, const gsl_matrix *A, gsl_vector *x);
 int gsl_blas_dsyrk(CBLAS_UPLO_t Uplo, CBLAS_TRANSPOSE_t Trans, double alpha, const gsl_matrix *A, double beta, gsl_matrix *C);
 
 int gsl_linalg_LU_decomp(gsl_matrix *A, gsl_permutation *p, int *signum);
@@ -144,6 +157,13 @@ int gsl_linalg_LU_invert(const gsl_matrix *LU, const gsl_permutation *p, gsl_mat
 double gsl_linalg_LU_det(gsl_matrix *LU, int signum);
 double gsl_linalg_LU_lndet(gsl_matrix *LU);
 
+int gsl_linalg_QR_decomp(gsl_matrix *A, gsl_vector *tau);
+int gsl_linalg_QR_solve(const gsl_matrix *QR, const gsl_vector *tau, const gsl_vector *b, gsl_vector *x);
+double gsl_sf_exp(const double x);
+double gsl_sf_log_1plusx(const double x);
+double gsl_sf_lngamma(double x);
+double gsl_sf_gamma(double x);
+double gsl_sf_lnbeta(const double a, const double b);
 int gsl_linalg_cholesky_decomp(gsl_matrix *A);
 int gsl_linalg_cholesky_decomp1(gsl_matrix *A);
 int gsl_linalg_cholesky_solve(const gsl_matrix *cholesky, const gsl_vector *b, gsl_vector *x);
@@ -230,6 +250,19 @@ int gsl_root_fdfsolver_iterate(gsl_root_fdfsolver *s);
 double gsl_root_fdfsolver_root(const gsl_root_fdfsolver *s);
 int gsl_root_test_interval(double x_lower, double x_upper, double epsabs, double epsrel);
 int gsl_root_test_delta(double x1, double x0, double epsabs, double epsrel);
+
+/* multiroots (logistic.cpp; off the validated path: declarations only) */
+typedef struct { int (*f)(const gsl_vector *x, void *params, gsl_vector *f); int (*df)(const gsl_vector *x, void *params, gsl_matrix *df);
+                 int (*fdf)(const gsl_vector *x, void *params, gsl_vector *f, gsl_matrix *df); size_t n; void *params; } gsl_multiroot_function_fdf;
+typedef struct { const char *name; } gsl_multiroot_fdfsolver_type;
+typedef struct { const gsl_multiroot_fdfsolver_type *type; gsl_multiroot_function_fdf *fdf; gsl_vector *x; gsl_vector *f; gsl_matrix *J; gsl_vector *dx;
+                 void *state; } gsl_multiroot_fdfsolver;
+extern const gsl_multiroot_fdfsolver_type *gsl_multiroot_fdfsolver_hybridsj;
+gsl_multiroot_fdfsolver *gsl_multiroot_fdfsolver_alloc(const gsl_multiroot_fdfsolver_type *T, size_t n);
+void gsl_multiroot_fdfsolver_free(gsl_multiroot_fdfsolver *s);
+int gsl_multiroot_fdfsolver_set(gsl_multiroot_fdfsolver *s, gsl_multiroot_function_fdf *fdf, const gsl_vector *x);
+int gsl_multiroot_fdfsolver_iterate(gsl_multiroot_fdfsolver *s);
+int gsl_multiroot_test_residual(const gsl_vector *f, double epsabs);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,7 @@ int gsl_blas_dsyr2(CBLAS_UPLO_t U, double alpha, const gsl_vector *x, const gsl_
   return 0;
 }
 int gsl_blas_dger(double alpha, const gsl_vector *x, const gsl_vector *y, gsl_matrix *A) { for (size_t i = 0; i < A->size1; ++i) for (size_t j = 0; j < A->size2; ++j) A->data[i * A->tda + j] += alpha * x->data[i * x->stride] * y->data[j * y->stride]; return 0; }
+#ifndef GB_HAVE_OPENBLAS
 void cblas_dgemm(const enum CBLAS_ORDER, const enum CBLAS_TRANSPOSE TA, const enum CBLAS_TRANSPOSE TB, const int M, const int N, const int K, const double alpha,
                  const double *A, const int lda, const double *B, const int ldb, const double beta, double *C, const int ldc) {
   // Row-major reference loops, k ascending.  The reference multiplies its 20000-column staging matrix even when only a few
@@ -142,6 +143,7 @@ void cblas_dgemm(const enum CBLAS_ORDER, const enum CBLAS_TRANSPOSE TA, const en
   }
   free(live); free(idx);
 }
+#endif
 int gsl_blas_dgemm(CBLAS_TRANSPOSE_t TA, CBLAS_TRANSPOSE_t TB, double alpha, const gsl_matrix *A, const gsl_matrix *B, double beta, gsl_matrix *C) {
   const int K = (int)(TA == CblasNoTrans ? A->size2 : A->size1);
   cblas_dgemm(CblasRowMajor, TA, TB, (int)C->size1, (int)C->size2, K, alpha, A->data, (int)A->tda, B->data, (int)B->tda, beta, C->data, (int)C->tda);
@@ -182,10 +184,35 @@ double gsl_linalg_LU_lndet(gsl_matrix *LU) { double d = 0.0; for (size_t i = 0; 
 
 // ---- cdf tails --------------------------------------------------------------------------------------------------------
 double gsl_cdf_fdist_Q(const double x, const double nu1, const double nu2) { return go_cdf_fdist_Q(x, nu1, nu2); }
-double gsl_cdf_chisq_Q(const double x, const double nu) {
-  if (nu != 1.0) { fprintf(stderr, "gsl shim: gsl_cdf_chisq_Q only restated for nu = 1\n"); abort(); }
-  return go_cdf_chisq1_Q(x);
+// regularised upper incomplete gamma Q(a, x): series for x < a + 1, modified Lentz continued fraction otherwise (relative
+// accuracy ~1e-14); used for gsl_cdf_chisq_Q with nu != 1 (the multivariate tests); nu == 1 keeps the pinned restatement
+static double gamma_Q(double a, double x) {
+  if (x <= 0.0) return 1.0;
+  const double lg = lgamma(a);
+  if (x < a + 1.0) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 10000; ++n) { ap += 1.0; del *= x / ap; sum += del; if (fabs(del) < fabs(sum) * 1e-17) break; }
+    return 1.0 - sum * exp(-x + a * log(x) - lg);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 10000; ++i) {
+    const double an = -i * (i - a);
+    b += 2.0;
+    d = an * d + b; if (fabs(d) < tiny) d = tiny;
+    c = b + an / c; if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < 1e-16) break;
+  }
+  return exp(-x + a * log(x) - lg) * h;
 }
+double gsl_cdf_chisq_Q(const double x, const double nu) {
+  if (nu == 1.0) return go_cdf_chisq1_Q(x);
+  return gamma_Q(0.5 * nu, 0.5 * x);
+}
+double gsl_cdf_chisq_P(const double x, const double nu) { return 1.0 - gsl_cdf_chisq_Q(x, nu); }
 
 // ---- root solvers: roots/fsolver.c + roots/brent.c, roots/fdfsolver.c + roots/newton.c, roots/convergence.c -----------
 typedef struct { double a, b, c, d, e, fa, fb, fc; } brent_state_t;
@@ -288,9 +315,29 @@ int gsl_root_test_delta(double x1, double x0, double epsabs, double epsrel) {
   return (fabs(x1 - x0) < tolerance || x1 == x0) ? GSL_SUCCESS : GSL_CONTINUE;
 }
 
+gsl_vector_int *gsl_vector_int_alloc(size_t n) { gsl_vector_int *v = (gsl_vector_int *)calloc(1, sizeof(gsl_vector_int)); v->size = n; v->stride = 1; v->data = (int *)calloc(n ? n : 1, sizeof(int)); v->owner = 1; return v; }
+void gsl_vector_int_free(gsl_vector_int *v) { if (v) { free(v->data); free(v); } }
+gsl_matrix_int *gsl_matrix_int_alloc(size_t n1, size_t n2) { gsl_matrix_int *m = (gsl_matrix_int *)calloc(1, sizeof(gsl_matrix_int)); m->size1 = n1; m->size2 = n2; m->tda = n2; m->data = (int *)calloc(n1 * n2 ? n1 * n2 : 1, sizeof(int)); m->owner = 1; return m; }
+void gsl_matrix_int_free(gsl_matrix_int *m) { if (m) { free(m->data); free(m); } }
+int gsl_blas_dsyrk(CBLAS_UPLO_t, CBLAS_TRANSPOSE_t T, double alpha, const gsl_matrix *A, double beta, gsl_matrix *C) {
+  const size_t n = C->size1, k = (T == CblasNoTrans) ? A->size2 : A->size1;
+  for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) { double s = 0.0; for (size_t q = 0; q < k; ++q) s += (T == CblasNoTrans ? gsl_matrix_get(A, i, q) * gsl_matrix_get(A, j, q) : gsl_matrix_get(A, q, i) * gsl_matrix_get(A, q, j)); C->data[i * C->tda + j] = alpha * s + (beta == 0.0 ? 0.0 : beta * C->data[i * C->tda + j]); }
+  return 0;
+}
+double gsl_sf_exp(const double x) { return exp(x); }
+double gsl_sf_log_1plusx(const double x) { return log1p(x); }
+double gsl_sf_lngamma(double x) { return lgamma(x); }
+
 // data symbols referenced by param.cpp (never used on the validated path)
 static const gsl_rng_type rng_default_type = {"shim"};
 const gsl_rng_type *gsl_rng_default = &rng_default_type;
 const gsl_rng_type *gsl_rng_mt19937 = &rng_default_type;
 unsigned long int gsl_rng_default_seed = 0;
+// the reference allocates a generator at start-up (src/param.cpp:827-844) whether or not the analysis draws numbers; the
+// univariate / multivariate LMM paths never do.  Allocation works, drawing is off-path (offpath_stubs.c).
+const gsl_rng_type *gsl_rng_env_setup(void) { return gsl_rng_default; }
+gsl_rng *gsl_rng_alloc(const gsl_rng_type *) { return (gsl_rng *)calloc(1, sizeof(gsl_rng)); }
+void gsl_rng_free(gsl_rng *r) { free(r); }
+void gsl_rng_set(const gsl_rng *, unsigned long int) {}
+const char *gsl_rng_name(const gsl_rng *) { return "none (GSL API shim)"; }
 }  // extern "C"

@@ -183,3 +183,18 @@ def center_matrix(G):
     G = _f(G).copy()
     lib().ref_center_matrix(_p(G), G.shape[0])
     return G
+
+
+EXE = os.path.join(_HERE, "_ref", "gemma_ref")
+
+
+def run_cli(args, cwd):
+    """Run the reference's whole CLI (oracle/_ref/gemma_ref: every src/*.cpp compiled in place against the GSL API shim, BLAS /
+    LAPACK from the OpenBLAS bundled with scipy).  Returns stdout+stderr; outputs land in <cwd>/output like the reference's."""
+    build()
+    if not os.path.exists(EXE):
+        raise RuntimeError("oracle/_ref/gemma_ref is missing")
+    r = subprocess.run([EXE] + list(args), cwd=cwd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference CLI failed (%d): %s" % (r.returncode, (r.stdout + r.stderr)[-2000:]))
+    return r.stdout + r.stderr

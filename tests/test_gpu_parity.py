@@ -506,6 +506,81 @@ def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
     assert np.allclose(a, b, rtol=1e-5, atol=1e-8) and [l.split("\t")[:7] for l in lb] == [l.split("\t")[:7] for l in lines]
 
 
+def _assoc_table(path):
+    lines = open(path).read().splitlines()
+    hdr = lines[0].split("\t")
+    rows = [ln.split("\t") for ln in lines[1:]]
+    nonnum = [r[:7] for r in rows]
+    num = np.array([[float(x) for x in r[7:]] for r in rows])
+    return hdr, nonnum, num
+
+
+def test_cli_against_the_reference_cli_end_to_end(golden_dir, tmp_path):
+    """gemma-b200 vs the reference's own CLI (oracle/_ref/gemma_ref: all src/*.cpp compiled in place against the GSL API shim),
+    same command lines, whole output files: mouse example (-gk, -lmm 4 over all 10 768 SNPs, LOCO) and a synthetic PLINK set with
+    covariates (-gk 2 like the reference's HLC test, -lmm 4)."""
+    import subprocess
+    from oracle import ref as REF
+    if not os.path.exists(REF.EXE):
+        pytest.skip("reference CLI not shipped")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+    if not os.path.exists(cli):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    cwd = str(tmp_path); out = os.path.join(cwd, "output")
+
+    def mine(args):
+        r = subprocess.run([cli] + args + ["-outdir", out], capture_output=True, text=True, cwd=cwd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+
+    def compare(a, b, rtol=2e-6):
+        ha, na, xa = _assoc_table(os.path.join(out, a + ".assoc.txt")); hb, nb, xb = _assoc_table(os.path.join(out, b + ".assoc.txt"))
+        assert ha == hb and na == nb                                   # ids, positions, n_miss, alleles, af: text for text
+        lam = [i for i, h in enumerate(ha[7:]) if h.startswith("l_")]
+        for j in range(xa.shape[1]):
+            ok = np.isfinite(xb[:, j])
+            assert np.array_equal(np.isfinite(xa[:, j]), ok), ha[7 + j]
+            tol = 2e-5 if j in lam else rtol                            # 7 printed digits; lambda: Newton tolerance
+            bad = ~np.isclose(xa[ok, j], xb[ok, j], rtol=tol, atol=0)
+            assert bad.mean() <= 0.001, (ha[7 + j], int(bad.sum()))     # borderline Brent/Newton iteration counts flip rarely
+        return xa.shape[0]
+
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+    REF.run_cli(base + ["-gk", "-o", "rk"], cwd)
+    mine(base + ["-gk", "-o", "mk"])
+    Kr = np.loadtxt(os.path.join(out, "rk.cXX.txt")); Km = np.loadtxt(os.path.join(out, "mk.cXX.txt"))
+    assert np.allclose(Kr, Km, rtol=1e-8, atol=1e-9)
+    REF.run_cli(base + ["-k", "output/rk.cXX.txt", "-lmm", "4", "-o", "r4"], cwd)
+    mine(base + ["-k", os.path.join(out, "rk.cXX.txt"), "-lmm", "4", "-o", "m4"])
+    assert compare("m4", "r4") == 10768
+    loco = ["-snps", d + "/mouse_hs1940_snps.txt", "-nind", "400", "-loco", "1"]
+    REF.run_cli(base + loco + ["-gk", "-o", "rl"], cwd)
+    REF.run_cli(base + loco + ["-k", "output/rl.cXX.txt", "-lmm", "-no-check", "-o", "rl"], cwd)
+    mine(base + loco + ["-k", os.path.join(out, "rl.cXX.txt"), "-lmm", "-o", "ml"])
+    assert compare("ml", "rl") == 67
+    # synthetic PLINK with two covariates + intercept, standardised kinship
+    n, l = 700, 500
+    rng = np.random.default_rng(11)
+    bed, G = synth.make_bed(n, l, seed=555, miss_rate=0.01)
+    y = rng.standard_normal(n) + 0.5 * np.where(G[2] < 0, 0, G[2])
+    y[rng.choice(n, 19, replace=False)] = np.nan
+    prefix = os.path.join(cwd, "syn")
+    _write_plink(prefix, bed, y)
+    cov = os.path.join(cwd, "cov.txt")
+    with open(cov, "w") as f:
+        for i in range(n):
+            f.write("1 %.6f %.6f\n" % (rng.standard_normal(), rng.uniform(20, 70)))
+    REF.run_cli(["-bfile", prefix, "-gk", "2", "-o", "rs"], cwd)
+    mine(["-bfile", prefix, "-gk", "2", "-o", "ms"])
+    Kr = np.loadtxt(os.path.join(out, "rs.sXX.txt")); Km = np.loadtxt(os.path.join(out, "ms.sXX.txt"))
+    assert np.allclose(Kr, Km, rtol=1e-8, atol=1e-9)
+    REF.run_cli(["-bfile", prefix, "-c", cov, "-k", "output/rs.sXX.txt", "-lmm", "4", "-o", "rp"], cwd)
+    mine(["-bfile", prefix, "-c", cov, "-k", os.path.join(out, "rs.sXX.txt"), "-lmm", "4", "-o", "mp"])
+    compare("mp", "rp")
+
+
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
 def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     n = 1300

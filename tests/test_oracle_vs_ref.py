@@ -160,3 +160,42 @@ def test_plink_readers_kinship_and_analyzeplink_match_reference_code(tmp_path):
                 ok = np.isfinite(b)
                 tol = 1e-6 if k.startswith("lambda") else 1e-8
                 assert np.allclose(a[ok], b[ok], rtol=tol, atol=1e-300), (mode, k, lo)
+
+
+def test_reference_cli_reproduces_demo_txt_and_agrees_with_the_oracle(golden_dir, tmp_path):
+    """The reference's whole CLI (oracle/_ref/gemma_ref) on the mouse example: its own published outputs (example/demo.txt) come
+    out digit for digit -- which also validates the GSL shim (Brent / Newton / cdf tails, dsyevr via OpenBLAS) -- and the oracle
+    agrees with it over many more SNPs than demo.txt prints.  The multivariate rows (-n 1 6, demo.txt:62-66) pin the compiled
+    reference for the mvLMM row of SURVEY 8(f)."""
+    import json
+    if not os.path.exists(REF.EXE) and not os.path.isdir(REF.REF_SRC):
+        pytest.skip("reference CLI not built")
+    EXP = json.load(open(os.path.join(golden_dir, "expected.json")))
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+    cwd = str(tmp_path)
+    REF.run_cli(base + ["-gk", "-o", "mouse"], cwd)
+    K = np.loadtxt(os.path.join(cwd, "output", "mouse.cXX.txt"))
+    assert [[float("%.6g" % K[i, j]) for j in range(3)] for i in range(3)] == EXP["mouse_K3"]
+    out = REF.run_cli(base + ["-n", "1", "-k", "output/mouse.cXX.txt", "-lmm", "-o", "lmm1"], cwd)
+    assert "pve estimate =0.608801" in out and "se(pve) =0.032774" in out
+    lines = open(os.path.join(cwd, "output", "lmm1.assoc.txt")).read().splitlines()
+    assert len(lines) == 10769
+    for line, e in zip(lines[1:6], EXP["mouse_lmm1_rows"]):
+        f = line.split("\t")
+        assert f[:7] == [e["chr"], e["rs"], e["ps"], e["n_miss"], e["allele1"], e["allele0"], e["af"]]
+        assert [f[7], f[8], f[10], f[11]] == [e["beta"], e["se"], e["l_remle"], e["p_wald"]]
+    # the oracle pipeline on the first 400 analysed SNPs against the reference's own assoc file
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1,))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, _, _ = R.qc_bimbam(bb, idv)
+    prep = R.lmm_prepare(K, idv, ph[:, 0], W)
+    sel = np.nonzero(isnp)[0][:400]
+    o = R.lmm_analyze(prep, R.lmm_genotypes_bimbam(bb, isnp, idv, sel), 1)
+    ref = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:401]])        # beta se logl_H1 l_remle p_wald
+    for j, k in enumerate(("beta", "se", "logl_H1", "lambda_remle", "p_wald")):
+        assert np.allclose(o[k], ref[:, j], rtol=2e-6 if k != "lambda_remle" else 2e-5, atol=0), k      # 7 printed digits
+    REF.run_cli(base + ["-n", "1", "6", "-k", "output/mouse.cXX.txt", "-lmm", "-o", "mv"], cwd)
+    mv = open(os.path.join(cwd, "output", "mv.assoc.txt")).read().splitlines()
+    assert [ln.split("\t") for ln in mv[1:6]] == EXP["mouse_mvlmm_rows"]["rows"]
