@@ -77,6 +77,9 @@ SIGNATURES = {
     "gb200_lmm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_lmm_batch_bed_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "gb200_lmm_gxe_setup": (C.c_int, [_vp, _vp]),
+    "gb200_lmm_gxe_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
+    "gb200_lmm_gxe_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_lmm_assoc_utx": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_project": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_project_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
@@ -282,6 +285,25 @@ class Context:
         out = np.zeros(bed.shape[0], dtype=SUMSTAT_DTYPE)
         self._chk(self.lib.gb200_lmm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1],
                                                _ptr(out)))
+        return out
+
+    # ---- G x E (AnalyzePlinkGXE / AnalyzeBimbamGXE)
+    def lmm_gxe_setup(self, env):
+        env = _f64(env)
+        assert env.shape == (self.n,)
+        self._chk(self.lib.gb200_lmm_gxe_setup(self.h, _ptr(env)))
+
+    def lmm_gxe_batch_geno(self, G):
+        G = _f64(G)
+        out = np.zeros(G.shape[0], dtype=SUMSTAT_DTYPE)
+        self._chk(self.lib.gb200_lmm_gxe_batch_geno(self.h, _ptr(G), G.shape[0], G.shape[1], _ptr(out)))
+        return out
+
+    def lmm_gxe_batch_bed(self, bed, ni_total, idv_mask=None):
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        m = None if idv_mask is None else np.ascontiguousarray(idv_mask, dtype=np.uint8)
+        out = np.zeros(bed.shape[0], dtype=SUMSTAT_DTYPE)
+        self._chk(self.lib.gb200_lmm_gxe_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1], _ptr(out)))
         return out
 
     def lmm_batch_bed_dev(self, bed_dev, mask_dev, ni_total, l, bytes_per_snp, out_dev):

@@ -355,7 +355,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
   if (n_cvt > GB200_MAX_CVT)
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false; c->gxe_ready = false;
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
   c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
   GB_CUDA(c, c->dU.reserve(n * n * sizeof(double)));
@@ -427,7 +427,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
     return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated_dev: bad argument");
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false; c->gxe_ready = false;
   const size_t n_c = round_up(n, 512);
   c->dUtXt.release(); c->dUtXt2.release();
   c->dU.adopt(const_cast<double *>(U_dev), n * n * 8);          // borrowed: caller keeps it alive
@@ -450,7 +450,7 @@ static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
-  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0;
+  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.xcov = nullptr; D.xcov_idx = 0;
   D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
   D.gen_stride = 0;
   return D;
@@ -759,6 +759,104 @@ static int upload_idx_from_mask(gb200_ctx *c, const unsigned char *idv_mask, siz
     GB_CUDA(c, cudaMemcpyAsync(c->dIdx.p, c->idx_host.data(), c->n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   }
   *idx_dev = c->dIdx.as<int>();
+  return GB200_OK;
+}
+
+// ---- G x E (src/gemma.cpp:2580-2582, 2809-2828; LMM::AnalyzePlinkGXE / AnalyzeBimbamGXE, src/lmm.cpp:2283-2608) ----------------
+int gb200_lmm_gxe_setup(gb200_ctx *c, const double *env) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, "gb200_lmm_gxe_setup before gb200_lmm_setup");
+  if (!env) return set_err(c, GB200_ERR_ARG, "gb200_lmm_gxe_setup: null env");
+  if (c->n_cvt + 2 > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "G x E needs n_cvt + 2 <= GB200_MAX_CVT");
+  const size_t n = c->n, n_c = c->n_c, cN = c->n_cvt;
+  GB_CUDA(c, c->dEnv.reserve(n * 8));
+  GB_CUDA(c, c->dWtx.reserve((cN + 2) * n_c * 8));
+  GB_CUDA(c, cudaMemsetAsync(c->dWtx.p, 0, (cN + 2) * n_c * 8, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dEnv.p, env, n * 8, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dWtx.p, c->dWt.p, cN * n_c * 8, cudaMemcpyDeviceToDevice, c->stream));
+  // U^T env (gsl_blas_dgemv(CblasTrans, 1.0, U, env, ...), src/lmm.cpp:2319): row cN of the expanded covariate rows
+  GB_CUDA(c, launch_dgemm(n, 1, n, 1.0, c->dU.as<double>(), 1, n, c->dEnv.as<double>(), 1, 1, 0.0,
+                          c->dWtx.as<double>() + cN * n_c, 1, false, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->gxe_ready = true;
+  return GB200_OK;
+}
+
+// dX holds l mean-imputed SNP rows (n doubles each) on the device
+static int lmm_gxe_core(gb200_ctx *c, size_t l, gb200_sumstat *out_dev) {
+  const size_t n = c->n;
+  GB_CUDA(c, c->dX2.reserve(n * l * 8));
+  GB_CUDA(c, c->dFlip.reserve(l));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt2, l * c->n_c * 8, c->stream));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_gxe_prepare(c->dX.as<double>(), c->dX2.as<double>(), c->dEnv.as<double>(), l, n, c->dFlip.as<unsigned char>(), c->stream));
+  }
+  int rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+  if (rc) return rc;
+  rc = project_fp64_snpmajor(c, c->dX2.as<double>(), l, c->dUtXt2.as<double>());
+  if (rc) return rc;
+  LmmConst D = make_const(c);
+  D.Wt = c->dWtx.as<double>();
+  ProfScope ps(c, "lmm");
+  GB_CUDA(c, launch_lmm_gxe((int)c->n_cvt, D, c->prm, c->dUtXt.as<double>(), c->dUtXt2.as<double>(), c->n_c, (int)l,
+                            c->dFlip.as<unsigned char>(), out_dev, c->dTicket.as<unsigned int>(), c->num_sms, c->stream));
+  return GB200_OK;
+}
+
+static int gxe_check(gb200_ctx *c, const char *who) {
+  int rc = lmm_check_ready(c, who);
+  if (rc) return rc;
+  if (!c->gxe_ready) return set_err(c, GB200_ERR_STATE, std::string(who) + " before gb200_lmm_gxe_setup");
+  return GB200_OK;
+}
+
+int gb200_lmm_gxe_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = gxe_check(c, "gb200_lmm_gxe_batch_geno");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;
+  const size_t n = c->n;
+  if (!G || !out || ldg < n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_gxe_batch_geno: bad argument");
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  }
+  rc = lmm_gxe_core(c, l, c->dOut.as<gb200_sumstat>());
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_lmm_gxe_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l,
+                            size_t bytes_per_snp, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  int rc = gxe_check(c, "gb200_lmm_gxe_batch_bed");
+  if (rc) return rc;
+  if (l == 0) return GB200_OK;
+  if (!bed || !out || bytes_per_snp != (ni_total + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_lmm_gxe_batch_bed: bad argument");
+  const int *idx_dev = nullptr;
+  rc = upload_idx_from_mask(c, idv_mask, ni_total, &idx_dev);
+  if (rc) return rc;
+  const size_t n = c->n;
+  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode", 2);
+    GB_CUDA(c, launch_bed_decode(c->dBed.as<unsigned char>(), l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  }
+  rc = lmm_gxe_core(c, l, c->dOut.as<gb200_sumstat>());
+  if (rc) return rc;
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
   return GB200_OK;
 }
 

@@ -84,6 +84,8 @@ struct gb200_ctx {
   gb::DevBuf dU, dEval, dWt, dY;
   gb::LmmParams prm{};
   gb::DevBuf dNull;
+  gb::DevBuf dWtx, dEnv, dX2, dFlip;   // G x E: expanded covariate rows (W, env, -), env, x*env batch, allele-flip flags
+  bool gxe_ready = false;
   gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
   bool common_ready = false;
   // scratch
@@ -161,6 +163,9 @@ cudaError_t launch_lmm_assoc(int n_cvt, const LmmConst &D, const LmmParams &prm,
                              size_t ldu, int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,
                              cudaStream_t st);
 bool lmm_v2_supported(int n_cvt, int n_region);
+cudaError_t launch_lmm_gxe(int c_base, LmmConst D, const LmmParams &prm, const double *UtX1t, const double *UtX2t, size_t ldu, int l,
+                           const unsigned char *flip, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st);
+cudaError_t launch_gxe_prepare(double *X1, double *X2, const double *env, size_t l, size_t n, unsigned char *flip, cudaStream_t st);
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st);
 size_t lmm_common_record_doubles(int n_cvt);
 cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,

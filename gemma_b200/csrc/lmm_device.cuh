@@ -39,6 +39,8 @@ struct LmmConst {
   const double *Hrows;   // n_common rows of n_c doubles: h_i = 1/(lambda_j delta_i + 1)
   const double *ctab;    // n_common records: SNP-independent sums at lambda_j (v2c_stride doubles each)
   int n_common;
+  const double *xcov;    // G x E: covariate column xcov_idx is this per-SNP vector (U^T x) instead of a row of Wt; null otherwise
+  int xcov_idx;
   int nc_gen;            // generic-covariate path (NC < 0 instantiations): number of swept covariates
   int gen_stride;        // doubles of shared-memory scratch per warp on that path (3 tables of (nc_gen+3)(nc_gen+2)/2)
 };
@@ -318,11 +320,11 @@ __device__ __noinline__ void gen_pass(const LmmConst &D, const double *__restric
   for (int a0 = 0; a0 < NV; a0 += 4) {
     const double *ca[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) { const int a = a0 + r; ca[r] = (a < nc) ? D.Wt + (size_t)a * D.ldv : (a == nc ? x : D.y); }
+    for (int r = 0; r < 4; ++r) { const int a = a0 + r; ca[r] = (a < nc) ? ((D.xcov && a == D.xcov_idx) ? D.xcov : D.Wt + (size_t)a * D.ldv) : (a == nc ? x : D.y); }
     for (int b0 = a0; b0 < NV; b0 += 4) {
       const double *cb[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { const int b = b0 + r; cb[r] = (b < nc) ? D.Wt + (size_t)b * D.ldv : (b == nc ? x : D.y); }
+      for (int r = 0; r < 4; ++r) { const int b = b0 + r; cb[r] = (b < nc) ? ((D.xcov && b == D.xcov_idx) ? D.xcov : D.Wt + (size_t)b * D.ldv) : (b == nc ? x : D.y); }
       const bool first = (a0 == 0 && b0 == 0);
       double acc[NK][4][4];
 #pragma unroll

@@ -182,6 +182,87 @@ static cudaError_t launch_assoc_generic(int n_cvt, LmmConst D, const LmmParams &
   return cudaGetLastError();
 }
 
+// ---- G x E (LMM::AnalyzePlinkGXE / AnalyzeBimbamGXE, src/lmm.cpp:2283-2608): covariates = [W, env, x], tested variable = x * env.
+// D.Wt holds c_base rows of U^T W followed by the U^T env row; the per-SNP covariate U^T x comes in through D.xcov.
+__global__ void __launch_bounds__(128) lmm_gxe_kernel(LmmConst D, LmmParams prm, const double *__restrict__ UtX1t,
+                                                      const double *__restrict__ UtX2t, size_t ldu, int l, int c_base,
+                                                      const unsigned char *__restrict__ flip, gb200_sumstat *__restrict__ out,
+                                                      unsigned int *__restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned int s = 0;
+    if (lane == 0) s = atomicAdd(ticket, 1u);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s >= (unsigned int)l) break;
+    const double *x1 = UtX1t + (size_t)s * ldu, *x2 = UtX2t + (size_t)s * ldu;
+    double logl_H0 = 0.0;                                  // stays 0 in modes 3 / 9 like the reference's local (:2301, never assigned there)
+    if (prm.a_mode == 2 || prm.a_mode == 4) {              // param0: calc_null with c+2 covariates == alternative with [W, env] and x = U^T x (:2560-2563)
+      LmmConst Dn = D; Dn.nc_gen = c_base + 1; Dn.xcov = nullptr;
+      RootState R, L;
+      calc_lambda_both<-1>(Dn, x1, prm.l_min, prm.l_max, prm.n_region, false, true, R, L);
+      logl_H0 = L.logf;
+    }
+    LmmConst Da = D; Da.nc_gen = c_base + 2; Da.xcov = x1; Da.xcov_idx = c_base + 1;
+    LmmParams p2 = prm; p2.logl_mle_H0 = logl_H0; p2.plink_rule = 0;
+    gb200_sumstat r;
+    analyze_snp<-1>(Da, p2, x2, r);
+    if (flip[s]) r.beta = -r.beta;                          // allele flip when the mean genotype exceeds 1 (:2537-2540, :2587-2589)
+    if (lane == 0) out[s] = r;
+  }
+}
+
+cudaError_t launch_lmm_gxe(int c_base, LmmConst D, const LmmParams &prm, const double *UtX1t, const double *UtX2t, size_t ldu, int l,
+                           const unsigned char *flip, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st) {
+  const int nc = c_base + 2;
+  D.nc_gen = nc; D.gen_stride = 3 * ((nc + 3) * (nc + 2) / 2); D.xcov = nullptr; D.xcov_idx = 0;
+  const size_t smem = gen_smem_bytes(nc, 4);
+  cudaError_t e = cudaFuncSetAttribute(lmm_gxe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lmm_gxe_kernel, 128, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long want = ((long)l + 3) / 4, grid = (long)num_sms * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  lmm_gxe_kernel<<<(unsigned)grid, 128, smem, st>>>(D, prm, UtX1t, UtX2t, ldu, l, c_base, flip, out, ticket);
+  return cudaGetLastError();
+}
+
+// one CTA per SNP row of the mean-imputed SNP-major batch X1 (l x n): flip = mean > 1 -> x := 2 - x; X2 := x * env
+__global__ void __launch_bounds__(256) gxe_prepare_kernel(double *__restrict__ X1, double *__restrict__ X2, const double *__restrict__ env,
+                                                          int n, unsigned char *__restrict__ flip) {
+  __shared__ double part[8];
+  __shared__ int do_flip;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  double *row = X1 + (size_t)s * n, *row2 = X2 + (size_t)s * n;
+  double acc = 0.0;
+  for (int i = tid; i < n; i += 256) acc += row[i];
+  acc = warp_allsum(acc);
+  if ((tid & 31) == 0) part[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    do_flip = (t / (double)n > 1.0) ? 1 : 0;                // mean of the imputed vector == mean over the observed entries
+    flip[s] = (unsigned char)do_flip;
+  }
+  __syncthreads();
+  const bool f = do_flip != 0;
+  for (int i = tid; i < n; i += 256) {
+    double v = row[i];
+    if (f) { v = 2.0 - v; row[i] = v; }
+    row2[i] = v * env[i];
+  }
+}
+cudaError_t launch_gxe_prepare(double *X1, double *X2, const double *env, size_t l, size_t n, unsigned char *flip, cudaStream_t st) {
+  if (l == 0) return cudaSuccess;
+  gxe_prepare_kernel<<<(unsigned)l, 256, 0, st>>>(X1, X2, env, (int)n, flip);
+  return cudaGetLastError();
+}
+
 template <int NC>
 static cudaError_t launch_assoc_nc(const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,
                                    int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,

@@ -49,7 +49,7 @@ struct SnpInfo {   // SNPINFO, src/param.h:37-51
 };
 
 struct Params {
-  string file_geno, file_pheno, file_anno, file_cvt, file_bfile, file_kin, file_ku, file_kd, file_snps, file_ksnps, file_gwasnps, loco;
+  string file_geno, file_pheno, file_anno, file_cvt, file_bfile, file_kin, file_ku, file_kd, file_snps, file_ksnps, file_gwasnps, loco, file_gxe;
   string path_out = "./output/", file_out = "result";
   vector<size_t> p_column;
   int a_mode = 0;            // 21/22 -gk, 31 -eigen, 1/2/3/4/9 -lmm
@@ -134,6 +134,7 @@ struct Run {
   Params P;
   vector<vector<double>> pheno; vector<vector<int>> ind_pheno;
   vector<vector<double>> cvt; vector<int> ind_cvt; size_t n_cvt = 1;
+  vector<double> gxe; vector<int> ind_gxe;          // -gxe: ReadFile_column(file_gxe, indicator_gxe, gxe, 1), src/param.cpp:236-240
   vector<int> indicator_idv; size_t ni_total = 0, ni_test = 0;
   std::map<string, std::tuple<string, long, double>> anno;
   std::set<string> setSnps, setKSnps, setGWASnps;
@@ -179,6 +180,18 @@ static void read_cvt(Run &R) {                         // ReadFile_cvt, src/gemm
     if (!R.ind_cvt[i]) continue;
     if (first) { R.n_cvt = R.cvt[i].size(); first = false; }
     else if (R.cvt[i].size() != R.n_cvt) die("number of covariates in row " + std::to_string(i) + " do not match other rows.");
+  }
+}
+
+static void read_gxe(Run &R) {                         // ReadFile_column(.., 1), src/gemma_io.cpp:344-383
+  LineReader in(R.P.file_gxe);
+  if (!in.ok()) die("fail to open phenotype file: " + R.P.file_gxe);
+  string line;
+  while (in.next(line)) {
+    char *p = tok(&line[0]);
+    if (!p) die("Problem reading PHENO column");
+    if (strcmp(p, "NA") == 0) { R.ind_gxe.push_back(0); R.gxe.push_back(-9); }
+    else { R.ind_gxe.push_back(1); R.gxe.push_back(atof(p)); }
   }
 }
 
@@ -252,6 +265,10 @@ static void process_cvt_phen(Run &R) {                 // ProcessCvtPhen + Check
   if (!R.ind_cvt.empty()) {
     if (R.ind_cvt.size() != R.ni_total) die("number of rows in the covariates file do not match the number of individuals");
     for (size_t i = 0; i < R.ni_total; ++i) R.indicator_idv[i] *= R.ind_cvt[i];
+  }
+  if (!R.ind_gxe.empty()) {                            // src/param.cpp:1008-1014, 2016-2020
+    if (R.ind_gxe.size() != R.ni_total) die("number of rows in the gxe file do not match the number of individuals. ");
+    for (size_t i = 0; i < R.ni_total; ++i) R.indicator_idv[i] *= R.ind_gxe[i];
   }
   R.ni_test = 0; for (int v : R.indicator_idv) R.ni_test += v;
   if (R.ni_test == 0) die("number of analyzed individuals equals 0. ");
@@ -738,6 +755,12 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
   std::cout << "pve estimate =" << R.nm.pve_null << std::endl;            // PrintSummary, src/param.cpp:1252-1259
   std::cout << "se(pve) =" << R.nm.pve_se_null << std::endl;
   GB(gb200_lmm_params(ctx, R.P.a_mode, R.P.l_min, R.P.l_max, R.P.n_region, R.nm.l_mle_null, R.nm.logl_mle_H0));
+  const bool gxe = !R.P.file_gxe.empty();
+  if (gxe) {                                            // PARAM::CopyGxe, src/param.cpp:2116-2128
+    vector<double> env; env.reserve(n);
+    for (size_t i = 0; i < R.ni_total; ++i) if (R.indicator_idv[i]) env.push_back(R.gxe[i]);
+    GB(gb200_lmm_gxe_setup(ctx, env.data()));
+  }
   R.sumStat.clear(); R.sumStat.reserve(R.ns_test);
   vector<gb200_sumstat> out;
   if (!R.P.file_bfile.empty()) {                       // AnalyzePlink, src/lmm.cpp:1710-1903
@@ -747,7 +770,8 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
     auto flush = [&]() {
       if (!l) return;
       out.resize(l);
-      GB(gb200_lmm_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, out.data()));
+      if (gxe) GB(gb200_lmm_gxe_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, out.data()));      // AnalyzePlinkGXE
+      else GB(gb200_lmm_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, out.data()));
       R.sumStat.insert(R.sumStat.end(), out.begin(), out.end());
       rows.clear(); l = 0;
     };
@@ -789,7 +813,9 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
     auto flush = [&]() {
       if (!l) return;
       out.resize(l);
-      GB(gb200_lmm_batch_geno(ctx, G.data(), l, n, out.data()));
+      // (the reference's AnalyzeBimbamGXE opens file_gene instead of file_geno, src/lmm.cpp:2288: BIMBAM + -gxe fails there)
+      if (gxe) GB(gb200_lmm_gxe_batch_geno(ctx, G.data(), l, n, out.data()));
+      else GB(gb200_lmm_batch_geno(ctx, G.data(), l, n, out.data()));
       R.sumStat.insert(R.sumStat.end(), out.begin(), out.end());
       l = 0;
     };
@@ -841,7 +867,7 @@ static void usage() {
   std::cout << "gemma-b200: GEMMA-compatible -gk / -eigen / -lmm on a B200\n"
                " -g/-p/-a/-c files (BIMBAM)  |  -bfile prefix (PLINK)   -n col...   -o prefix  -outdir dir\n"
                " -gk [1|2]   -eigen   -lmm [1|2|3|4|9]   -k K.txt [-km 1|2]   -d D.txt -u U.txt\n"
-               " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -gwasnps file -loco chr -lmin x -lmax x -region n -nind n -silence\n"
+               " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -gwasnps file -loco chr -gxe file -lmin x -lmax x -region n -nind n -silence\n"
                " -bin  also write K / U / D as <file>.bin (exact doubles); -k/-u/-d accept such .bin files\n";
 }
 
@@ -867,6 +893,7 @@ int main(int argc, char **argv) {
     else if (a == "-ksnps") P.file_ksnps = need(i);
     else if (a == "-gwasnps") P.file_gwasnps = need(i);
     else if (a == "-loco") P.loco = need(i);
+    else if (a == "-gxe") P.file_gxe = need(i);
     else if (a == "-o") P.file_out = need(i);
     else if (a == "-outdir") P.path_out = need(i);
     else if (a == "-n") { while (i + 1 < argc && argv[i + 1][0] != '-') P.p_column.push_back((size_t)atoi(argv[++i])); }
@@ -919,6 +946,10 @@ int main(int argc, char **argv) {
   if (!P.file_bfile.empty()) { read_bim(R); read_fam(R); if (!P.file_pheno.empty()) { R.pheno.clear(); R.ind_pheno.clear(); read_pheno(R); } }
   else read_pheno(R);
   if (!P.file_cvt.empty()) read_cvt(R);
+  if (!P.file_gxe.empty()) {
+    if (!P.loco.empty()) die("LOCO does not support GXE (yet)");                    // src/param.cpp:927
+    read_gxe(R);
+  }
   process_cvt_phen(R);
   trim_individuals(R);
   gb200_ctx *ctx = nullptr;

@@ -184,6 +184,18 @@ GB200_API int gb200_lmm_assoc_utx(gb200_ctx *ctx, const double *UtXt, size_t l, 
 /* Projection only: UtXt (l x n, ld n, host) = (U^T Xb)^T for a host batch Xb (n x l). */
 GB200_API int gb200_lmm_project(gb200_ctx *ctx, const double *Xb, size_t l, size_t ldx, double *UtXt);
 
+/* ---- G x E: LMM::AnalyzePlinkGXE / AnalyzeBimbamGXE, src/lmm.cpp:2283-2608; wiring src/gemma.cpp:2580-2582, 2809-2828.
+ * After gb200_lmm_setup (and, before the batches, gb200_lmm_params): env = the environmental variable of the n analysed individuals (PARAM::CopyGxe,
+ * src/param.cpp:2116-2128).  Per SNP the covariates are [W, env, x] (x mean-imputed, flipped to 2 - x when its mean exceeds 1) and
+ * the tested variable is x * env; -lmm 2/4 compare with the per-SNP null that contains x (calc_null with n_cvt + 2 covariates);
+ * beta changes sign for flipped SNPs.  No NaN rule (the reference's GXE loops have none).  n_cvt + 2 <= GB200_MAX_CVT. */
+GB200_API int gb200_lmm_gxe_setup(gb200_ctx *ctx, const double *env);
+/* G: l x n SNP-major dosages of the analysed individuals, NaN = missing (BIMBAM); same layout as gb200_lmm_batch_geno */
+GB200_API int gb200_lmm_gxe_batch_geno(gb200_ctx *ctx, const double *G, size_t l, size_t ldg, gb200_sumstat *out);
+/* raw PLINK rows; same arguments as gb200_lmm_batch_bed */
+GB200_API int gb200_lmm_gxe_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
+                            size_t l, size_t bytes_per_snp, gb200_sumstat *out);
+
 /* Projection only for a PLINK 2-bit batch (same decode / imputation as gb200_lmm_batch_bed),
  * through whichever projection path the options select.  UtXt: l x n host buffer. */
 GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask,

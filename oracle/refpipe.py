@@ -231,6 +231,36 @@ def lmm_analyze(prep, X, a_mode, **kw):
                              l_mle_null=prep["l_mle_null"], logl_mle_H0=prep["logl_mle_H0"], **kw)
 
 
+def lmm_gxe(prep, G, env, a_mode, l_min=1e-5, l_max=1e5, n_region=10, l_mle_null=0.0):
+    """G x E restatement (LMM::AnalyzePlinkGXE / AnalyzeBimbamGXE, src/lmm.cpp:2283-2608) composed from the oracle's univariate
+    pieces.  G: l x n genotypes of the analysed individuals (NaN = missing); env: n.  Per SNP: mean-impute, flip to 2 - x when
+    the mean exceeds 1 (:2537-2540), covariates [W, env, x], tested variable x * env; -lmm 2/4 compare with the per-SNP null that
+    contains x (param0 = calc_null with n_cvt + 2 covariates, :2560-2563); beta changes sign for flipped SNPs (:2587-2589).
+    logl_H0 stays 0 in the other modes, as the reference's local does."""
+    U, ev, Uty = prep["U"], prep["eval"], prep["Uty"]
+    l = G.shape[0]
+    out = np.zeros(l, dtype=O.SUMSTAT_DTYPE)
+    Ute = U.T @ env
+    for t in range(l):
+        x = G[t].copy()
+        miss = np.isnan(x)
+        x_mean = float(np.cumsum(x[~miss])[-1]) / float((~miss).sum())
+        x[miss] = x_mean
+        flip = x_mean > 1
+        if flip:
+            x = 2 - x
+        UtW_e = np.column_stack([prep["UtW"], Ute, U.T @ x])
+        Utx = U.T @ (x * env)
+        logl_H0 = 0.0
+        if a_mode in (2, 4):
+            _, logl_H0 = O.calc_lambda_null("L", ev, UtW_e, Uty, l_min, l_max, n_region)
+        r = O.lmm_analyze_utx(ev, UtW_e, Uty, Utx[:, None], a_mode, l_min, l_max, n_region, l_mle_null, logl_H0)[0]
+        out[t] = r
+        if flip:
+            out["beta"][t] = -out["beta"][t]
+    return out
+
+
 # ---- PLINK (test infrastructure; src/gemma_io.cpp:514-636, 876-1064, 1599-1738) -------------------------
 class Plink:
     """.bim/.fam/.bed trio: rs ids, alleles, phenotypes (column 6+, -9/NA missing) and G[p, n] with NaN = missing."""

@@ -581,6 +581,49 @@ def test_cli_against_the_reference_cli_end_to_end(golden_dir, tmp_path):
     compare("mp", "rp")
 
 
+def test_gxe_entry_points_and_cli_match_oracle_and_reference_cli(ctx, tmp_path):
+    """G x E: gb200_lmm_gxe_batch_bed / _geno vs the oracle composition (itself checked against the reference
+    CLI in tests/test_oracle_vs_ref.py), and gemma-b200 -gxe vs the reference CLI on whole assoc files."""
+    import subprocess
+    from oracle import ref as REF
+    from test_oracle_vs_ref import _plink_gxe_case
+    prefix, gxe_file, bed, G, env, y = _plink_gxe_case(tmp_path, n=310, l=120, seed=79)
+    pl = R.Plink(prefix)
+    ind_gxe = np.ones(len(y), dtype=np.int32); ind_gxe[[5, 17]] = 0
+    idv, W = R.process_cvt_phen(pl.ind_pheno)
+    idv2 = idv * ind_gxe
+    isnp, _, _ = R.qc_plink(pl, idv2)
+    K = R.kinship_plink(pl, R.qc_plink(pl, idv)[0], 1)
+    prep = R.lmm_prepare(K, idv2, pl.pheno[:, 0], W)
+    keep = idv2 == 1
+    sel = np.nonzero(isnp)[0]
+    Gs = np.where(pl.G[np.ix_(sel, keep)] < 0, np.nan, pl.G[np.ix_(sel, keep)])
+    ctx.lmm_setup(prep["U"], prep["eval"], prep["W"], prep["y"])
+    nm = ctx.lmm_null(prep["trace_G"])
+    ctx.lmm_gxe_setup(env[keep])
+    for mode in (1, 2, 3, 4):
+        ref = R.lmm_gxe(prep, Gs, env[keep], mode, l_mle_null=prep["l_mle_null"])
+        ctx.lmm_params(mode, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+        got_bed = ctx.lmm_gxe_batch_bed(pl.bed[sel], len(idv2), idv2.astype(np.uint8))
+        got_geno = ctx.lmm_gxe_batch_geno(Gs)
+        check_sumstat(got_bed, ref, mode)
+        check_sumstat(got_geno, ref, mode)
+    if not os.path.exists(REF.EXE):
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+    cwd = str(tmp_path); out = os.path.join(cwd, "output")
+    REF.run_cli(["-bfile", prefix, "-gk", "1", "-o", "k"], cwd)
+    REF.run_cli(["-bfile", prefix, "-gxe", gxe_file, "-k", "output/k.cXX.txt", "-lmm", "4", "-o", "rg"], cwd)
+    r = subprocess.run([cli, "-bfile", prefix, "-gxe", gxe_file, "-k", os.path.join(out, "k.cXX.txt"), "-lmm", "4", "-o", "mg", "-outdir", out],
+                       capture_output=True, text=True, cwd=cwd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ha, na, xa = _assoc_table(os.path.join(out, "mg.assoc.txt")); hb, nb, xb = _assoc_table(os.path.join(out, "rg.assoc.txt"))
+    assert ha == hb and na == nb
+    for j, h in enumerate(ha[7:]):
+        assert np.allclose(xa[:, j], xb[:, j], rtol=2e-5 if h.startswith("l_") else 2e-6, atol=0), h
+
+
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
 def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     n = 1300

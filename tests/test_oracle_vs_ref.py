@@ -199,3 +199,58 @@ def test_reference_cli_reproduces_demo_txt_and_agrees_with_the_oracle(golden_dir
     REF.run_cli(base + ["-n", "1", "6", "-k", "output/mouse.cXX.txt", "-lmm", "-o", "mv"], cwd)
     mv = open(os.path.join(cwd, "output", "mv.assoc.txt")).read().splitlines()
     assert [ln.split("\t") for ln in mv[1:6]] == EXP["mouse_mvlmm_rows"]["rows"]
+
+
+def _plink_gxe_case(tmp_path, n=260, l=90, seed=77):
+    from gemma_b200 import synth
+    rng = np.random.default_rng(seed)
+    bed, G = synth.make_bed(n, l, seed=seed, miss_rate=0.02)
+    # make a third of the SNPs "major-allele coded" (mean genotype > 1) so that the allele flip of the GXE loops is exercised
+    for s_ in range(0, l, 3):
+        for i in range(n):
+            byte, sh = i >> 2, 2 * (i & 3)
+            code = (int(bed[s_, byte]) >> sh) & 3
+            new = {0: 3, 3: 0, 2: 2, 1: 1}[code]
+            bed[s_, byte] = (int(bed[s_, byte]) & (0xFF ^ (3 << sh))) | (new << sh)
+            if G[s_, i] >= 0:
+                G[s_, i] = 2 - G[s_, i]
+    env = rng.standard_normal(n)
+    y = rng.standard_normal(n) + 0.4 * np.where(G[4] < 0, 0, G[4]) * env
+    y[rng.choice(n, 11, replace=False)] = np.nan
+    prefix = str(tmp_path / "gxe")
+    _write_plink(prefix, bed, y)
+    gxe_file = str(tmp_path / "env.txt")
+    with open(gxe_file, "w") as f:
+        for i in range(n):
+            f.write("NA\n" if i in (5, 17) else "%.8f\n" % env[i])
+    return prefix, gxe_file, bed, G, env, y
+
+
+def test_gxe_restatement_matches_reference_cli(tmp_path):
+    """G x E: refpipe.lmm_gxe (oracle composition) against the reference's own CLI with -gxe on a PLINK set (AnalyzePlinkGXE)."""
+    if not os.path.exists(REF.EXE) and not os.path.isdir(REF.REF_SRC):
+        pytest.skip("reference CLI not built")
+    prefix, gxe_file, bed, G, env, y = _plink_gxe_case(tmp_path)
+    cwd = str(tmp_path)
+    REF.run_cli(["-bfile", prefix, "-gk", "1", "-o", "k"], cwd)
+    pl = R.Plink(prefix)
+    ind_gxe = np.ones(len(y), dtype=np.int32); ind_gxe[[5, 17]] = 0
+    idv, W = R.process_cvt_phen(pl.ind_pheno)
+    isnp_k, _, _ = R.qc_plink(pl, idv)                                   # -gk run: no gxe file
+    idv2 = idv * ind_gxe                                                  # src/param.cpp:2016-2020
+    isnp, _, _ = R.qc_plink(pl, idv2)
+    K = np.loadtxt(os.path.join(cwd, "output", "k.cXX.txt"))
+    prep = R.lmm_prepare(K, idv2, pl.pheno[:, 0], W)
+    keep = idv2 == 1
+    Gs = np.where(pl.G[np.ix_(np.nonzero(isnp)[0], keep)] < 0, np.nan, pl.G[np.ix_(np.nonzero(isnp)[0], keep)])
+    cols = {1: ("beta", "se", "logl_H1", "lambda_remle", "p_wald"), 2: ("logl_H1", "lambda_mle", "p_lrt"), 3: ("beta", "se", "p_score"),
+            4: ("beta", "se", "logl_H1", "lambda_remle", "lambda_mle", "p_wald", "p_lrt", "p_score")}
+    for mode in (1, 2, 3, 4):
+        REF.run_cli(["-bfile", prefix, "-gxe", gxe_file, "-k", "output/k.cXX.txt", "-lmm", str(mode), "-o", "g%d" % mode], cwd)
+        lines = open(os.path.join(cwd, "output", "g%d.assoc.txt" % mode)).read().splitlines()
+        assert len(lines) == 1 + int(isnp.sum())
+        ref = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:]])
+        got = R.lmm_gxe(prep, Gs, env[keep], mode, l_mle_null=prep["l_mle_null"])
+        for j, k in enumerate(cols[mode]):
+            tol = 2e-5 if k.startswith("lambda") else 2e-6
+            assert np.allclose(got[k], ref[:, j], rtol=tol, atol=0), (mode, k, np.max(np.abs(got[k] - ref[:, j]) / np.abs(ref[:, j])))
