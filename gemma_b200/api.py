@@ -77,6 +77,9 @@ SIGNATURES = {
     "gb200_lmm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_lmm_batch_bed_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "gb200_lm_setup": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp]),
+    "gb200_lm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _vp]),
+    "gb200_lm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, C.c_int, _vp]),
     "gb200_lmm_gxe_setup": (C.c_int, [_vp, _vp]),
     "gb200_lmm_gxe_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_gxe_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
@@ -285,6 +288,24 @@ class Context:
         out = np.zeros(bed.shape[0], dtype=SUMSTAT_DTYPE)
         self._chk(self.lib.gb200_lmm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1],
                                                _ptr(out)))
+        return out
+
+    # ---- -lm (linear model, src/lm.cpp)
+    def lm_setup(self, W, y):
+        W, y = _f64(W), _f64(y)
+        self._chk(self.lib.gb200_lm_setup(self.h, W.shape[0], W.shape[1], _ptr(W), W.shape[1], _ptr(y)))
+
+    def lm_batch_geno(self, G, a_mode):
+        G = _f64(G)
+        out = np.zeros(G.shape[0], dtype=SUMSTAT_DTYPE)
+        self._chk(self.lib.gb200_lm_batch_geno(self.h, _ptr(G), G.shape[0], G.shape[1], int(a_mode), _ptr(out)))
+        return out
+
+    def lm_batch_bed(self, bed, ni_total, a_mode, idv_mask=None):
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        m = None if idv_mask is None else np.ascontiguousarray(idv_mask, dtype=np.uint8)
+        out = np.zeros(bed.shape[0], dtype=SUMSTAT_DTYPE)
+        self._chk(self.lib.gb200_lm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1], int(a_mode), _ptr(out)))
         return out
 
     # ---- G x E (AnalyzePlinkGXE / AnalyzeBimbamGXE)

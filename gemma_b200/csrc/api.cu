@@ -860,6 +860,117 @@ int gb200_lmm_gxe_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsign
   return GB200_OK;
 }
 
+// ---- -lm (linear model, no kinship): LM::AnalyzeBimbam / AnalyzePlink + CalcvPv + LmCalcP, src/lm.cpp:224-288, 382-640 ----------
+int gb200_lm_setup(gb200_ctx *c, size_t n, size_t n_cvt, const double *W, size_t ldw, const double *y) {
+  if (!c) return GB200_ERR_ARG;
+  if (n == 0 || n_cvt == 0 || !W || !y || ldw < n_cvt) return set_err(c, GB200_ERR_ARG, "gb200_lm_setup: bad argument");
+  if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lm_setup: n_cvt exceeds GB200_MAX_CVT");
+  if (n <= n_cvt + 1) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
+  c->lm_ready = false;
+  // W'W, W'y, y'y are run constants over c <= 32 columns: formed and inverted on the host like the reference does
+  // (gsl_blas_dgemm + LUDecomp/LUInvert, src/lm.cpp:404-413); the per-SNP sums run on the device
+  std::vector<double> Wt(n_cvt * n), WtW(n_cvt * n_cvt, 0.0), Wty(n_cvt, 0.0), small(n_cvt * n_cvt + n_cvt);
+  double yy = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    yy += y[i] * y[i];
+    for (size_t a = 0; a < n_cvt; ++a) {
+      const double wa = W[i * ldw + a];
+      Wt[a * n + i] = wa; Wty[a] += wa * y[i];
+      for (size_t b = 0; b < n_cvt; ++b) WtW[a * n_cvt + b] += wa * W[i * ldw + b];
+    }
+  }
+  // inverse by Gauss-Jordan with partial pivoting
+  std::vector<double> M(n_cvt * 2 * n_cvt);
+  const size_t w2 = 2 * n_cvt;
+  for (size_t i = 0; i < n_cvt; ++i) for (size_t j = 0; j < n_cvt; ++j) { M[i * w2 + j] = WtW[i * n_cvt + j]; M[i * w2 + n_cvt + j] = (i == j) ? 1.0 : 0.0; }
+  for (size_t k = 0; k < n_cvt; ++k) {
+    size_t pr = k;
+    for (size_t i = k + 1; i < n_cvt; ++i) if (fabs(M[i * w2 + k]) > fabs(M[pr * w2 + k])) pr = i;
+    if (M[pr * w2 + k] == 0.0) return set_err(c, GB200_ERR_ARG, "gb200_lm_setup: W'W is singular");
+    if (pr != k) for (size_t j = 0; j < w2; ++j) std::swap(M[k * w2 + j], M[pr * w2 + j]);
+    const double piv = M[k * w2 + k];
+    for (size_t j = 0; j < w2; ++j) M[k * w2 + j] /= piv;
+    for (size_t i = 0; i < n_cvt; ++i) if (i != k) { const double f = M[i * w2 + k]; if (f != 0.0) for (size_t j = 0; j < w2; ++j) M[i * w2 + j] -= f * M[k * w2 + j]; }
+  }
+  double quad = 0.0;
+  for (size_t a = 0; a < n_cvt; ++a) {
+    double t = 0.0;
+    for (size_t b = 0; b < n_cvt; ++b) { small[a * n_cvt + b] = M[a * w2 + n_cvt + b]; t += M[a * w2 + n_cvt + b] * Wty[b]; }
+    quad += t * Wty[a];
+    small[n_cvt * n_cvt + a] = Wty[a];
+  }
+  c->lm_yPwy = yy - quad;                                  // CalcvPv(WtWi, Wty, y, yPwy), src/lm.cpp:247-264
+  GB_CUDA(c, c->dLmW.reserve(n_cvt * n * 8));
+  GB_CUDA(c, c->dLmY.reserve(n * 8));
+  GB_CUDA(c, c->dLmSmall.reserve(small.size() * 8));
+  GB_CUDA(c, cudaMemcpyAsync(c->dLmW.p, Wt.data(), n_cvt * n * 8, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dLmY.p, y, n * 8, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(c->dLmSmall.p, small.data(), small.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->lm_n = n; c->lm_c = n_cvt; c->lm_ready = true;
+  return GB200_OK;
+}
+
+static int lm_core(gb200_ctx *c, size_t l, int a_mode, gb200_sumstat *out) {
+  const int test_mode = a_mode > 50 ? a_mode - 50 : a_mode;
+  if (test_mode < 1 || test_mode > 4) return set_err(c, GB200_ERR_ARG, "-lm mode must be 1..4 (or 51..54)");
+  GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
+  {
+    ProfScope ps(c, "lmm");
+    GB_CUDA(c, launch_lm(c->dX.as<double>(), l, (int)c->lm_n, (int)c->lm_c, c->dLmW.as<double>(), c->dLmY.as<double>(), c->dLmSmall.as<double>(),
+                         c->dLmSmall.as<double>() + c->lm_c * c->lm_c, c->lm_yPwy, test_mode, c->dOut.as<gb200_sumstat>(), c->stream));
+  }
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_lm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, int a_mode, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->lm_ready) return set_err(c, GB200_ERR_STATE, "gb200_lm_batch_geno before gb200_lm_setup");
+  if (l == 0) return GB200_OK;
+  const size_t n = c->lm_n;
+  if (!G || !out || ldg < n) return set_err(c, GB200_ERR_ARG, "gb200_lm_batch_geno: bad argument");
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  }
+  return lm_core(c, l, a_mode, out);
+}
+
+int gb200_lm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l, size_t bytes_per_snp,
+                       int a_mode, gb200_sumstat *out) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->lm_ready) return set_err(c, GB200_ERR_STATE, "gb200_lm_batch_bed before gb200_lm_setup");
+  if (l == 0) return GB200_OK;
+  if (!bed || !out || bytes_per_snp != (ni_total + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_lm_batch_bed: bad argument");
+  const size_t n = c->lm_n;
+  // analysed-individual index list (same convention as gb200_lmm_batch_bed)
+  std::vector<int> idx;
+  if (idv_mask) { for (size_t i = 0; i < ni_total; ++i) if (idv_mask[i]) idx.push_back((int)i); }
+  else { if (ni_total != n) return set_err(c, GB200_ERR_ARG, "idv_mask == NULL requires ni_total == n"); }
+  if (idv_mask && idx.size() != n) return set_err(c, GB200_ERR_ARG, "idv_mask selects a number of individuals different from n");
+  const int *idx_dev = nullptr;
+  if (idv_mask) {
+    GB_CUDA(c, c->dIdx.reserve(n * sizeof(int)));
+    GB_CUDA(c, cudaMemcpyAsync(c->dIdx.p, idx.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->mask_host.clear();                                   // the cached mask of the -lmm entry points no longer matches dIdx
+    idx_dev = c->dIdx.as<int>();
+  }
+  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode", 2);
+    GB_CUDA(c, launch_bed_decode(c->dBed.as<unsigned char>(), l, bytes_per_snp, idx_dev, n, c->dX.as<double>(), n, c->stream));
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  }
+  return lm_core(c, l, a_mode, out);
+}
+
 int gb200_lmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
                         size_t l, size_t bytes_per_snp, gb200_sumstat *out) {
   if (!c) return GB200_ERR_ARG;

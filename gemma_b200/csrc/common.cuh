@@ -86,6 +86,8 @@ struct gb200_ctx {
   gb::DevBuf dNull;
   gb::DevBuf dWtx, dEnv, dX2, dFlip;   // G x E: expanded covariate rows (W, env, -), env, x*env batch, allele-flip flags
   bool gxe_ready = false;
+  gb::DevBuf dLmW, dLmY, dLmSmall;     // -lm: W rows (c x n), y, [WtWi (c x c) | Wty (c)]
+  size_t lm_n = 0, lm_c = 0; double lm_yPwy = 0.0; bool lm_ready = false;
   gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
   bool common_ready = false;
   // scratch
@@ -166,6 +168,8 @@ bool lmm_v2_supported(int n_cvt, int n_region);
 cudaError_t launch_lmm_gxe(int c_base, LmmConst D, const LmmParams &prm, const double *UtX1t, const double *UtX2t, size_t ldu, int l,
                            const unsigned char *flip, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st);
 cudaError_t launch_gxe_prepare(double *X1, double *X2, const double *env, size_t l, size_t n, unsigned char *flip, cudaStream_t st);
+cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double *Wt, const double *y, const double *WtWi, const double *Wty,
+                      double yPwy, int test_mode, gb200_sumstat *out, cudaStream_t st);
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st);
 size_t lmm_common_record_doubles(int n_cvt);
 cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,

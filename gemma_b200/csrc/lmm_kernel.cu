@@ -263,6 +263,62 @@ cudaError_t launch_gxe_prepare(double *X1, double *X2, const double *env, size_t
   return cudaGetLastError();
 }
 
+// ---- -lm: linear model without random effect (LM::AnalyzeBimbam / AnalyzePlink, CalcvPv, LmCalcP: src/lm.cpp:224-288, 382-640).
+// One CTA per SNP row of the mean-imputed SNP-major batch X: x'x, x'y and W'x in one pass; then
+// xPwx = x'x - (W'x)' (W'W)^-1 (W'x), xPwy = x'y - (W'x)' (W'W)^-1 (W'y), and the three tests of LmCalcP.
+__global__ void __launch_bounds__(128) lm_kernel(const double *__restrict__ X, int n, int n_cvt, const double *__restrict__ Wt /* c rows of n */,
+                                                 const double *__restrict__ y, const double *__restrict__ WtWi, const double *__restrict__ Wty,
+                                                 double yPwy, int test_mode, gb200_sumstat *__restrict__ out) {
+  __shared__ double sh[4][GB200_MAX_CVT + 2];
+  const double *x = X + (size_t)blockIdx.x * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[GB200_MAX_CVT + 2];
+#pragma unroll
+  for (int a = 0; a < GB200_MAX_CVT + 2; ++a) acc[a] = 0.0;
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const double xi = x[i];
+    acc[GB200_MAX_CVT] = fma(xi, xi, acc[GB200_MAX_CVT]);
+    acc[GB200_MAX_CVT + 1] = fma(xi, __ldg(y + i), acc[GB200_MAX_CVT + 1]);
+    for (int a = 0; a < n_cvt; ++a) acc[a] = fma(__ldg(Wt + (size_t)a * n + i), xi, acc[a]);
+  }
+#pragma unroll
+  for (int a = 0; a < GB200_MAX_CVT + 2; ++a) {
+    const double v = warp_allsum(acc[a]);
+    if (lane == 0) sh[warp][a] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double wtx[GB200_MAX_CVT];
+    for (int a = 0; a < n_cvt; ++a) wtx[a] = sh[0][a] + sh[1][a] + sh[2][a] + sh[3][a];
+    double xPwx = sh[0][GB200_MAX_CVT] + sh[1][GB200_MAX_CVT] + sh[2][GB200_MAX_CVT] + sh[3][GB200_MAX_CVT];
+    double xPwy = sh[0][GB200_MAX_CVT + 1] + sh[1][GB200_MAX_CVT + 1] + sh[2][GB200_MAX_CVT + 1] + sh[3][GB200_MAX_CVT + 1];
+    double d1 = 0.0, d2 = 0.0;
+    for (int a = 0; a < n_cvt; ++a) {
+      double t = 0.0;
+      for (int b = 0; b < n_cvt; ++b) t += WtWi[a * n_cvt + b] * wtx[b];      // WtWiWtx
+      d1 += t * wtx[a]; d2 += t * Wty[a];
+    }
+    xPwx -= d1; xPwy -= d2;
+    const double df = (double)n - (double)n_cvt - 1.0;
+    const double yPxy = yPwy - xPwy * xPwy / xPwx;
+    const double beta = xPwy / xPwx;
+    const double se_wald = sqrt(yPxy / (df * xPwx)), se_score = sqrt(yPwy / ((double)n * xPwx));
+    gb200_sumstat r;
+    r.beta = beta; r.se = (test_mode == 3) ? se_score : se_wald; r.lambda_remle = 0.0; r.lambda_mle = 0.0;
+    r.p_wald = fdist_Q_dev(beta * beta / (se_wald * se_wald), 1.0, df);
+    r.p_score = fdist_Q_dev(beta * beta / (se_score * se_score), 1.0, df);
+    r.p_lrt = chisq1_Q_dev((double)n * (log(yPwy) - log(yPxy)));
+    r.logl_H1 = -0.0;
+    out[blockIdx.x] = r;
+  }
+}
+cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double *Wt, const double *y, const double *WtWi, const double *Wty,
+                      double yPwy, int test_mode, gb200_sumstat *out, cudaStream_t st) {
+  if (l == 0) return cudaSuccess;
+  lm_kernel<<<(unsigned)l, 128, 0, st>>>(X, n, n_cvt, Wt, y, WtWi, Wty, yPwy, test_mode, out);
+  return cudaGetLastError();
+}
+
 template <int NC>
 static cudaError_t launch_assoc_nc(const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,
                                    int l, gb200_sumstat *out, unsigned int *ticket, int num_sms,

@@ -832,6 +832,95 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
   write_assoc(R);
 }
 
+// -lm: LM branch of BatchRun (src/gemma.cpp:1867-1911), LM::AnalyzeBimbam / AnalyzePlink (src/lm.cpp:382-640), LM::WriteFiles (:83-222)
+static void run_lm(Run &R, gb200_ctx *ctx) {
+  const size_t n = R.ni_test;
+  vector<double> W, y; copy_cvt_phen(R, W, y);
+  const double t0 = now_s();
+  GB(gb200_lm_setup(ctx, n, R.n_cvt, W.data(), R.n_cvt, y.data()));
+  R.sumStat.clear(); R.sumStat.reserve(R.ns_test);
+  vector<gb200_sumstat> out;
+  if (!R.P.file_bfile.empty()) {
+    vector<unsigned char> mask(R.ni_total); for (size_t i = 0; i < R.ni_total; ++i) mask[i] = (unsigned char)R.indicator_idv[i];
+    vector<unsigned char> rows; rows.reserve(BATCH * g_nbit);
+    size_t l = 0;
+    auto flush = [&]() {
+      if (!l) return;
+      out.resize(l);
+      GB(gb200_lm_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, R.P.a_mode, out.data()));
+      R.sumStat.insert(R.sumStat.end(), out.begin(), out.end());
+      rows.clear(); l = 0;
+    };
+    for (size_t t = 0; t < R.ns_total; ++t) {
+      if (!R.indicator_snp[t]) continue;
+      rows.insert(rows.end(), g_bed.begin() + t * g_nbit, g_bed.begin() + (t + 1) * g_nbit);
+      if (++l == BATCH) flush();
+    }
+    flush();
+  } else {
+    const Run *Rc = &R;
+    LinePipeline<RowBlock> pipe(R.P.file_geno, [Rc, n](LineBlock &blk, RowBlock &o) {
+      const Run &R = *Rc;
+      o.ncol = n;
+      for (size_t k = 0; k < blk.lines.size(); ++k) {
+        const size_t cur_line = blk.first_line + k;
+        if (cur_line >= R.indicator_snp.size() || !R.indicator_snp[cur_line]) continue;
+        char *cur = blk.lines[k];
+        char *p = next_token(cur); p = next_token(cur); p = next_token(cur);
+        const size_t off = o.v.size();
+        o.v.resize(off + n);
+        double *g = o.v.data() + off; size_t pos = 0;
+        for (size_t i = 0; i < R.ni_total; ++i) {
+          p = next_token(cur);
+          if (!p) die("Problem reading geno file (not enough genotypes in line)");
+          if (!R.indicator_idv[i]) continue;
+          g[pos++] = (p[0] == 'N' && p[1] == 'A' && p[2] == 0) ? NAN : token_to_double(p);
+        }
+        o.rows++;
+      }
+    });
+    if (!pipe.ok()) die("error reading genotype file:" + R.P.file_geno);
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(BATCH, (size_t(1) << 28) / n));
+    vector<double> G(chunk * n);
+    size_t l = 0;
+    auto flush = [&]() {
+      if (!l) return;
+      out.resize(l);
+      GB(gb200_lm_batch_geno(ctx, G.data(), l, n, R.P.a_mode, out.data()));
+      R.sumStat.insert(R.sumStat.end(), out.begin(), out.end());
+      l = 0;
+    };
+    RowBlock blk;
+    while (pipe.next(blk)) {
+      for (size_t r = 0; r < blk.rows; ++r) {
+        std::memcpy(G.data() + l * n, blk.v.data() + r * n, n * sizeof(double));
+        if (++l == chunk) flush();
+      }
+    }
+    flush();
+  }
+  R.t_lmm = now_s() - t0;
+  std::ofstream o(out_path(R, "assoc"));
+  if (!o) { std::cout << "error writing file: " << out_path(R, "assoc") << std::endl; return; }
+  const int m = R.P.a_mode;
+  o << "chr\trs\tps\tn_mis\tn_obs\tallele1\tallele0\taf\t";
+  if (m == 51) o << "beta\tse\tp_wald" << std::endl;
+  else if (m == 52) o << "p_lrt" << std::endl;
+  else if (m == 53) o << "beta\tse\tp_score" << std::endl;
+  else o << "beta\tse\tp_wald\tp_lrt\tp_score" << std::endl;
+  size_t t = 0;
+  for (size_t i = 0; i < R.snpInfo.size(); ++i) {
+    if (!R.indicator_snp[i]) continue;
+    const SnpInfo &s = R.snpInfo[i]; const gb200_sumstat &st = R.sumStat[t++];
+    o << s.chr << "\t" << s.rs << "\t" << s.bp << "\t" << s.n_miss << "\t" << (long)R.ni_test - s.n_miss << "\t" << s.a_minor << "\t" << s.a_major << "\t"
+      << std::fixed << std::setprecision(3) << s.maf << "\t" << std::scientific << std::setprecision(6);
+    if (m == 51) o << st.beta << "\t" << st.se << "\t" << st.p_wald << std::endl;
+    else if (m == 52) o << st.p_lrt << std::endl;
+    else if (m == 53) o << st.beta << "\t" << st.se << "\t" << st.p_score << std::endl;
+    else o << st.beta << "\t" << st.se << "\t" << st.p_wald << "\t" << st.p_lrt << "\t" << st.p_score << std::endl;
+  }
+}
+
 static void write_log(const Run &R) {                  // WriteLog, src/gemma.cpp:3148-3597 (the -gk/-lmm lines)
   std::ofstream out(out_path(R, "log"));
   if (!out) return;
@@ -866,7 +955,7 @@ static void write_log(const Run &R) {                  // WriteLog, src/gemma.cp
 static void usage() {
   std::cout << "gemma-b200: GEMMA-compatible -gk / -eigen / -lmm on a B200\n"
                " -g/-p/-a/-c files (BIMBAM)  |  -bfile prefix (PLINK)   -n col...   -o prefix  -outdir dir\n"
-               " -gk [1|2]   -eigen   -lmm [1|2|3|4|9]   -k K.txt [-km 1|2]   -d D.txt -u U.txt\n"
+               " -gk [1|2]   -eigen   -lmm [1|2|3|4|9]   -lm [1|2|3|4]   -k K.txt [-km 1|2]   -d D.txt -u U.txt\n"
                " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -gwasnps file -loco chr -gxe file -lmin x -lmax x -region n -nind n -silence\n"
                " -bin  also write K / U / D as <file>.bin (exact doubles); -k/-u/-d accept such .bin files\n";
 }
@@ -910,6 +999,7 @@ int main(int argc, char **argv) {
     else if (a == "-gk") { P.a_mode = 20 + optnum(i, 1); n_modes++; }            // src/gemma.cpp:1124-1139
     else if (a == "-eigen") { P.a_mode = 31; n_modes++; }
     else if (a == "-lmm") { P.a_mode = optnum(i, 1); n_modes++; }                 // src/gemma.cpp:1299-1314
+    else if (a == "-lm") { P.a_mode = 50 + optnum(i, 1); n_modes++; }             // src/gemma.cpp:1283-1298
     else if (a == "-silence") P.silence = true;
     else if (a == "-qc-only") P.qc_only = true;
     else if (a == "-bin") P.bin = true;
@@ -919,10 +1009,12 @@ int main(int argc, char **argv) {
   }
   if (n_modes > 1) die("only one of -gk -eigen -lmm is allowed");                  // src/gemma.cpp:1125-1131
   if (n_modes == 0 && !P.qc_only) die("no analysis selected (use -gk, -eigen or -lmm)");
-  if (!(P.a_mode == 21 || P.a_mode == 22 || P.a_mode == 31 || P.a_mode == 1 || P.a_mode == 2 || P.a_mode == 3 || P.a_mode == 4 || P.a_mode == 9) && !P.qc_only)
-    die("analysis mode not supported by gemma-b200 (only -gk 1/2, -eigen, -lmm 1/2/3/4/9)");
+  if (!(P.a_mode == 21 || P.a_mode == 22 || P.a_mode == 31 || P.a_mode == 1 || P.a_mode == 2 || P.a_mode == 3 || P.a_mode == 4 || P.a_mode == 9 ||
+        (P.a_mode >= 51 && P.a_mode <= 54)) && !P.qc_only)
+    die("analysis mode not supported by gemma-b200 (only -gk 1/2, -eigen, -lmm 1/2/3/4/9, -lm 1/2/3/4)");
   if (P.p_column.empty()) P.p_column.push_back(1);                                 // src/param.cpp:635-636
-  if (P.p_column.size() > 1 && P.a_mode < 20 && !P.qc_only) die("multivariate LMM (-n with several columns) is not part of this engine");
+  if (P.a_mode >= 51 && (!P.file_gxe.empty() || !P.loco.empty())) die("-lm does not take -gxe / -loco");
+  if (P.p_column.size() > 1 && (P.a_mode < 20 || P.a_mode >= 51) && !P.qc_only) die("multivariate LMM (-n with several columns) is not part of this engine");
   if (P.file_bfile.empty() && (P.file_geno.empty() || P.file_pheno.empty())) die("need -g and -p, or -bfile");
   const bool is_lmm = (P.a_mode < 20 && P.a_mode > 0) || P.a_mode == 31;
   if (is_lmm && P.file_kin.empty() && (P.file_kd.empty() || P.file_ku.empty())) die("missing relatedness file (-k) or eigen files (-d and -u)");   // src/param.cpp:951-956
@@ -965,7 +1057,7 @@ int main(int argc, char **argv) {
   }
   if (R.ns_test == 0) die("number of analyzed SNPs equals 0");
 
-  if (P.a_mode == 21 || P.a_mode == 22) run_kinship(R, ctx); else run_lmm(R, ctx);
+  if (P.a_mode == 21 || P.a_mode == 22) run_kinship(R, ctx); else if (P.a_mode >= 51) run_lm(R, ctx); else run_lmm(R, ctx);
   R.t_total = now_s() - t_start;
   write_log(R);
   gb200_destroy(ctx);

@@ -196,6 +196,14 @@ GB200_API int gb200_lmm_gxe_batch_geno(gb200_ctx *ctx, const double *G, size_t l
 GB200_API int gb200_lmm_gxe_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
                             size_t l, size_t bytes_per_snp, gb200_sumstat *out);
 
+/* ---- -lm: linear model without random effect, LM::AnalyzeBimbam / AnalyzePlink + CalcvPv + LmCalcP
+ * (src/lm.cpp:224-288, 382-640).  W: n x n_cvt (ld ldw, intercept included), y: n, both of the analysed individuals.
+ * a_mode 1..4 or 51..54 (Wald / LRT / score / all).  SUMSTAT like the reference's: {beta, se, 0, 0, p_wald, p_lrt, p_score, -0}. */
+GB200_API int gb200_lm_setup(gb200_ctx *ctx, size_t n, size_t n_cvt, const double *W, size_t ldw, const double *y);
+GB200_API int gb200_lm_batch_geno(gb200_ctx *ctx, const double *G, size_t l, size_t ldg, int a_mode, gb200_sumstat *out);
+GB200_API int gb200_lm_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l,
+                       size_t bytes_per_snp, int a_mode, gb200_sumstat *out);
+
 /* Projection only for a PLINK 2-bit batch (same decode / imputation as gb200_lmm_batch_bed),
  * through whichever projection path the options select.  UtXt: l x n host buffer. */
 GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask,

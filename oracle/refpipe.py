@@ -231,6 +231,36 @@ def lmm_analyze(prep, X, a_mode, **kw):
                              l_mle_null=prep["l_mle_null"], logl_mle_H0=prep["logl_mle_H0"], **kw)
 
 
+def lm_analyze(W, y, G, a_mode):
+    """-lm restatement (LM::AnalyzeBimbam / AnalyzePlink + CalcvPv + LmCalcP, src/lm.cpp:224-288, 382-640).  W: n x c, y: n, G: l x n
+    genotypes of the analysed individuals (NaN = missing, mean-imputed per SNP).  Returns SUMSTAT rows {beta, se, 0, 0, p_wald, p_lrt,
+    p_score, -0}; se is the score-test one in mode 3 (:281-285)."""
+    n, c = W.shape
+    test_mode = a_mode - 50 if a_mode > 50 else a_mode
+    WtWi = np.linalg.inv(W.T @ W)
+    Wty = W.T @ y
+    yPwy = float(y @ y - (WtWi @ Wty) @ Wty)
+    df = float(n) - float(c) - 1.0
+    out = np.zeros(G.shape[0], dtype=O.SUMSTAT_DTYPE)
+    for t in range(G.shape[0]):
+        x = G[t].copy()
+        miss = np.isnan(x)
+        x[miss] = float(np.cumsum(x[~miss])[-1]) / float((~miss).sum())
+        Wtx = W.T @ x
+        WtWiWtx = WtWi @ Wtx
+        xPwx = float(x @ x - WtWiWtx @ Wtx)
+        xPwy = float(x @ y - WtWiWtx @ Wty)
+        yPxy = yPwy - xPwy * xPwy / xPwx
+        beta = xPwy / xPwx
+        se_wald = np.sqrt(yPxy / (df * xPwx)); se_score = np.sqrt(yPwy / (float(n) * xPwx))
+        out["beta"][t] = beta; out["se"][t] = se_score if test_mode == 3 else se_wald
+        out["p_wald"][t] = O.fdist_Q(beta * beta / (se_wald * se_wald), 1.0, df)
+        out["p_score"][t] = O.fdist_Q(beta * beta / (se_score * se_score), 1.0, df)
+        out["p_lrt"][t] = O.chisq1_Q(float(n) * (np.log(yPwy) - np.log(yPxy)))
+        out["logl_H1"][t] = -0.0
+    return out
+
+
 def lmm_gxe(prep, G, env, a_mode, l_min=1e-5, l_max=1e5, n_region=10, l_mle_null=0.0):
     """G x E restatement (LMM::AnalyzePlinkGXE / AnalyzeBimbamGXE, src/lmm.cpp:2283-2608) composed from the oracle's univariate
     pieces.  G: l x n genotypes of the analysed individuals (NaN = missing); env: n.  Per SNP: mean-impute, flip to 2 - x when

@@ -624,6 +624,48 @@ def test_gxe_entry_points_and_cli_match_oracle_and_reference_cli(ctx, tmp_path):
         assert np.allclose(xa[:, j], xb[:, j], rtol=2e-5 if h.startswith("l_") else 2e-6, atol=0), h
 
 
+def test_lm_entry_points_and_cli_match_oracle_and_reference_cli(ctx, tmp_path):
+    """-lm 1..4 (src/lm.cpp): gb200_lm_batch_bed / _geno vs the restatement (checked against the reference CLI in
+    tests/test_oracle_vs_ref.py), and gemma-b200 -lm vs the reference CLI on whole assoc files (PLINK with covariates, BIMBAM mouse)."""
+    import subprocess
+    from oracle import ref as REF
+    from test_oracle_vs_ref import _plink_lm_case
+    prefix, cov = _plink_lm_case(tmp_path, n=333, l=140, seed=89)
+    pl = R.Plink(prefix)
+    rows, icvt = R.read_cvt(cov)
+    idv, W = R.process_cvt_phen(pl.ind_pheno, rows, icvt)
+    isnp, _, _ = R.qc_plink(pl, idv, W)
+    keep = idv == 1
+    sel = np.nonzero(isnp)[0]
+    Gs = np.where(pl.G[np.ix_(sel, keep)] < 0, np.nan, pl.G[np.ix_(sel, keep)])
+    ctx.lm_setup(W[keep], pl.pheno[keep, 0])
+    for mode in (1, 2, 3, 4):
+        ref = R.lm_analyze(W[keep], pl.pheno[keep, 0], Gs, mode)
+        for got in (ctx.lm_batch_bed(pl.bed[sel], len(idv), 50 + mode, idv.astype(np.uint8)), ctx.lm_batch_geno(Gs, mode)):
+            for k in ("beta", "se", "p_wald", "p_lrt", "p_score"):
+                assert rel_err(got[k], ref[k]) < REL, (mode, k)
+            assert np.all(got["lambda_remle"] == 0) and np.all(got["lambda_mle"] == 0)
+    if not os.path.exists(REF.EXE):
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+    cwd = str(tmp_path); out = os.path.join(cwd, "output")
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mouse_hs1940")
+    cases = [(["-bfile", prefix, "-c", cov], "p"), (["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"], "b")]
+    for base, tag in cases:
+        for mode in ("1", "4"):
+            REF.run_cli(base + ["-lm", mode, "-o", "r" + tag + mode], cwd)
+            r = subprocess.run([cli] + base + ["-lm", mode, "-o", "m" + tag + mode, "-outdir", out], capture_output=True, text=True, cwd=cwd)
+            assert r.returncode == 0, r.stdout + r.stderr
+            a = open(os.path.join(out, "m" + tag + mode + ".assoc.txt")).read().splitlines()
+            b = open(os.path.join(out, "r" + tag + mode + ".assoc.txt")).read().splitlines()
+            assert len(a) == len(b) and a[0] == b[0]
+            fa = [x.split("\t") for x in a[1:]]; fb = [x.split("\t") for x in b[1:]]
+            assert [x[:8] for x in fa] == [x[:8] for x in fb]              # chr rs ps n_mis n_obs alleles af: text for text
+            xa = np.array([[float(v) for v in x[8:]] for x in fa]); xb = np.array([[float(v) for v in x[8:]] for x in fb])
+            assert np.allclose(xa, xb, rtol=2e-6, atol=0), (tag, mode)
+
+
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
 def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     n = 1300

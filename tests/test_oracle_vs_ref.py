@@ -254,3 +254,42 @@ def test_gxe_restatement_matches_reference_cli(tmp_path):
         for j, k in enumerate(cols[mode]):
             tol = 2e-5 if k.startswith("lambda") else 2e-6
             assert np.allclose(got[k], ref[:, j], rtol=tol, atol=0), (mode, k, np.max(np.abs(got[k] - ref[:, j]) / np.abs(ref[:, j])))
+
+
+def _plink_lm_case(tmp_path, n=280, l=110, seed=88):
+    from gemma_b200 import synth
+    rng = np.random.default_rng(seed)
+    bed, G = synth.make_bed(n, l, seed=seed, miss_rate=0.015)
+    y = rng.standard_normal(n) + 0.35 * np.where(G[6] < 0, 0, G[6])
+    y[rng.choice(n, 9, replace=False)] = np.nan
+    prefix = str(tmp_path / "lm")
+    _write_plink(prefix, bed, y)
+    cov = str(tmp_path / "lmcov.txt")
+    with open(cov, "w") as f:
+        for i in range(n):
+            f.write("1 %.6f %.6f\n" % (rng.standard_normal(), rng.uniform(20, 70)))
+    return prefix, cov
+
+
+def test_lm_restatement_matches_reference_cli(tmp_path):
+    """-lm 1..4 (src/lm.cpp): refpipe.lm_analyze against the reference's own CLI on a PLINK set with covariates."""
+    if not os.path.exists(REF.EXE) and not os.path.isdir(REF.REF_SRC):
+        pytest.skip("reference CLI not built")
+    prefix, cov = _plink_lm_case(tmp_path)
+    cwd = str(tmp_path)
+    pl = R.Plink(prefix)
+    rows, icvt = R.read_cvt(cov)
+    idv, W = R.process_cvt_phen(pl.ind_pheno, rows, icvt)
+    isnp, _, _ = R.qc_plink(pl, idv, W)
+    keep = idv == 1
+    sel = np.nonzero(isnp)[0]
+    Gs = np.where(pl.G[np.ix_(sel, keep)] < 0, np.nan, pl.G[np.ix_(sel, keep)])
+    cols = {1: ("beta", "se", "p_wald"), 2: ("p_lrt",), 3: ("beta", "se", "p_score"), 4: ("beta", "se", "p_wald", "p_lrt", "p_score")}
+    for mode in (1, 2, 3, 4):
+        REF.run_cli(["-bfile", prefix, "-c", cov, "-lm", str(mode), "-o", "lm%d" % mode], cwd)
+        lines = open(os.path.join(cwd, "output", "lm%d.assoc.txt" % mode)).read().splitlines()
+        assert len(lines) == 1 + len(sel)
+        ref = np.array([[float(x) for x in ln.split("\t")[8:]] for ln in lines[1:]])
+        got = R.lm_analyze(W[keep], pl.pheno[keep, 0], Gs, mode)
+        for j, k in enumerate(cols[mode]):
+            assert np.allclose(got[k], ref[:, j], rtol=2e-6, atol=0), (mode, k)
