@@ -293,3 +293,42 @@ def test_lm_restatement_matches_reference_cli(tmp_path):
         got = R.lm_analyze(W[keep], pl.pheno[keep, 0], Gs, mode)
         for j, k in enumerate(cols[mode]):
             assert np.allclose(got[k], ref[:, j], rtol=2e-6, atol=0), (mode, k)
+
+
+def test_mvlmm_restatement_matches_reference_cli(golden_dir, tmp_path):
+    """Multivariate LMM (BASELINE config 5): oracle/mvlmm_oracle.py (EM + Newton-Raphson in closed block form,
+    MphCalcP) against the reference's own CLI on the mouse example with two phenotypes (-n 1 6): null-model Vg / Ve and their
+    standard errors (example/demo.txt:69-80), the first SNPs and the most significant ones (p < 0.001 takes the NR branch)."""
+    from oracle import mvlmm_oracle as MV
+    if not os.path.exists(REF.EXE) and not os.path.isdir(REF.REF_SRC):
+        pytest.skip("reference CLI not built")
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+    cwd = str(tmp_path)
+    REF.run_cli(base + ["-gk", "-o", "mouse"], cwd)
+    log = REF.run_cli(base + ["-n", "1", "6", "-k", "output/mouse.cXX.txt", "-lmm", "-o", "mv"], cwd)
+    K = np.loadtxt(os.path.join(cwd, "output", "mouse.cXX.txt"))
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1, 6))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, _, _ = R.qc_bimbam(bb, idv)
+    keep = idv == 1
+    U, ev, _ = R.eigen_decomp_zeroed(O.center_matrix(np.ascontiguousarray(K[np.ix_(keep, keep)])))
+    UtW = U.T @ W[keep]; UtY = U.T @ ph[keep]
+    nm = MV.null_model(ev, UtW, UtY)
+    # demo.txt:69-80 (4 significant digits in the reference's console output)
+    assert np.allclose([nm["Vg_remle"][0, 0], nm["Vg_remle"][0, 1], nm["Vg_remle"][1, 1]], [1.39398, -0.226714, 2.08168], rtol=5e-6)     # 6 printed digits
+    assert np.allclose([nm["Ve_remle"][0, 0], nm["Ve_remle"][0, 1], nm["Ve_remle"][1, 1]], [0.348882, 0.0490525, 0.414433], rtol=5e-6)
+    se = np.sqrt(np.diag(nm["cov_remle"]))
+    assert np.allclose(se, [0.156661, 0.136319, 0.235858, 0.0206226, 0.0166233, 0.0266869], rtol=5e-6)
+    lines = open(os.path.join(cwd, "output", "mv.assoc.txt")).read().splitlines()
+    sel_all = np.nonzero(isnp)[0]
+    assert len(lines) == 1 + len(sel_all)
+    ref = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:]])          # beta_1 beta_2 V11 V12 V22 p_wald
+    pick = sorted(set(range(25)) | set(np.argsort(ref[:, 5])[:15].tolist()))
+    assert (ref[pick, 5] < MV.P_NR).sum() >= 5                                             # the NR branch is exercised
+    X = R.lmm_genotypes_bimbam(bb, isnp, idv, sel_all[pick])
+    for q, r in enumerate(pick):
+        beta, Vb, p = MV.analyze_snp_wald(ev, UtW, UtY, U.T @ X[:, q], nm)
+        got = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], p])
+        assert np.allclose(got, ref[r], rtol=3e-6, atol=0), (r, got, ref[r])
