@@ -77,6 +77,10 @@ SIGNATURES = {
     "gb200_lmm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gb200_lmm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_lmm_batch_bed_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "gb200_mvlmm_setup": (C.c_int, [_vp, _sz, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
+    "gb200_mvlmm_null": (C.c_int, [_vp] * 9),
+    "gb200_mvlmm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
+    "gb200_mvlmm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_lm_setup": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp]),
     "gb200_lm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _vp]),
     "gb200_lm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, C.c_int, _vp]),
@@ -288,6 +292,34 @@ class Context:
         out = np.zeros(bed.shape[0], dtype=SUMSTAT_DTYPE)
         self._chk(self.lib.gb200_lmm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1],
                                                _ptr(out)))
+        return out
+
+    # ---- multivariate LMM (two phenotypes, src/mvlmm.cpp)
+    def mvlmm_setup(self, U, eval_, W, Y):
+        U, eval_, W, Y = _f64(U), _f64(eval_), _f64(W), _f64(Y)
+        n, c = W.shape
+        self._chk(self.lib.gb200_mvlmm_setup(self.h, n, c, Y.shape[1], _ptr(U), n, _ptr(eval_), _ptr(W), c, _ptr(Y), Y.shape[1]))
+        self.n, self.n_cvt = n, c
+
+    def mvlmm_null(self):
+        c = self.n_cvt
+        a = [np.zeros(4), np.zeros(4), np.zeros(2 * c), C.c_double(), np.zeros(4), np.zeros(4), np.zeros(2 * c), C.c_double()]
+        self._chk(self.lib.gb200_mvlmm_null(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), C.byref(a[3]), _ptr(a[4]), _ptr(a[5]), _ptr(a[6]),
+                                            C.byref(a[7])))
+        return dict(Vg_remle=a[0].reshape(2, 2), Ve_remle=a[1].reshape(2, 2), B_remle=a[2].reshape(2, c), logl_remle_H0=a[3].value,
+                    Vg_mle=a[4].reshape(2, 2), Ve_mle=a[5].reshape(2, 2), B_mle=a[6].reshape(2, c), logl_mle_H0=a[7].value)
+
+    def mvlmm_batch_geno(self, G):
+        G = _f64(G)
+        out = np.zeros((G.shape[0], 6))
+        self._chk(self.lib.gb200_mvlmm_batch_geno(self.h, _ptr(G), G.shape[0], G.shape[1], _ptr(out)))
+        return out
+
+    def mvlmm_batch_bed(self, bed, ni_total, idv_mask=None):
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        m = None if idv_mask is None else np.ascontiguousarray(idv_mask, dtype=np.uint8)
+        out = np.zeros((bed.shape[0], 6))
+        self._chk(self.lib.gb200_mvlmm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1], _ptr(out)))
         return out
 
     # ---- -lm (linear model, src/lm.cpp)

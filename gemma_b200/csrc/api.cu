@@ -971,6 +971,110 @@ int gb200_lm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned ch
   return lm_core(c, l, a_mode, out);
 }
 
+// ---- multivariate LMM, two phenotypes (MVLMM::AnalyzeBimbam / AnalyzePlink, src/mvlmm.cpp:2972-3899; -lmm 1) -------------------
+int gb200_mvlmm_setup(gb200_ctx *c, size_t n, size_t n_cvt, size_t n_ph, const double *U, size_t ldu, const double *eval, const double *W,
+                      size_t ldw, const double *Y, size_t ldy) {
+  if (!c) return GB200_ERR_ARG;
+  if (!Y || !W || ldy < n_ph) return set_err(c, GB200_ERR_ARG, "gb200_mvlmm_setup: bad argument");
+  if (n_ph != 2) return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_mvlmm_setup: two phenotypes are supported in this round");
+  if (n_cvt < 1 || n_cvt > 3) return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_mvlmm_setup: 1..3 covariates (incl. intercept) are supported");
+  c->mv_ready = false; c->mv_null_ready = false;
+  std::vector<double> y0(n);
+  for (size_t i = 0; i < n; ++i) y0[i] = Y[i * ldy];
+  int rc = gb200_lmm_setup(c, n, n_cvt, U, ldu, eval, W, ldw, y0.data(), nullptr, nullptr);      // U, eval, U^T W and U^T y_1 on the device
+  if (rc) return rc;
+  const size_t n_c = c->n_c;
+  GB_CUDA(c, c->dMvY.reserve(2 * n_c * 8));
+  GB_CUDA(c, cudaMemsetAsync(c->dMvY.p, 0, 2 * n_c * 8, c->stream));
+  GB_CUDA(c, c->dTmp.reserve(2 * n * 8));
+  std::vector<double> Yt(2 * n);
+  for (size_t i = 0; i < n; ++i) { Yt[i] = Y[i * ldy]; Yt[n + i] = Y[i * ldy + 1]; }
+  GB_CUDA(c, cudaMemcpyAsync(c->dTmp.p, Yt.data(), 2 * n * 8, cudaMemcpyHostToDevice, c->stream));
+  // U^T Y (CalcUtX, src/gemma.cpp:2700): row s of dMvY = y_s' U
+  GB_CUDA(c, launch_dgemm(2, n, n, 1.0, c->dTmp.as<double>(), n, 1, c->dU.as<double>(), n, 1, 0.0, c->dMvY.as<double>(), n_c, false, c->stream));
+  // MphInitial diagonals (src/mvlmm.cpp:2786-2796): univariate REML lambda + CalcLmmVgVeBeta per trait, on the univariate device path
+  gb::MvConst &K = c->mvK;
+  for (int s = 0; s < 2; ++s) {
+    GB_CUDA(c, cudaMemcpyAsync(c->dY.p, c->dMvY.as<double>() + (size_t)s * n_c, n_c * 8, cudaMemcpyDeviceToDevice, c->stream));
+    gb200_nullmodel nm;
+    std::vector<double> b1(n_cvt), b2(n_cvt), b3(n_cvt), b4(n_cvt);
+    rc = gb200_lmm_null(c, 1e-5, 1e5, 10, 1.0, &nm, b1.data(), b2.data(), b3.data(), b4.data());
+    if (rc) return rc;
+    K.vg0[s] = nm.vg_remle; K.ve0[s] = nm.ve_remle;
+  }
+  K.n = (int)n; K.ld = (int)n_c; K.delta = c->dEval.as<double>(); K.Wt = c->dWt.as<double>(); K.Yt = c->dMvY.as<double>();
+  K.em_iter = 10000; K.nr_iter = 100; K.em_prec = 1e-4; K.nr_prec = 1e-4; K.p_nr = 0.001;           // src/param.cpp:98-99
+  c->mv_ready = true;
+  return GB200_OK;
+}
+
+int gb200_mvlmm_null(gb200_ctx *c, double *Vg_remle, double *Ve_remle, double *B_remle, double *logl_remle, double *Vg_mle, double *Ve_mle,
+                     double *B_mle, double *logl_mle) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->mv_ready) return set_err(c, GB200_ERR_STATE, "gb200_mvlmm_null before gb200_mvlmm_setup");
+  GB_CUDA(c, c->dMvNull.reserve(sizeof(gb::MvNull)));
+  {
+    ProfScope ps(c, "lmm");
+    GB_CUDA(c, launch_mv_null((int)c->n_cvt, c->mvK, c->dMvNull.as<gb::MvNull>(), c->stream));
+  }
+  gb::MvNull r;
+  GB_CUDA(c, cudaMemcpyAsync(&r, c->dMvNull.p, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t cN = c->n_cvt;
+  for (int i = 0; i < 4; ++i) { if (Vg_remle) Vg_remle[i] = r.Vg_remle[i]; if (Ve_remle) Ve_remle[i] = r.Ve_remle[i]; if (Vg_mle) Vg_mle[i] = r.Vg_mle[i]; if (Ve_mle) Ve_mle[i] = r.Ve_mle[i]; }
+  for (int i = 0; i < 2; ++i) for (size_t j = 0; j < cN; ++j) { if (B_remle) B_remle[i * cN + j] = r.B_remle[i * 4 + j]; if (B_mle) B_mle[i * cN + j] = r.B_mle[i * 4 + j]; }
+  if (logl_remle) *logl_remle = r.logl_remle;
+  if (logl_mle) *logl_mle = r.logl_mle;
+  c->mv_null_ready = true;
+  return GB200_OK;
+}
+
+static int mv_assoc_core(gb200_ctx *c, size_t l, double *out) {
+  GB_CUDA(c, c->dMvOut.reserve(l * 6 * 8));
+  {
+    ProfScope ps(c, "lmm");
+    GB_CUDA(c, launch_mv_assoc((int)c->n_cvt, c->mvK, c->dMvNull.as<gb::MvNull>(), c->dUtXt.as<double>(), c->n_c, (int)l, c->dMvOut.as<double>(),
+                               c->dTicket.as<unsigned int>(), c->num_sms, c->stream));
+  }
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dMvOut.p, l * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GB200_OK;
+}
+
+int gb200_mvlmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, double *out) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->mv_ready || !c->mv_null_ready) return set_err(c, GB200_ERR_STATE, "gb200_mvlmm_batch_geno before gb200_mvlmm_setup / gb200_mvlmm_null");
+  if (l == 0) return GB200_OK;
+  const size_t n = c->n;
+  if (!G || !out || ldg < n) return set_err(c, GB200_ERR_ARG, "gb200_mvlmm_batch_geno: bad argument");
+  GB_CUDA(c, c->dX.reserve(n * l * 8));
+  GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
+  GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, "decode");
+    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  }
+  int rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+  if (rc) return rc;
+  return mv_assoc_core(c, l, out);
+}
+
+int gb200_mvlmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l, size_t bytes_per_snp,
+                          double *out) {
+  if (!c) return GB200_ERR_ARG;
+  if (!c->mv_ready || !c->mv_null_ready) return set_err(c, GB200_ERR_STATE, "gb200_mvlmm_batch_bed before gb200_mvlmm_setup / gb200_mvlmm_null");
+  if (l == 0) return GB200_OK;
+  if (!bed || !out || bytes_per_snp != (ni_total + 3) / 4) return set_err(c, GB200_ERR_ARG, "gb200_mvlmm_batch_bed: bad argument");
+  const int *idx_dev = nullptr;
+  int rc = upload_idx_from_mask(c, idv_mask, ni_total, &idx_dev);
+  if (rc) return rc;
+  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
+  rc = project_bed_dev(c, c->dBed.as<unsigned char>(), idx_dev, ni_total, l, bytes_per_snp);      // int8 tensor-core projection for n >= 1024
+  if (rc) return rc;
+  return mv_assoc_core(c, l, out);
+}
+
 int gb200_lmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,
                         size_t l, size_t bytes_per_snp, gb200_sumstat *out) {
   if (!c) return GB200_ERR_ARG;

@@ -60,6 +60,18 @@ struct I8State {
   void *tmap_ka = nullptr, *tmap_kb = nullptr;
 };
 
+// multivariate LMM (two phenotypes): run constants and null-model results on the device
+struct MvConst {
+  int n, ld;                      // individuals, leading dimension of the rows below
+  const double *delta, *Wt, *Yt;  // eigenvalues; c rows of U^T W; 2 rows of U^T Y
+  double vg0[2], ve0[2];          // univariate REML estimates (MphInitial diagonals)
+  int em_iter, nr_iter; double em_prec, nr_prec, p_nr;
+};
+struct MvNull {
+  double Vg_remle[4], Ve_remle[4], B_remle[8], logl_remle;
+  double Vg_mle[4], Ve_mle[4], B_mle[8], logl_mle;
+};
+
 }  // namespace gb
 
 struct gb200_ctx {
@@ -88,6 +100,8 @@ struct gb200_ctx {
   bool gxe_ready = false;
   gb::DevBuf dLmW, dLmY, dLmSmall;     // -lm: W rows (c x n), y, [WtWi (c x c) | Wty (c)]
   size_t lm_n = 0, lm_c = 0; double lm_yPwy = 0.0; bool lm_ready = false;
+  gb::DevBuf dMvY, dMvNull, dMvOut;      // multivariate LMM: U^T Y rows (2 x n_c), MvNull, per-SNP output rows
+  gb::MvConst mvK; bool mv_ready = false, mv_null_ready = false;
   gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
   bool common_ready = false;
   // scratch
@@ -168,6 +182,9 @@ bool lmm_v2_supported(int n_cvt, int n_region);
 cudaError_t launch_lmm_gxe(int c_base, LmmConst D, const LmmParams &prm, const double *UtX1t, const double *UtX2t, size_t ldu, int l,
                            const unsigned char *flip, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st);
 cudaError_t launch_gxe_prepare(double *X1, double *X2, const double *env, size_t l, size_t n, unsigned char *flip, cudaStream_t st);
+cudaError_t launch_mv_null(int c, const MvConst &K, MvNull *out, cudaStream_t st);
+cudaError_t launch_mv_assoc(int c, const MvConst &K, const MvNull *nm, const double *UtXt, size_t ldu, int l, double *out, unsigned int *ticket,
+                            int num_sms, cudaStream_t st);
 cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double *Wt, const double *y, const double *WtWi, const double *Wty,
                       double yPwy, int test_mode, gb200_sumstat *out, cudaStream_t st);
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st);

@@ -1,0 +1,65 @@
+// Host instantiation of gemma_b200/csrc/mvlmm_core.cuh (GB_MV_HOST: one "lane") for tests/test_mvlmm_core.py: the moment
+// formulation that the CUDA kernels run is checked against the numpy oracle (oracle/mvlmm_oracle.py) without a GPU.
+#define GB_MV_HOST 1
+#include "../../gemma_b200/csrc/mvlmm_core.cuh"
+
+using namespace gbmv;
+
+template <int C>
+static int null_t(int n, const double *ev, const double *X, const double *Y, const double *Vg0, const double *Ve0, double *out) {
+  constexpr int D = 2;
+  MvData<C + D> dat; dat.n = n; dat.delta = ev;
+  for (int j = 0; j < C; ++j) dat.z[j] = X + (size_t)j * n;
+  for (int s = 0; s < D; ++s) dat.z[C + s] = Y + (size_t)s * n;
+  Fit<D, C> fit;
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { fit.V_g[i][j] = Vg0[i * D + j]; fit.V_e[i][j] = Ve0[i * D + j]; }
+  mph_calc_beta<D, C>(dat, fit.V_g, fit.V_e, fit.B);
+  mph_em<D, C>(true, 10000, 1e-4, dat, fit);
+  const double lr = mph_nr<D, C>(true, 100, 1e-4, dat, fit);
+  mph_calc_beta<D, C>(dat, fit.V_g, fit.V_e, fit.B);
+  int o = 0;
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[o++] = fit.V_g[i][j];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[o++] = fit.V_e[i][j];
+  out[o++] = lr;
+  mph_em<D, C>(false, 10000, 1e-4, dat, fit);
+  const double lm = mph_nr<D, C>(false, 100, 1e-4, dat, fit);
+  mph_calc_beta<D, C>(dat, fit.V_g, fit.V_e, fit.B);
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[o++] = fit.V_g[i][j];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[o++] = fit.V_e[i][j];
+  out[o++] = lm;
+  for (int i = 0; i < D; ++i) for (int j = 0; j < C; ++j) out[o++] = fit.B[i][j];
+  return o;
+}
+
+template <int C>
+static int snp_t(int n, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn,
+                 double *out) {
+  constexpr int D = 2, C1 = C + 1;
+  MvData<C1 + D> dat; dat.n = n; dat.delta = ev;
+  for (int j = 0; j < C; ++j) dat.z[j] = X + (size_t)j * n;
+  dat.z[C] = x;
+  for (int s = 0; s < D; ++s) dat.z[C1 + s] = Y + (size_t)s * n;
+  Fit<D, C1> fit;
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { fit.V_g[i][j] = Vg[i * D + j]; fit.V_e[i][j] = Ve[i * D + j]; }
+  for (int i = 0; i < D; ++i) { for (int j = 0; j < C; ++j) fit.B[i][j] = Bn[i * C + j]; fit.B[i][C] = 0.0; }
+  mph_em<D, C1>(true, 1000, 1e-3, dat, fit);                       // em_iter / 10, em_prec * 10 (mvlmm.cpp:3336)
+  double beta[D], Vb[D][D];
+  double p = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
+  if (p < 0.001) {                                                  // p_nr (mvlmm.cpp:3341-3347)
+    mph_nr<D, C1>(true, 10, 1e-3, dat, fit);
+    p = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
+  }
+  out[0] = beta[0]; out[1] = beta[1]; out[2] = Vb[0][0]; out[3] = Vb[0][1]; out[4] = Vb[1][1]; out[5] = p;
+  return 6;
+}
+
+extern "C" {
+int mvh_null(int n, int c, const double *ev, const double *X, const double *Y, const double *Vg0, const double *Ve0, double *out) {
+  switch (c) { case 1: return null_t<1>(n, ev, X, Y, Vg0, Ve0, out); case 2: return null_t<2>(n, ev, X, Y, Vg0, Ve0, out); case 3: return null_t<3>(n, ev, X, Y, Vg0, Ve0, out); }
+  return -1;
+}
+int mvh_snp(int n, int c, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn, double *out) {
+  switch (c) { case 1: return snp_t<1>(n, ev, X, x, Y, Vg, Ve, Bn, out); case 2: return snp_t<2>(n, ev, X, x, Y, Vg, Ve, Bn, out); case 3: return snp_t<3>(n, ev, X, x, Y, Vg, Ve, Bn, out); }
+  return -1;
+}
+}

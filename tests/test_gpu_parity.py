@@ -666,6 +666,58 @@ def test_lm_entry_points_and_cli_match_oracle_and_reference_cli(ctx, tmp_path):
             assert np.allclose(xa, xb, rtol=2e-6, atol=0), (tag, mode)
 
 
+def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir, tmp_path):
+    """Multivariate LMM, two phenotypes (BASELINE config 5): gb200_mvlmm_setup / _null / _batch_geno / _batch_bed vs
+    oracle/mvlmm_oracle.py on random problems (c = 1..3, Newton-Raphson branch included) and vs the reference CLI's mouse run
+    (-n 1 6: example/demo.txt:62-80)."""
+    from oracle import mvlmm_oracle as MV
+    from oracle import ref as REF
+    from test_mvlmm_core import _problem
+    for n, c, seed in ((240, 1, 1), (300, 3, 3)):
+        pb = _problem(n, c, seed)
+        rng = np.random.default_rng(seed)
+        W = pb["U"] @ pb["UtW"]; Y = pb["U"] @ pb["UtY"]
+        ctx.mvlmm_setup(pb["U"], pb["ev"], W, Y)
+        nm = ctx.mvlmm_null()
+        ref = MV.null_model(pb["ev"], pb["UtW"], pb["UtY"])
+        for k in ("Vg_remle", "Ve_remle", "Vg_mle", "Ve_mle"):
+            assert np.allclose(nm[k], ref[k], rtol=1e-6, atol=1e-9), k
+        assert nm["logl_remle_H0"] == pytest.approx(ref["logl_remle_H0"], rel=1e-9) and nm["logl_mle_H0"] == pytest.approx(ref["logl_mle_H0"], rel=1e-9)
+        G = (pb["U"] @ pb["UtX"].T).T                                  # genotypes back in the original basis (exact integers up to rounding)
+        G = np.rint(G)
+        got = ctx.mvlmm_batch_geno(G)
+        for q in range(G.shape[0]):
+            beta, Vb, p = MV.analyze_snp_wald(pb["ev"], pb["UtW"], pb["UtY"], pb["U"].T @ G[q], ref)
+            exp = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], p])
+            assert np.allclose(got[q], exp, rtol=2e-6, atol=1e-300), (c, q, got[q], exp)
+    # mouse example, two phenotypes, through the PLINK-free BIMBAM entry point; reference CLI rows as the expectation
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1, 6))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, _, _ = R.qc_bimbam(bb, idv)
+    keep = idv == 1
+    K = R.text_roundtrip(R.kinship_bimbam(bb, R.qc_bimbam(bb, R.process_cvt_phen(R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1,))[1])[0])[0], 1))
+    U, ev, _ = R.eigen_decomp_zeroed(O.center_matrix(np.ascontiguousarray(K[np.ix_(keep, keep)])))
+    ctx.mvlmm_setup(U, ev, W[keep], ph[keep])
+    nm = ctx.mvlmm_null()
+    assert np.allclose([nm["Vg_remle"][0, 0], nm["Vg_remle"][0, 1], nm["Vg_remle"][1, 1]], [1.39398, -0.226714, 2.08168], rtol=5e-6)   # demo.txt:70-72
+    assert np.allclose([nm["Ve_remle"][0, 0], nm["Ve_remle"][0, 1], nm["Ve_remle"][1, 1]], [0.348882, 0.0490525, 0.414433], rtol=5e-6)  # demo.txt:76-78
+    sel = np.nonzero(isnp)[0][:64]
+    Gs = bb.G[np.ix_(sel, np.nonzero(keep)[0])]
+    got = ctx.mvlmm_batch_geno(Gs)
+    exp = np.array([[float(x) for x in row[7:]] for row in EXP["mouse_mvlmm_rows"]["rows"]])
+    assert np.allclose(got[:5], exp, rtol=2e-6, atol=0)                                                   # demo.txt:62-66
+    if os.path.exists(REF.EXE):
+        cwd = str(tmp_path)
+        base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+        REF.run_cli(base + ["-gk", "-o", "mouse"], cwd)
+        REF.run_cli(base + ["-n", "1", "6", "-k", "output/mouse.cXX.txt", "-lmm", "-o", "mv"], cwd)
+        lines = open(os.path.join(cwd, "output", "mv.assoc.txt")).read().splitlines()
+        refrows = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:65]])
+        assert np.allclose(got, refrows, rtol=3e-6, atol=0)
+
+
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
 def test_kinship_int8_tensor_core_path_matches_oracle(ctx):
     n = 1300

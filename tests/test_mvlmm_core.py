@@ -1,0 +1,70 @@
+"""The moment formulation of the multivariate LMM that the CUDA kernels run (gemma_b200/csrc/mvlmm_core.cuh), instantiated for the
+host (tests/host/mvlmm_check.cpp, one "lane"), against the numpy restatement oracle/mvlmm_oracle.py (itself pinned against the
+compiled reference CLI in tests/test_oracle_vs_ref.py).  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import oracle as O
+from oracle import mvlmm_oracle as MV
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+@pytest.fixture(scope="module")
+def core(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("mvh") / "libmvh.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "host", "mvlmm_check.cpp")])
+    return C.CDLL(so)
+
+
+def _problem(n, c, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, 3 * n))
+    K = O.center_matrix(A @ A.T / (3 * n))
+    ev, U = scipy.linalg.eigh(K)
+    ev, _ = O.zero_small_eval(ev)
+    W = np.ones((n, c))
+    if c > 1:
+        W[:, :c - 1] = rng.standard_normal((n, c - 1))
+    G = rng.binomial(2, rng.uniform(0.1, 0.5, 12)[:, None], size=(12, n)).astype(float)
+    g = U @ (np.sqrt(ev)[:, None] * rng.standard_normal((n, 2)))
+    E = rng.standard_normal((n, 2)) @ np.array([[1.0, 0.3], [0.0, 0.8]])
+    Y = 0.9 * g @ np.array([[1.0, 0.4], [0.0, 0.7]]) + E
+    Y[:, 0] += 0.9 * (G[0] - G[0].mean()); Y[:, 1] -= 0.7 * (G[0] - G[0].mean())       # a strong SNP -> Newton-Raphson branch
+    return dict(ev=ev, U=U, UtW=U.T @ W, UtY=U.T @ Y, UtX=(U.T @ G.T).T)
+
+
+@pytest.mark.parametrize("n,c,seed", [(240, 1, 1), (300, 2, 2), (260, 3, 3)])
+def test_moment_form_matches_restatement(core, n, c, seed):
+    pb = _problem(n, c, seed)
+    ev = np.ascontiguousarray(pb["ev"]); X = np.ascontiguousarray(pb["UtW"].T); Y = np.ascontiguousarray(pb["UtY"].T)
+    Vg0, Ve0, _ = MV.mph_initial(ev, X, Y)
+    out = np.zeros(64)
+    k = core.mvh_null(n, c, _p(ev), _p(X), _p(Y), _p(np.ascontiguousarray(Vg0)), _p(np.ascontiguousarray(Ve0)), _p(out))
+    assert k == 18 + 2 * c
+    nm = MV.null_model(ev, pb["UtW"], pb["UtY"])
+    assert np.allclose(out[0:4], nm["Vg_remle"].ravel(), rtol=1e-7, atol=1e-10) and np.allclose(out[4:8], nm["Ve_remle"].ravel(), rtol=1e-7, atol=1e-10)
+    assert out[8] == pytest.approx(nm["logl_remle_H0"], rel=1e-10)
+    assert np.allclose(out[9:13], nm["Vg_mle"].ravel(), rtol=1e-7, atol=1e-10) and np.allclose(out[13:17], nm["Ve_mle"].ravel(), rtol=1e-7, atol=1e-10)
+    assert out[17] == pytest.approx(nm["logl_mle_H0"], rel=1e-10)
+    assert np.allclose(out[18:18 + 2 * c], nm["B_mle"].ravel(), rtol=1e-6, atol=1e-9)
+    Vg = np.ascontiguousarray(out[9:13]); Ve = np.ascontiguousarray(out[13:17]); Bn = np.ascontiguousarray(out[18:18 + 2 * c])
+    o = np.zeros(6); n_nr = 0
+    for q in range(pb["UtX"].shape[0]):
+        x = np.ascontiguousarray(pb["UtX"][q])
+        core.mvh_snp(n, c, _p(ev), _p(X), _p(x), _p(Y), _p(Vg), _p(Ve), _p(Bn), _p(o))
+        beta, Vb, p = MV.analyze_snp_wald(ev, pb["UtW"], pb["UtY"], x, nm)
+        ref = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], p])
+        assert np.allclose(o, ref, rtol=2e-6, atol=1e-300), (q, o, ref)
+        n_nr += p < MV.P_NR
+    assert n_nr >= 1
