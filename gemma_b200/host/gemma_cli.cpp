@@ -725,6 +725,97 @@ static void write_assoc(const Run &R) {                // LMM::WriteFiles, src/l
   }
 }
 
+// multivariate LMM, two phenotypes: MVLMM::AnalyzeBimbam / AnalyzePlink (src/mvlmm.cpp:2972-3899), MVLMM::WriteFiles (:117-210)
+static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vector<double> &eval, const vector<double> &W) {
+  const size_t n = R.ni_test, d = 2;
+  vector<double> Y(n * d);
+  { size_t k = 0; for (size_t i = 0; i < R.ni_total; ++i) { if (!R.indicator_idv[i]) continue; Y[k * d] = R.pheno[i][0]; Y[k * d + 1] = R.pheno[i][1]; k++; } }
+  const double t0 = now_s();
+  GB(gb200_mvlmm_setup(ctx, n, R.n_cvt, d, U.data(), n, eval.data(), W.data(), R.n_cvt, Y.data(), d));
+  double Vg[4], Ve[4], Vgm[4], Vem[4], lr, lm; vector<double> Br(d * R.n_cvt), Bm(d * R.n_cvt);
+  GB(gb200_mvlmm_null(ctx, Vg, Ve, Br.data(), &lr, Vgm, Vem, Bm.data(), &lm));
+  std::cout.setf(std::ios_base::fixed, std::ios_base::floatfield); std::cout.precision(4);                  // src/mvlmm.cpp:3087-3088
+  std::cout << "REMLE estimate for Vg in the null model: " << std::endl << Vg[0] << "\t" << std::endl << Vg[2] << "\t" << Vg[3] << "\t" << std::endl;
+  std::cout << "REMLE estimate for Ve in the null model: " << std::endl << Ve[0] << "\t" << std::endl << Ve[2] << "\t" << Ve[3] << "\t" << std::endl;
+  std::cout << "REMLE likelihood = " << lr << std::endl;
+  std::cout << "MLE estimate for Vg in the null model: " << std::endl << Vgm[0] << "\t" << std::endl << Vgm[2] << "\t" << Vgm[3] << "\t" << std::endl;
+  std::cout << "MLE estimate for Ve in the null model: " << std::endl << Vem[0] << "\t" << std::endl << Vem[2] << "\t" << Vem[3] << "\t" << std::endl;
+  std::cout << "MLE likelihood = " << lm << std::endl;
+  std::cout.unsetf(std::ios_base::floatfield); std::cout.precision(6);
+  vector<double> stat; stat.reserve(R.ns_test * 6);
+  vector<double> out;
+  if (!R.P.file_bfile.empty()) {
+    vector<unsigned char> mask(R.ni_total); for (size_t i = 0; i < R.ni_total; ++i) mask[i] = (unsigned char)R.indicator_idv[i];
+    vector<unsigned char> rows; rows.reserve(BATCH * g_nbit);
+    size_t l = 0;
+    auto flush = [&]() {
+      if (!l) return;
+      out.resize(l * 6);
+      GB(gb200_mvlmm_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, out.data()));
+      stat.insert(stat.end(), out.begin(), out.end());
+      rows.clear(); l = 0;
+    };
+    for (size_t t = 0; t < R.ns_total; ++t) {
+      if (!R.indicator_snp[t]) continue;
+      rows.insert(rows.end(), g_bed.begin() + t * g_nbit, g_bed.begin() + (t + 1) * g_nbit);
+      if (++l == BATCH) flush();
+    }
+    flush();
+  } else {
+    const Run *Rc = &R;
+    LinePipeline<RowBlock> pipe(R.P.file_geno, [Rc, n](LineBlock &blk, RowBlock &o) {
+      const Run &R = *Rc;
+      o.ncol = n;
+      for (size_t k = 0; k < blk.lines.size(); ++k) {
+        const size_t cur_line = blk.first_line + k;
+        if (cur_line >= R.indicator_snp.size() || !R.indicator_snp[cur_line]) continue;
+        char *cur = blk.lines[k];
+        char *p = next_token(cur); p = next_token(cur); p = next_token(cur);
+        const size_t off = o.v.size();
+        o.v.resize(off + n);
+        double *g = o.v.data() + off; size_t pos = 0;
+        for (size_t i = 0; i < R.ni_total; ++i) {
+          p = next_token(cur);
+          if (!p) die("Problem reading geno file (not enough genotypes in line)");
+          if (!R.indicator_idv[i]) continue;
+          g[pos++] = (p[0] == 'N' && p[1] == 'A' && p[2] == 0) ? NAN : token_to_double(p);
+        }
+        o.rows++;
+      }
+    });
+    if (!pipe.ok()) die("error reading genotype file:" + R.P.file_geno);
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(BATCH, (size_t(1) << 28) / n));
+    vector<double> G(chunk * n);
+    size_t l = 0;
+    auto flush = [&]() {
+      if (!l) return;
+      out.resize(l * 6);
+      GB(gb200_mvlmm_batch_geno(ctx, G.data(), l, n, out.data()));
+      stat.insert(stat.end(), out.begin(), out.end());
+      l = 0;
+    };
+    RowBlock blk;
+    while (pipe.next(blk)) {
+      for (size_t r = 0; r < blk.rows; ++r) {
+        std::memcpy(G.data() + l * n, blk.v.data() + r * n, n * sizeof(double));
+        if (++l == chunk) flush();
+      }
+    }
+    flush();
+  }
+  R.t_lmm = now_s() - t0;
+  std::ofstream o(out_path(R, "assoc"));
+  if (!o) { std::cout << "error writing file: " << out_path(R, "assoc") << std::endl; return; }
+  o << "chr\trs\tps\tn_miss\tallele1\tallele0\taf\tbeta_1\tbeta_2\tVbeta_1_1\tVbeta_1_2\tVbeta_2_2\tp_wald" << std::endl;
+  size_t t = 0;
+  for (size_t i = 0; i < R.snpInfo.size(); ++i) {
+    if (!R.indicator_snp[i]) continue;
+    const SnpInfo &s = R.snpInfo[i]; const double *st = stat.data() + 6 * (t++);
+    o << s.chr << "\t" << s.rs << "\t" << s.bp << "\t" << s.n_miss << "\t" << s.a_minor << "\t" << s.a_major << "\t" << std::fixed << std::setprecision(3) << s.maf
+      << "\t" << std::scientific << std::setprecision(6) << st[0] << "\t" << st[1] << "\t" << st[2] << "\t" << st[3] << "\t" << st[4] << "\t" << st[5] << std::endl;
+  }
+}
+
 // LMM branch of BatchRun (src/gemma.cpp:2556-2871) incl. -eigen
 static void run_lmm(Run &R, gb200_ctx *ctx) {
   const size_t n = R.ni_test;
@@ -747,6 +838,7 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
   R.t_eigen = now_s() - t0;
   if (R.P.a_mode == 31) { write_matrix(R, U.data(), n, n, "eigenU"); write_vector(R, eval.data(), n, "eigenD"); return; }
 
+  if (R.P.p_column.size() == 2) { run_mvlmm(R, ctx, U, eval, W); return; }
   t0 = now_s();
   GB(gb200_lmm_setup(ctx, n, R.n_cvt, U.data(), n, eval.data(), W.data(), R.n_cvt, y.data(), nullptr, nullptr));
   R.beta_mle.resize(R.n_cvt); R.se_mle.resize(R.n_cvt); R.beta_remle.resize(R.n_cvt); R.se_remle.resize(R.n_cvt);
@@ -1014,7 +1106,10 @@ int main(int argc, char **argv) {
     die("analysis mode not supported by gemma-b200 (only -gk 1/2, -eigen, -lmm 1/2/3/4/9, -lm 1/2/3/4)");
   if (P.p_column.empty()) P.p_column.push_back(1);                                 // src/param.cpp:635-636
   if (P.a_mode >= 51 && (!P.file_gxe.empty() || !P.loco.empty())) die("-lm does not take -gxe / -loco");
-  if (P.p_column.size() > 1 && (P.a_mode < 20 || P.a_mode >= 51) && !P.qc_only) die("multivariate LMM (-n with several columns) is not part of this engine");
+  if (P.p_column.size() > 1 && (P.a_mode < 20 || P.a_mode >= 51) && !P.qc_only) {
+    if (!(P.a_mode == 1 && P.p_column.size() == 2)) die("multivariate analysis: only -lmm 1 with two phenotypes (-n a b) is supported");
+    if (!P.file_gxe.empty()) die("multivariate G x E is not supported");
+  }
   if (P.file_bfile.empty() && (P.file_geno.empty() || P.file_pheno.empty())) die("need -g and -p, or -bfile");
   const bool is_lmm = (P.a_mode < 20 && P.a_mode > 0) || P.a_mode == 31;
   if (is_lmm && P.file_kin.empty() && (P.file_kd.empty() || P.file_ku.empty())) die("missing relatedness file (-k) or eigen files (-d and -u)");   // src/param.cpp:951-956

@@ -716,6 +716,21 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
         lines = open(os.path.join(cwd, "output", "mv.assoc.txt")).read().splitlines()
         refrows = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:65]])
         assert np.allclose(got, refrows, rtol=3e-6, atol=0)
+        # whole file through the CLI
+        import subprocess
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
+        out = os.path.join(cwd, "output")
+        r = subprocess.run([cli] + base + ["-n", "1", "6", "-k", os.path.join(out, "mouse.cXX.txt"), "-lmm", "-o", "mymv", "-outdir", out],
+                           capture_output=True, text=True, cwd=cwd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        mine = open(os.path.join(out, "mymv.assoc.txt")).read().splitlines()
+        assert len(mine) == len(lines) and mine[0] == lines[0]
+        fa = [x.split("\t") for x in mine[1:]]; fb = [x.split("\t") for x in lines[1:]]
+        assert [x[:7] for x in fa] == [x[:7] for x in fb]
+        xa = np.array([[float(v) for v in x[7:]] for x in fa]); xb = np.array([[float(v) for v in x[7:]] for x in fb])
+        bad = ~np.isclose(xa, xb, rtol=5e-6, atol=0)
+        assert bad.any(axis=1).mean() <= 0.002, int(bad.any(axis=1).sum())       # EM stops on |dlogl| < 1e-3: borderline iteration counts flip rarely
 
 
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
