@@ -79,8 +79,8 @@ SIGNATURES = {
     "gb200_lmm_batch_bed_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "gb200_mvlmm_setup": (C.c_int, [_vp, _sz, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _sz]),
     "gb200_mvlmm_null": (C.c_int, [_vp] * 9),
-    "gb200_mvlmm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
-    "gb200_mvlmm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "gb200_mvlmm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _vp]),
+    "gb200_mvlmm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, C.c_int, _vp]),
     "gb200_lm_setup": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp]),
     "gb200_lm_batch_geno": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _vp]),
     "gb200_lm_batch_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, C.c_int, _vp]),
@@ -309,17 +309,18 @@ class Context:
         return dict(Vg_remle=a[0].reshape(2, 2), Ve_remle=a[1].reshape(2, 2), B_remle=a[2].reshape(2, c), logl_remle_H0=a[3].value,
                     Vg_mle=a[4].reshape(2, 2), Ve_mle=a[5].reshape(2, 2), B_mle=a[6].reshape(2, c), logl_mle_H0=a[7].value)
 
-    def mvlmm_batch_geno(self, G):
+    def mvlmm_batch_geno(self, G, a_mode=1):
+        """rows: beta_1, beta_2, Vbeta_11, Vbeta_12, Vbeta_22, p_wald, p_lrt, p_score"""
         G = _f64(G)
-        out = np.zeros((G.shape[0], 6))
-        self._chk(self.lib.gb200_mvlmm_batch_geno(self.h, _ptr(G), G.shape[0], G.shape[1], _ptr(out)))
+        out = np.zeros((G.shape[0], 8))
+        self._chk(self.lib.gb200_mvlmm_batch_geno(self.h, _ptr(G), G.shape[0], G.shape[1], int(a_mode), _ptr(out)))
         return out
 
-    def mvlmm_batch_bed(self, bed, ni_total, idv_mask=None):
+    def mvlmm_batch_bed(self, bed, ni_total, idv_mask=None, a_mode=1):
         bed = np.ascontiguousarray(bed, dtype=np.uint8)
         m = None if idv_mask is None else np.ascontiguousarray(idv_mask, dtype=np.uint8)
-        out = np.zeros((bed.shape[0], 6))
-        self._chk(self.lib.gb200_mvlmm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1], _ptr(out)))
+        out = np.zeros((bed.shape[0], 8))
+        self._chk(self.lib.gb200_mvlmm_batch_bed(self.h, _ptr(bed), _ptr(m), ni_total, bed.shape[0], bed.shape[1], int(a_mode), _ptr(out)))
         return out
 
     # ---- -lm (linear model, src/lm.cpp)

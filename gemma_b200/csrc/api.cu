@@ -1029,19 +1029,21 @@ int gb200_mvlmm_null(gb200_ctx *c, double *Vg_remle, double *Ve_remle, double *B
   return GB200_OK;
 }
 
-static int mv_assoc_core(gb200_ctx *c, size_t l, double *out) {
-  GB_CUDA(c, c->dMvOut.reserve(l * 6 * 8));
+static int mv_assoc_core(gb200_ctx *c, size_t l, int a_mode, double *out) {
+  if (a_mode < 1 || a_mode > 4) return set_err(c, GB200_ERR_ARG, "multivariate -lmm mode must be 1..4");
+  c->mvK.a_mode = a_mode;
+  GB_CUDA(c, c->dMvOut.reserve(l * 8 * 8));
   {
     ProfScope ps(c, "lmm");
     GB_CUDA(c, launch_mv_assoc((int)c->n_cvt, c->mvK, c->dMvNull.as<gb::MvNull>(), c->dUtXt.as<double>(), c->n_c, (int)l, c->dMvOut.as<double>(),
                                c->dTicket.as<unsigned int>(), c->num_sms, c->stream));
   }
-  GB_CUDA(c, cudaMemcpyAsync(out, c->dMvOut.p, l * 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaMemcpyAsync(out, c->dMvOut.p, l * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   return GB200_OK;
 }
 
-int gb200_mvlmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, double *out) {
+int gb200_mvlmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, int a_mode, double *out) {
   if (!c) return GB200_ERR_ARG;
   if (!c->mv_ready || !c->mv_null_ready) return set_err(c, GB200_ERR_STATE, "gb200_mvlmm_batch_geno before gb200_mvlmm_setup / gb200_mvlmm_null");
   if (l == 0) return GB200_OK;
@@ -1056,11 +1058,11 @@ int gb200_mvlmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, 
   }
   int rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
   if (rc) return rc;
-  return mv_assoc_core(c, l, out);
+  return mv_assoc_core(c, l, a_mode, out);
 }
 
 int gb200_mvlmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l, size_t bytes_per_snp,
-                          double *out) {
+                          int a_mode, double *out) {
   if (!c) return GB200_ERR_ARG;
   if (!c->mv_ready || !c->mv_null_ready) return set_err(c, GB200_ERR_STATE, "gb200_mvlmm_batch_bed before gb200_mvlmm_setup / gb200_mvlmm_null");
   if (l == 0) return GB200_OK;
@@ -1072,7 +1074,7 @@ int gb200_mvlmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned
   GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
   rc = project_bed_dev(c, c->dBed.as<unsigned char>(), idx_dev, ni_total, l, bytes_per_snp);      // int8 tensor-core projection for n >= 1024
   if (rc) return rc;
-  return mv_assoc_core(c, l, out);
+  return mv_assoc_core(c, l, a_mode, out);
 }
 
 int gb200_lmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,

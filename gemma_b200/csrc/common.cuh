@@ -66,6 +66,7 @@ struct MvConst {
   const double *delta, *Wt, *Yt;  // eigenvalues; c rows of U^T W; 2 rows of U^T Y
   double vg0[2], ve0[2];          // univariate REML estimates (MphInitial diagonals)
   int em_iter, nr_iter; double em_prec, nr_prec, p_nr;
+  int a_mode;                     // 1 Wald, 2 LRT, 3 score, 4 all
 };
 struct MvNull {
   double Vg_remle[4], Ve_remle[4], B_remle[8], logl_remle;

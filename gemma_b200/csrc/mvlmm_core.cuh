@@ -19,11 +19,13 @@
 
 #ifdef GB_MV_HOST
 #define GB_HD
+#define GB_HD_BIG
 #define GB_MV_LANE 0
 #define GB_MV_NLANE 1
 static inline double gb_mv_allsum(double v) { return v; }
 #else
 #define GB_HD __device__ __forceinline__
+#define GB_HD_BIG __device__ __noinline__      /* the EM / NR / test routines are called, not inlined: keeps ptxas time and code size bounded */
 #define GB_MV_LANE (threadIdx.x & 31)
 #define GB_MV_NLANE 32
 __device__ __forceinline__ double gb_mv_allsum(double v) {
@@ -39,7 +41,7 @@ constexpr int pair_index(int a, int b, int nz) { return a <= b ? (2 * nz - a + 1
 
 // ---- small dense helpers (N <= 8) ---------------------------------------------------------------------------------------
 template <int N>
-GB_HD bool inv_small(const double (&A)[N][N], double (&Ai)[N][N], double &logabsdet) {
+GB_HD_BIG bool inv_small(const double (&A)[N][N], double (&Ai)[N][N], double &logabsdet) {
   double M[N][2 * N];
   for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { M[i][j] = A[i][j]; M[i][N + j] = (i == j) ? 1.0 : 0.0; }
   logabsdet = 0.0;
@@ -59,7 +61,7 @@ GB_HD bool inv_small(const double (&A)[N][N], double (&Ai)[N][N], double &logabs
 
 // symmetric eigenproblem, cyclic Jacobi: A = V diag(ev) V^T (columns of V); order unspecified (nothing below depends on it)
 template <int N>
-GB_HD void sym_eig(const double (&A0)[N][N], double (&ev)[N], double (&V)[N][N]) {
+GB_HD_BIG void sym_eig(const double (&A0)[N][N], double (&ev)[N], double (&V)[N][N]) {
   double A[N][N];
   for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { A[i][j] = A0[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
   for (int sweep = 0; sweep < 60; ++sweep) {
@@ -115,7 +117,7 @@ struct Basis {                    // EigenProc
 };
 
 template <int D>
-GB_HD void eigen_proc(const double (&V_g)[D][D], const double (&V_e)[D][D], Basis<D> &b) {
+GB_HD_BIG void eigen_proc(const double (&V_g)[D][D], const double (&V_e)[D][D], Basis<D> &b) {
   double de[D], U[D][D], Veh[D][D], Vehi[D][D];
   sym_eig<D>(V_e, de, U);
   b.logdet_Ve = 0.0;
@@ -158,7 +160,7 @@ struct Eval {
 
 // moments with weights w_l (+ log terms), then Q, xHiy, logl.  x rows used: the first CX of the C1 (CX = C1 normally; MphCalcP uses the covariates only)
 template <int D, int C1>
-GB_HD bool evaluate(const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], bool reml, Eval<D, C1> &e) {
+GB_HD_BIG bool evaluate(const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], bool reml, Eval<D, C1> &e) {
   constexpr int NZ = C1 + D;
   eigen_proc<D>(V_g, V_e, e.bs);
   const Basis<D> &b = e.bs;
@@ -194,7 +196,7 @@ struct Fit { double V_g[D][D], V_e[D][D], B[D][C1]; double logl; };
 
 // log-likelihood constant (mvlmm.cpp:641-648): needs X X' of the C1 x rows (unit-weight moments)
 template <int D, int C1>
-GB_HD double logl_const(const MvData<C1 + D> &dat, bool reml) {
+GB_HD_BIG double logl_const(const MvData<C1 + D> &dat, bool reml) {
   constexpr int NZ = C1 + D;
   const double l2pi = 1.8378770664093453;
   if (!reml) return -0.5 * (double)dat.n * (double)D * l2pi;
@@ -215,7 +217,7 @@ GB_HD double quad(const double *M, const double *u, const double *v) {
 
 // MphEM (mvlmm.cpp:599-724).  fit.V_g / V_e / B are the starting values and receive the result.
 template <int D, int C1>
-GB_HD double mph_em(bool reml, int max_iter, double max_prec, const MvData<C1 + D> &dat, Fit<D, C1> &fit) {
+GB_HD_BIG double mph_em(bool reml, int max_iter, double max_prec, const MvData<C1 + D> &dat, Fit<D, C1> &fit) {
   constexpr int NZ = C1 + D, NP = NZ * (NZ + 1) / 2, DD = D * (D + 1) / 2;
   const double cst = logl_const<D, C1>(dat, reml);
   double M0[1][NP], s0[1];
@@ -316,7 +318,7 @@ GB_HD double chisq_Q_int(double x) {
 
 // MphCalcP (mvlmm.cpp:727-831).  The SNP is x row C1-1; the covariates are rows 0..C1-2.  beta: D, Vbeta: D x D.
 template <int D, int C1>
-GB_HD double mph_calc_p(const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], double (&beta)[D], double (&Vbeta)[D][D]) {
+GB_HD_BIG double mph_calc_p(const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], double (&beta)[D], double (&Vbeta)[D][D]) {
   constexpr int NZ = C1 + D, NP = NZ * (NZ + 1) / 2, C = C1 - 1;
   Basis<D> b;
   eigen_proc<D>(V_g, V_e, b);
@@ -352,7 +354,7 @@ GB_HD double mph_calc_p(const MvData<C1 + D> &dat, const double (&V_g)[D][D], co
 
 // GLS B for given (V_g, V_e): MphCalcBeta (mvlmm.cpp:835-937) / the last part of MphInitial (:2882-2935)
 template <int D, int C1>
-GB_HD void mph_calc_beta(const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], double (&B)[D][C1]) {
+GB_HD_BIG void mph_calc_beta(const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], double (&B)[D][C1]) {
   Eval<D, C1> e;
   if (!evaluate<D, C1>(dat, V_g, V_e, true, e)) return;
   for (int i = 0; i < D; ++i) for (int j = 0; j < C1; ++j) { double v = 0.0; for (int l = 0; l < D; ++l) v += e.bs.UltVeh[l][i] * e.Bp[l][j]; B[i][j] = v; }
@@ -382,7 +384,7 @@ struct NrState {
 
 // gradient and Hessian of the log (restricted) likelihood at (V_g, V_e): closed block form of CalcDev: grad_t = -1/2 tr(P D_t) + 1/2 y'P D_t P y, Hess_tu = 1/2 tr(P D_t P D_u) - y'P D_t P D_u P y
 template <int D, int C1>
-GB_HD bool nr_quantities(bool reml, const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], double cst, NrState<D, C1> &st) {
+GB_HD_BIG bool nr_quantities(bool reml, const MvData<C1 + D> &dat, const double (&V_g)[D][D], const double (&V_e)[D][D], double cst, NrState<D, C1> &st) {
   constexpr int NZ = C1 + D, NP = NZ * (NZ + 1) / 2, DD = D * (D + 1) / 2, V = D * (D + 1) / 2, V2 = 2 * V;
   Eval<D, C1> e;
   if (!evaluate<D, C1>(dat, V_g, V_e, reml, e)) return false;
@@ -487,7 +489,7 @@ GB_HD bool nr_quantities(bool reml, const MvData<C1 + D> &dat, const double (&V_
 }
 
 template <int D, int C1>
-GB_HD double mph_nr(bool reml, int max_iter, double max_prec, const MvData<C1 + D> &dat, Fit<D, C1> &fit) {
+GB_HD_BIG double mph_nr(bool reml, int max_iter, double max_prec, const MvData<C1 + D> &dat, Fit<D, C1> &fit) {
   constexpr int V = D * (D + 1) / 2, V2 = 2 * V;
   const double cst = logl_const<D, C1>(dat, reml);
   double logl_old = 0.0, logl_new = 0.0;
@@ -527,6 +529,38 @@ GB_HD double mph_nr(bool reml, int max_iter, double max_prec, const MvData<C1 + 
   }
   fit.logl = logl_new;
   return logl_new;
+}
+
+// per-SNP body of MVLMM::AnalyzeBimbam / AnalyzePlink for -lmm 1/2/3/4 (mvlmm.cpp:3286-3360, crt = 0).  fit enters with the null
+// (ML) estimates; out = {beta_1..D, Vbeta upper triangle, p_wald, p_lrt, p_score}.
+template <int D, int C1>
+GB_HD_BIG void analyze_snp(const MvData<C1 + D> &dat, Fit<D, C1> &fit, int a_mode, int em_iter, double em_prec, int nr_iter, double nr_prec,
+                       double p_nr, double logl_mle_H0, double *out) {
+  double beta[D], Vb[D][D], p_wald = 0.0, p_lrt = 0.0, p_score = 0.0;
+  for (int i = 0; i < D; ++i) { beta[i] = 0.0; for (int j = 0; j < D; ++j) Vb[i][j] = 0.0; }
+  if (a_mode == 3 || a_mode == 4) p_score = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);               // at the null estimates
+  if (a_mode == 2 || a_mode == 4) {
+    double logl_H1 = mph_em<D, C1>(false, em_iter / 10, em_prec * 10.0, dat, fit);
+    mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
+    p_lrt = chisq_Q_int<D>(2.0 * (logl_H1 - logl_mle_H0));
+    if (p_lrt < p_nr) {
+      logl_H1 = mph_nr<D, C1>(false, nr_iter / 10, nr_prec * 10.0, dat, fit);
+      mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
+      p_lrt = chisq_Q_int<D>(2.0 * (logl_H1 - logl_mle_H0));
+    }
+  }
+  if (a_mode == 1 || a_mode == 4) {
+    mph_em<D, C1>(true, em_iter / 10, em_prec * 10.0, dat, fit);
+    p_wald = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
+    if (p_wald < p_nr) {
+      mph_nr<D, C1>(true, nr_iter / 10, nr_prec * 10.0, dat, fit);
+      p_wald = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
+    }
+  }
+  int o = 0;
+  for (int i = 0; i < D; ++i) out[o++] = beta[i];
+  for (int i = 0; i < D; ++i) for (int j = i; j < D; ++j) out[o++] = Vb[i][j];
+  out[o++] = p_wald; out[o++] = p_lrt; out[o++] = p_score;
 }
 
 }  // namespace gbmv

@@ -742,7 +742,7 @@ static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vec
   std::cout << "MLE estimate for Ve in the null model: " << std::endl << Vem[0] << "\t" << std::endl << Vem[2] << "\t" << Vem[3] << "\t" << std::endl;
   std::cout << "MLE likelihood = " << lm << std::endl;
   std::cout.unsetf(std::ios_base::floatfield); std::cout.precision(6);
-  vector<double> stat; stat.reserve(R.ns_test * 6);
+  vector<double> stat; stat.reserve(R.ns_test * 8);
   vector<double> out;
   if (!R.P.file_bfile.empty()) {
     vector<unsigned char> mask(R.ni_total); for (size_t i = 0; i < R.ni_total; ++i) mask[i] = (unsigned char)R.indicator_idv[i];
@@ -750,8 +750,8 @@ static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vec
     size_t l = 0;
     auto flush = [&]() {
       if (!l) return;
-      out.resize(l * 6);
-      GB(gb200_mvlmm_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, out.data()));
+      out.resize(l * 8);
+      GB(gb200_mvlmm_batch_bed(ctx, rows.data(), mask.data(), R.ni_total, l, g_nbit, R.P.a_mode, out.data()));
       stat.insert(stat.end(), out.begin(), out.end());
       rows.clear(); l = 0;
     };
@@ -789,8 +789,8 @@ static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vec
     size_t l = 0;
     auto flush = [&]() {
       if (!l) return;
-      out.resize(l * 6);
-      GB(gb200_mvlmm_batch_geno(ctx, G.data(), l, n, out.data()));
+      out.resize(l * 8);
+      GB(gb200_mvlmm_batch_geno(ctx, G.data(), l, n, R.P.a_mode, out.data()));
       stat.insert(stat.end(), out.begin(), out.end());
       l = 0;
     };
@@ -806,13 +806,17 @@ static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vec
   R.t_lmm = now_s() - t0;
   std::ofstream o(out_path(R, "assoc"));
   if (!o) { std::cout << "error writing file: " << out_path(R, "assoc") << std::endl; return; }
-  o << "chr\trs\tps\tn_miss\tallele1\tallele0\taf\tbeta_1\tbeta_2\tVbeta_1_1\tVbeta_1_2\tVbeta_2_2\tp_wald" << std::endl;
+  const int m = R.P.a_mode;
+  o << "chr\trs\tps\tn_miss\tallele1\tallele0\taf\tbeta_1\tbeta_2\tVbeta_1_1\tVbeta_1_2\tVbeta_2_2\t"
+    << (m == 1 ? "p_wald" : m == 2 ? "p_lrt" : m == 3 ? "p_score" : "p_wald\tp_lrt\tp_score") << std::endl;
   size_t t = 0;
   for (size_t i = 0; i < R.snpInfo.size(); ++i) {
     if (!R.indicator_snp[i]) continue;
-    const SnpInfo &s = R.snpInfo[i]; const double *st = stat.data() + 6 * (t++);
+    const SnpInfo &s = R.snpInfo[i]; const double *st = stat.data() + 8 * (t++);
     o << s.chr << "\t" << s.rs << "\t" << s.bp << "\t" << s.n_miss << "\t" << s.a_minor << "\t" << s.a_major << "\t" << std::fixed << std::setprecision(3) << s.maf
-      << "\t" << std::scientific << std::setprecision(6) << st[0] << "\t" << st[1] << "\t" << st[2] << "\t" << st[3] << "\t" << st[4] << "\t" << st[5] << std::endl;
+      << "\t" << std::scientific << std::setprecision(6) << st[0] << "\t" << st[1] << "\t" << st[2] << "\t" << st[3] << "\t" << st[4] << "\t";
+    if (m == 1) o << st[5] << std::endl; else if (m == 2) o << st[6] << std::endl; else if (m == 3) o << st[7] << std::endl;
+    else o << st[5] << "\t" << st[6] << "\t" << st[7] << std::endl;
   }
 }
 
@@ -1107,7 +1111,7 @@ int main(int argc, char **argv) {
   if (P.p_column.empty()) P.p_column.push_back(1);                                 // src/param.cpp:635-636
   if (P.a_mode >= 51 && (!P.file_gxe.empty() || !P.loco.empty())) die("-lm does not take -gxe / -loco");
   if (P.p_column.size() > 1 && (P.a_mode < 20 || P.a_mode >= 51) && !P.qc_only) {
-    if (!(P.a_mode == 1 && P.p_column.size() == 2)) die("multivariate analysis: only -lmm 1 with two phenotypes (-n a b) is supported");
+    if (!(P.a_mode >= 1 && P.a_mode <= 4 && P.p_column.size() == 2)) die("multivariate analysis: only -lmm 1/2/3/4 with two phenotypes (-n a b) is supported");
     if (!P.file_gxe.empty()) die("multivariate G x E is not supported");
   }
   if (P.file_bfile.empty() && (P.file_geno.empty() || P.file_pheno.empty())) die("need -g and -p, or -bfile");

@@ -204,19 +204,20 @@ GB200_API int gb200_lm_batch_geno(gb200_ctx *ctx, const double *G, size_t l, siz
 GB200_API int gb200_lm_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l,
                        size_t bytes_per_snp, int a_mode, gb200_sumstat *out);
 
-/* ---- multivariate LMM (BASELINE config 5): MVLMM::AnalyzeBimbam / AnalyzePlink, src/mvlmm.cpp:2972-3899, -lmm 1 (Wald).
+/* ---- multivariate LMM (BASELINE config 5): MVLMM::AnalyzeBimbam / AnalyzePlink, src/mvlmm.cpp:2972-3899, -lmm 1/2/3/4.
  * Two phenotypes, 1..3 covariates in this round.  Y: n x n_ph (ld ldy) of the analysed individuals.  setup rotates W and Y, and runs the
  * univariate REML fits of MphInitial (:2786-2796); null = EM + Newton-Raphson for REML then ML (:3047-3133; the per-SNP fits start from the
  * ML estimates, :3205-3207); batch = per SNP: REML EM (em_iter/10, em_prec*10), MphCalcP, Newton-Raphson refinement when p < 0.001
- * (:3334-3347).  out: l rows of 6 doubles {beta_1, beta_2, Vbeta_11, Vbeta_12, Vbeta_22, p_wald} (the columns of MVLMM::WriteFiles, :117-210).
+ * (:3334-3347); a_mode 2 / 3 / 4 add the likelihood-ratio (ML EM + NR, :3310-3332) and score (:3297-3307) branches.  out: l rows of 8 doubles
+ * {beta_1, beta_2, Vbeta_11, Vbeta_12, Vbeta_22, p_wald, p_lrt, p_score} (the columns of MVLMM::WriteFiles, :117-210; tests not run stay 0).
  * V_g / V_e outputs are 2 x 2 row-major, B is 2 x n_cvt. */
 GB200_API int gb200_mvlmm_setup(gb200_ctx *ctx, size_t n, size_t n_cvt, size_t n_ph, const double *U, size_t ldu, const double *eval,
                       const double *W, size_t ldw, const double *Y, size_t ldy);
 GB200_API int gb200_mvlmm_null(gb200_ctx *ctx, double *Vg_remle, double *Ve_remle, double *B_remle, double *logl_remle, double *Vg_mle,
                      double *Ve_mle, double *B_mle, double *logl_mle);
-GB200_API int gb200_mvlmm_batch_geno(gb200_ctx *ctx, const double *G, size_t l, size_t ldg, double *out);
+GB200_API int gb200_mvlmm_batch_geno(gb200_ctx *ctx, const double *G, size_t l, size_t ldg, int a_mode, double *out);
 GB200_API int gb200_mvlmm_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total, size_t l,
-                          size_t bytes_per_snp, double *out);
+                          size_t bytes_per_snp, int a_mode, double *out);
 
 /* Projection only for a PLINK 2-bit batch (same decode / imputation as gb200_lmm_batch_bed),
  * through whichever projection path the options select.  UtXt: l x n host buffer. */

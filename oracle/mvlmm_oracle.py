@@ -307,3 +307,32 @@ def analyze_snp_wald(ev, UtW, UtY, Utx, nm):
         mph_nr("R", NR_ITER // 10, NR_PREC * 10, ev, X, Y, V_g, V_e)
         p, beta, Vbeta = mph_calc_p(ev, Utx, W, Y, V_g, V_e)
     return beta, Vbeta, p
+
+
+def analyze_snp(ev, UtW, UtY, Utx, nm, a_mode):
+    """Per-SNP body of MVLMM::AnalyzeBimbam for -lmm 1/2/3/4 (mvlmm.cpp:3286-3360; crt = 0).  V_g, V_e, B are reset to the null
+    (ML) estimates once per SNP and then carried from the LRT block into the Wald block, as in the reference.
+    Returns beta (d), Vbeta (d x d), p_wald, p_lrt, p_score."""
+    W = np.ascontiguousarray(UtW.T); Y = np.ascontiguousarray(UtY.T)
+    X = np.vstack([W, Utx[None, :]])
+    d = Y.shape[0]
+    V_g, V_e = nm["Vg_mle"].copy(), nm["Ve_mle"].copy()
+    B = np.hstack([nm["B_mle"], np.zeros((d, 1))])
+    beta = np.zeros(d); Vbeta = np.zeros((d, d)); p_wald = p_lrt = p_score = 0.0
+    if a_mode in (3, 4):
+        p_score, beta, Vbeta = mph_calc_p(ev, Utx, W, Y, nm["Vg_mle"], nm["Ve_mle"])
+    if a_mode in (2, 4):
+        logl_H1 = mph_em("L", EM_ITER // 10, EM_PREC * 10, ev, X, Y, V_g, V_e, B)
+        _, beta, Vbeta = mph_calc_p(ev, Utx, W, Y, V_g, V_e)
+        p_lrt = float(scipy.stats.chi2.sf(2.0 * (logl_H1 - nm["logl_mle_H0"]), d))
+        if p_lrt < P_NR:
+            logl_H1, _ = mph_nr("L", NR_ITER // 10, NR_PREC * 10, ev, X, Y, V_g, V_e)
+            _, beta, Vbeta = mph_calc_p(ev, Utx, W, Y, V_g, V_e)
+            p_lrt = float(scipy.stats.chi2.sf(2.0 * (logl_H1 - nm["logl_mle_H0"]), d))
+    if a_mode in (1, 4):
+        mph_em("R", EM_ITER // 10, EM_PREC * 10, ev, X, Y, V_g, V_e, B)
+        p_wald, beta, Vbeta = mph_calc_p(ev, Utx, W, Y, V_g, V_e)
+        if p_wald < P_NR:
+            mph_nr("R", NR_ITER // 10, NR_PREC * 10, ev, X, Y, V_g, V_e)
+            p_wald, beta, Vbeta = mph_calc_p(ev, Utx, W, Y, V_g, V_e)
+    return beta, Vbeta, p_wald, p_lrt, p_score

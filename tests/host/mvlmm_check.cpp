@@ -33,7 +33,7 @@ static int null_t(int n, const double *ev, const double *X, const double *Y, con
 
 template <int C>
 static int snp_t(int n, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn,
-                 double *out) {
+                 int a_mode, double logl_mle_H0, double *out) {
   constexpr int D = 2, C1 = C + 1;
   MvData<C1 + D> dat; dat.n = n; dat.delta = ev;
   for (int j = 0; j < C; ++j) dat.z[j] = X + (size_t)j * n;
@@ -42,15 +42,8 @@ static int snp_t(int n, const double *ev, const double *X, const double *x, cons
   Fit<D, C1> fit;
   for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { fit.V_g[i][j] = Vg[i * D + j]; fit.V_e[i][j] = Ve[i * D + j]; }
   for (int i = 0; i < D; ++i) { for (int j = 0; j < C; ++j) fit.B[i][j] = Bn[i * C + j]; fit.B[i][C] = 0.0; }
-  mph_em<D, C1>(true, 1000, 1e-3, dat, fit);                       // em_iter / 10, em_prec * 10 (mvlmm.cpp:3336)
-  double beta[D], Vb[D][D];
-  double p = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
-  if (p < 0.001) {                                                  // p_nr (mvlmm.cpp:3341-3347)
-    mph_nr<D, C1>(true, 10, 1e-3, dat, fit);
-    p = mph_calc_p<D, C1>(dat, fit.V_g, fit.V_e, beta, Vb);
-  }
-  out[0] = beta[0]; out[1] = beta[1]; out[2] = Vb[0][0]; out[3] = Vb[0][1]; out[4] = Vb[1][1]; out[5] = p;
-  return 6;
+  analyze_snp<D, C1>(dat, fit, a_mode, 10000, 1e-4, 100, 1e-4, 0.001, logl_mle_H0, out);     // src/param.cpp:98-99 defaults
+  return 8;
 }
 
 extern "C" {
@@ -58,8 +51,10 @@ int mvh_null(int n, int c, const double *ev, const double *X, const double *Y, c
   switch (c) { case 1: return null_t<1>(n, ev, X, Y, Vg0, Ve0, out); case 2: return null_t<2>(n, ev, X, Y, Vg0, Ve0, out); case 3: return null_t<3>(n, ev, X, Y, Vg0, Ve0, out); }
   return -1;
 }
-int mvh_snp(int n, int c, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn, double *out) {
-  switch (c) { case 1: return snp_t<1>(n, ev, X, x, Y, Vg, Ve, Bn, out); case 2: return snp_t<2>(n, ev, X, x, Y, Vg, Ve, Bn, out); case 3: return snp_t<3>(n, ev, X, x, Y, Vg, Ve, Bn, out); }
+int mvh_snp(int n, int c, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn,
+            int a_mode, double logl_mle_H0, double *out) {
+  switch (c) { case 1: return snp_t<1>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); case 2: return snp_t<2>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out);
+               case 3: return snp_t<3>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); }
   return -1;
 }
 }

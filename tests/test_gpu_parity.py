@@ -685,11 +685,12 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
         assert nm["logl_remle_H0"] == pytest.approx(ref["logl_remle_H0"], rel=1e-9) and nm["logl_mle_H0"] == pytest.approx(ref["logl_mle_H0"], rel=1e-9)
         G = (pb["U"] @ pb["UtX"].T).T                                  # genotypes back in the original basis (exact integers up to rounding)
         G = np.rint(G)
-        got = ctx.mvlmm_batch_geno(G)
-        for q in range(G.shape[0]):
-            beta, Vb, p = MV.analyze_snp_wald(pb["ev"], pb["UtW"], pb["UtY"], pb["U"].T @ G[q], ref)
-            exp = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], p])
-            assert np.allclose(got[q], exp, rtol=2e-6, atol=1e-300), (c, q, got[q], exp)
+        for mode in (1, 4):
+            got = ctx.mvlmm_batch_geno(G, mode)
+            for q in range(G.shape[0]):
+                beta, Vb, pw, pl, ps = MV.analyze_snp(pb["ev"], pb["UtW"], pb["UtY"], pb["U"].T @ G[q], ref, mode)
+                exp = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], pw, pl, ps])
+                assert np.allclose(got[q], exp, rtol=2e-6, atol=1e-300), (c, mode, q, got[q], exp)
     # mouse example, two phenotypes, through the PLINK-free BIMBAM entry point; reference CLI rows as the expectation
     d = os.path.join(golden_dir, "mouse_hs1940")
     bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
@@ -705,7 +706,7 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
     assert np.allclose([nm["Ve_remle"][0, 0], nm["Ve_remle"][0, 1], nm["Ve_remle"][1, 1]], [0.348882, 0.0490525, 0.414433], rtol=5e-6)  # demo.txt:76-78
     sel = np.nonzero(isnp)[0][:64]
     Gs = bb.G[np.ix_(sel, np.nonzero(keep)[0])]
-    got = ctx.mvlmm_batch_geno(Gs)
+    got = ctx.mvlmm_batch_geno(Gs)[:, :6]
     exp = np.array([[float(x) for x in row[7:]] for row in EXP["mouse_mvlmm_rows"]["rows"]])
     assert np.allclose(got[:5], exp, rtol=2e-6, atol=0)                                                   # demo.txt:62-66
     if os.path.exists(REF.EXE):
@@ -731,6 +732,19 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
         xa = np.array([[float(v) for v in x[7:]] for x in fa]); xb = np.array([[float(v) for v in x[7:]] for x in fb])
         bad = ~np.isclose(xa, xb, rtol=5e-6, atol=0)
         assert bad.any(axis=1).mean() <= 0.002, int(bad.any(axis=1).sum())       # EM stops on |dlogl| < 1e-3: borderline iteration counts flip rarely
+        # -lmm 4 (Wald + LRT + score) on every 12th SNP
+        snps = os.path.join(cwd, "sub.txt")
+        with open(snps, "w") as f:
+            f.write("\n".join(bb.rs[::12]) + "\n")
+        REF.run_cli(base + ["-n", "1", "6", "-snps", snps, "-k", "output/mouse.cXX.txt", "-lmm", "4", "-o", "mv4"], cwd)
+        r = subprocess.run([cli] + base + ["-n", "1", "6", "-snps", snps, "-k", os.path.join(out, "mouse.cXX.txt"), "-lmm", "4", "-o", "mymv4", "-outdir", out],
+                           capture_output=True, text=True, cwd=cwd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        a4 = open(os.path.join(out, "mymv4.assoc.txt")).read().splitlines(); b4 = open(os.path.join(out, "mv4.assoc.txt")).read().splitlines()
+        assert len(a4) == len(b4) and a4[0] == b4[0]
+        xa = np.array([[float(v) for v in x.split("\t")[7:]] for x in a4[1:]]); xb = np.array([[float(v) for v in x.split("\t")[7:]] for x in b4[1:]])
+        bad = ~np.isclose(xa, xb, rtol=5e-6, atol=0)
+        assert bad.any(axis=1).mean() <= 0.005, int(bad.any(axis=1).sum())
 
 
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------

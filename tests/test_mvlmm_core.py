@@ -59,12 +59,14 @@ def test_moment_form_matches_restatement(core, n, c, seed):
     assert out[17] == pytest.approx(nm["logl_mle_H0"], rel=1e-10)
     assert np.allclose(out[18:18 + 2 * c], nm["B_mle"].ravel(), rtol=1e-6, atol=1e-9)
     Vg = np.ascontiguousarray(out[9:13]); Ve = np.ascontiguousarray(out[13:17]); Bn = np.ascontiguousarray(out[18:18 + 2 * c])
-    o = np.zeros(6); n_nr = 0
-    for q in range(pb["UtX"].shape[0]):
-        x = np.ascontiguousarray(pb["UtX"][q])
-        core.mvh_snp(n, c, _p(ev), _p(X), _p(x), _p(Y), _p(Vg), _p(Ve), _p(Bn), _p(o))
-        beta, Vb, p = MV.analyze_snp_wald(ev, pb["UtW"], pb["UtY"], x, nm)
-        ref = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], p])
-        assert np.allclose(o, ref, rtol=2e-6, atol=1e-300), (q, o, ref)
-        n_nr += p < MV.P_NR
+    core.mvh_snp.argtypes = [C.c_int, C.c_int] + [_dp] * 7 + [C.c_int, C.c_double, _dp]
+    o = np.zeros(8); n_nr = 0
+    for mode in (1, 2, 3, 4):
+        for q in range(pb["UtX"].shape[0]):
+            x = np.ascontiguousarray(pb["UtX"][q])
+            core.mvh_snp(n, c, _p(ev), _p(X), _p(x), _p(Y), _p(Vg), _p(Ve), _p(Bn), mode, nm["logl_mle_H0"], _p(o))
+            beta, Vb, pw, pl, ps = MV.analyze_snp(ev, pb["UtW"], pb["UtY"], x, nm, mode)
+            ref = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], pw, pl, ps])
+            assert np.allclose(o, ref, rtol=2e-6, atol=1e-300), (mode, q, o, ref)
+            n_nr += (mode == 1) and pw < MV.P_NR
     assert n_nr >= 1

@@ -332,3 +332,37 @@ def test_mvlmm_restatement_matches_reference_cli(golden_dir, tmp_path):
         beta, Vb, p = MV.analyze_snp_wald(ev, UtW, UtY, U.T @ X[:, q], nm)
         got = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], p])
         assert np.allclose(got, ref[r], rtol=3e-6, atol=0), (r, got, ref[r])
+
+
+def test_mvlmm_lrt_and_score_modes_match_reference_cli(golden_dir, tmp_path):
+    """-lmm 4 with two phenotypes: Wald, likelihood-ratio and score p-values of oracle/mvlmm_oracle.py vs the reference CLI."""
+    from oracle import mvlmm_oracle as MV
+    if not os.path.exists(REF.EXE) and not os.path.isdir(REF.REF_SRC):
+        pytest.skip("reference CLI not built")
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+    cwd = str(tmp_path)
+    snps = os.path.join(cwd, "sub.txt")
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    with open(snps, "w") as f:                      # every 12th SNP keeps the reference run short
+        f.write("\n".join(bb.rs[::12]) + "\n")
+    REF.run_cli(base + ["-gk", "-o", "mouse"], cwd)
+    REF.run_cli(base + ["-n", "1", "6", "-snps", snps, "-k", "output/mouse.cXX.txt", "-lmm", "4", "-o", "mv4"], cwd)
+    K = np.loadtxt(os.path.join(cwd, "output", "mouse.cXX.txt"))
+    ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", (1, 6))
+    idv, W = R.process_cvt_phen(ind)
+    isnp, _, _ = R.qc_bimbam(bb, idv, snps=set(bb.rs[::12]))
+    keep = idv == 1
+    U, ev, _ = R.eigen_decomp_zeroed(O.center_matrix(np.ascontiguousarray(K[np.ix_(keep, keep)])))
+    UtW = U.T @ W[keep]; UtY = U.T @ ph[keep]
+    nm = MV.null_model(ev, UtW, UtY)
+    lines = open(os.path.join(cwd, "output", "mv4.assoc.txt")).read().splitlines()
+    sel_all = np.nonzero(isnp)[0]
+    assert len(lines) == 1 + len(sel_all) and lines[0].split("\t")[-3:] == ["p_wald", "p_lrt", "p_score"]
+    ref = np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:]])      # beta_1 beta_2 V11 V12 V22 p_wald p_lrt p_score
+    pick = sorted(set(range(12)) | set(np.argsort(ref[:, 5])[:10].tolist()))
+    X = R.lmm_genotypes_bimbam(bb, isnp, idv, sel_all[pick])
+    for q, r in enumerate(pick):
+        beta, Vb, pw, pl, ps = MV.analyze_snp(ev, UtW, UtY, U.T @ X[:, q], nm, 4)
+        got = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], pw, pl, ps])
+        assert np.allclose(got, ref[r], rtol=5e-6, atol=0), (r, got, ref[r])
