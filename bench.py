@@ -375,6 +375,19 @@ def run_b200(args):
                     "note": "algorithmic bytes 8n+64 per SNP; the kernel is FP64-pipe bound by construction (~16 lockstep passes, ~1000 FP64 "
                             "instructions per individual and SNP): see DESIGN.md 4.1"}
 
+    # (before the CPU baseline: the host BLAS worker threads it starts keep spinning for a while and slow the synchronous
+    #  per-chunk calls of the kinship entry point by an order of magnitude)
+    gk = None
+    if not args.no_gk:
+        try:
+            del beds, out_dev, scratch
+            torch.cuda.empty_cache()
+            g = measure_gk(10000, 65536, 3, 3, ctx=ctx, stream=stream, local=local)
+            gk = {"value": g["value"], "unit": g["unit"], "config": g["config"]["workload"], "ms_per_step": g["ms_per_step"],
+                  "kernel_tflops": g["roofline"]["achieved"], "frac_of_bf16_peak": g["roofline"]["frac"], "clocks": g["clocks"]}
+        except Exception as ex:                     # the side measurement must never cost the headline line
+            gk = {"error": str(ex)[:200]}
+
     cpu = None
     if not args.no_cpu_baseline:
         sample = args.cpu_sample or max(8, min(64, int(2.0e6 / n)))
@@ -386,17 +399,6 @@ def run_b200(args):
         cpu = {"value": v_cpu, "unit": "SNPs/s", "cores": cores, "kind": cpu_kind(),
                "sample": "%d SNPs of the same workload; U^T X by OpenBLAS dgemm on %d threads (%.2f s), %s (%.2f s)"
                          % (sample, cores, tu, cpu_sample_note(), to)}
-
-    gk = None
-    if not args.no_gk:
-        try:
-            del beds, out_dev, scratch
-            torch.cuda.empty_cache()
-            g = measure_gk(10000, 65536, 3, 3, ctx=ctx, stream=stream, local=local)
-            gk = {"value": g["value"], "unit": g["unit"], "config": g["config"]["workload"], "ms_per_step": g["ms_per_step"],
-                  "kernel_tflops": g["roofline"]["achieved"], "frac_of_bf16_peak": g["roofline"]["frac"], "clocks": g["clocks"]}
-        except Exception as ex:                     # the side measurement must never cost the headline line
-            gk = {"error": str(ex)[:200]}
 
     line = {"metric": "snps_per_sec_lmm%d" % args.mode, "value": value, "unit": "SNPs/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
