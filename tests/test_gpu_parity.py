@@ -691,6 +691,15 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
                 beta, Vb, pw, pl, ps = MV.analyze_snp(pb["ev"], pb["UtW"], pb["UtY"], pb["U"].T @ G[q], ref, mode)
                 exp = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], pw, pl, ps])
                 assert np.allclose(got[q], exp, rtol=2e-6, atol=1e-300), (c, mode, q, got[q], exp)
+    # PLINK rows (int8 tensor-core projection, n >= 1024) give the same statistics as the dosage entry point
+    n = 1100
+    pbp = _problem(n, 2, 9)
+    bedp, Gp = synth.make_bed(n, 96, seed=321, miss_rate=0.01)
+    ctx.mvlmm_setup(pbp["U"], pbp["ev"], pbp["U"] @ pbp["UtW"], pbp["U"] @ pbp["UtY"])
+    ctx.mvlmm_null()
+    a = ctx.mvlmm_batch_bed(bedp, n, a_mode=4)
+    b = ctx.mvlmm_batch_geno(np.where(Gp < 0, np.nan, Gp), 4)
+    assert np.allclose(a, b, rtol=1e-6, atol=1e-300)
     # mouse example, two phenotypes, through the PLINK-free BIMBAM entry point; reference CLI rows as the expectation
     d = os.path.join(golden_dir, "mouse_hs1940")
     bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
