@@ -25,5 +25,19 @@ exp["bxd_lmm2_assoc_words"] = 73180      # test/dev_test_suite.sh:83
 ut = open(REF + "/test/src/unittests-math.cpp").read()
 exp["getab"] = [[int(a), int(b), int(c), int(r)] for a, b, c, r in
                 re.findall(r"GetabIndex\((\d+),\s*(\d+),\s*(\d+)\)\s*==\s*(\d+)", ut)]
+# HLC PLINK / -gk 2 / covariates pins, test/dev_tests.rb:81-95 (kept as literals in tests/test_oracle_golden.py)
+# LOCO / -nind pins: test/dev_tests.rb:57-77 (row 2 logl_H1, max p_wald), test/dev_test_suite.sh:121-153 (cXX / assoc shape oracles)
+m = re.search(r'mouse_hs1940_loco\.assoc\.txt",\[\[2,9,"([0-9.e+-]+)"\],\s*\[:max,"p_wald","([0-9.e+-]+)"\]\]', rb)
+sh = open(REF + "/test/dev_test_suite.sh").read()
+loco = sh[sh.index("testCenteredRelatednessMatrixKLOCO1"):sh.index("testPlinkCenteredRelatednessMatrixKLOCO1")]
+exp["mouse_loco"] = {"source": "test/dev_tests.rb:57-77; test/dev_test_suite.sh:121-153", "row2_logl_H1": m.group(1), "max_p_wald": m.group(2),
+                     "cxx_lines": int(re.search(r'assertEquals "(\d+)" `wc -l < \$outfn`', loco).group(1)),
+                     "assoc_lines": int(re.findall(r'assertEquals "(\d+)" `wc -l < \$outfn`', loco)[1]),
+                     "cxx_head5": re.search(r'assertEquals "([0-9.]+)" `head -c 5', loco).group(1),
+                     "cxx_sum2": re.search(r'assertEquals "([0-9.]+)" `perl', loco).group(1)}
+# multivariate rows (-n 1 6 -lmm), demo.txt:62-66
+mv_hdr = [i for i, ln in enumerate(demo) if ln.startswith("chr\trs") and "beta_1" in ln][0]
+exp["mouse_mvlmm_rows"] = {"source": "example/demo.txt:62-66 (-n 1 6 -lmm): " + " ".join(demo[mv_hdr].split("\t")),
+                           "rows": [demo[i].split("\t") for i in range(mv_hdr + 1, mv_hdr + 6)]}
 json.dump(exp, open(__file__.replace("make_expected.py", "expected.json"), "w"), indent=1)
 print(json.dumps(exp, indent=1)[:1500])
