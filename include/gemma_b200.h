@@ -228,7 +228,8 @@ GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, co
  * (exact int8 digit planes of U, integer genotypes only); n_slices = digit planes of that path (0 = smallest count whose
  * truncation noise sqrt(n) 2^-(6+8(T-1)) stays below 2^-30: 5 up to n = 65 536, else 6); lmm_kernel 0 auto,
  * 1 warp-per-SNP register kernel (n_cvt <= 6), 2 lockstep-CTA pipeline kernel (n_cvt <= 3, n_region <= 64), 3 the
- * any-covariate-count kernel (default for n_cvt >= 7); kin_miss_max_permille: chunks with a larger share of missing
+ * any-covariate-count kernel (default for n_cvt >= 7); lmm_hoist 0|1: lockstep kernel with the SNP-independent sums at the
+ * lambdas shared by all SNPs computed once per run (default 1); kin_miss_max_permille: chunks with a larger share of missing
  * genotypes take the dense FP64 kinship path (default 200); cta_pair /
  * kin_cta_pair 0|1 run the projection / kinship tensor-core kernel as CTA pairs (cta_group::2);
  * kin_path 0 auto, 1 FP64 only; overlap 0|1 pipelines 2048-SNP sub-batches of the bed entry points on two streams

@@ -5,9 +5,8 @@
 
 using namespace gbmv;
 
-template <int C>
+template <int D, int C>
 static int null_t(int n, const double *ev, const double *X, const double *Y, const double *Vg0, const double *Ve0, double *out) {
-  constexpr int D = 2;
   MvData<C + D> dat; dat.n = n; dat.delta = ev;
   for (int j = 0; j < C; ++j) dat.z[j] = X + (size_t)j * n;
   for (int s = 0; s < D; ++s) dat.z[C + s] = Y + (size_t)s * n;
@@ -31,10 +30,10 @@ static int null_t(int n, const double *ev, const double *X, const double *Y, con
   return o;
 }
 
-template <int C>
+template <int D, int C>
 static int snp_t(int n, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn,
                  int a_mode, double logl_mle_H0, double *out) {
-  constexpr int D = 2, C1 = C + 1;
+  constexpr int C1 = C + 1;
   MvData<C1 + D> dat; dat.n = n; dat.delta = ev;
   for (int j = 0; j < C; ++j) dat.z[j] = X + (size_t)j * n;
   dat.z[C] = x;
@@ -43,18 +42,28 @@ static int snp_t(int n, const double *ev, const double *X, const double *x, cons
   for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { fit.V_g[i][j] = Vg[i * D + j]; fit.V_e[i][j] = Ve[i * D + j]; }
   for (int i = 0; i < D; ++i) { for (int j = 0; j < C; ++j) fit.B[i][j] = Bn[i * C + j]; fit.B[i][C] = 0.0; }
   analyze_snp<D, C1>(dat, fit, a_mode, 10000, 1e-4, 100, 1e-4, 0.001, logl_mle_H0, out);     // src/param.cpp:98-99 defaults
-  return 8;
+  return D + D * (D + 1) / 2 + 3;
 }
 
 extern "C" {
 int mvh_null(int n, int c, const double *ev, const double *X, const double *Y, const double *Vg0, const double *Ve0, double *out) {
-  switch (c) { case 1: return null_t<1>(n, ev, X, Y, Vg0, Ve0, out); case 2: return null_t<2>(n, ev, X, Y, Vg0, Ve0, out); case 3: return null_t<3>(n, ev, X, Y, Vg0, Ve0, out); }
+  switch (c) { case 1: return null_t<2, 1>(n, ev, X, Y, Vg0, Ve0, out); case 2: return null_t<2, 2>(n, ev, X, Y, Vg0, Ve0, out); case 3: return null_t<2, 3>(n, ev, X, Y, Vg0, Ve0, out); }
   return -1;
 }
 int mvh_snp(int n, int c, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn,
             int a_mode, double logl_mle_H0, double *out) {
-  switch (c) { case 1: return snp_t<1>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); case 2: return snp_t<2>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out);
-               case 3: return snp_t<3>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); }
+  switch (c) { case 1: return snp_t<2, 1>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); case 2: return snp_t<2, 2>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out);
+               case 3: return snp_t<2, 3>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); }
+  return -1;
+}
+// three phenotypes (the kernels of this round instantiate two; the core itself is generic in D)
+int mvh3_null(int n, int c, const double *ev, const double *X, const double *Y, const double *Vg0, const double *Ve0, double *out) {
+  switch (c) { case 1: return null_t<3, 1>(n, ev, X, Y, Vg0, Ve0, out); case 2: return null_t<3, 2>(n, ev, X, Y, Vg0, Ve0, out); }
+  return -1;
+}
+int mvh3_snp(int n, int c, const double *ev, const double *X, const double *x, const double *Y, const double *Vg, const double *Ve, const double *Bn,
+             int a_mode, double logl_mle_H0, double *out) {
+  switch (c) { case 1: return snp_t<3, 1>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); case 2: return snp_t<3, 2>(n, ev, X, x, Y, Vg, Ve, Bn, a_mode, logl_mle_H0, out); }
   return -1;
 }
 }
