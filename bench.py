@@ -378,7 +378,7 @@ def run_b200(args):
     # (before the CPU baseline: the host BLAS worker threads it starts keep spinning for a while and slow the synchronous
     #  per-chunk calls of the kinship entry point by an order of magnitude)
     gk = None
-    if not args.no_gk:
+    if not args.no_gk and world == 1:               # side measurements: N = 1 only
         try:
             del beds, out_dev, scratch
             torch.cuda.empty_cache()
@@ -389,7 +389,7 @@ def run_b200(args):
             gk = {"error": str(ex)[:200]}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         sample = args.cpu_sample or max(8, min(64, int(2.0e6 / n)))
         U_h = U.cpu().numpy()
         UtW_h = UtWt.cpu().numpy().T.copy(); Uty_h = Uty.cpu().numpy()
