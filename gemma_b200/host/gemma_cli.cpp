@@ -928,7 +928,7 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
   write_assoc(R);
 }
 
-// -lm: LM branch of BatchRun (src/gemma.cpp:1867-1911), LM::AnalyzeBimbam / AnalyzePlink (src/lm.cpp:382-640), LM::WriteFiles (:83-222)
+// -lm: LM branch of BatchRun (src/gemma.cpp:2062-2107), LM::AnalyzeBimbam / AnalyzePlink (src/lm.cpp:382-640), LM::WriteFiles (:83-222)
 static void run_lm(Run &R, gb200_ctx *ctx) {
   const size_t n = R.ni_test;
   vector<double> W, y; copy_cvt_phen(R, W, y);
