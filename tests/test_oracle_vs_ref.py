@@ -366,3 +366,83 @@ def test_mvlmm_lrt_and_score_modes_match_reference_cli(golden_dir, tmp_path):
         beta, Vb, pw, pl, ps = MV.analyze_snp(ev, UtW, UtY, U.T @ X[:, q], nm, 4)
         got = np.array([beta[0], beta[1], Vb[0, 0], Vb[0, 1], Vb[1, 1], pw, pl, ps])
         assert np.allclose(got, ref[r], rtol=5e-6, atol=0), (r, got, ref[r])
+
+
+def test_mvlmm_three_phenotypes_pins_and_ml_em_conditioning(golden_dir, tmp_path):
+    """Three phenotypes (-n 1 4 6: 626 mice, traits 1 and 4 correlate at 0.8) against the reference CLI.
+
+    * -lmm 1 (REML EM + MphCalcP + the NR branch): every SNP of the subset within 3e-6 -- pins the d = 3 restatement.
+    * -lmm 4: the score test again everywhere; the likelihood-ratio test on most SNPs, but NOT on all of them, and that is a
+      property of the reference, not of the restatement: its ML EM keeps U_l^T V_e^-1/2 B from the previous iteration's basis
+      (src/mvlmm.cpp:673-690), and with d >= 3 the dsyevr eigenvector signs of consecutive iterations are not a continuous
+      function of V_g, V_e.  On those SNPs a 1e-14 relative perturbation of the phenotypes moves p_lrt by percents (shown
+      below on the oracle itself), so no implementation -- the reference linked against another BLAS included -- can
+      reproduce them to 1e-6.  With two phenotypes the same probe moves p_lrt by < 1e-10 on every SNP (asserted), which is
+      why the d = 2 device path is held to the 1e-6 bar on all three tests."""
+    from oracle import mvlmm_oracle as MV
+    if not os.path.exists(REF.EXE) and not os.path.isdir(REF.REF_SRC):
+        pytest.skip("reference CLI not built")
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+    cwd = str(tmp_path)
+    bb = R.Bimbam(d + "/mouse_hs1940.geno.txt.gz")
+    sub = bb.rs[::40]
+    snps = os.path.join(cwd, "sub.txt")
+    with open(snps, "w") as f:
+        f.write("\n".join(sub) + "\n")
+    REF.run_cli(base + ["-gk", "-o", "mouse"], cwd)
+    for mode in ("1", "4"):
+        REF.run_cli(base + ["-n", "1", "4", "6", "-snps", snps, "-k", "output/mouse.cXX.txt", "-lmm", mode, "-o", "mv3_" + mode], cwd)
+    K = np.loadtxt(os.path.join(cwd, "output", "mouse.cXX.txt"))
+
+    def prepare(cols):
+        ph, ind = R.read_pheno(d + "/mouse_hs1940.pheno.txt", cols)
+        idv, W = R.process_cvt_phen(ind)
+        isnp, _, _ = R.qc_bimbam(bb, idv, snps=set(sub))
+        keep = idv == 1
+        U, ev, _ = R.eigen_decomp_zeroed(O.center_matrix(np.ascontiguousarray(K[np.ix_(keep, keep)])))
+        UtW = U.T @ W[keep]; UtY = U.T @ ph[keep]
+        sel = np.nonzero(isnp)[0]
+        return ev, UtW, UtY, U.T @ R.lmm_genotypes_bimbam(bb, isnp, idv, sel), MV.null_model(ev, UtW, UtY), sel
+
+    ev, UtW, UtY, UtX, nm, sel = prepare((1, 4, 6))
+    assert UtY.shape[0] == 626
+    iu = np.triu_indices(3)
+
+    def table(name):
+        lines = open(os.path.join(cwd, "output", name + ".assoc.txt")).read().splitlines()
+        assert len(lines) == 1 + len(sel)
+        return lines[0].split("\t"), np.array([[float(x) for x in ln.split("\t")[7:]] for ln in lines[1:]])
+
+    hdr, ref1 = table("mv3_1")
+    assert hdr[7:] == ["beta_1", "beta_2", "beta_3", "Vbeta_1_1", "Vbeta_1_2", "Vbeta_1_3", "Vbeta_2_2", "Vbeta_2_3", "Vbeta_3_3", "p_wald"]
+    assert (ref1[:, -1] < MV.P_NR).sum() >= 1
+    for q in range(len(sel)):
+        beta, Vb, pw, _, _ = MV.analyze_snp(ev, UtW, UtY, UtX[:, q], nm, 1)
+        got = np.concatenate([beta, Vb[iu], [pw]])
+        assert np.allclose(got, ref1[q], rtol=3e-6, atol=0), (q, got, ref1[q])
+
+    hdr, ref4 = table("mv3_4")
+    assert hdr[-3:] == ["p_wald", "p_lrt", "p_score"]
+    rng = np.random.default_rng(0)
+    perts = [1.0 + 1e-14 * rng.standard_normal(UtY.shape) for _ in range(6)]
+    rel_lrt = np.zeros(len(sel)); sens = np.zeros(len(sel))
+    for q in range(len(sel)):
+        _, _, _, pl, ps = MV.analyze_snp(ev, UtW, UtY, UtX[:, q], nm, 4)
+        assert abs(ps - ref4[q, -1]) <= 3e-6 * ref4[q, -1], (q, ps, ref4[q, -1])
+        rel_lrt[q] = abs(pl - ref4[q, -2]) / ref4[q, -2]
+        sens[q] = max(abs(MV.analyze_snp(ev, UtW, UtY * p_, UtX[:, q], nm, 2)[3] - pl) for p_ in perts) / pl
+    ok = rel_lrt < 5e-6
+    assert ok.mean() > 0.5 and rel_lrt.max() < 0.25, (ok.mean(), rel_lrt.max())
+    # every SNP the restatement misses is one where the reference's own output is ill-conditioned (one sampling miss allowed) ...
+    assert (sens[~ok] > 1e-6).sum() >= (~ok).sum() - 2, (sens[~ok].min(), (~ok).sum())
+    # ... and the well-conditioned ones are reproduced
+    assert (ok[sens < 1e-10]).mean() > 0.97
+
+    # two phenotypes: the same probe does not move p_lrt anywhere
+    ev, UtW, UtY, UtX, nm, sel = prepare((1, 6))
+    perts = [1.0 + 1e-14 * rng.standard_normal(UtY.shape) for _ in range(3)]
+    for q in range(0, len(sel), 3):
+        pl = MV.analyze_snp(ev, UtW, UtY, UtX[:, q], nm, 2)[3]
+        for p_ in perts:
+            assert abs(MV.analyze_snp(ev, UtW, UtY * p_, UtX[:, q], nm, 2)[3] - pl) < 1e-10 * pl
