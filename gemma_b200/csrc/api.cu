@@ -72,7 +72,9 @@ void gb200_destroy(gb200_ctx *c) {
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   gb::DevBuf *bufs[] = {&c->dK, &c->dU, &c->dEval, &c->dWt, &c->dY, &c->dNull, &c->dX, &c->dUtXt, &c->dOut,
                         &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale,
-                        &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles};
+                        &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles,
+                        &c->i8.kin_qbits, &c->i8.kin_y, &c->dWtx, &c->dEnv, &c->dX2, &c->dFlip, &c->dLmW, &c->dLmY,
+                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab};
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
