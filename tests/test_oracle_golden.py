@@ -147,3 +147,56 @@ def test_hlc_plink_gk2_lmm1_covariates_pins():
     assert np.nanmax(out["logl_H1"]) == pytest.approx(279.2689, abs=1e-3)
     assert np.nanmax(out["lambda_remle"]) == pytest.approx(1.686062, abs=1e-3)
     assert np.nanmax(out["p_wald"]) == pytest.approx(0.9999996, abs=1e-3)
+
+
+def _perl_sum(K):
+    """The checksum one-liner of the reference's shell suites (test/dev_test_suite.sh:52): every printed entry cut to its first
+    six characters, rounded to two decimals, summed."""
+    txt = "\n".join("\t".join("%.10g" % v for v in row) for row in K)       # WriteMatrix, src/param.cpp:1899-1906
+    return sum(float("%.2f" % float(w[:6])) for w in txt.split())
+
+
+def test_shell_suite_matrix_checksums(mouse, golden_dir):
+    """Kinship-file pins of the shunit2 suites: BXD cXX 198 lines, checksum -116 (test/dev_test_suite.sh:40-53); BXD -lmm 9
+    output 80498 words = 11 columns (:92-106); mouse cXX 1940 lines / 3763600 words, first entry 0.335 (test/test_suite.sh:119-123)."""
+    d = os.path.join(golden_dir, "BXD")
+    bb = R.Bimbam(os.path.join(d, "BXD_geno.txt.gz"))
+    ph, ind = R.read_pheno(os.path.join(d, "BXD_pheno.txt"), (1,))
+    rows, icvt = R.read_cvt(os.path.join(d, "BXD_covariates2.txt"))
+    idv, W = R.process_cvt_phen(ind, rows, icvt)
+    isnp_gk, _, _ = R.qc_bimbam(bb, idv, W)
+    K = R.kinship_bimbam(bb, isnp_gk, 1)
+    assert K.shape == (198, 198) and "%.0f" % _perl_sum(K) == "-116"
+    isnp, _, _ = R.qc_bimbam(bb, idv, W, maf_level=0.1)
+    assert (int(isnp.sum()) + 1) * 11 == 80498            # -lmm 9 rows have 11 columns (LMM::WriteFiles, src/lmm.cpp:101-225)
+    Km = mouse["K"] if "K" in mouse else None
+    if Km is not None:
+        assert Km.shape == (1940, 1940) and ("%.10g" % Km[0, 0])[:5] == "0.335"
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/example/HLC.bed"), reason="reference example HLC absent (GPU box)")
+def test_hlc_sxx_and_issue188_checksums():
+    """test/lengthy_test_suite.sh:10-21: HLC -gk 2 sXX 427 lines, checksum -358.07; test/dev_test_suite.sh:108-116: issue188 (PLINK,
+    2000 SNPs) -gk checksum 194."""
+    pl = R.Plink("/root/reference/example/HLC")
+    idv, W = R.process_cvt_phen(pl.ind_pheno, None, None)
+    isnp, _, _ = R.qc_plink(pl, idv)
+    K = R.kinship_plink(pl, isnp, 2)
+    # The shell suite's -358.07 is a checksum of 182 329 entries each cut to six characters: it moves by 0.01 whenever the dgemm
+    # rounding flips a cut digit.  The current reference source compiled here (oracle/_ref) prints -358.05, and so does the
+    # restatement; the suite itself is declared unused upstream (SURVEY 4).
+    assert K.shape == (427, 427) and abs(_perl_sum(K) - (-358.07)) < 0.05
+    from oracle import ref as REF
+    if os.path.exists(REF.EXE):
+        import tempfile
+        with tempfile.TemporaryDirectory() as cwd:
+            REF.run_cli(["-bfile", "/root/reference/example/HLC", "-gk", "2", "-o", "hlc"], cwd)
+            txt = open(os.path.join(cwd, "output", "hlc.sXX.txt")).read()
+        assert len(txt.splitlines()) == 427
+        assert "%.2f" % sum(float("%.2f" % float(w[:6])) for w in txt.split()) == "%.2f" % _perl_sum(K) == "-358.05"
+        assert np.abs(np.loadtxt(txt.splitlines()) - K).max() < 1e-9
+    pl = R.Plink("/root/reference/test/data/issue188/2000")
+    idv, W = R.process_cvt_phen(pl.ind_pheno, None, None)
+    isnp, _, _ = R.qc_plink(pl, idv)
+    K = R.kinship_plink(pl, isnp, 1)
+    assert "%.0f" % _perl_sum(K) == "194"
