@@ -77,6 +77,26 @@ def test_cli_rejects_unknown_flags_and_missing_inputs():
     assert r.returncode != 0 and "unrecognized option" in r.stdout
     r = subprocess.run([CLI, "-g", "x", "-p", "y", "-lmm", "1"], capture_output=True, text=True)
     assert r.returncode != 0 and "missing relatedness file" in r.stdout
+    # flag combinations the reference refuses (src/gemma.cpp:1125-1131, src/param.cpp:923-933) or that are outside this framework
+    for argv, msg in ((["-g", "x", "-p", "y", "-gk", "-lmm", "1"], "only one of"),
+                      (["-g", "x", "-p", "y", "-k", "k", "-lmm", "7"], "not supported"),
+                      (["-g", "x", "-p", "y", "-lm", "1", "-gxe", "e"], "-lm does not take"),
+                      (["-g", "x", "-p", "y", "-k", "k", "-n", "1", "2", "3", "-lmm", "1"], "two phenotypes"),
+                      (["-g", "x", "-p", "y", "-k", "k", "-n", "1", "2", "-lmm", "1", "-gxe", "e"], "multivariate G x E"),
+                      (["-p", "y", "-gk"], "need -g and -p")):
+        r = subprocess.run([CLI] + argv, capture_output=True, text=True)
+        assert r.returncode != 0 and msg in r.stdout + r.stderr, (argv, r.stdout, r.stderr)
+
+
+def test_cli_loco_needs_annotation_and_bimbam_input(golden_dir):
+    _build()
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt"]
+    r = subprocess.run([CLI] + base + ["-gk", "-loco", "1", "-qc-only"], capture_output=True, text=True)
+    assert r.returncode != 0 and "LOCO requires annotation file" in r.stdout + r.stderr       # src/param.cpp:924-926
+    r = subprocess.run([CLI] + base + ["-a", d + "/mouse_hs1940.anno.txt", "-ksnps", d + "/mouse_hs1940_snps.txt", "-gk", "-loco", "1", "-qc-only"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "LOCO does not allow -ksnps" in r.stdout + r.stderr
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/example/mouse_hs1940.bed"), reason="reference examples absent")
