@@ -128,14 +128,20 @@ def test_center_matrix_and_bed_decode_small():
     assert g[0] == 2 and g[1] == 1 and g[2] == 0 and np.isnan(g[3])
 
 
-@pytest.mark.skipif(not os.path.exists("/root/reference/example/HLC.bed"), reason="reference example HLC absent (GPU box)")
-def test_hlc_plink_gk2_lmm1_covariates_pins():
-    """test/dev_tests.rb:81-95: PLINK input, -gk 2 (standardised K), -lmm 1 -maf 0.1 with covariates (c = 3+1...)."""
+@pytest.fixture(scope="module")
+def hlc():
+    """example/HLC read once: the -gk 2 run of both HLC tests (no covariates, default maf 0.01)."""
     pl = R.Plink("/root/reference/example/HLC")
-    rows, icvt = R.read_cvt("/root/reference/example/HLC_covariates.txt")
     idv, W = R.process_cvt_phen(pl.ind_pheno, None, None)
-    isnp_gk, _, _ = R.qc_plink(pl, idv)                      # -gk run: no covariates, default maf 0.01
-    K = R.kinship_plink(pl, isnp_gk, 2)
+    isnp_gk, _, _ = R.qc_plink(pl, idv)
+    return dict(pl=pl, K2=R.kinship_plink(pl, isnp_gk, 2))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/example/HLC.bed"), reason="reference example HLC absent (GPU box)")
+def test_hlc_plink_gk2_lmm1_covariates_pins(hlc):
+    """test/dev_tests.rb:81-95: PLINK input, -gk 2 (standardised K), -lmm 1 -maf 0.1 with covariates (c = 3+1...)."""
+    pl, K = hlc["pl"], hlc["K2"]
+    rows, icvt = R.read_cvt("/root/reference/example/HLC_covariates.txt")
     idv, W = R.process_cvt_phen(pl.ind_pheno, rows, icvt)
     isnp, _, _ = R.qc_plink(pl, idv, W, maf_level=0.1)
     prep = R.lmm_prepare(R.text_roundtrip(K), idv, pl.pheno[:, 0], W)
@@ -175,13 +181,10 @@ def test_shell_suite_matrix_checksums(mouse, golden_dir):
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/example/HLC.bed"), reason="reference example HLC absent (GPU box)")
-def test_hlc_sxx_and_issue188_checksums():
+def test_hlc_sxx_and_issue188_checksums(hlc):
     """test/lengthy_test_suite.sh:10-21: HLC -gk 2 sXX 427 lines, checksum -358.07; test/dev_test_suite.sh:108-116: issue188 (PLINK,
     2000 SNPs) -gk checksum 194."""
-    pl = R.Plink("/root/reference/example/HLC")
-    idv, W = R.process_cvt_phen(pl.ind_pheno, None, None)
-    isnp, _, _ = R.qc_plink(pl, idv)
-    K = R.kinship_plink(pl, isnp, 2)
+    K = hlc["K2"]
     # The shell suite's -358.07 is a checksum of 182 329 entries each cut to six characters: it moves by 0.01 whenever the dgemm
     # rounding flips a cut digit.  The current reference source compiled here (oracle/_ref) prints -358.05, and so does the
     # restatement; the suite itself is declared unused upstream (SURVEY 4).
