@@ -1060,7 +1060,7 @@ int main(int argc, char **argv) {
   Run R; Params &P = R.P;
   for (int i = 0; i < argc; ++i) { if (i) R.cmdline += " "; R.cmdline += argv[i]; }
   if (argc <= 1) { usage(); return 0; }
-  auto need = [&](int &i) -> const char * { if (i + 1 >= argc || argv[i + 1][0] == '-' && !isdigit((unsigned char)argv[i + 1][1]) && argv[i + 1][1] != '.') die(string("missing value for ") + argv[i]); return argv[++i]; };
+  auto need = [&](int &i) -> const char * { if (i + 1 >= argc || (argv[i + 1][0] == '-' && !isdigit((unsigned char)argv[i + 1][1]) && argv[i + 1][1] != '.')) die(string("missing value for ") + argv[i]); return argv[++i]; };
   auto optnum = [&](int &i, int dflt) -> int { if (i + 1 < argc && argv[i + 1][0] != '-') return atoi(argv[++i]); return dflt; };
   int n_modes = 0;
   for (int i = 1; i < argc; ++i) {
