@@ -1,0 +1,56 @@
+"""The int8 digit-plane representation behind the tensor-core projection (oracle/i8_planes.py restates
+gemma_b200/csrc/i8gemm_sm100.cu: col_scale_kernel, slice_kernel, the plane recombination): reconstruction, digit ranges,
+the error bound that fixes the default plane count.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import i8_planes as P
+
+
+def _orthogonal(n, seed):
+    q, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((n, n)))
+    return q
+
+
+def test_default_plane_count_rule():
+    assert [P.default_planes(n) for n in (2, 1024, 10000, 50000, 65536)] == [5] * 5
+    assert P.default_planes(65537) == 6 and P.default_planes(10 ** 6) == 6
+    for n in (100, 50000, 65536, 200000):                       # the rule: sqrt(n) 2^-B <= 2^-30, and T - 1 planes would miss it
+        T = P.default_planes(n)
+        assert np.sqrt(n) * 2.0 ** -(6 + 8 * (T - 1)) <= 2.0 ** -30 < np.sqrt(n) * 2.0 ** -(6 + 8 * (T - 2))
+
+
+@pytest.mark.parametrize("n,T", [(96, 5), (257, 4), (257, 6), (300, 8)])
+def test_planes_reconstruct_the_rounded_matrix(n, T):
+    U = _orthogonal(n, n)
+    U[:, 3] = 0.0; U[5, 7] = 0.5; U[:, 7] = np.clip(U[:, 7], -0.5, 0.5)        # an empty column; a column whose maximum is a power of two
+    planes, scale = P.slice_planes(U, T)
+    assert planes.dtype == np.int8 and np.abs(planes[0].astype(int)).max() <= 65
+    Q = np.zeros((n, n), dtype=np.int64)
+    for t in range(T):
+        Q = Q * 256 + planes[t]
+    B = 6 + 8 * (T - 1)
+    back = Q.T * scale[None, :]
+    assert np.abs(back - U).max() <= 2.0 ** -(B + 1) * 1.0000001                # |U| < sigma <= 1: half a unit of the last kept bit
+    if B >= 52:
+        assert np.array_equal(back[:, 10], U[:, 10]) or np.abs(back - U).max() < 2e-16
+
+
+@pytest.mark.parametrize("n,miss", [(384, False), (500, True)])
+def test_projection_error_bound(n, miss):
+    rng = np.random.default_rng(n)
+    U = _orthogonal(n, 7)
+    X = rng.binomial(2, rng.uniform(0.05, 0.5, 40)[None, :], size=(n, 40)).astype(np.int64)
+    if miss:
+        X[rng.random(X.shape) < 0.02] = 0                    # holes enter the int8 operand as 0 (the mean term is added in FP64 afterwards)
+    exact = U.T @ X.astype(np.float64)
+    for T in (3, 4, 5):
+        B = 6 + 8 * (T - 1)
+        planes, scale = P.slice_planes(U, T)
+        err = np.abs(P.project(planes, scale, X) - exact).max()
+        worst = n * 2.0 ** -(B + 1) * 2                       # every entry off by half a unit, |x| <= 2, sigma <= 1
+        typical = np.sqrt(n) * 2.0 ** -B * 2
+        assert err <= worst and err <= 3 * typical + 64 * np.finfo(float).eps * np.abs(exact).max(), (T, err, typical)
+    # at the default plane count the projection is indistinguishable from the FP64 product at the 1e-6 parity bar
+    planes, scale = P.slice_planes(U, P.default_planes(n))
+    assert np.abs(P.project(planes, scale, X) - exact).max() < 1e-9 * max(1.0, np.abs(exact).max())
