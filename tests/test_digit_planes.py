@@ -54,3 +54,27 @@ def test_projection_error_bound(n, miss):
     # at the default plane count the projection is indistinguishable from the FP64 product at the 1e-6 parity bar
     planes, scale = P.slice_planes(U, P.default_planes(n))
     assert np.abs(P.project(planes, scale, X) - exact).max() < 1e-9 * max(1.0, np.abs(exact).max())
+
+
+def test_kinship_missing_genotype_identity():
+    """The algebra of the int8 kinship path with holes (i8gemm_sm100.cu, kin_miss_fix_kernel): with z = 0 at missing entries,
+    q the missing indicator and m_s the SNP mean over the observed entries, the reference's mean-imputed centred product
+    (src/gemma_io.cpp:1688-1706) equals Z Z^T - a 1^T - 1 a^T + beta + (Y + Y^T) - b 1^T - 1 b^T with
+    a_i = sum_s m_s z_si, beta = sum_s m_s^2, b_i = sum_s m_s^2 q_si, Y_ji = sum_s q_sj (m_s z_si + m_s^2 q_si / 2):
+    the dense part is exact integer arithmetic, everything else is O(#missing x n)."""
+    rng = np.random.default_rng(3)
+    n, l = 60, 400
+    G = rng.binomial(2, rng.uniform(0.05, 0.5, l)[:, None], size=(l, n)).astype(float)
+    q = rng.random((l, n)) < 0.03
+    z = np.where(q, 0.0, G)
+    m = z.sum(1) / (n - q.sum(1))
+    Xc = np.where(q, 0.0, G - m[:, None])                     # what the reference accumulates: imputed entries centre to 0
+    ref = Xc.T @ Xc
+    a = z.T @ m
+    beta = float(m @ m)
+    b = q.T.astype(float) @ (m * m)
+    Y = q.T.astype(float) @ (m[:, None] * z + 0.5 * (m * m)[:, None] * q)      # row j: sum over the SNPs where j is missing
+    got = z.T @ z - a[:, None] - a[None, :] + beta + Y + Y.T - b[:, None] - b[None, :]
+    assert np.allclose(got, ref, rtol=0, atol=1e-9)
+    ZZ = z.T.astype(np.int64) @ z.astype(np.int64)            # the tensor-pipe part is integer-exact
+    assert np.array_equal(ZZ, (z.T @ z).astype(np.int64))
