@@ -412,8 +412,15 @@ static void qc_plink(Run &R, gb200_ctx *ctx) {
   g_nbit = (R.ni_total + 3) / 4;
   R.ns_total = R.snpInfo.size();
   g_bed.resize(g_nbit * R.ns_total);
-  in.seekg(3);
+  // The reference skips the three magic bytes unread (seekg(3), src/gemma_io.cpp:951-953) and would decode an individual-major
+  // or truncated file into garbage; refuse both loudly instead.
+  unsigned char magic[3] = {0, 0, 0};
+  in.read(reinterpret_cast<char *>(magic), 3);
+  if (in.gcount() != 3 || magic[0] != 0x6c || magic[1] != 0x1b) die("not a PLINK .bed file: " + R.P.file_bfile + ".bed");
+  if (magic[2] != 0x01) die("individual-major .bed files are not supported (the reference assumes SNP-major): " + R.P.file_bfile + ".bed");
   in.read(reinterpret_cast<char *>(g_bed.data()), (std::streamsize)g_bed.size());
+  if ((size_t)in.gcount() != g_bed.size()) die("truncated .bed file: expected " + std::to_string(g_bed.size()) + " genotype bytes for " +
+                                                std::to_string(R.ns_total) + " SNPs x " + std::to_string(R.ni_total) + " individuals");
   R2Filter r2; r2.init(R);
   if (ctx) {
     vector<unsigned char> mask(R.ni_total); for (size_t i = 0; i < R.ni_total; ++i) mask[i] = (unsigned char)R.indicator_idv[i];

@@ -104,3 +104,35 @@ def test_plink_qc_counts_match_bimbam_counts(tmp_path):
     out, rows = _qc(["-bfile", "/root/reference/example/mouse_hs1940"], tmp_path, "plink")
     # same cohort through the PLINK reader: .fam phenotype column 1, 2-bit genotypes
     assert "## number of total individuals = 1940" in out and "## number of total SNPs/var        =    12226" in out
+
+
+def test_plink_reader_refuses_malformed_bed(tmp_path):
+    """A synthetic PLINK triple (no reference files needed): the valid file passes QC; a truncated payload, a wrong magic number
+    and an individual-major file fail loudly instead of decoding garbage."""
+    from gemma_b200 import synth
+    _build()
+    n, l = 37, 25
+    bed, G = synth.make_bed(n, l, seed=5, miss_rate=0.02)
+    base = str(tmp_path / "toy")
+    with open(base + ".fam", "w") as f:
+        for i in range(n):
+            f.write("f%d i%d 0 0 1 %.3f\n" % (i, i, 0.1 * i))
+    with open(base + ".bim", "w") as f:
+        for s in range(l):
+            f.write("1\trs%d\t0\t%d\tA\tG\n" % (s, 100 + s))
+    payload = bytes(bytearray(np.ascontiguousarray(bed).reshape(-1)))
+    assert len(payload) == l * ((n + 3) // 4)
+
+    def run(blob):
+        with open(base + ".bed", "wb") as f:
+            f.write(blob)
+        return subprocess.run([CLI, "-bfile", base, "-gk", "-qc-only", "-o", "toy", "-outdir", str(tmp_path)], capture_output=True, text=True)
+
+    r = run(b"\x6c\x1b\x01" + payload)
+    assert r.returncode == 0 and "## number of total SNPs/var        =" in r.stdout, r.stdout + r.stderr
+    r = run(b"\x6c\x1b\x01" + payload[:-5])
+    assert r.returncode != 0 and "truncated .bed file" in r.stdout + r.stderr
+    r = run(b"\x00\x00\x01" + payload)
+    assert r.returncode != 0 and "not a PLINK .bed file" in r.stdout + r.stderr
+    r = run(b"\x6c\x1b\x00" + payload)
+    assert r.returncode != 0 and "individual-major" in r.stdout + r.stderr
