@@ -25,3 +25,14 @@ def ctx():
     c = gemma_b200.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _fresh_cli():
+    """The gemma-b200 binary is a build product (not tracked): (re)build it once per session from the sources so
+    that a stale executable can never pass tests the source would fail."""
+    import subprocess
+    host = os.path.join(ROOT, "gemma_b200", "host")
+    if os.path.exists(os.path.join(ROOT, "gemma_b200", "csrc", "libgemma_b200.so")):
+        subprocess.check_call(["make", "-s", "-C", host])
+    yield

@@ -436,8 +436,7 @@ def test_cli_mouse_gk_then_lmm_matches_demo_txt(golden_dir, tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
-    if not os.path.exists(cli):
-        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])     # always: a stale binary must not pass for the source
     d = os.path.join(golden_dir, "mouse_hs1940")
     base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt",
             "-outdir", str(tmp_path)]
@@ -472,8 +471,7 @@ def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
-    if not os.path.exists(cli):
-        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])     # always: a stale binary must not pass for the source
     d = os.path.join(golden_dir, "mouse_hs1940")
     e = EXP["mouse_loco"]
     base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt",
@@ -525,8 +523,7 @@ def test_cli_against_the_reference_cli_end_to_end(golden_dir, tmp_path):
         pytest.skip("reference CLI not shipped")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
-    if not os.path.exists(cli):
-        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])     # always: a stale binary must not pass for the source
     cwd = str(tmp_path); out = os.path.join(cwd, "output")
 
     def mine(args):
@@ -927,8 +924,7 @@ def test_cli_plink_gk_and_lmm4_match_oracle(tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cli = os.path.join(root, "gemma_b200", "host", "gemma-b200")
-    if not os.path.exists(cli):
-        subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])     # always: a stale binary must not pass for the source
     n, l = 1150, 900
     rng = np.random.default_rng(3)
     bed, G = synth.make_bed(n, l, seed=444, miss_rate=0.01)
