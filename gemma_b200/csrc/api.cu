@@ -358,6 +358,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false; c->common_ready = false; c->gxe_ready = false;
+  c->mask_host.clear();                           // the cached gather index belongs to the previous n
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
   c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
   GB_CUDA(c, c->dU.reserve(n * n * sizeof(double)));
@@ -430,6 +431,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
   c->lmm_ready = false; c->i8.ready = false; c->common_ready = false; c->gxe_ready = false;
+  c->mask_host.clear();
   const size_t n_c = round_up(n, 512);
   c->dUtXt.release(); c->dUtXt2.release();
   c->dU.adopt(const_cast<double *>(U_dev), n * n * 8);          // borrowed: caller keeps it alive
@@ -1000,10 +1002,18 @@ int gb200_mvlmm_setup(gb200_ctx *c, size_t n, size_t n_cvt, size_t n_ph, const d
     GB_CUDA(c, cudaMemcpyAsync(c->dY.p, c->dMvY.as<double>() + (size_t)s * n_c, n_c * 8, cudaMemcpyDeviceToDevice, c->stream));
     gb200_nullmodel nm;
     std::vector<double> b1(n_cvt), b2(n_cvt), b3(n_cvt), b4(n_cvt);
-    rc = gb200_lmm_null(c, 1e-5, 1e5, 10, 1.0, &nm, b1.data(), b2.data(), b3.data(), b4.data());
+    // CalcLambda('R', ..., cPar.l_min, cPar.l_max, cPar.n_region, ...) of MphInitial: the limits of gb200_lmm_params when the caller set them
+    const double lmin = c->prm_ready ? c->prm.l_min : 1e-5, lmax = c->prm_ready ? c->prm.l_max : 1e5;
+    const size_t nreg = c->prm_ready ? (size_t)c->prm.n_region : 10;
+    rc = gb200_lmm_null(c, lmin, lmax, nreg, 1.0, &nm, b1.data(), b2.data(), b3.data(), b4.data());
     if (rc) return rc;
     K.vg0[s] = nm.vg_remle; K.ve0[s] = nm.ve_remle;
   }
+  // leave the univariate state as gb200_lmm_setup built it (U^T y of the FIRST phenotype): a later gb200_lmm_null / gb200_lmm_batch*
+  // on this context must not silently analyse phenotype 2
+  GB_CUDA(c, cudaMemcpyAsync(c->dY.p, c->dMvY.as<double>(), n_c * 8, cudaMemcpyDeviceToDevice, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->common_ready = false;
   K.n = (int)n; K.ld = (int)n_c; K.delta = c->dEval.as<double>(); K.Wt = c->dWt.as<double>(); K.Yt = c->dMvY.as<double>();
   K.em_iter = 10000; K.nr_iter = 100; K.em_prec = 1e-4; K.nr_prec = 1e-4; K.p_nr = 0.001;           // src/param.cpp:98-99
   c->mv_ready = true;

@@ -952,7 +952,8 @@ __global__ void kin_commit_kernel(double *a, const double *a_pending, double *be
 
 __global__ void kin_finish_kernel(double *K, size_t n, size_t ld, const double *__restrict__ a, const double *__restrict__ beta_flag,
                                   const double *__restrict__ Y, const double *__restrict__ b, double inv_ns) {
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  // rows on grid.x (limit 2^31 - 1), column blocks on grid.y: n / 256 stays far below the 65 535 limit of grid.y
+  const size_t j = (size_t)blockIdx.y * blockDim.x + threadIdx.x, i = blockIdx.x;
   if (j > i || i >= n) return;
   double v = K[i * ld + j] - a[i] - a[j] + beta_flag[0];
   if (Y) v += (Y[i * n + j] + Y[j * n + i]) - b[i] - b[j];      // missing-genotype terms (kin_miss_fix_kernel)
@@ -1117,7 +1118,7 @@ int kin_i8_finish(gb200_ctx *c, double inv_ns) {
   if (rc) return rc;
   const size_t n = c->kin_n;
   double *a = S.kin_a.as<double>();
-  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  dim3 grid((unsigned)n, (unsigned)((n + 255) / 256));
   const double *Y = S.kin_y_used ? S.kin_y.as<double>() : nullptr;
   kin_finish_kernel<<<grid, 256, 0, c->stream>>>(c->dK.as<double>(), n, n, a, a + 2 * n, Y, Y ? Y + n * n : nullptr, inv_ns);
   GB_CUDA(c, cudaGetLastError());

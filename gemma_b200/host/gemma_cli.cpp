@@ -61,7 +61,9 @@ struct Params {
   int device = -1;
 };
 
-static void die(const string &msg) { std::cout << "error! " << msg << std::endl; std::exit(1); }
+// may be called from a worker thread of the line pipeline while the others are still running: flush and leave without
+// running static destructors under them
+static void die(const string &msg) { std::cout << "error! " << msg << std::endl; std::cout.flush(); std::fflush(nullptr); std::_Exit(1); }
 
 // ---- line readers (plain or gzip, like gzstream's igzstream) --------------------------------------
 struct LineReader {
@@ -738,6 +740,7 @@ static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vec
   vector<double> Y(n * d);
   { size_t k = 0; for (size_t i = 0; i < R.ni_total; ++i) { if (!R.indicator_idv[i]) continue; Y[k * d] = R.pheno[i][0]; Y[k * d + 1] = R.pheno[i][1]; k++; } }
   const double t0 = now_s();
+  GB(gb200_lmm_params(ctx, 1, R.P.l_min, R.P.l_max, R.P.n_region, 0.0, 0.0));     // -lmin / -lmax / -region reach MphInitial's univariate fits (src/mvlmm.cpp:2786-2796)
   GB(gb200_mvlmm_setup(ctx, n, R.n_cvt, d, U.data(), n, eval.data(), W.data(), R.n_cvt, Y.data(), d));
   double Vg[4], Ve[4], Vgm[4], Vem[4], lr, lm; vector<double> Br(d * R.n_cvt), Bm(d * R.n_cvt);
   GB(gb200_mvlmm_null(ctx, Vg, Ve, Br.data(), &lr, Vgm, Vem, Bm.data(), &lm));
@@ -880,6 +883,9 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
     };
     for (size_t t = 0; t < R.ns_total; ++t) {
       if (!R.indicator_snp[t]) continue;
+      // -gwasnps: the reference's AnalyzePlink ignores the set while WriteFiles applies it (src/lmm.cpp:209-210), which shifts
+      // every later row onto another SNP's statistics; here the set filters the tested SNPs, as in the BIMBAM loop below
+      if (!R.setGWASnps.empty() && !R.setGWASnps.count(R.snpInfo[t].rs)) continue;
       rows.insert(rows.end(), g_bed.begin() + t * g_nbit, g_bed.begin() + (t + 1) * g_nbit);
       if (++l == BATCH) flush();
     }

@@ -22,7 +22,7 @@
 #include <vector>
 
 struct LineBlock {
-  size_t first_line = 0;              // 0-based index of lines[0] in the file
+  size_t first_line = 0;              // 0-based index of lines[0] among the file's non-blank lines
   std::unique_ptr<char[]> data;       // the block's text; every line NUL-terminated in place
   std::vector<char *> lines;          // line starts inside data (without the trailing "\n" / "\r\n"); workers may write into them
 };
@@ -94,7 +94,11 @@ class LinePipeline {
         char *stop = nl ? nl : end;
         *stop = 0;
         if (stop > p && stop[-1] == '\r') stop[-1] = 0;
-        blk.lines.push_back(p);
+        // lines without a token (empty or delimiters only) are dropped HERE, so that every pass over the file numbers the
+        // remaining lines identically (QC records one entry per line it sees; the later passes index by line number)
+        const char *q = p;
+        while (*q == ' ' || *q == ',' || *q == '\t') ++q;
+        if (*q) blk.lines.push_back(p);
         p = stop + 1;
       }
       line_no += blk.lines.size();

@@ -41,7 +41,10 @@ def combine_partial_kinship(K_local, ns_local, group=None):
     import torch
     import torch.distributed as dist
     cnt = torch.tensor([float(ns_local)], dtype=torch.float64, device=K_local.device)
-    K_local.mul_(float(ns_local))
+    if ns_local == 0:
+        K_local.zero_()                      # a rank without SNPs contributes nothing (and never a NaN * 0)
+    else:
+        K_local.mul_(float(ns_local))
     dist.all_reduce(K_local, group=group)
     dist.all_reduce(cnt, group=group)
     K_local.div_(cnt.item())

@@ -206,7 +206,8 @@ GB200_API int gb200_lm_batch_bed(gb200_ctx *ctx, const unsigned char *bed, const
 
 /* ---- multivariate LMM (BASELINE config 5): MVLMM::AnalyzeBimbam / AnalyzePlink, src/mvlmm.cpp:2972-3899, -lmm 1/2/3/4.
  * Two phenotypes, 1..3 covariates in this round.  Y: n x n_ph (ld ldy) of the analysed individuals.  setup rotates W and Y, and runs the
- * univariate REML fits of MphInitial (:2786-2796); null = EM + Newton-Raphson for REML then ML (:3047-3133; the per-SNP fits start from the
+ * univariate REML fits of MphInitial (:2786-2796; with the l_min / l_max / n_region of a preceding gb200_lmm_params call, else 1e-5 / 1e5 / 10;
+ * on return the univariate state of the context is that of gb200_lmm_setup with the FIRST phenotype); null = EM + Newton-Raphson for REML then ML (:3047-3133; the per-SNP fits start from the
  * ML estimates, :3205-3207); batch = per SNP: REML EM (em_iter/10, em_prec*10), MphCalcP, Newton-Raphson refinement when p < 0.001
  * (:3334-3347); a_mode 2 / 3 / 4 add the likelihood-ratio (ML EM + NR, :3310-3332) and score (:3297-3307) branches.  out: l rows of 8 doubles
  * {beta_1, beta_2, Vbeta_11, Vbeta_12, Vbeta_22, p_wald, p_lrt, p_score} (the columns of MVLMM::WriteFiles, :117-210; tests not run stay 0).

@@ -136,3 +136,20 @@ def test_plink_reader_refuses_malformed_bed(tmp_path):
     assert r.returncode != 0 and "not a PLINK .bed file" in r.stdout + r.stderr
     r = run(b"\x6c\x1b\x00" + payload)
     assert r.returncode != 0 and "individual-major" in r.stdout + r.stderr
+
+
+def test_blank_lines_in_the_genotype_file_do_not_shift_snps(golden_dir, tmp_path):
+    """Lines without a token (empty, or blanks / tabs only) are dropped by the line pipeline itself, so the QC pass and the later
+    passes (which index the QC flags by line number) number the SNP lines identically."""
+    import gzip
+    d = os.path.join(golden_dir, "BXD")
+    args = ["-p", d + "/BXD_pheno.txt", "-a", d + "/BXD_snps.txt", "-maf", "0.1"]
+    _, rows0 = _qc(["-g", d + "/BXD_geno.txt.gz"] + args, tmp_path, "plain")
+    lines = gzip.open(d + "/BXD_geno.txt.gz", "rt").read().split("\n")
+    for pos, junk in ((3, ""), (40, " \t "), (41, ""), (2000, "\t")):
+        lines.insert(pos, junk)
+    holes = str(tmp_path / "holes.txt")
+    with open(holes, "w") as f:
+        f.write("\n".join(lines) + "\n\n")
+    _, rows1 = _qc(["-g", holes] + args, tmp_path, "holes")
+    assert rows1 == rows0

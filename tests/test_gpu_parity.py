@@ -504,6 +504,39 @@ def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
     assert np.allclose(a, b, rtol=1e-5, atol=1e-8) and [l.split("\t")[:7] for l in lb] == [l.split("\t")[:7] for l in lines]
 
 
+_REPORT = {}
+
+
+def _record_cli_deviations(name, header, ids, xa, xb, rtol, lam_cols=()):
+    """Whole-file comparison of two CLIs' statistics columns: returns the mask of rows with a cell beyond its tolerance and
+    RECORDS them -- count, worst relative deviation per column and the SNPs concerned -- in gpurun_out/cli_parity_report.json
+    (copied to profiles/ after a GPU run), so that an allowance in an assert is never a blind one."""
+    cols = header[7:]
+    ok = np.isfinite(xb)
+    assert np.array_equal(np.isfinite(xa), ok), "NaN pattern differs"
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(ok, np.abs(xa - xb) / np.maximum(np.abs(xb), 1e-300), 0.0)
+    tol = np.array([2e-5 if j in lam_cols else rtol for j in range(len(cols))])      # lambda: the Newton stopping tolerance is 1e-5
+    bad = rel > tol[None, :]
+    rows = np.nonzero(bad.any(axis=1))[0]
+    entry = {"rows_compared": int(xa.shape[0]), "rows_beyond_tolerance": int(len(rows)), "tolerance": {c: float(t) for c, t in zip(cols, tol)},
+             "max_rel_dev_all_rows": {c: float(rel[:, j].max()) for j, c in enumerate(cols)},
+             "cells_beyond_tolerance": {c: int(bad[:, j].sum()) for j, c in enumerate(cols)},
+             "snps": [{"rs": ids[r][1], "cols": {cols[j]: [float(xa[r, j]), float(xb[r, j])] for j in np.nonzero(bad[r])[0]},
+                       "lambda_rel_dev": {cols[j]: float(rel[r, j]) for j in lam_cols}} for r in rows[:40]]}
+    _REPORT[name] = entry
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    path = os.path.join(root, "gpurun_out", "cli_parity_report.json")
+    try:
+        prev = json.load(open(path))
+    except Exception:
+        prev = {}
+    prev.update(_REPORT)
+    json.dump(prev, open(path, "w"), indent=1)
+    return bad, rel
+
+
 def _assoc_table(path):
     lines = open(path).read().splitlines()
     hdr = lines[0].split("\t")
@@ -535,12 +568,15 @@ def test_cli_against_the_reference_cli_end_to_end(golden_dir, tmp_path):
         ha, na, xa = _assoc_table(os.path.join(out, a + ".assoc.txt")); hb, nb, xb = _assoc_table(os.path.join(out, b + ".assoc.txt"))
         assert ha == hb and na == nb                                   # ids, positions, n_miss, alleles, af: text for text
         lam = [i for i, h in enumerate(ha[7:]) if h.startswith("l_")]
-        for j in range(xa.shape[1]):
-            ok = np.isfinite(xb[:, j])
-            assert np.array_equal(np.isfinite(xa[:, j]), ok), ha[7 + j]
-            tol = 2e-5 if j in lam else rtol                            # 7 printed digits; lambda: Newton tolerance
-            bad = ~np.isclose(xa[ok, j], xb[ok, j], rtol=tol, atol=0)
-            assert bad.mean() <= 0.001, (ha[7 + j], int(bad.sum()))     # borderline Brent/Newton iteration counts flip rarely
+        bad, rel = _record_cli_deviations("lmm:%s_vs_%s" % (a, b), ha, na, xa, xb, rtol, lam)     # 7 printed digits -> 2e-6
+        # The only rows allowed beyond the tolerance are those where the optimiser itself stopped on another iterate: CalcLambda
+        # reports the Newton iterate BEFORE the one that met |dl| < 1e-5 |l| (src/lmm.cpp:2096), so a last-bit difference in a
+        # borderline convergence test moves lambda by ~1e-5 and the lambda-dependent columns with it.  Such a row must show the
+        # lambda shift, stay within 1e-4 everywhere, and the rows are counted and named in the report.
+        for r in np.nonzero(bad.any(axis=1))[0]:
+            assert lam and max(rel[r, j] for j in lam) > 1e-6, ("deviation without a lambda shift", na[r][1], rel[r].tolist())
+            assert rel[r].max() < 1e-4, (na[r][1], rel[r].tolist())
+        assert bad.any(axis=1).mean() <= 0.001, int(bad.any(axis=1).sum())
         return xa.shape[0]
 
     d = os.path.join(golden_dir, "mouse_hs1940")
@@ -736,8 +772,9 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
         fa = [x.split("\t") for x in mine[1:]]; fb = [x.split("\t") for x in lines[1:]]
         assert [x[:7] for x in fa] == [x[:7] for x in fb]
         xa = np.array([[float(v) for v in x[7:]] for x in fa]); xb = np.array([[float(v) for v in x[7:]] for x in fb])
-        bad = ~np.isclose(xa, xb, rtol=5e-6, atol=0)
-        assert bad.any(axis=1).mean() <= 0.002, int(bad.any(axis=1).sum())       # EM stops on |dlogl| < 1e-3: borderline iteration counts flip rarely
+        bad, rel = _record_cli_deviations("mvlmm:-lmm 1 whole mouse file", mine[0].split("\t"), fa, xa, xb, 5e-6)
+        # MphEM stops on |dlogl| < em_prec (src/mvlmm.cpp:1177-1181): a borderline step flips the iteration count; counted + named in the report
+        assert bad.any(axis=1).mean() <= 0.002 and rel.max() < 1e-3, (int(bad.any(axis=1).sum()), float(rel.max()))
         # -lmm 4 (Wald + LRT + score) on every 12th SNP
         snps = os.path.join(cwd, "sub.txt")
         with open(snps, "w") as f:
@@ -749,8 +786,8 @@ def test_mvlmm_entry_points_match_restatement_and_reference_cli(ctx, golden_dir,
         a4 = open(os.path.join(out, "mymv4.assoc.txt")).read().splitlines(); b4 = open(os.path.join(out, "mv4.assoc.txt")).read().splitlines()
         assert len(a4) == len(b4) and a4[0] == b4[0]
         xa = np.array([[float(v) for v in x.split("\t")[7:]] for x in a4[1:]]); xb = np.array([[float(v) for v in x.split("\t")[7:]] for x in b4[1:]])
-        bad = ~np.isclose(xa, xb, rtol=5e-6, atol=0)
-        assert bad.any(axis=1).mean() <= 0.005, int(bad.any(axis=1).sum())
+        bad, rel = _record_cli_deviations("mvlmm:-lmm 4 every 12th mouse SNP", a4[0].split("\t"), [x.split("\t") for x in a4[1:]], xa, xb, 5e-6)
+        assert bad.any(axis=1).mean() <= 0.005 and rel.max() < 1e-3, (int(bad.any(axis=1).sum()), float(rel.max()))
 
 
 # ---- kinship on the int8 tensor pipe (exact Z Z^T + rank-one centring) vs the FP64 oracle -------------
@@ -967,6 +1004,19 @@ def test_cli_plink_gk_and_lmm4_match_oracle(tmp_path):
     for col, key in zip(range(8), ("beta", "se", "logl_H1", "lambda_remle", "lambda_mle", "p_wald", "p_lrt", "p_score")):
         tol = 2e-4 if key.startswith("lambda") else 2e-6
         assert np.allclose(got[:, col], ref[key], rtol=tol, atol=1e-12), key
+    # -gwasnps with PLINK input: every row of the filtered run is, text for text, the row of the same SNP in the unfiltered run
+    # (the reference's AnalyzePlink tests all SNPs while WriteFiles skips rows, which shifts statistics onto other SNPs)
+    sub = [int(s) for s in sel[3::7]]
+    gw = str(tmp_path / "gw.txt")
+    with open(gw, "w") as f:
+        f.write("".join("snp%d\n" % s for s in sub))
+    r = subprocess.run([cli, "-bfile", prefix, "-gwasnps", gw, "-k", out + "/k.cXX.txt", "-lmm", "4", "-o", "g", "-outdir", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    full = {ln.split("\t")[1]: ln for ln in lines[1:]}
+    glines = open(out + "/g.assoc.txt").read().splitlines()
+    assert glines[0] == lines[0] and len(glines) == 1 + len(sub)
+    assert glines[1:] == [full["snp%d" % s] for s in sub]
 
 
 def test_qc_bed_statistics_match_host_restatement(ctx):
