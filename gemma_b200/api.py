@@ -55,6 +55,8 @@ SIGNATURES = {
     "gb200_profile_enable": (C.c_int, [_vp, C.c_int]),
     "gb200_profile_reset": (C.c_int, [_vp]),
     "gb200_profile_get": (C.c_int, [_vp, C.c_char_p, _dp, C.POINTER(C.c_long)]),
+    "gb200_measure_fp64_fma": (C.c_int, [_vp, C.c_double, _dp, _dp]),
+    "gb200_lmm_counters": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.c_int]),
     "gb200_dgemm": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_double, _vp, _sz, _sz, _sz, _vp, _sz, _sz, _sz,
                               C.c_double, _vp, _sz, _sz, _sz]),
     "gb200_kin_begin": (C.c_int, [_vp, _sz, C.c_int]),
@@ -66,6 +68,7 @@ SIGNATURES = {
     "gb200_kin_finish_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "gb200_eigh": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, _vp, _sz, _vp, _dp, C.POINTER(C.c_int),
                              C.POINTER(C.c_int)]),
+    "gb200_eigh_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _vp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gb200_qc_bed": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp]),
     "gb200_lmm_setup": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
     "gb200_lmm_setup_rotated": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
@@ -175,6 +178,16 @@ class Context:
         self._chk(self.lib.gb200_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def measure_fp64_fma(self, seconds=0.5):
+        t, ms = C.c_double(), C.c_double()
+        self._chk(self.lib.gb200_measure_fp64_fma(self.h, seconds, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    def lmm_counters(self, reset=False):
+        a = (C.c_ulonglong * 6)()
+        self._chk(self.lib.gb200_lmm_counters(self.h, a, int(reset)))
+        return dict(zip(("common_slots", "order1", "order2", "order3", "with_logdet", "snps"), [int(x) for x in a]))
+
     # ---- fast_dgemm seam
     def dgemm(self, TransA, TransB, alpha, A, B, beta, Cm):
         A, B = _f64(A), _f64(B)
@@ -225,6 +238,12 @@ class Context:
         self._chk(self.lib.gb200_eigh(self.h, _ptr(G), n, n, int(center), _ptr(U), n, _ptr(ev), C.byref(tr),
                                       C.byref(nz), C.byref(nn)))
         return U, ev, tr.value, nz.value
+
+    def eigh_dev(self, G_dev, n, U_dev, eval_dev, center=True):
+        """Device pointers (ints): G_dev is destroyed; returns (trace_G, n_zero, n_negative)."""
+        tr = C.c_double(); nz = C.c_int(); nn = C.c_int()
+        self._chk(self.lib.gb200_eigh_dev(self.h, G_dev, n, int(center), U_dev, eval_dev, C.byref(tr), C.byref(nz), C.byref(nn)))
+        return tr.value, nz.value, nn.value
 
     # ---- SNP QC statistics (PLINK)
     def qc_bed(self, bed, ni_total, idv_mask=None, W=None):

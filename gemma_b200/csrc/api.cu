@@ -35,6 +35,17 @@ static bool trans_flag(const char *t, bool *ok) {
   return t && (t[0] == 'T' || t[0] == 't');
 }
 
+// SNPs per internal sub-batch of the bed entry points: the FP64 U^T X staging buffer (chunk x n_c doubles) stays near 4 GB
+// (8192 SNPs at n = 50 000: 32 x 1042 tile pairs = 450.6 waves of the 74 CTA pairs, 99.9% wave efficiency)
+static size_t lmm_chunk_snps(const gb200_ctx *c) {
+  if (c->batch_chunk > 0) return (size_t)c->batch_chunk;
+  size_t ch = ((size_t)4 << 30) / (c->n_c * sizeof(double));
+  ch = ch / 2048 * 2048;
+  if (ch < 2048) ch = 2048;
+  if (ch > 65536) ch = 65536;
+  return ch;
+}
+
 extern "C" {
 
 int gb200_abi_version(void) { return GB200_ABI_VERSION; }
@@ -58,7 +69,7 @@ int gb200_create(gb200_ctx **out, int device, void *stream) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return GB200_ERR_CUDA; }
   c->num_sms = prop.multiProcessorCount;
-  if (c->dTicket.reserve(64) != cudaSuccess) { delete c; return GB200_ERR_CUDA; }
+  if (c->dTicket.reserve(128) != cudaSuccess || cudaMemset(c->dTicket.p, 0, 128) != cudaSuccess) { delete c; return GB200_ERR_CUDA; }
   *out = c;
   return GB200_OK;
 }
@@ -81,6 +92,10 @@ void gb200_destroy(gb200_ctx *c) {
   if (c->i8.tmap_ka) free(c->i8.tmap_ka);
   if (c->i8.tmap_kb) free(c->i8.tmap_kb);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+  for (int k = 0; k < 2; ++k) { if (c->evCopy[k]) cudaEventDestroy(c->evCopy[k]); if (c->evUsed[k]) cudaEventDestroy(c->evUsed[k]); }
+  if (c->evStart) cudaEventDestroy(c->evStart);
+  c->dBed2.release();
   for (int k = 0; k < 2; ++k) { if (c->evG[k]) cudaEventDestroy(c->evG[k]); if (c->evL[k]) cudaEventDestroy(c->evL[k]); }
   c->dUtXt2.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -126,6 +141,15 @@ int gb200_profile_get(gb200_ctx *c, const char *name, double *ms, long *launches
   return GB200_OK;
 }
 
+int gb200_lmm_counters(gb200_ctx *c, unsigned long long counts[6], int reset) {
+  if (!c) return GB200_ERR_ARG;
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (counts) GB_CUDA(c, cudaMemcpy(counts, c->dTicket.as<unsigned long long>() + 4, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) GB_CUDA(c, cudaMemset(c->dTicket.as<unsigned long long>() + 4, 0, 8 * sizeof(unsigned long long)));
+  c->count_work = true;                  // counting starts with the first query
+  return GB200_OK;
+}
+
 int gb200_set_option(gb200_ctx *c, const char *name, long value) {
   if (!c || !name) return GB200_ERR_ARG;
   if (!strcmp(name, "utx_path")) {
@@ -160,6 +184,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "lmm_hoist must be 0 or 1");
     c->lmm_hoist = value; return GB200_OK;
   }
+  if (!strcmp(name, "batch_chunk")) {
+    if (value < 0 || value > (1 << 20) || (value % 256) != 0) return set_err(c, GB200_ERR_ARG, "batch_chunk must be 0 (auto) or a multiple of 256");
+    c->batch_chunk = value; return GB200_OK;
+  }
   if (!strcmp(name, "n_slices")) {
     if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "n_slices must be 0..8");
     if (value != c->n_slices) c->i8.ready = false;
@@ -180,6 +208,8 @@ int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
   if (!strcmp(name, "kin_miss_max_permille")) { *value = (long)(c->kin_miss_max * 1000.0 + 0.5); return GB200_OK; }
   if (!strcmp(name, "lmm_kernel")) { *value = c->lmm_kernel; return GB200_OK; }
   if (!strcmp(name, "lmm_hoist")) { *value = c->lmm_hoist; return GB200_OK; }
+  if (!strcmp(name, "batch_chunk")) { *value = c->n_c ? (long)lmm_chunk_snps(c) : c->batch_chunk; return GB200_OK; }
+  if (!strcmp(name, "eigh_workspace_bytes")) { *value = (long)c->eigh_workspace_bytes; return GB200_OK; }
   return set_err(c, GB200_ERR_ARG, std::string("unknown option ") + name);
 }
 
@@ -455,6 +485,7 @@ static LmmConst make_const(gb200_ctx *c) {
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
   D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.xcov = nullptr; D.xcov_idx = 0;
+  D.cnt = c->count_work ? c->dTicket.as<unsigned long long>() + 4 : nullptr;     // 8 words behind the ticket words
   D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
   D.gen_stride = 0;
   return D;
@@ -743,6 +774,18 @@ static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *i
   int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
   if (rc) return rc;
   return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, out_dev, /*plink_rule=*/true);   // AnalyzePlink semantics
+}
+
+// any number of device-resident rows: sub-batches of lmm_chunk_snps() through lmm_bed_core, serially on the context stream
+static int lmm_bed_chunked_dev(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total, size_t l,
+                               size_t bytes_per_snp, gb200_sumstat *out_dev) {
+  const size_t chunk = lmm_chunk_snps(c);
+  for (size_t s0 = 0; s0 < l; s0 += chunk) {
+    const size_t lc = (l - s0 < chunk) ? (l - s0) : chunk;
+    int rc = lmm_bed_core(c, bed_dev + s0 * bytes_per_snp, idx_dev, ni_total, lc, bytes_per_snp, out_dev + s0);
+    if (rc) return rc;
+  }
+  return GB200_OK;
 }
 
 static int upload_idx_from_mask(gb200_ctx *c, const unsigned char *idv_mask, size_t ni_total, const int **idx_dev) {
@@ -1099,11 +1142,38 @@ int gb200_lmm_batch_bed(gb200_ctx *c, const unsigned char *bed, const unsigned c
   const int *idx_dev = nullptr;
   rc = upload_idx_from_mask(c, idv_mask, ni_total, &idx_dev);
   if (rc) return rc;
-  GB_CUDA(c, c->dBed.reserve(l * bytes_per_snp));
+  // Double-buffered streamer: the rows of sub-batch i+1 travel host -> device on a copy stream while the
+  // kernels of sub-batch i run on the context stream; with pinned host rows the copies are fully asynchronous, with pageable
+  // rows the call blocks in the driver's staging copy while the already queued kernels execute.  One small D2H of the
+  // SUMSTAT rows (64 B per SNP) ends the call.
+  const size_t chunk = lmm_chunk_snps(c);
+  const size_t cl = l < chunk ? l : chunk;
+  GB_CUDA(c, c->dBed.reserve(cl * bytes_per_snp));
+  if (l > chunk) GB_CUDA(c, c->dBed2.reserve(cl * bytes_per_snp));
   GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
-  GB_CUDA(c, cudaMemcpyAsync(c->dBed.p, bed, l * bytes_per_snp, cudaMemcpyHostToDevice, c->stream));
-  rc = lmm_bed_core(c, c->dBed.as<unsigned char>(), idx_dev, ni_total, l, bytes_per_snp, c->dOut.as<gb200_sumstat>());
-  if (rc) return rc;
+  if (!c->copy) {
+    GB_CUDA(c, cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      GB_CUDA(c, cudaEventCreateWithFlags(&c->evCopy[k], cudaEventDisableTiming));
+      GB_CUDA(c, cudaEventCreateWithFlags(&c->evUsed[k], cudaEventDisableTiming));
+    }
+    GB_CUDA(c, cudaEventCreateWithFlags(&c->evStart, cudaEventDisableTiming));
+  }
+  unsigned char *buf[2] = {c->dBed.as<unsigned char>(), l > chunk ? c->dBed2.as<unsigned char>() : c->dBed.as<unsigned char>()};
+  GB_CUDA(c, cudaEventRecord(c->evStart, c->stream));            // everything queued earlier on the context stream (mask upload, ...)
+  GB_CUDA(c, cudaStreamWaitEvent(c->copy, c->evStart, 0));
+  size_t i = 0;
+  for (size_t s0 = 0; s0 < l; s0 += chunk, ++i) {
+    const size_t lc = (l - s0 < chunk) ? (l - s0) : chunk;
+    const int b = (int)(i & 1);
+    if (i >= 2) GB_CUDA(c, cudaStreamWaitEvent(c->copy, c->evUsed[b], 0));          // the kernels of sub-batch i-2 are done with this buffer
+    GB_CUDA(c, cudaMemcpyAsync(buf[b], bed + s0 * bytes_per_snp, lc * bytes_per_snp, cudaMemcpyHostToDevice, c->copy));
+    GB_CUDA(c, cudaEventRecord(c->evCopy[b], c->copy));
+    GB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopy[b], 0));
+    rc = lmm_bed_core(c, buf[b], idx_dev, ni_total, lc, bytes_per_snp, c->dOut.as<gb200_sumstat>() + s0);
+    if (rc) return rc;
+    GB_CUDA(c, cudaEventRecord(c->evUsed[b], c->stream));
+  }
   GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   return GB200_OK;
@@ -1127,7 +1197,7 @@ int gb200_lmm_batch_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const un
   } else if (ni_total != c->n) {
     return set_err(c, GB200_ERR_ARG, "idv_mask == NULL requires ni_total == n");
   }
-  return lmm_bed_core(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, out_dev);
+  return lmm_bed_chunked_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp, out_dev);
 }
 
 int gb200_lmm_project_bed(gb200_ctx *c, const unsigned char *bed, const unsigned char *idv_mask, size_t ni_total,

@@ -114,8 +114,14 @@ struct gb200_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t evG[2] = {nullptr, nullptr}, evL[2] = {nullptr, nullptr};
   gb::DevBuf dUtXt2;
+  // double-buffered host -> device streamer of gb200_lmm_batch_bed
+  cudaStream_t copy = nullptr;
+  cudaEvent_t evCopy[2] = {nullptr, nullptr}, evUsed[2] = {nullptr, nullptr}, evStart = nullptr;
+  gb::DevBuf dBed2;
+  long batch_chunk = 0;       // SNPs per internal sub-batch of the bed entry points (0 = auto, see lmm_chunk_snps)
   long overlap = 0;           // 1 = pipelined sub-batches.  Measured SLOWER on B200 (136 vs 113 ms per 8192 SNPs at n = 50 000:
                               // the co-resident kernels contend and the power cap bites harder), so off by default
+  bool count_work = false;    // lockstep kernel tallies its executed passes (gb200_lmm_counters)
   long kernel_launches = 0;   // kernels of this library launched so far (bench "gpu_launches")
   // options
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
@@ -127,6 +133,7 @@ struct gb200_ctx {
   long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA, 3 = any-covariate-count kernel
   long lmm_hoist = 1;    // lockstep kernel: SNP-independent sums at the shared lambdas computed once per run
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)
+  size_t eigh_workspace_bytes = 0;   // device workspace of the last eigendecomposition (reported by bench.py)
   gb::I8State i8;
 };
 

@@ -34,18 +34,17 @@ __global__ void zero_small_kernel(double *eval, size_t n, double *stats) {
 
 using namespace gb;
 
-extern "C" int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int center, double *U,
-                          size_t ldu, double *eval, double *trace_G, int *n_zero, int *n_negative) {
-  if (!ctx) return GB200_ERR_ARG;
-  if (!G || !U || !eval || n == 0 || ldg < n || ldu < n) return set_err(ctx, GB200_ERR_ARG, "gb200_eigh: bad argument");
+// Device-resident core: dA (n x n, ld n; destroyed) -> dV (n x n, eigenvectors in COLUMNS of the row-major matrix), dW (n + 4 doubles:
+// eigenvalues ascending with the < 1e-10 zeroing applied, then 3 statistics).  The only large temporary is cuSOLVER's workspace.
+static int eigh_device(gb200_ctx *ctx, double *dA, size_t n, int center, double *dV, double *dW, double *trace_G, int *n_zero,
+                       int *n_negative) {
   cudaStream_t st = ctx->stream;
-  DevBuf dA, dV, dW, dWork, dInfo, dRow;
-  int rc = GB200_OK;
+  DevBuf dWork, dInfo, dRow;
   cusolverDnHandle_t h = nullptr;
   cusolverDnParams_t params = nullptr;
   void *hWork = nullptr;
   auto cleanup = [&]() {
-    dA.release(); dV.release(); dW.release(); dWork.release(); dInfo.release(); dRow.release();
+    dWork.release(); dInfo.release(); dRow.release();
     if (params) cusolverDnDestroyParams(params);
     if (h) cusolverDnDestroy(h);
     if (hWork) free(hWork);
@@ -67,17 +66,12 @@ extern "C" int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int c
                                                  std::to_string((int)_s));                 \
     }                                                                                      \
   } while (0)
-
-  EIGH_CUDA(dA.reserve(n * n * sizeof(double)));
-  EIGH_CUDA(dW.reserve((n + 4) * sizeof(double)));
   EIGH_CUDA(dInfo.reserve(sizeof(int)));
-  EIGH_CUDA(cudaMemcpy2DAsync(dA.p, n * sizeof(double), G, ldg * sizeof(double), n * sizeof(double), n,
-                              cudaMemcpyHostToDevice, st));
   {
     ProfScope ps(ctx, "eigh");
     if (center) {
       EIGH_CUDA(dRow.reserve((n + 1) * sizeof(double)));
-      EIGH_CUDA(launch_center_matrix(dA.as<double>(), n, n, dRow.as<double>(), st));
+      EIGH_CUDA(launch_center_matrix(dA, n, n, dRow.as<double>(), st));
     }
     EIGH_SOLVER(cusolverDnCreate(&h));
     EIGH_SOLVER(cusolverDnSetStream(h, st));
@@ -87,12 +81,13 @@ extern "C" int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int c
     // Fortran with UPLO='L' (src/lapack.cpp:205), i.e. the row-major UPPER triangle; for
     // cuSOLVER's column-major view that is CUBLAS_FILL_MODE_LOWER as well.
     EIGH_SOLVER(cusolverDnXsyevd_bufferSize(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
-                                            (int64_t)n, CUDA_R_64F, dA.p, (int64_t)n, CUDA_R_64F, dW.p,
+                                            (int64_t)n, CUDA_R_64F, dA, (int64_t)n, CUDA_R_64F, dW,
                                             CUDA_R_64F, &wdev, &whost));
+    ctx->eigh_workspace_bytes = wdev;
     EIGH_CUDA(dWork.reserve(wdev ? wdev : 8));
     if (whost) { hWork = malloc(whost); if (!hWork) { cleanup(); return set_err(ctx, GB200_ERR_NOMEM, "host workspace"); } }
     EIGH_SOLVER(cusolverDnXsyevd(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int64_t)n,
-                                 CUDA_R_64F, dA.p, (int64_t)n, CUDA_R_64F, dW.p, CUDA_R_64F, dWork.p, wdev,
+                                 CUDA_R_64F, dA, (int64_t)n, CUDA_R_64F, dW, CUDA_R_64F, dWork.p, wdev,
                                  hWork, whost, dInfo.as<int>()));
     int info = 0;
     EIGH_CUDA(cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -104,20 +99,62 @@ extern "C" int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int c
     dWork.release();
     // cuSOLVER leaves eigenvector j in column j of the column-major array == row j of the
     // row-major view; transpose so that U[i][j] = v_j[i] (eigenvectors in columns).
-    EIGH_CUDA(dV.reserve(n * n * sizeof(double)));
-    EIGH_CUDA(launch_transpose(dA.as<double>(), n, n, n, dV.as<double>(), n, st));
-    zero_small_kernel<<<1, 256, 0, st>>>(dW.as<double>(), n, dW.as<double>() + n);
+    EIGH_CUDA(launch_transpose(dA, n, n, n, dV, n, st));
+    zero_small_kernel<<<1, 256, 0, st>>>(dW, n, dW + n);
     EIGH_CUDA(cudaGetLastError());
   }
   double stats[3];
-  EIGH_CUDA(cudaMemcpy2DAsync(U, ldu * sizeof(double), dV.p, n * sizeof(double), n * sizeof(double), n,
-                              cudaMemcpyDeviceToHost, st));
-  EIGH_CUDA(cudaMemcpyAsync(eval, dW.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  EIGH_CUDA(cudaMemcpyAsync(stats, dW.as<double>() + n, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  EIGH_CUDA(cudaMemcpyAsync(stats, dW + n, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   EIGH_CUDA(cudaStreamSynchronize(st));
   if (trace_G) *trace_G = stats[0] / (double)n;
   if (n_zero) *n_zero = (int)stats[1];
   if (n_negative) *n_negative = (int)stats[2];
   cleanup();
+  return GB200_OK;
+#undef EIGH_CUDA
+#undef EIGH_SOLVER
+}
+
+extern "C" int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int center, double *U,
+                          size_t ldu, double *eval, double *trace_G, int *n_zero, int *n_negative) {
+  if (!ctx) return GB200_ERR_ARG;
+  if (!G || !U || !eval || n == 0 || ldg < n || ldu < n) return set_err(ctx, GB200_ERR_ARG, "gb200_eigh: bad argument");
+  cudaStream_t st = ctx->stream;
+  DevBuf dA, dV, dW;
+  auto fail = [&](cudaError_t e, const char *what) {
+    dA.release(); dV.release(); dW.release();
+    return set_err(ctx, GB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  if ((e = dA.reserve(n * n * sizeof(double))) != cudaSuccess) return fail(e, "gb200_eigh: alloc A");
+  if ((e = dV.reserve(n * n * sizeof(double))) != cudaSuccess) return fail(e, "gb200_eigh: alloc V");
+  if ((e = dW.reserve((n + 4) * sizeof(double))) != cudaSuccess) return fail(e, "gb200_eigh: alloc W");
+  if ((e = cudaMemcpy2DAsync(dA.p, n * sizeof(double), G, ldg * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return fail(e, "gb200_eigh: copy in");
+  int rc = eigh_device(ctx, dA.as<double>(), n, center, dV.as<double>(), dW.as<double>(), trace_G, n_zero, n_negative);
+  if (rc) { dA.release(); dV.release(); dW.release(); return rc; }
+  dA.release();
+  if ((e = cudaMemcpy2DAsync(U, ldu * sizeof(double), dV.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+    return fail(e, "gb200_eigh: copy U");
+  if ((e = cudaMemcpyAsync(eval, dW.p, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(e, "gb200_eigh: copy eval");
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "gb200_eigh: sync");
+  dA.release(); dV.release(); dW.release();
+  return GB200_OK;
+}
+
+// Device-resident variant: G_dev (n x n, ld n) is destroyed, U_dev (n x n, ld n) and eval_dev (n) are caller-owned device buffers.
+extern "C" int gb200_eigh_dev(gb200_ctx *ctx, double *G_dev, size_t n, int center, double *U_dev, double *eval_dev, double *trace_G,
+                              int *n_zero, int *n_negative) {
+  if (!ctx) return GB200_ERR_ARG;
+  if (!G_dev || !U_dev || !eval_dev || n == 0 || G_dev == U_dev) return set_err(ctx, GB200_ERR_ARG, "gb200_eigh_dev: bad argument");
+  DevBuf dW;
+  if (dW.reserve((n + 4) * sizeof(double)) != cudaSuccess) return set_err(ctx, GB200_ERR_NOMEM, "gb200_eigh_dev: alloc");
+  int rc = eigh_device(ctx, G_dev, n, center, U_dev, dW.as<double>(), trace_G, n_zero, n_negative);
+  if (rc == GB200_OK) {
+    cudaError_t e = cudaMemcpyAsync(eval_dev, dW.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = set_err(ctx, GB200_ERR_CUDA, std::string("gb200_eigh_dev: ") + cudaGetErrorString(e));
+  }
+  dW.release();
   return rc;
 }

@@ -41,6 +41,7 @@ struct LmmConst {
   int n_common;
   const double *xcov;    // G x E: covariate column xcov_idx is this per-SNP vector (U^T x) instead of a row of Wt; null otherwise
   int xcov_idx;
+  unsigned long long *cnt;  // optional work counters of the lockstep kernel (gb200_lmm_counters); null = off
   int nc_gen;            // generic-covariate path (NC < 0 instantiations): number of swept covariates
   int gen_stride;        // doubles of shared-memory scratch per warp on that path (3 tables of (nc_gen+3)(nc_gen+2)/2)
 };

@@ -631,6 +631,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   double logdetI = 0.0, fRmin = 0.0, fLmin = 0.0, fRmax = 0.0, fLmax = 0.0;
   const bool need_search = needR || needL;
   double dummy[NIDX];
+  unsigned int tally2 = 0, tally3 = 0, tallyld = 0, tallyc = 0;   // executed passes of this warp by kind (work counters)
 
 #if GB_V2_TMA
   const bool hoist = (D.ctab != nullptr);
@@ -657,6 +658,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc);
       else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc);
       if (valid) {
+        tallyc += V2_NSC;
         if (with_I) {
           v2_assemble<NC>(D.ctab, acc.I, S1);
           Derived<NC, 1> dI;
@@ -778,6 +780,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       const bool wl[2] = {rq[0].need && rq[0].logdet, rq[1].need && rq[1].logdet};
       V2Eval ev[2];
       const bool any_ld = wl[0] || wl[1];
+      if (active) { if (Kmax >= 3) tally3++; else tally2++; if (any_ld) tallyld++; }
       if (Kmax >= 3) {
         V2Acc<NC, 2, 1, 3> acc;
         if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
@@ -817,6 +820,11 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   }
   out.beta = beta; out.se = se; out.lambda_remle = lambda_remle; out.lambda_mle = lambda_mle;
   out.p_wald = p_wald; out.p_lrt = p_lrt; out.p_score = p_score; out.logl_H1 = logl_H1;
+  if (D.cnt && valid && (threadIdx.x & 31) == 0) {
+    atomicAdd(D.cnt + 0, (unsigned long long)tallyc); atomicAdd(D.cnt + 1, (unsigned long long)tally2);
+    atomicAdd(D.cnt + 2, (unsigned long long)tally3); atomicAdd(D.cnt + 3, (unsigned long long)tallyld);
+    atomicAdd(D.cnt + 5, 1ull);
+  }
 }
 
 }  // namespace gb

@@ -80,6 +80,14 @@ GB200_API int gb200_profile_enable(gb200_ctx *ctx, int on);
 GB200_API int gb200_profile_reset(gb200_ctx *ctx);
 GB200_API int gb200_profile_get(gb200_ctx *ctx, const char *name, double *ms, long *launches);
 
+/* Measured plain (non-tensor) FP64 FMA rate of this device, TFLOP/s with an FMA counted as 2 flops: independent DFMA chains on every SM
+ * for about `seconds` -- the roofline denominator of the per-SNP kernel, which is FP64-issue bound (MEASURED_PEAKS.json has no FP64 figure). */
+GB200_API int gb200_measure_fp64_fma(gb200_ctx *ctx, double seconds, double *tflops, double *ms);
+/* Work counters of the lockstep per-SNP kernel since the last reset: lambda evaluations by kind
+ * {0: hoisted common-lambda slots, 1: order-1 (f / Wald), 2: order-2 (Brent), 3: order-3 (Newton), 4: evaluations with log-determinant,
+ *  5: SNPs}.  counts may be NULL to reset only.  Used by bench.py to state the kernel's executed FP64 flops. */
+GB200_API int gb200_lmm_counters(gb200_ctx *ctx, unsigned long long counts[6], int reset);
+
 /* ---- dense GEMM seam -------------------------------------------------------- */
 /* fast_dgemm / fast_eigen_dgemm (src/fastblas.h:36-41, src/fastblas.cpp:175-236):
  * C = alpha*op(A)*op(B) + beta*C on row-major matrices with leading dimensions.
@@ -123,6 +131,12 @@ GB200_API int gb200_kin_finish_dev(gb200_ctx *ctx, double **K_dev, size_t *ns_us
 GB200_API int gb200_eigh(gb200_ctx *ctx, double *G, size_t n, size_t ldg, int center,
                double *U, size_t ldu, double *eval, double *trace_G,
                int *n_zero, int *n_negative);
+
+/* Same with DEVICE buffers (e.g. the K gb200_kin_finish_dev left on the device): G_dev (n x n, ld n) is destroyed; U_dev (n x n, ld n)
+ * and eval_dev (n) are caller-owned device buffers distinct from G_dev.  At n = 50 000: 20 GB each for G and U plus cuSOLVER's
+ * workspace (option "eigh_workspace_bytes" reports it after the call). */
+GB200_API int gb200_eigh_dev(gb200_ctx *ctx, double *G_dev, size_t n, int center, double *U_dev, double *eval_dev,
+                   double *trace_G, int *n_zero, int *n_negative);
 
 /* ---- SNP QC statistics for PLINK input ------------------------------------- */
 /* The per-SNP counting pass of ReadFile_bed (src/gemma_io.cpp:951-1005) and the covariate-correlation terms of its

@@ -1,0 +1,123 @@
+"""Parity AT THE SIZES THE BENCH RUNS (BASELINE configs 2-4): the CUDA path through the C ABI against the reference's own
+code (oracle/_ref/libgemma_ref.so: src/lmm.cpp / src/gemma_io.cpp compiled in place) at n = 10 000 and n = 50 000, with the
+DEFAULT digit-plane count of the tensor-core projection, with and without 1 % missing genotypes.
+
+n = 10 000 runs the whole chain on the device: gb200_kin_* -> gb200_eigh -> gb200_lmm_setup / _null -> gb200_lmm_batch_bed.
+n = 50 000 uses a Haar-distributed orthogonal U (QR of a Gaussian matrix on the GPU, entries ~ N(0, 1/n) like the eigenvectors
+of a kinship matrix of unstructured genotypes) because a 50 000-wide eigendecomposition takes minutes; bench.py checks the same
+entry point on the U that gb200_eigh itself produced (its `parity` object)."""
+import os
+
+import numpy as np
+import pytest
+
+import gemma_b200
+from gemma_b200 import synth
+from oracle import oracle as O
+from oracle import ref as REF
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6          # north_star tolerance on beta / se / p-values
+FIELDS = ("beta", "se", "p_wald", "p_lrt", "p_score")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    m = ~np.isnan(b)
+    return float(np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-300))) if m.any() else 0.0
+
+
+def _check(got, ref, tag):
+    errs = {k: _rel(got[k], ref[k]) for k in FIELDS + ("lambda_remle", "lambda_mle", "logl_H1")}
+    for k in FIELDS:
+        assert errs[k] < REL, (tag, k, errs)
+    assert errs["lambda_remle"] < 5e-5 and errs["lambda_mle"] < 5e-5 and errs["logl_H1"] < 1e-8, (tag, errs)
+    return errs
+
+
+def _reference_rows(U_h, ev, UtW, Uty, G, nm):
+    """The reference's per-SNP code (LMM::Analyze's batch_compute, src/lmm.cpp:1513-1564) on the mean-imputed genotypes."""
+    X = O.lmm_impute(np.where(G < 0, np.nan, G))                 # n x l (src/lmm.cpp:1611-1618)
+    UtX = U_h.T @ X                                              # fast_dgemm("T","N",U,X) of src/lmm.cpp:1521
+    return REF.assoc_utx(ev, UtW, Uty, UtX, 4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+
+
+def _plink_rows(ctx, bed, n):
+    """AnalyzePlink semantics only differ from Analyze's on NaN rows (none here): same statistics."""
+    return ctx.lmm_batch_bed(bed, n)
+
+
+@pytest.fixture(scope="module")
+def have_ref():
+    try:
+        REF.lib()
+    except Exception as ex:                                      # pragma: no cover
+        pytest.skip("compiled reference (oracle/_ref) not shipped: %s" % ex)
+
+
+def test_whole_device_chain_vs_compiled_reference_n10000(have_ref, tmp_path):
+    """BASELINE configs 2/3 size: kinship (int8 tensor cores) vs the reference's PlinkKin, then eigendecomposition, null model and
+    -lmm 4 on PLINK rows with and without missing genotypes vs the reference's per-SNP code."""
+    n, pk = 10000, 6000
+    ctx = gemma_b200.Context(0)
+    # --- -gk 1 on 1 % missing data: gb200_kin_* vs PlinkKin (src/gemma_io.cpp:1599-1738) on the same PLINK files
+    bedk, Gk = synth.make_bed(n, pk, seed=71, miss_rate=0.01)
+    prefix = str(tmp_path / "k10k")
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01])); f.write(bedk.tobytes())
+    ctx.kin_begin(n, 1)
+    ctx.kin_add_bed(bedk)
+    K, ns = ctx.kin_finish()
+    assert ns == pk
+    Kref = REF.plink_kin(prefix, np.ones(pk, dtype=np.int32), 1, n)
+    dev = np.abs(K - Kref).max()
+    assert dev < 1e-11, dev                                      # entries O(1): exact integer GEMM + FP64 rank-one terms
+    # --- eigen + null model + association
+    U, ev, trace_G, _ = ctx.eigh(K, center=True)
+    rng = np.random.default_rng(5)
+    y = synth.phenotype(n, np.where(Gk[:64] < 0, 0, Gk[:64]), seed=9) + rng.standard_normal(n) * 0.1
+    W = np.ones((n, 1))
+    UtW, Uty = ctx.lmm_setup(U, ev, W, y)
+    nm = ctx.lmm_null(trace_G)
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    assert ctx.get_option("n_slices") == 5                       # the default plane count is what is being tested
+    for miss, seed in ((0.0, 72), (0.01, 73)):
+        bed, G = synth.make_bed(n, 48, seed=seed, snp_offset=10 ** 6, miss_rate=miss)
+        got = _plink_rows(ctx, bed, n)
+        ref = _reference_rows(U, ev, UtW, Uty, G, nm)
+        _check(got, ref, "n=10000 miss=%g" % miss)
+    ctx.close()
+
+
+def test_lmm4_bed_vs_compiled_reference_n50000_default_planes(have_ref):
+    """BASELINE config 4 size.  U is Haar (see the module docstring); the spectrum is kinship-like."""
+    import torch
+    n = 50000
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device=dev); g.manual_seed(20260923)
+        A = torch.randn((n, n), dtype=torch.float64, device=dev, generator=g)
+        U, _ = torch.linalg.qr(A)
+        del A
+        U = U.contiguous()
+        ev_h = synth.spectrum_like_kinship(n, 3)
+        y_h = synth.phenotype(n, synth.genotypes(n, 64, seed=4, snp_offset=10 ** 9).astype(np.float64), 4)
+        ev = torch.from_numpy(ev_h).to(dev); y = torch.from_numpy(y_h).to(dev)
+        UtWt = (torch.ones((1, n), dtype=torch.float64, device=dev) @ U).contiguous()
+        Uty = (y @ U).contiguous()
+        stream.synchronize()
+        ctx = gemma_b200.Context(0, stream=stream.cuda_stream)
+        ctx.lmm_setup_rotated_dev(n, 1, U.data_ptr(), ev.data_ptr(), UtWt.data_ptr(), Uty.data_ptr())
+        nm = ctx.lmm_null(float(ev_h.mean()))
+        ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+        assert ctx.get_option("n_slices") == 5
+        U_h = U.cpu().numpy(); UtW_h = UtWt.cpu().numpy().T.copy(); Uty_h = Uty.cpu().numpy()
+        for miss, seed in ((0.0, 81), (0.01, 82)):
+            bed, G = synth.make_bed(n, 32, seed=seed, miss_rate=miss)
+            got = ctx.lmm_batch_bed(bed, n)
+            ref = _reference_rows(U_h, ev_h, UtW_h, Uty_h, G, nm)
+            _check(got, ref, "n=50000 miss=%g" % miss)
+        ctx.close()
