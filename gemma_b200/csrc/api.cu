@@ -89,6 +89,8 @@ void gb200_destroy(gb200_ctx *c) {
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
+  if (c->i8.tmap_q) free(c->i8.tmap_q);
+  c->i8.holeq.release();
   if (c->i8.tmap_ka) free(c->i8.tmap_ka);
   if (c->i8.tmap_kb) free(c->i8.tmap_kb);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
@@ -184,6 +186,18 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "lmm_hoist must be 0 or 1");
     c->lmm_hoist = value; return GB200_OK;
   }
+  if (!strcmp(name, "gemm_groups")) {
+    if (value < 1 || value > 2) return set_err(c, GB200_ERR_ARG, "gemm_groups must be 1 or 2");
+    c->gemm_groups = value; return GB200_OK;
+  }
+  if (!strcmp(name, "gemm_panel")) {
+    if (value < 0 || value > 64) return set_err(c, GB200_ERR_ARG, "gemm_panel must be 0..64");
+    c->gemm_panel = value; return GB200_OK;
+  }
+  if (!strcmp(name, "stage_mask")) {
+    if (value < 1 || value > 3) return set_err(c, GB200_ERR_ARG, "stage_mask must be 1 (projection only), 2 (tests only, on the last projection) or 3");
+    c->stage_mask = value; return GB200_OK;
+  }
   if (!strcmp(name, "batch_chunk")) {
     if (value < 0 || value > (1 << 20) || (value % 256) != 0) return set_err(c, GB200_ERR_ARG, "batch_chunk must be 0 (auto) or a multiple of 256");
     c->batch_chunk = value; return GB200_OK;
@@ -209,6 +223,9 @@ int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
   if (!strcmp(name, "lmm_kernel")) { *value = c->lmm_kernel; return GB200_OK; }
   if (!strcmp(name, "lmm_hoist")) { *value = c->lmm_hoist; return GB200_OK; }
   if (!strcmp(name, "batch_chunk")) { *value = c->n_c ? (long)lmm_chunk_snps(c) : c->batch_chunk; return GB200_OK; }
+  if (!strcmp(name, "stage_mask")) { *value = c->stage_mask; return GB200_OK; }
+  if (!strcmp(name, "gemm_groups")) { *value = c->gemm_groups; return GB200_OK; }
+  if (!strcmp(name, "gemm_panel")) { *value = c->gemm_panel; return GB200_OK; }
   if (!strcmp(name, "eigh_workspace_bytes")) { *value = (long)c->eigh_workspace_bytes; return GB200_OK; }
   return set_err(c, GB200_ERR_ARG, std::string("unknown option ") + name);
 }
@@ -771,8 +788,11 @@ static int lmm_bed_core(gb200_ctx *c, const unsigned char *bed_dev, const int *i
     GB_CUDA(c, cudaStreamWaitEvent(c->stream, c->evL[1], 0));
     return GB200_OK;
   }
-  int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
-  if (rc) return rc;
+  if (c->stage_mask & 1) {
+    int rc = project_bed_dev(c, bed_dev, idx_dev, ni_total, l, bytes_per_snp);
+    if (rc) return rc;
+  }
+  if (!(c->stage_mask & 2)) return GB200_OK;       // measurement runs only: projection without the tests (stage_mask = 1)
   return lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, out_dev, /*plink_rule=*/true);   // AnalyzePlink semantics
 }
 

@@ -43,8 +43,9 @@ struct I8State {
   DevBuf slices;                 // n_slices x [n_pad(i: eigvec) x n_pad(j: individual)] int8, j contiguous
   DevBuf scale;                  // per-eigenvector power-of-two scale (n doubles)
   DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
-  DevBuf miss_mean;              // per-SNP mean (for the missing correction)
-  void *tmap_a = nullptr, *tmap_b = nullptr;   // CUtensorMap storage (host)
+  DevBuf miss_mean;              // per-SNP mean + hole count (+ holes per 256-SNP tile)
+  DevBuf holeq;                  // l_pad x n_pad int8 hole-indicator rows (second GEMM pass of the mean imputation)
+  void *tmap_a = nullptr, *tmap_b = nullptr, *tmap_q = nullptr;   // CUtensorMap storage (host)
   // kinship (K = Z Z^T on the int8 tensor pipe)
   DevBuf kin_zt;                 // individual-major int8 genotypes: n rows x kin_cap SNP columns
   DevBuf kin_stats;              // per staged SNP: int sum, int nmiss, double mean
@@ -118,6 +119,7 @@ struct gb200_ctx {
   cudaStream_t copy = nullptr;
   cudaEvent_t evCopy[2] = {nullptr, nullptr}, evUsed[2] = {nullptr, nullptr}, evStart = nullptr;
   gb::DevBuf dBed2;
+  long stage_mask = 3;        // measurement knob of the bed entry points: bit 0 = projection, bit 1 = per-SNP tests (kernel-isolated power / ncu runs)
   long batch_chunk = 0;       // SNPs per internal sub-batch of the bed entry points (0 = auto, see lmm_chunk_snps)
   long overlap = 0;           // 1 = pipelined sub-batches.  Measured SLOWER on B200 (136 vs 113 ms per 8192 SNPs at n = 50 000:
                               // the co-resident kernels contend and the power cap bites harder), so off by default
@@ -127,6 +129,8 @@ struct gb200_ctx {
   long utx_path = 0;     // 0 auto, 1 fp64 tiled, 2 int8 tensor core
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
+  long gemm_groups = 1;  // 2: pair kernel with two eigenvector groups per tile (shared genotype tile) and the hole pass on the tensor pipe; 1: one group, FP64 hole fix-up
+  long gemm_panel = 0;   // raster panel width of that kernel in 2-group units (0 = default 6)
   long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K; sparse FP64 terms for missing genotypes), 1 = FP64 only
   double kin_miss_max = 0.2;   // chunks with a larger fraction of missing genotypes take the dense FP64 path

@@ -132,6 +132,10 @@ struct I8KernelParams {
   int mode;                 // 0 = projection (T planes recombined, scaled, stored), 1 = kinship (K[i][j] += Z Z^T, lower triangle)
   const int2 *tiles;        // mode 1: explicit (m_blk, n_blk) list (lower-triangle tiles only)
   int num_tiles;
+  // i8_gemm_pair2_kernel only
+  const double *row_mean;   // mode 2: C[s][:] += row_mean[s] * (A . planes) * scale   (A = hole indicator rows)
+  const int *tile_holes;    // mode 2: holes per 256-row tile; tiles without a hole are skipped
+  int panel;                // raster panel width in units of NB eigenvector groups
 };
 
 __device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_groups, int &m_blk, int &n_grp) {
@@ -481,6 +485,174 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair kernel, TWO eigenvector groups per tile: the pair's 256 x 128 B genotype tile of a K-block is staged once and
+// multiplied with the plane rows of NB = 2 neighbouring groups (accumulators at TMEM columns 0 and 256: all 512 columns, single
+// buffered).  The L2 -> shared-memory bytes per MAC drop from (256 + 240) to (256 + 480) / 2 rows per 256 x 240 x 128 MACs (-26 %):
+// at 15 TB/s of operand traffic the projection sat on the L2 fabric (~6.3 kB/clk chip-wide), not on the tensor pipe.
+// The price is an epilogue that no longer overlaps the next tile's MMAs (~3 % of a tile).
+// mode 0: C = (A . planes) * scale          (A = genotypes with 0 at the holes)
+// mode 2: C += row_mean * (A . planes) * scale   (A = hole-indicator rows: the mean imputation of src/lmm.cpp:1819-1827 as a second
+//         GEMM pass on the same kernel; tiles whose 256 SNPs have no hole are skipped)
+template <int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+i8_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const I8KernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int halfN = p.N / 2;
+  const int a_bytes = I8_BM * I8_BK;
+  const int b_bytes = halfN * I8_BK;                       // this CTA's half of ONE group's plane rows
+  const int stage_bytes = a_bytes + NB * b_bytes;
+  uint64_t *bars = (uint64_t *)(smem + I8_STAGES * stage_bytes);
+  uint64_t *full = bars, *empty = bars + I8_STAGES;
+  uint64_t *tfull = bars + 2 * I8_STAGES, *tempty = bars + 2 * I8_STAGES + 1;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * I8_STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int n_units = (p.n_groups + NB - 1) / NB;
+  const int num_tiles = p.m_tiles * n_units;               // m_tiles counts 256-row tiles
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 8);              // 4 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto coords = [&](int tile, int &m_blk, int &unit) {
+    const int panel_tiles = p.panel * p.m_tiles;
+    const int pn = tile / panel_tiles;
+    const int first = pn * p.panel;
+    const int width = (n_units - first < p.panel) ? (n_units - first) : p.panel;
+    const int r = tile - pn * panel_tiles;
+    m_blk = r / width;
+    unit = first + r % width;
+  };
+  auto skip = [&](int m_blk) -> bool { return p.mode == 2 && p.tile_holes && __ldg(p.tile_holes + m_blk) == 0; };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, unit; coords(tile, m_blk, unit);
+        if (skip(m_blk)) continue;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+          if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * stage_bytes));
+          uint8_t *st = smem + stage * stage_bytes;
+          tma_load_2d_pair(&tmap_a, full_leader, st, kb * I8_BK, m_blk * 256 + (int)rank * I8_BM);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)        // rows past the last group are out of bounds of the tensor map: zero-filled
+            tma_load_2d_pair(&tmap_b, full_leader, st + a_bytes + b * b_bytes, kb * I8_BK, (unit * NB + b) * p.N + (int)rank * halfN);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_i8_idesc(256, p.N, 0, 1);
+      int stage = 0; uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, unit; coords(tile, m_blk, unit);
+        if (skip(m_blk)) continue;
+        mbar_wait(tempty, acc_phase ^ 1);                   // the epilogue of the previous tile has drained TMEM
+        tc_fence_after();
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa, p.lbo_units);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const uint64_t bdesc = make_sw128_kmajor_desc(sa + a_bytes + b * b_bytes, p.lbo_units);
+#pragma unroll
+            for (int k = 0; k < I8_BK / I8_UK; ++k)
+              tc_mma_i8_pair(tmem_base + (uint32_t)(b * I8_ACC_COLS), adesc + (uint64_t)(k * (I8_UK >> 4)), bdesc + (uint64_t)(k * (I8_UK >> 4)),
+                             idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_pair(&empty[stage]);
+          if (kb == p.num_k_blocks - 1) tc_commit_pair(tfull);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, each its own 128 rows) =====================
+    const int ew = warp - 4;
+    uint32_t acc_phase = 0;
+    const double w256 = 256.0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int m_blk, unit; coords(tile, m_blk, unit);
+      if (skip(m_blk)) continue;
+      mbar_wait(tfull, acc_phase);
+      tc_fence_after();
+      const int s = m_blk * 256 + (int)rank * I8_BM + ew * 32 + lane;
+      const double rm = (p.mode == 2 && s < p.l) ? __ldg(p.row_mean + s) : 0.0;
+      double *crow = p.C + (size_t)s * p.ldc;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int i0 = (unit * NB + b) * p.NE;
+        if (i0 >= p.n) break;
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * I8_ACC_COLS);
+        for (int e0 = 0; e0 < p.NE; e0 += 8) {
+          double v[8];
+          int32_t d[8];
+          tc_ld8(taddr + (uint32_t)e0, d);
+          tc_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (double)d[q];
+          for (int t = 1; t < p.T; ++t) {
+            tc_ld8(taddr + (uint32_t)(t * p.NE + e0), d);
+            tc_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fma(v[q], w256, (double)d[q]);
+          }
+          if (s < p.l) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int i = i0 + e0 + q;
+              if (i < p.n) {
+                const double val = v[q] * __ldg(p.scale + i);
+                if (p.mode == 2) crow[i] = fma(rm, val, crow[i]); else crow[i] = val;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tempty), 0));
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // U -> int8 digit planes
 __global__ void col_absmax_kernel(const double *__restrict__ U, int n, double *__restrict__ colmax) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -535,27 +707,30 @@ __global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U
 __global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__restrict__ bed, size_t bytes_per_snp,
                                                         const int *__restrict__ idx, int n, int n_padk, int l,
                                                         int8_t *__restrict__ G, double *__restrict__ mean,
-                                                        int *__restrict__ nmiss) {
+                                                        int *__restrict__ nmiss, int8_t *__restrict__ Q,
+                                                        int *__restrict__ tile_holes) {
   __shared__ int sh_sum[8], sh_miss[8];
   const int s = blockIdx.x;
   int8_t *g = G + (size_t)s * n_padk;
-  if (s >= l) {                                   // zero padding rows of the last 128-SNP tile
-    for (int p = threadIdx.x; p < n_padk; p += 256) g[p] = 0;
+  int8_t *qr = Q ? Q + (size_t)s * n_padk : nullptr;     // hole-indicator row (second GEMM pass of the mean imputation)
+  if (s >= l) {                                   // zero padding rows of the last tile
+    for (int p = threadIdx.x; p < n_padk; p += 256) { g[p] = 0; if (qr) qr[p] = 0; }
     return;
   }
   const unsigned char *row = bed + (size_t)s * bytes_per_snp;
   int sum = 0, miss = 0;
   for (int p = threadIdx.x; p < n_padk; p += 256) {
-    int8_t v = 0;
+    int8_t v = 0, hq = 0;
     if (p < n) {
       const size_t j = idx ? (size_t)idx[p] : (size_t)p;
       const unsigned b = (unsigned)row[j >> 2] >> (2 * (j & 3));
       const unsigned lo = b & 1u, hi = (b >> 1) & 1u;
       if (lo == 0) v = hi == 0 ? 2 : 1;
-      else if (hi == 0) { miss++; }
+      else if (hi == 0) { miss++; hq = 1; }
       sum += v;
     }
     g[p] = v;
+    if (qr) qr[p] = hq;
   }
   for (int m = 16; m >= 1; m >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, m); miss += __shfl_xor_sync(0xffffffffu, miss, m); }
   if ((threadIdx.x & 31) == 0) { sh_sum[threadIdx.x >> 5] = sum; sh_miss[threadIdx.x >> 5] = miss; }
@@ -565,6 +740,7 @@ __global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__r
     for (int w = 0; w < 8; ++w) { ts += sh_sum[w]; tm += sh_miss[w]; }
     nmiss[s] = tm;
     mean[s] = (double)ts / (double)(n - tm);          // x_mean of src/lmm.cpp:1819
+    if (tile_holes && tm) atomicAdd(tile_holes + (s >> 8), tm);
   }
 }
 
@@ -689,16 +865,23 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   if (rc) return rc;
   const I8Geom g = make_geom(c->n, c->i8.n_slices);
   const bool pair = c->cta_pair != 0 && (g.N % 32 == 0 || g.N == 240);     // half of N must stay a multiple of 8 rows
+  const bool pair2 = pair && c->gemm_groups == 2;                          // two eigenvector groups per tile + hole pass on the tensor pipe
   const size_t m_rows = pair ? 256 : I8_BM;
   const size_t l_pad = (l + m_rows - 1) / m_rows * m_rows;
   GB_CUDA(c, c->i8.geno.reserve(l_pad * (size_t)g.n_padk));
-  GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int))));
+  GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int)) + (l_pad / 256 + 1) * sizeof(int)));
   double *mean = c->i8.miss_mean.as<double>();
   int *nmiss = reinterpret_cast<int *>(mean + l_pad);
+  int *tile_holes = nmiss + l_pad;
+  if (pair2) {
+    GB_CUDA(c, c->i8.holeq.reserve(l_pad * (size_t)g.n_padk));
+    GB_CUDA(c, cudaMemsetAsync(tile_holes, 0, (l_pad / 256 + 1) * sizeof(int), c->stream));
+  }
   {
   ProfScope ps(c, "decode");
   bed_to_i8_kernel<<<(unsigned)l_pad, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, g.n_padk, (int)l,
-                                                           c->i8.geno.as<int8_t>(), mean, nmiss);
+                                                           c->i8.geno.as<int8_t>(), mean, nmiss,
+                                                           pair2 ? c->i8.holeq.as<int8_t>() : nullptr, pair2 ? tile_holes : nullptr);
   GB_CUDA(c, cudaGetLastError());
   }
   if (!make_tmap((CUtensorMap *)c->i8.tmap_a, c->i8.geno.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
@@ -710,20 +893,39 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
   p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : 6;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int tiles = p.m_tiles * p.n_groups;
+  if (pair2) {
+    // B tensor map with a half-N box; the SAME kernel runs twice: genotypes (store), then hole indicators (accumulate with the SNP mean)
+    if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, (uint64_t)g.n_groups * (uint64_t)g.N, (uint64_t)g.n_padk, (uint32_t)(g.N / 2)))
+      return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes (pair)");
+    c->i8.tmap_b_half = true;
+    if (!c->i8.tmap_q) c->i8.tmap_q = aligned_alloc(64, sizeof(CUtensorMap));
+    if (!make_tmap((CUtensorMap *)c->i8.tmap_q, c->i8.holeq.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
+      return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the hole-indicator tile");
+    GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int units = (p.n_groups + 1) / 2;
+    int pairs = c->num_sms / 2; if (pairs > p.m_tiles * units) pairs = p.m_tiles * units; if (pairs < 1) pairs = 1;
+    const size_t smem2 = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;      // A + 2 x half of B per stage
+    {
+      ProfScope ps(c, "utx");
+      i8_gemm_pair2_kernel<2><<<2 * pairs, I8_THREADS, smem2, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+      GB_CUDA(c, cudaGetLastError());
+    }
+    p.mode = 2; p.row_mean = mean; p.tile_holes = tile_holes;
+    ProfScope ps2(c, "fix");
+    i8_gemm_pair2_kernel<2><<<2 * pairs, I8_THREADS, smem2, c->stream>>>(*(CUtensorMap *)c->i8.tmap_q, *(CUtensorMap *)c->i8.tmap_b, p);
+    GB_CUDA(c, cudaGetLastError());
+    return GB200_OK;
+  }
+  GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (pair) {
     // B tensor map with a half-N box (each CTA of the pair loads its own half of the plane rows)
     if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, (uint64_t)g.n_groups * (uint64_t)g.N, (uint64_t)g.n_padk, (uint32_t)(g.N / 2)))
       return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes (pair)");
     c->i8.tmap_b_half = true;
-    static bool attr2 = false;
-    if (!attr2) { GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
+    GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
     const size_t smem_pair = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK) + 256;   // A + half of B per stage
     ProfScope ps(c, "utx");

@@ -1,0 +1,217 @@
+// gemma_seams.cpp -- the reference-side binding of libgemma_b200.so, as ONE extra translation unit for GEMMA itself.
+//
+// INTEGRATION.md describes the edits a GEMMA maintainer makes at the four seams of the -gk / -eigen / -lmm path.  This file IS
+// those edits, written so that they can be linked into the UNMODIFIED reference sources: the recipe `make -C oracle ref_b200`
+// compiles /root/reference/src/*.cpp in place, renaming the reference's own definitions of the seam functions in the one
+// translation unit that defines each (-Dfast_dgemm=ref_fast_dgemm ... on fastblas.cpp, lapack.cpp, gemma_io.cpp, lmm.cpp only),
+// and links this file, which supplies the same functions on top of the C ABI (include/gemma_b200.h).  The result,
+// oracle/_ref/gemma_ref_b200, is the reference's own CLI -- its flag parsing, readers, QC, null model, writers -- running its hot
+// path on the GPU; tests/test_gpu_parity.py::test_reference_cli_with_the_plugin_reproduces_demo_txt runs it on the mouse example.
+//
+//   seam (reference file:line)                                   defined here on top of
+//   fast_dgemm / fast_eigen_dgemm     src/fastblas.cpp:216-236   gb200_dgemm
+//   EigenDecomp_Zeroed                src/lapack.cpp:260-291     gb200_eigh (center = 0: the caller has run CenterMatrix)
+//   BimbamKin / PlinkKin              src/gemma_io.cpp:1418-1738 gb200_kin_begin / _add_geno / _add_bed / _finish
+//   LMM::AnalyzeBimbam / AnalyzePlink src/lmm.cpp:1660-1903      gb200_lmm_setup_rotated / _params / _batch_geno / _batch_bed
+//                                     (their batch_compute closure, :1513-1564, is not reachable from outside the function)
+// Test / integration infrastructure: the product (libgemma_b200.so, the gemma-b200 CLI) does not contain this file.
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "gsl/gsl_matrix.h"
+#include "gsl/gsl_vector.h"
+
+#include "debug.h"
+#include "fastblas.h"
+#include "gemma_io.h"
+#include "gzstream.h"
+#include "lapack.h"
+#include "lmm.h"
+#include "param.h"
+
+#include "gemma_b200.h"
+
+using namespace std;
+
+static gb200_ctx *gpu() {                                  // one context per run
+  static gb200_ctx *ctx = nullptr;
+  if (!ctx && gb200_create(&ctx, -1, nullptr) != GB200_OK) {
+    cerr << "gemma_b200: no CUDA device (there is no CPU fallback)" << endl;
+    exit(2);
+  }
+  return ctx;
+}
+static void check(int rc, const char *what) {
+  if (rc == GB200_OK) return;
+  cerr << "gemma_b200: " << what << ": " << gb200_last_error(gpu()) << endl;
+  exit(2);
+}
+
+// ---- seam 1: dense GEMM ------------------------------------------------------------------------------------------------
+void fast_dgemm(const char *TransA, const char *TransB, const double alpha, const gsl_matrix *A, const gsl_matrix *B,
+                const double beta, gsl_matrix *C) {
+  const int rc = gb200_dgemm(gpu(), TransA, TransB, alpha, A->data, A->size1, A->size2, A->tda, B->data, B->size1, B->size2, B->tda, beta,
+                             C->data, C->size1, C->size2, C->tda);
+  if (rc == GB200_ERR_ARG) fail_msg("Range error in dgemm");          // src/fastblas.cpp:207
+  check(rc, "gb200_dgemm");
+}
+void fast_eigen_dgemm(const char *TransA, const char *TransB, const double alpha, const gsl_matrix *A, const gsl_matrix *B,
+                      const double beta, gsl_matrix *C) {
+  fast_dgemm(TransA, TransB, alpha, A, B, beta, C);
+}
+
+// ---- seam 2: eigendecomposition ----------------------------------------------------------------------------------------
+double EigenDecomp_Zeroed(gsl_matrix *G, gsl_matrix *U, gsl_vector *eval, const size_t) {
+  double trace = 0.0;
+  int n_zero = 0, n_neg = 0;
+  check(gb200_eigh(gpu(), G->data, G->size1, G->tda, /*center=*/0, U->data, U->tda, eval->data, &trace, &n_zero, &n_neg), "gb200_eigh");
+  if (n_zero > 1) warning_msg("Matrix G has " + std::to_string(n_zero) + " eigenvalues close to zero");      // src/lapack.cpp:278-283
+  return trace;
+}
+
+// ---- seam 3: kinship ---------------------------------------------------------------------------------------------------
+static char *next_field(char *&cur) {                      // strtok(" ,\t") without the global state
+  while (*cur == ' ' || *cur == ',' || *cur == '\t') ++cur;
+  if (!*cur) return nullptr;
+  char *b = cur;
+  while (*cur && *cur != ' ' && *cur != ',' && *cur != '\t') ++cur;
+  if (*cur) *cur++ = 0;
+  return b;
+}
+
+bool BimbamKin(const string file_geno, const set<string> ksnps, vector<int> &indicator_snp, const int k_mode, const int, gsl_matrix *matrix_kin,
+               const bool) {
+  igzstream infile(file_geno.c_str(), igzstream::in);
+  enforce_msg(infile, "error reading genotype file");
+  const size_t ni_total = matrix_kin->size1, msize = 4096;
+  check(gb200_kin_begin(gpu(), ni_total, k_mode), "gb200_kin_begin");      // gsl_matrix_set_zero(matrix_kin), src/param.cpp:1301
+  vector<double> G(msize * ni_total);
+  size_t l = 0, ns_test = 0;
+  for (size_t t = 0; t < indicator_snp.size(); ++t) {
+    string line;
+    safeGetline(infile, line);
+    if (indicator_snp[t] == 0) continue;
+    char *cur = &line[0];
+    char *snp = next_field(cur);
+    enforce_msg(snp, "Parsing BIMBAM genofile");
+    if (ksnps.size() && ksnps.count(snp) == 0) continue;                   // -ksnps / LOCO, src/gemma_io.cpp:1479
+    next_field(cur); next_field(cur);
+    double *row = G.data() + l * ni_total;
+    for (size_t i = 0; i < ni_total; ++i) {
+      char *f = next_field(cur);
+      enforce_msg(f, "not enough genotype fields for marker");
+      row[i] = (strncmp(f, "NA", 2) == 0) ? NAN : atof(f);                 // src/gemma_io.cpp:1496-1509
+    }
+    ns_test++;
+    if (++l == msize) { check(gb200_kin_add_geno(gpu(), G.data(), l, ni_total, ni_total), "gb200_kin_add_geno"); l = 0; }
+  }
+  if (l) check(gb200_kin_add_geno(gpu(), G.data(), l, ni_total, ni_total), "gb200_kin_add_geno");
+  size_t used = 0;
+  check(gb200_kin_finish(gpu(), matrix_kin->data, matrix_kin->tda, &used), "gb200_kin_finish");       // scaling by 1/ns_test inside (:1570)
+  return used == ns_test;
+}
+
+bool PlinkKin(const string &file_bed, vector<int> &indicator_snp, const int k_mode, const int, gsl_matrix *matrix_kin) {
+  ifstream infile(file_bed.c_str(), ios::binary);
+  if (!infile) { cout << "error reading bed file:" << file_bed << endl; return false; }
+  const size_t ni_total = matrix_kin->size1, n_bit = (ni_total + 3) / 4, msize = 16384;
+  check(gb200_kin_begin(gpu(), ni_total, k_mode), "gb200_kin_begin");
+  vector<unsigned char> rows(msize * n_bit);
+  size_t l = 0;
+  for (size_t t = 0; t < indicator_snp.size(); ++t) {
+    if (indicator_snp[t] == 0) continue;
+    infile.seekg((std::streamoff)(t * n_bit + 3));                          // src/gemma_io.cpp:1648
+    infile.read((char *)rows.data() + l * n_bit, (std::streamsize)n_bit);
+    if (++l == msize) { check(gb200_kin_add_bed(gpu(), rows.data(), l, n_bit), "gb200_kin_add_bed"); l = 0; }
+  }
+  if (l) check(gb200_kin_add_bed(gpu(), rows.data(), l, n_bit), "gb200_kin_add_bed");
+  size_t used = 0;
+  check(gb200_kin_finish(gpu(), matrix_kin->data, matrix_kin->tda, &used), "gb200_kin_finish");
+  return true;
+}
+
+// ---- seam 4: the batched association loop --------------------------------------------------------------------------------
+static void lmm_begin(const LMM &L, const gsl_matrix *U, const gsl_vector *eval, const gsl_matrix *UtW, const gsl_vector *Uty) {
+  vector<double> uty(Uty->size);
+  for (size_t i = 0; i < Uty->size; ++i) uty[i] = gsl_vector_get(Uty, i);                 // may be a strided column view
+  check(gb200_lmm_setup_rotated(gpu(), U->size1, UtW->size2, U->data, U->tda, eval->data, UtW->data, UtW->tda, uty.data()), "gb200_lmm_setup_rotated");
+  check(gb200_lmm_params(gpu(), L.a_mode, L.l_min, L.l_max, L.n_region, L.l_mle_null, L.logl_mle_H0), "gb200_lmm_params");
+}
+static void push_rows(LMM &L, const vector<gb200_sumstat> &out, size_t l) {
+  for (size_t k = 0; k < l; ++k) {
+    const gb200_sumstat &s = out[k];
+    SUMSTAT SNPs = {s.beta, s.se, s.lambda_remle, s.lambda_mle, s.p_wald, s.p_lrt, s.p_score, s.logl_H1};      // src/lmm.cpp:1559-1561
+    L.sumStat.push_back(SNPs);
+  }
+}
+
+void LMM::AnalyzeBimbam(const gsl_matrix *U, const gsl_vector *eval, const gsl_matrix *UtW, const gsl_vector *Uty, const gsl_matrix *,
+                        const gsl_vector *, const set<string> gwasnps) {
+  igzstream infile(file_geno.c_str(), igzstream::in);
+  enforce_msg(infile, "error reading genotype file");
+  lmm_begin(*this, U, eval, UtW, Uty);
+  const size_t n = U->size1, msize = 4096;
+  vector<double> G(msize * n);
+  vector<gb200_sumstat> out(msize);
+  size_t l = 0;
+  auto flush = [&]() {
+    if (!l) return;
+    check(gb200_lmm_batch_geno(gpu(), G.data(), l, n, out.data()), "gb200_lmm_batch_geno");      // batch_compute(l), src/lmm.cpp:1513-1564
+    push_rows(*this, out, l);
+    l = 0;
+  };
+  for (size_t t = 0; t < indicator_snp.size(); ++t) {
+    string line;
+    safeGetline(infile, line);
+    if (indicator_snp[t] == 0) continue;
+    char *cur = &line[0];
+    char *snp = next_field(cur);
+    enforce_msg(snp, "Parsing BIMBAM genofile");
+    if (gwasnps.size() && gwasnps.count(snp) == 0) continue;               // src/lmm.cpp:1585-1587
+    next_field(cur); next_field(cur);
+    double *row = G.data() + l * n;
+    size_t pos = 0;
+    for (size_t i = 0; i < ni_total; ++i) {
+      char *f = next_field(cur);
+      enforce_msg(f, "not enough genotype fields for marker");
+      if (indicator_idv[i] == 0) continue;
+      row[pos++] = (strcmp(f, "NA") == 0) ? NAN : atof(f);                 // src/lmm.cpp:1690-1694; imputation on the device
+    }
+    enforce(pos == ni_test);
+    if (++l == msize) flush();
+  }
+  flush();
+  cout << endl;
+}
+
+void LMM::AnalyzePlink(const gsl_matrix *U, const gsl_vector *eval, const gsl_matrix *UtW, const gsl_vector *Uty, const gsl_matrix *,
+                       const gsl_vector *, const set<string>) {
+  const string file_bed = file_bfile + ".bed";
+  ifstream infile(file_bed.c_str(), ios::binary);
+  enforce_msg(infile, "error reading genotype (.bed) file");
+  lmm_begin(*this, U, eval, UtW, Uty);
+  const size_t n_bit = (ni_total + 3) / 4, msize = 16384;
+  vector<unsigned char> mask(ni_total), rows(msize * n_bit);
+  for (size_t i = 0; i < ni_total; ++i) mask[i] = (unsigned char)(indicator_idv[i] != 0);
+  vector<gb200_sumstat> out(msize);
+  size_t l = 0;
+  auto flush = [&]() {
+    if (!l) return;
+    check(gb200_lmm_batch_bed(gpu(), rows.data(), mask.data(), ni_total, l, n_bit, out.data()), "gb200_lmm_batch_bed");
+    push_rows(*this, out, l);
+    l = 0;
+  };
+  for (size_t t = 0; t < snpInfo.size(); ++t) {
+    if (indicator_snp[t] == 0) continue;
+    infile.seekg((std::streamoff)(t * n_bit + 3));                          // src/lmm.cpp:1774
+    infile.read((char *)rows.data() + l * n_bit, (std::streamsize)n_bit);
+    if (++l == msize) flush();
+  }
+  flush();
+  cout << endl;
+}

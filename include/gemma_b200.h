@@ -248,7 +248,9 @@ GB200_API int gb200_lmm_project_bed(gb200_ctx *ctx, const unsigned char *bed, co
  * genotypes take the dense FP64 kinship path (default 200); cta_pair /
  * kin_cta_pair 0|1 run the projection / kinship tensor-core kernel as CTA pairs (cta_group::2);
  * kin_path 0 auto, 1 FP64 only; overlap 0|1 pipelines 2048-SNP sub-batches of the bed entry points on two streams
- * (projection of sub-batch i+1 || tests of sub-batch i; measured slower on B200, default 0). */
+ * (projection of sub-batch i+1 || tests of sub-batch i; measured slower on B200, default 0); batch_chunk: SNPs per internal
+ * sub-batch of the bed entry points (0 = auto: the FP64 U^T X staging buffer stays near 4 GB); stage_mask 1|2|3: measurement
+ * runs only -- the bed entry points run just the projection (1) or just the tests on the last projection (2). */
 GB200_API int gb200_set_option(gb200_ctx *ctx, const char *name, long value);
 /* Current value of a knob; "n_slices" returns the EFFECTIVE plane count for the individuals of the last gb200_lmm_setup*. */
 GB200_API int gb200_get_option(gb200_ctx *ctx, const char *name, long *value);

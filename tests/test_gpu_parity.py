@@ -504,6 +504,64 @@ def test_cli_mouse_loco_nind_matches_reference_pins(golden_dir, tmp_path):
     assert np.allclose(a, b, rtol=1e-5, atol=1e-8) and [l.split("\t")[:7] for l in lb] == [l.split("\t")[:7] for l in lines]
 
 
+def test_reference_cli_with_the_plugin_reproduces_demo_txt(golden_dir, tmp_path):
+    """The drop-in boundary, BUILT: oracle/_ref/gemma_ref_b200 is the reference's own CLI (every src/*.cpp compiled in place,
+    unmodified) whose four hot-path seams -- fast_dgemm, EigenDecomp_Zeroed, BimbamKin / PlinkKin, LMM::AnalyzeBimbam /
+    AnalyzePlink -- are bound to libgemma_b200.so by ONE extra translation unit (gemma_b200/host/gemma_seams.cpp; recipe
+    `make -C oracle ref_b200`).  Its flag parsing, readers, QC, null model and writers are the reference's.  It must reproduce
+    example/demo.txt:10-12 (K), :32-36 (first five -lmm 1 rows) and :41-42 (pve, se(pve)), and the PLINK seams must agree with
+    the unbound reference CLI on a synthetic PLINK set."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "gemma_ref_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gemma_ref_b200 not shipped (built where /root/reference is present)")
+    cwd = str(tmp_path); out = os.path.join(cwd, "output")
+    d = os.path.join(golden_dir, "mouse_hs1940")
+    base = ["-g", d + "/mouse_hs1940.geno.txt.gz", "-p", d + "/mouse_hs1940.pheno.txt", "-a", d + "/mouse_hs1940.anno.txt"]
+
+    def run(args):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        return r.stdout + r.stderr
+
+    run(base + ["-gk", "-o", "k"])
+    k = open(os.path.join(out, "k.cXX.txt")).read().splitlines()
+    assert len(k) == 1940
+    assert [[float("%.6g" % float(x)) for x in k[i].split("\t")[:3]] for i in range(3)] == EXP["mouse_K3"]          # demo.txt:10-12
+    run(base + ["-n", "1", "-k", "output/k.cXX.txt", "-lmm", "-o", "lmm"])
+    lines = open(os.path.join(out, "lmm.assoc.txt")).read().splitlines()
+    assert len(lines) == 1 + EXP["mouse_counts"]["ns_test"]
+    hdr = lines[0].split("\t")
+    for ln, e in zip(lines[1:6], EXP["mouse_lmm1_rows"]):                                                        # demo.txt:32-36
+        f = dict(zip(hdr, ln.split("\t")))
+        for key, val in e.items():
+            assert f[key] == val, (key, f[key], val)
+    log = open(os.path.join(out, "lmm.log.txt")).read()
+    assert "## pve estimate in the null model = %s" % EXP["mouse_pve"] in log                                    # demo.txt:41
+    assert "## se(pve) in the null model = %s" % EXP["mouse_pve_se"] in log                                      # demo.txt:42
+    # PLINK seams (PlinkKin, AnalyzePlink) against the unbound reference CLI, whole files
+    from oracle import ref as REF
+    if os.path.exists(REF.EXE):
+        n, l = 400, 300
+        rng = np.random.default_rng(21)
+        bed, G = synth.make_bed(n, l, seed=777, miss_rate=0.02)
+        y = rng.standard_normal(n) + 0.5 * np.where(G[5] < 0, 0, G[5])
+        y[rng.choice(n, 9, replace=False)] = np.nan
+        _write_plink(os.path.join(cwd, "syn"), bed, y)
+        REF.run_cli(["-bfile", "syn", "-gk", "1", "-o", "rk"], cwd)
+        run(["-bfile", "syn", "-gk", "1", "-o", "pk"])
+        Kr = np.loadtxt(os.path.join(out, "rk.cXX.txt")); Kp = np.loadtxt(os.path.join(out, "pk.cXX.txt"))
+        assert np.allclose(Kr, Kp, rtol=1e-8, atol=1e-9)
+        REF.run_cli(["-bfile", "syn", "-k", "output/rk.cXX.txt", "-lmm", "4", "-o", "ra"], cwd)
+        run(["-bfile", "syn", "-k", "output/rk.cXX.txt", "-lmm", "4", "-o", "pa"])
+        ha, na, xa = _assoc_table(os.path.join(out, "pa.assoc.txt")); hb, nb, xb = _assoc_table(os.path.join(out, "ra.assoc.txt"))
+        assert ha == hb and na == nb
+        bad, rel = _record_cli_deviations("plugin:gemma_ref_b200 vs gemma_ref, synthetic PLINK -lmm 4", ha, na, xa, xb, 2e-6,
+                                          [i for i, h in enumerate(ha[7:]) if h.startswith("l_")])
+        assert bad.any(axis=1).mean() <= 0.01 and rel.max() < 1e-4, (int(bad.any(axis=1).sum()), float(rel.max()))
+
+
 _REPORT = {}
 
 
