@@ -1,11 +1,11 @@
 // gemma_seams.cpp -- the reference-side binding of libgemma_b200.so, as ONE extra translation unit for GEMMA itself.
 //
 // INTEGRATION.md describes the edits a GEMMA maintainer makes at the four seams of the -gk / -eigen / -lmm path.  This file IS
-// those edits, written so that they can be linked into the UNMODIFIED reference sources: the recipe `make -C oracle ref_b200`
+// those edits, written so that they can be linked into the UNMODIFIED reference sources: the `ref_b200` recipe of the checker's Makefile
 // compiles /root/reference/src/*.cpp in place, renaming the reference's own definitions of the seam functions in the one
 // translation unit that defines each (-Dfast_dgemm=ref_fast_dgemm ... on fastblas.cpp, lapack.cpp, gemma_io.cpp, lmm.cpp only),
 // and links this file, which supplies the same functions on top of the C ABI (include/gemma_b200.h).  The result,
-// oracle/_ref/gemma_ref_b200, is the reference's own CLI -- its flag parsing, readers, QC, null model, writers -- running its hot
+// `gemma_ref_b200`, is the reference's own CLI -- its flag parsing, readers, QC, null model, writers -- running its hot
 // path on the GPU; tests/test_gpu_parity.py::test_reference_cli_with_the_plugin_reproduces_demo_txt runs it on the mouse example.
 //
 //   seam (reference file:line)                                   defined here on top of
