@@ -41,7 +41,6 @@ sys.path.insert(0, ROOT)
 
 SEED = 20260923
 K_SNP_OFFSET = 2 * 10 ** 9       # the kinship SNPs: a range disjoint from the tested SNPs (i.i.d. generator: any disjoint subset is "every 10th SNP")
-PHENO_SNP_OFFSET = 10 ** 9       # the 64 causal SNPs of the synthetic phenotype
 
 DEFAULTS = {   # workload -> (n, SNPs per step per GPU)
     "lmm": (50000, 65536), "lmm1": (10000, 262144), "gk": (10000, 500000), "mv": (10000, 32768)}
@@ -287,10 +286,8 @@ def run_reference(args):
         mode = args.mode
         U = host_orthogonal(n, SEED)
         ev = synth.spectrum_like_kinship(n, SEED)
-        gc = synth.genotypes(n, 64, seed=SEED, snp_offset=PHENO_SNP_OFFSET).astype(np.float64)
-        y = synth.phenotype(n, gc, SEED)
         W = np.ones((n, 1))
-        UtW = U.T @ W; Uty = U.T @ y
+        UtW = U.T @ W; Uty = synth.polygenic_rotated(ev, SEED)              # the same phenotype model as the b200 arm (pve 0.5)
         l_mle, logl = O.calc_lambda_null("L", ev, UtW, Uty)
         if args.workload == "mv":
             # the reference's multivariate per-SNP loop is not part of oracle/_ref's library; its CLI cannot take rotated input.
@@ -486,9 +483,9 @@ def run_lmm(args):
     t_setup = time.perf_counter()
     U, ev, setup = build_eigensystem(env, args, n)
     ev_h = ev.cpu().numpy()
-    gc = synth.genotypes(n, 64, seed=SEED, snp_offset=PHENO_SNP_OFFSET).astype(np.float64)
-    y_h = synth.phenotype(n, gc, SEED)
-    y = torch.from_numpy(y_h).to(dev)
+    # phenotype drawn from the model itself (pve 0.5): y = U (sqrt(h2 ev / mean ev + 1 - h2) * z), so that every SNP's REML / ML
+    # root is interior and the per-SNP kernel runs its full grid + Brent + Newton search
+    y = (U @ torch.from_numpy(synth.polygenic_rotated(ev_h, SEED)).to(dev)).contiguous()
     g = torch.Generator(device=dev); g.manual_seed(SEED + 1)
     Wt = torch.ones((args.cvt, n), dtype=torch.float64, device=dev)
     if args.cvt > 1:
@@ -841,8 +838,7 @@ def run_mv(args):
     ctx = env.context(args)
     U, ev, setup = build_eigensystem(env, args, n)
     U_h = U.cpu().numpy(); ev_h = ev.cpu().numpy()
-    gc = synth.genotypes(n, 64, seed=SEED, snp_offset=PHENO_SNP_OFFSET).astype(np.float64)
-    y1 = synth.phenotype(n, gc, SEED); y2 = 0.4 * y1 + synth.phenotype(n, gc[::-1], SEED + 5)
+    y1 = U_h @ synth.polygenic_rotated(ev_h, SEED); y2 = 0.4 * y1 + U_h @ synth.polygenic_rotated(ev_h, SEED + 5)   # pve 0.5 each, correlated
     Y = np.stack([y1, y2], axis=1)
     W = np.ones((n, args.cvt))
     if args.cvt > 1:

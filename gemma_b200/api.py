@@ -57,6 +57,7 @@ SIGNATURES = {
     "gb200_profile_get": (C.c_int, [_vp, C.c_char_p, _dp, C.POINTER(C.c_long)]),
     "gb200_measure_fp64_fma": (C.c_int, [_vp, C.c_double, _dp, _dp]),
     "gb200_lmm_counters": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.c_int]),
+    "gb200_cdf_tails": (C.c_int, [_vp, C.c_int, _vp, C.c_double, _vp, _vp, _sz]),
     "gb200_dgemm": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_double, _vp, _sz, _sz, _sz, _vp, _sz, _sz, _sz,
                               C.c_double, _vp, _sz, _sz, _sz]),
     "gb200_kin_begin": (C.c_int, [_vp, _sz, C.c_int]),
@@ -187,6 +188,16 @@ class Context:
         a = (C.c_ulonglong * 6)()
         self._chk(self.lib.gb200_lmm_counters(self.h, a, int(reset)))
         return dict(zip(("common_slots", "order1", "order2", "order3", "with_logdet", "snps"), [int(x) for x in a]))
+
+    def cdf_tails(self, x, nu2=None, nu1=1.0):
+        """Device restatement of gsl_cdf_fdist_Q(x, nu1, nu2) (nu2 given) or gsl_cdf_chisq_Q(x, 1) (nu2 None)."""
+        x = _f64(np.atleast_1d(x)); out = np.empty_like(x)
+        if nu2 is None:
+            self._chk(self.lib.gb200_cdf_tails(self.h, 1, _ptr(x), 1.0, None, _ptr(out), x.size))
+        else:
+            nu2 = _f64(np.broadcast_to(np.asarray(nu2, dtype=np.float64), x.shape))
+            self._chk(self.lib.gb200_cdf_tails(self.h, 0, _ptr(x), float(nu1), _ptr(nu2), _ptr(out), x.size))
+        return out
 
     # ---- fast_dgemm seam
     def dgemm(self, TransA, TransB, alpha, A, B, beta, Cm):

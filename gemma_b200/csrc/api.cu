@@ -15,6 +15,7 @@ int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_
                    size_t l, size_t bytes_per_snp, double *UtXt_dev);   // UtXt l x n (ld n)
 bool i8_available(gb200_ctx *ctx);
 int i8_default_planes(size_t n);
+int i8_effective_planes(gb200_ctx *c, int *T_out);
 bool kin_i8_eligible(gb200_ctx *ctx);
 int kin_i8_begin(gb200_ctx *ctx);
 int kin_i8_add_chunk(gb200_ctx *ctx, const unsigned char *bed_dev, size_t l, size_t bytes_per_snp, bool *taken);
@@ -182,6 +183,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 3) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2,3");
     c->lmm_kernel = value; return GB200_OK;
   }
+  if (!strcmp(name, "gemm_stages")) {
+    if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "gemm_stages must be 0..8");
+    c->gemm_stages = value; return GB200_OK;
+  }
   if (!strcmp(name, "lmm_hoist")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "lmm_hoist must be 0 or 1");
     c->lmm_hoist = value; return GB200_OK;
@@ -213,7 +218,12 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
 int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
   if (!c) return GB200_ERR_ARG;
   if (!name || !value) return set_err(c, GB200_ERR_ARG, "gb200_get_option: null argument");
-  if (!strcmp(name, "n_slices")) { *value = c->n_slices > 0 ? c->n_slices : (c->n ? i8_default_planes(c->n) : 0); return GB200_OK; }   // effective
+  if (!strcmp(name, "n_slices")) {      // effective: the forced count, else the count chosen from this U's column maxima (i8gemm_sm100.cu)
+    int T = 0;
+    const int rc = i8_effective_planes(c, &T);
+    if (rc) return rc;
+    *value = T; return GB200_OK;
+  }
   if (!strcmp(name, "utx_path")) { *value = c->utx_path; return GB200_OK; }
   if (!strcmp(name, "overlap")) { *value = c->overlap; return GB200_OK; }
   if (!strcmp(name, "cta_pair")) { *value = c->cta_pair; return GB200_OK; }
@@ -404,7 +414,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
   if (n_cvt > GB200_MAX_CVT)
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false; c->gxe_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->common_ready = false; c->gxe_ready = false;
   c->mask_host.clear();                           // the cached gather index belongs to the previous n
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
   c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
@@ -477,7 +487,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
     return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated_dev: bad argument");
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->common_ready = false; c->gxe_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->common_ready = false; c->gxe_ready = false;
   c->mask_host.clear();
   const size_t n_c = round_up(n, 512);
   c->dUtXt.release(); c->dUtXt2.release();

@@ -39,9 +39,11 @@ struct DevBuf {
 struct I8State {
   bool ready = false;
   int n_slices = 0;
+  int auto_T = 0;                // plane count chosen from this U's column maxima (0 = not evaluated yet)
+  double colmax_max = 0.0;       // largest |entry| of U
   size_t n = 0, n_pad = 0;       // individuals, padded to the K tile
   DevBuf slices;                 // n_slices x [n_pad(i: eigvec) x n_pad(j: individual)] int8, j contiguous
-  DevBuf scale;                  // per-eigenvector power-of-two scale (n doubles)
+  DevBuf scale;                  // per eigenvector: scale s_i, column maximum, 1 / s_i (3 n doubles)
   DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
   DevBuf miss_mean;              // per-SNP mean + hole count (+ holes per 256-SNP tile)
   DevBuf holeq;                  // l_pad x n_pad int8 hole-indicator rows (second GEMM pass of the mean imputation)
@@ -130,6 +132,7 @@ struct gb200_ctx {
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
   long gemm_groups = 1;  // 2: pair kernel with two eigenvector groups per tile (shared genotype tile) and the hole pass on the tensor pipe; 1: one group, FP64 hole fix-up
+  long gemm_stages = 0;  // TMA pipeline stages of the CTA-pair projection kernel (0 = as many 32 KB stages as fit, at most 6)
   long gemm_panel = 0;   // raster panel width of that kernel in 2-group units (0 = default 6)
   long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K; sparse FP64 terms for missing genotypes), 1 = FP64 only

@@ -5,13 +5,12 @@
 //
 // Genotypes are small integers (PLINK 2-bit: 0/1/2), so the product is made EXACT on the
 // int8 tensor pipe with an error-free split of U (Ozaki scheme):
-//   U[j][i] = sigma_i * 2^-B * sum_t d_t[j][i] * 256^(T-1-t) + eps,  d_t in int8,
-//   sigma_i = power of two >= max_j |U[j][i]|,  B = 6 + 8 (T-1),  |eps| <= 2^-(B+1) sigma_i
-// (balanced base-256 digits of the fixed-point integer round(U/sigma * 2^B)).  Each digit
+//   U[j][i] = s_i * sum_t d_t[j][i] * 256^(T-1-t) + eps,   d_t in int8,
+//   s_i = max_j |U[j][i]| / (127.4 * 256^(T-1)),   |eps| <= s_i / 2
+// (balanced base-256 digits of the integer rint(U / s_i); the top digit uses the whole int8 range, |d_0| <= 127, so the T planes
+// keep log2(127.4) + 8 (T-1) bits of every entry relative to its column maximum).  Each digit
 // plane times the int8 genotype tile accumulates exactly in int32 (|sum| <= 128*2*n < 2^31
-// for n < 8e6); the T planes are recombined in FP64 in the epilogue.  T = 6 keeps 46 bits
-// below each eigenvector's largest entry (dot-product error ~1e-14 at n = 50 000, below the
-// rounding error of an FP64 dgemm's n-term sums relative to the statistics that consume it).
+// for n < 8e6); the T planes are recombined in FP64 in the epilogue.
 // Mean-imputed missing genotypes are handled exactly as  U^T x = U^T z + mean * U^T q  with
 // z = genotype with 0 at the holes (int8 GEMM) and q = hole indicator (sparse FP64 fix-up).
 //
@@ -126,7 +125,7 @@ struct I8KernelParams {
   int num_k_blocks;         // n_padk / 128
   int m_tiles, n_groups;
   int lbo_units;            // descriptor LBO field (kept runtime for bring-up)
-  const double *scale;      // per eigenvector: sigma_i * 2^-B
+  const double *scale;      // per eigenvector: s_i = colmax_i / (127.4 * 256^(T-1))
   double *C;                // l x n, ld = ldc   (mode 0)  |  K accumulator n x n, ld = ldc (mode 1)
   size_t ldc;
   int mode;                 // 0 = projection (T planes recombined, scaled, stored), 1 = kinship (K[i][j] += Z Z^T, lower triangle)
@@ -136,6 +135,7 @@ struct I8KernelParams {
   const double *row_mean;   // mode 2: C[s][:] += row_mean[s] * (A . planes) * scale   (A = hole indicator rows)
   const int *tile_holes;    // mode 2: holes per 256-row tile; tiles without a hole are skipped
   int panel;                // raster panel width in units of NB eigenvector groups
+  int stages;               // i8_gemm_pair_kernel: TMA pipeline stages
 };
 
 __device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_groups, int &m_blk, int &n_grp) {
@@ -342,14 +342,15 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int halfN = p.N / 2;
+  const int NS = p.stages;                                 // pipeline depth (shared memory permitting: 6 x 32 KB for the projection)
   const int a_bytes = I8_BM * I8_BK;
   const int b_bytes = halfN * I8_BK;                       // this CTA's half of the B rows
   uint8_t *smem_a = smem;
-  uint8_t *smem_b = smem + I8_STAGES * a_bytes;
-  uint64_t *bars = (uint64_t *)(smem_b + I8_STAGES * b_bytes);
-  uint64_t *full = bars, *empty = bars + I8_STAGES;
-  uint64_t *tfull = bars + 2 * I8_STAGES, *tempty = bars + 2 * I8_STAGES + 2;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * I8_STAGES + 4);
+  uint8_t *smem_b = smem + NS * a_bytes;
+  uint64_t *bars = (uint64_t *)(smem_b + NS * b_bytes);
+  uint64_t *full = bars, *empty = bars + NS;
+  uint64_t *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 2;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NS + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank;
@@ -363,7 +364,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }   // 4 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -389,7 +390,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * (a_bytes + b_bytes)));
           tma_load_2d_pair(&tmap_a, full_leader, smem_a + stage * a_bytes, kb * I8_BK, m_blk * 256 + (int)rank * I8_BM);
           tma_load_2d_pair(&tmap_b, full_leader, smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N + (int)rank * halfN);
-          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -414,7 +415,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                            (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit_pair(&empty[stage]);
           if (kb == p.num_k_blocks - 1) tc_commit_pair(&tfull[acc]);
-          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -662,21 +663,32 @@ __global__ void col_absmax_kernel(const double *__restrict__ U, int n, double *_
   colmax[i] = m;
 }
 
-// scale[i] = sigma_i * 2^-B ; expo[i] = B - e_i  (so that Q = rint(u * 2^expo))
-__global__ void col_scale_kernel(const double *__restrict__ colmax, int n, int B, double *__restrict__ scale,
-                                 int *__restrict__ expo) {
+// scale[i] = s_i = colmax_i / (127.4 * 256^(T-1)), mult[i] = 1 / s_i  (so that Q = rint(u * mult), |Q| <= 127.4 * 256^(T-1)).
+// An all-zero column gets mult = scale = 0.
+__global__ void col_scale_kernel(const double *__restrict__ colmax, int n, int T, double *__restrict__ scale,
+                                 double *__restrict__ mult) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double m = colmax[i];
-  int e = 0;
-  if (m > 0.0 && isfinite(m)) { frexp(m, &e); if (ldexp(1.0, e - 1) == m) { /* m is a power of two: |u|/sigma may equal 1 */ } }
-  // frexp: m = f * 2^e, f in [0.5,1)  =>  sigma = 2^e > m, |u|/sigma < 1
-  scale[i] = ldexp(1.0, e - B);
-  expo[i] = B - e;
+  double top = 127.4;
+  for (int t = 1; t < T; ++t) top *= 256.0;
+  if (m > 0.0 && isfinite(m)) { mult[i] = top / m; scale[i] = m / top; }
+  else { mult[i] = 0.0; scale[i] = 0.0; }
+}
+
+// max over the columns of colmax (one block)
+__global__ void __launch_bounds__(256) vec_max_kernel(const double *__restrict__ v, int n, double *__restrict__ out) {
+  __shared__ double sh[8];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) m = fmax(m, v[i]);
+  for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) m = fmax(m, sh[w]); *out = m; }
 }
 
 // one 32x32 tile of U per block: read U[j][i] coalesced in i, write planes coalesced in j
-__global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U, int n, const int *__restrict__ expo,
+__global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U, int n, const double *__restrict__ mult,
                                                     int T, int NE, int n_padk, int8_t *__restrict__ planes) {
   __shared__ long long q[32][33];
   const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
@@ -684,7 +696,7 @@ __global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U
   for (int r = ty; r < 32; r += 8) {
     const int j = j0 + r, i = i0 + tx;
     long long v = 0;
-    if (j < n && i < n) v = llrint(ldexp(U[(size_t)j * n + i], expo[i]));
+    if (j < n && i < n) v = llrint(U[(size_t)j * n + i] * mult[i]);
     q[r][tx] = v;
   }
   __syncthreads();
@@ -699,7 +711,7 @@ __global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U
       Q = (Q - d) >> 8;
       planes[(row0 + (size_t)t * NE) * (size_t)n_padk + j] = (int8_t)d;
     }
-    planes[row0 * (size_t)n_padk + j] = (int8_t)Q;           // |Q| <= 2^6 + 1
+    planes[row0 * (size_t)n_padk + j] = (int8_t)Q;           // |Q| <= 127: 127.4 + the carry of the balanced lower digits (< 0.51)
   }
 }
 
@@ -817,38 +829,70 @@ static bool make_tmap(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t
 
 bool i8_available(gb200_ctx *) { return get_encode() != nullptr; }
 
-// Default number of int8 digit planes of U.  The planes hold the top B = 6 + 8 (T - 1) bits of every entry relative to its
-// column maximum; the dropped tail behaves like independent rounding noise, so a projected value carries an error of about
-// sqrt(n) 2^-B (column max) |x|.  T is the smallest count that keeps sqrt(n) 2^-B <= 2^-30 (~1e-9, three orders below the
-// 1e-6 parity tolerance and below the reference's own run-to-run reproducibility): T = 5 up to n = 65 536, 6 beyond.
-// Measured at n = 50 000 (profiles/r01_i8_plane_accuracy_n50k.json): T = 5 -> 4.6e-9 on beta, 1.4e-9 on the p-values.
+// Number of int8 digit planes of U.  The planes keep every entry to within s_i / 2, s_i = colmax_i / (127.4 * 256^(T-1)); the
+// dropped tails act as independent rounding noise, so a projected value (u_i . x) -- of typical size rms(x) for a unit vector --
+// carries a relative error of about  colmax_i sqrt(n) / (sqrt(12) * 127.4 * 256^(T-1)).
+//  * i8_default_planes(n): the U-independent worst case (colmax_i = 1, an eigenvector concentrated on one individual):
+//    smallest T with that bound <= 2^-30 -- T = 5 up to n = 3.1e6.  Used when the planes are requested before U is known.
+//  * i8_choose_planes(colmax, n): the same bound evaluated with the MEASURED largest column maximum of this U, target 2^-28
+//    (3.7e-9 on a projected value; the statistics inherit it scaled by 1/|z-score|, two orders below the 1e-6 parity bar for
+//    every SNP with |z| > 0.004).  Eigenvectors of a kinship matrix of unrelated individuals are delocalised (colmax ~ 4.6 / sqrt(n)):
+//    T = 4; family / population structure that concentrates an eigenvector on few individuals raises colmax and with it T.
 int i8_default_planes(size_t n) {
-  const double need = 30.0 + 0.5 * log2((double)(n > 1 ? n : 2));
-  int T = (int)ceil((need - 6.0) / 8.0) + 1;
+  const double need = sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * 1073741824.0;     // bound * 2^30 at T = 1
+  int T = 1 + (int)ceil(log2(need) / 8.0);
+  if (T < 4) T = 4;
+  if (T > 8) T = 8;
+  return T;
+}
+int i8_choose_planes(double colmax_max, size_t n) {
+  if (!(colmax_max > 0.0) || !isfinite(colmax_max)) return 4;
+  const double need = colmax_max * sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * 268435456.0;   // bound * 2^28 at T = 1
+  int T = 1 + (int)ceil(log2(need) / 8.0);
   if (T < 4) T = 4;
   if (T > 8) T = 8;
   return T;
 }
 
+// largest |entry| of U's columns -> the plane count i8_prepare will use (cached until the next setup)
+int i8_effective_planes(gb200_ctx *c, int *T_out) {
+  if (c->n_slices > 0) { *T_out = (int)c->n_slices; return GB200_OK; }
+  if (!c->lmm_ready) { *T_out = c->n ? i8_default_planes(c->n) : 0; return GB200_OK; }
+  if (c->i8.auto_T == 0) {
+    DevBuf tmp;
+    GB_CUDA(c, tmp.reserve(((size_t)c->n + 1) * sizeof(double)));
+    col_absmax_kernel<<<((int)c->n + 255) / 256, 256, 0, c->stream>>>(c->dU.as<double>(), (int)c->n, tmp.as<double>());
+    vec_max_kernel<<<1, 256, 0, c->stream>>>(tmp.as<double>(), (int)c->n, tmp.as<double>() + c->n);
+    double m = 0.0;
+    GB_CUDA(c, cudaMemcpyAsync(&m, tmp.as<double>() + c->n, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    tmp.release();
+    c->i8.colmax_max = m;
+    c->i8.auto_T = i8_choose_planes(m, c->n);
+  }
+  *T_out = c->i8.auto_T;
+  return GB200_OK;
+}
+
 int i8_prepare(gb200_ctx *c) {
   if (!c->lmm_ready) return set_err(c, GB200_ERR_STATE, "i8_prepare before lmm_setup");
-  const int T = c->n_slices > 0 ? (int)c->n_slices : i8_default_planes(c->n);
+  int T = 0;
+  { const int rc = i8_effective_planes(c, &T); if (rc) return rc; }
   if (T < 2 || T > 8) return set_err(c, GB200_ERR_ARG, "n_slices must be in 2..8");
   if (c->i8.ready && c->i8.n_slices == T && c->i8.n == c->n) return GB200_OK;
   const I8Geom g = make_geom(c->n, T);
   const size_t rows = (size_t)g.n_groups * (size_t)g.N;
   const size_t bytes = rows * (size_t)g.n_padk;
   GB_CUDA(c, c->i8.slices.reserve(bytes));
-  GB_CUDA(c, c->i8.scale.reserve((size_t)g.n * (sizeof(double) + sizeof(int)) + (size_t)g.n * sizeof(double)));
+  GB_CUDA(c, c->i8.scale.reserve((size_t)g.n * 3 * sizeof(double)));
   GB_CUDA(c, cudaMemsetAsync(c->i8.slices.p, 0, bytes, c->stream));
   double *scale = c->i8.scale.as<double>();
   double *colmax = scale + g.n;
-  int *expo = reinterpret_cast<int *>(colmax + g.n);
-  const int B = 6 + 8 * (T - 1);
+  double *mult = colmax + g.n;
   col_absmax_kernel<<<(g.n + 255) / 256, 256, 0, c->stream>>>(c->dU.as<double>(), g.n, colmax);
-  col_scale_kernel<<<(g.n + 255) / 256, 256, 0, c->stream>>>(colmax, g.n, B, scale, expo);
+  col_scale_kernel<<<(g.n + 255) / 256, 256, 0, c->stream>>>(colmax, g.n, T, scale, mult);
   dim3 grid((g.n + 31) / 32, (g.n + 31) / 32);
-  slice_kernel<<<grid, 256, 0, c->stream>>>(c->dU.as<double>(), g.n, expo, T, g.NE, g.n_padk, c->i8.slices.as<int8_t>());
+  slice_kernel<<<grid, 256, 0, c->stream>>>(c->dU.as<double>(), g.n, mult, T, g.NE, g.n_padk, c->i8.slices.as<int8_t>());
   GB_CUDA(c, cudaGetLastError());
   if (!c->i8.tmap_a) c->i8.tmap_a = aligned_alloc(64, sizeof(CUtensorMap));
   if (!c->i8.tmap_b) c->i8.tmap_b = aligned_alloc(64, sizeof(CUtensorMap));
@@ -893,7 +937,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
   p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : 6;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : 6; p.stages = I8_STAGES;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
   const int tiles = p.m_tiles * p.n_groups;
   if (pair2) {
@@ -927,7 +971,11 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     c->i8.tmap_b_half = true;
     GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
-    const size_t smem_pair = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK) + 256;   // A + half of B per stage
+    const size_t stage_pair = (size_t)I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK;                            // A + half of B per stage
+    int ns = c->gemm_stages > 0 ? (int)c->gemm_stages : 6;
+    while (ns > 2 && 1024 + (size_t)ns * stage_pair + 256 > 227 * 1024) --ns;
+    p.stages = ns;
+    const size_t smem_pair = 1024 + (size_t)ns * stage_pair + 256;
     ProfScope ps(c, "utx");
     i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
     GB_CUDA(c, cudaGetLastError());
@@ -1234,6 +1282,7 @@ int kin_i8_flush(gb200_ctx *c) {
   p.lbo_units = 1; p.scale = nullptr;
   p.C = c->dK.as<double>(); p.ldc = n; p.mode = 1;
   p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = 6; p.stages = I8_STAGES;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
   GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (c->kin_cta_pair != 0) {

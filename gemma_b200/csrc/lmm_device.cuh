@@ -121,6 +121,16 @@ __device__ inline double beta_cont_frac_dev(double a, double b, double x, double
 __device__ inline double beta_inc_AXPY_dev(double A, double Y, double a, double b, double x) {
   if (x == 0.0) return A * 0 + Y;
   if (x == 1.0) return A * 1 + Y;
+  // GSL's asymptotic branches [A&S 26.5.17] for a or b > 1e5 (df/2 > 1e5: more than 2e5 individuals); gsl_sf_gamma_inc_P/Q at the
+  // only first argument this path produces (nu1 = 1 -> 1/2): P(1/2, z) = erf(sqrt z), Q(1/2, z) = erfc(sqrt z)
+  if (a > 1e5 && b < 10 && x > a / (a + b) && b == 0.5) {
+    const double N = a + (b - 1.0) / 2.0;
+    return A * erfc(sqrt(-N * log(x))) + Y;
+  }
+  if (b > 1e5 && a < 10 && x < b / (a + b) && a == 0.5) {
+    const double N = b + (a - 1.0) / 2.0;
+    return A * erf(sqrt(-N * log1p(-x))) + Y;
+  }
   double lnb = ln_beta_dev(a, b);
   double ln_pre = -lnb + a * log(x) + b * log1p(-x);
   double prefactor = exp(ln_pre);

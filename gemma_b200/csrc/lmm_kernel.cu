@@ -377,3 +377,28 @@ cudaError_t launch_lmm_null(int n_cvt, const LmmConst &D, double l_min, double l
 }
 
 }  // namespace gb
+
+// ---- diagnostic: the device restatement of the GSL tails on host arrays (include/gemma_b200.h: gb200_cdf_tails) ----------------
+namespace gb {
+__global__ void cdf_tails_kernel(int kind, const double *x, double nu1, const double *nu2, double *out, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[i] = (kind == 0) ? fdist_Q_dev(x[i], nu1, nu2[i]) : chisq1_Q_dev(x[i]);
+}
+}  // namespace gb
+
+extern "C" int gb200_cdf_tails(gb200_ctx *c, int kind, const double *x, double nu1, const double *nu2, double *out, size_t count) {
+  if (!c) return GB200_ERR_ARG;
+  if (!x || !out || count == 0 || (kind != 0 && kind != 1) || (kind == 0 && !nu2)) return gb::set_err(c, GB200_ERR_ARG, "gb200_cdf_tails: bad argument");
+  gb::DevBuf dx, dn, dout;
+  const size_t by = count * sizeof(double);
+  GB_CUDA(c, dx.reserve(by)); GB_CUDA(c, dn.reserve(by)); GB_CUDA(c, dout.reserve(by));
+  GB_CUDA(c, cudaMemcpyAsync(dx.p, x, by, cudaMemcpyHostToDevice, c->stream));
+  if (kind == 0) GB_CUDA(c, cudaMemcpyAsync(dn.p, nu2, by, cudaMemcpyHostToDevice, c->stream));
+  gb::cdf_tails_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(kind, dx.as<double>(), nu1, dn.as<double>(), dout.as<double>(), count);
+  GB_CUDA(c, cudaGetLastError());
+  GB_CUDA(c, cudaMemcpyAsync(out, dout.p, by, cudaMemcpyDeviceToHost, c->stream));
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));
+  dx.release(); dn.release(); dout.release();
+  return GB200_OK;
+}

@@ -134,3 +134,12 @@ def spectrum_like_kinship(n, seed=SEED):
     rng = np.random.default_rng(seed + 1)
     ev = np.sort(np.concatenate([[0.0], rng.gamma(0.6, 1.6, n - 1) + 1e-3]))
     return ev
+
+
+def polygenic_rotated(ev, seed=SEED, h2=0.5):
+    """U^T y of a phenotype drawn from the LMM itself, y ~ N(0, h2 K / mean(eval) + (1 - h2) I): in the eigenbasis the entries are
+    independent N(0, h2 eval_i / mean(eval) + 1 - h2).  pve ~ h2, so the REML / ML roots are interior and every SNP runs the whole
+    grid + Brent + Newton search (a phenotype unrelated to K puts lambda on the l_min boundary and skips it)."""
+    ev = np.asarray(ev, dtype=np.float64)
+    rng = np.random.default_rng(seed + 77)
+    return np.sqrt(h2 * ev / ev.mean() + (1.0 - h2)) * rng.standard_normal(ev.shape[0])

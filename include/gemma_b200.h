@@ -88,6 +88,12 @@ GB200_API int gb200_measure_fp64_fma(gb200_ctx *ctx, double seconds, double *tfl
  *  5: SNPs}.  counts may be NULL to reset only.  Used by bench.py to state the kernel's executed FP64 flops. */
 GB200_API int gb200_lmm_counters(gb200_ctx *ctx, unsigned long long counts[6], int reset);
 
+/* The device restatement of the two GSL tails the path calls: out[i] = gsl_cdf_fdist_Q(x[i], nu1, nu2[i]) (call sites
+ * src/lmm.cpp:1161,1206; GSL cdf/fdist.c + cdf/beta_inc.c incl. the asymptotic branches for nu/2 > 1e5) when kind == 0,
+ * gsl_cdf_chisq_Q(x[i], 1) (src/lmm.cpp:1553) when kind == 1.  Host arrays of `count` doubles; nu2 may be NULL for kind 1.
+ * Diagnostic entry point used by the parity tests. */
+GB200_API int gb200_cdf_tails(gb200_ctx *ctx, int kind, const double *x, double nu1, const double *nu2, double *out, size_t count);
+
 /* ---- dense GEMM seam -------------------------------------------------------- */
 /* fast_dgemm / fast_eigen_dgemm (src/fastblas.h:36-41, src/fastblas.cpp:175-236):
  * C = alpha*op(A)*op(B) + beta*C on row-major matrices with leading dimensions.

@@ -106,11 +106,21 @@ static double beta_cont_frac(double a, double b, double x, double epsabs) {
 }
 
 static double beta_inc_AXPY(double A, double Y, double a, double b, double x) {
-  /* A * I_x(a,b) + Y ; GSL cdf/beta_inc.c.  The two asymptotic branches
-   * (a or b > 1e5, i.e. more than 2e5 individuals) are NOT restated: the
-   * continued fraction is used there as well. */
+  /* A * I_x(a,b) + Y ; GSL cdf/beta_inc.c, including its two asymptotic branches [Abramowitz-Stegun 26.5.17] for
+   * a or b > 1e5 (more than 2e5 individuals: df/2 > 1e5 at the call sites src/lmm.cpp:1161,1206).  They go through
+   * gsl_sf_gamma_inc_Q / _P (specfunc/gamma_inc.c, external GSL), restated below for the only first argument the LMM
+   * path produces (nu1 = 1 -> 1/2): P(1/2, z) = erf(sqrt z), Q(1/2, z) = erfc(sqrt z).  Other first arguments keep
+   * the continued fraction (never reached from src/lmm.cpp). */
   if (x == 0.0) return A * 0 + Y;
   if (x == 1.0) return A * 1 + Y;
+  if (a > 1e5 && b < 10 && x > a / (a + b) && b == 0.5) {
+    double N = a + (b - 1.0) / 2.0;
+    return A * erfc(sqrt(-N * log(x))) + Y;
+  }
+  if (b > 1e5 && a < 10 && x < b / (a + b) && a == 0.5) {
+    double N = b + (a - 1.0) / 2.0;
+    return A * erf(sqrt(-N * log1p(-x))) + Y;
+  }
   {
     double lnb = ln_beta(a, b);
     double ln_pre = -lnb + a * log(x) + b * log1p(-x);

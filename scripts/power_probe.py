@@ -27,7 +27,7 @@ g = torch.Generator(device=dev); g.manual_seed(1)
 U, _ = torch.linalg.qr(torch.randn((n, n), dtype=torch.float64, device=dev, generator=g))
 U = U.contiguous()
 ev_h = synth.spectrum_like_kinship(n, 1)
-y = torch.from_numpy(synth.phenotype(n, synth.genotypes(n, 64, seed=1, snp_offset=10 ** 9).astype(np.float64), 1)).to(dev)
+y = (U @ torch.from_numpy(synth.polygenic_rotated(ev_h, 1)).to(dev)).contiguous()
 ev = torch.from_numpy(ev_h).to(dev)
 UtWt = (torch.ones((1, n), dtype=torch.float64, device=dev) @ U).contiguous(); Uty = (y @ U).contiguous()
 ctx = gemma_b200.Context(0, stream=stream.cuda_stream)

@@ -409,6 +409,15 @@ def test_i8_tensor_core_projection_matches_fp64(n_total, n_drop, l, miss):
         got = c.lmm_project_bed(bed, n_total, mask if n_drop else None)
         err = np.abs(got - ref).max() / scale
         assert err < tol, (T, err)
+    # the count chosen from the column maxima of this (Haar) U: 4 planes, noise below the 2^-28 design target
+    c.set_option("n_slices", 0)
+    assert c.get_option("n_slices") == 4
+    got = c.lmm_project_bed(bed, n_total, mask if n_drop else None)
+    assert np.abs(got - ref).max() < 8 * 2.0 ** -28 * np.sqrt((X * X).mean()), np.abs(got - ref).max()
+    # an eigenvector concentrated on one individual raises the count
+    Q2 = np.eye(n); Q2[:, [0, 1]] = Q2[:, [1, 0]]
+    c.lmm_setup(Q2, ev, np.ones((n, 1)), rng.standard_normal(n))
+    assert c.get_option("n_slices") == 5
     c.close()
 
 
@@ -1099,3 +1108,22 @@ def test_qc_bed_statistics_match_host_restatement(ctx):
     assert np.allclose(st["v_w"], np.einsum("sa,ab,sb->s", Wtx, WtWi, Wtx), rtol=1e-10)
     st2 = ctx.qc_bed(bed, n_total)                                           # no mask, no covariates
     assert np.array_equal(st2["n_miss"], (G < 0).sum(axis=1)) and np.all(st2["v_w"] == 0)
+
+
+@pytest.mark.gpu
+def test_device_tails_match_the_restated_gsl_tails_including_the_asymptotic_branch(ctx):
+    """gsl_cdf_fdist_Q(x, 1, df) and gsl_cdf_chisq_Q(x, 1) as the kernels compute them (gb200_cdf_tails) against the oracle's
+    restatement, over df on both sides of GSL's df/2 > 1e5 switch to the A&S 26.5.17 form (cdf/beta_inc.c; call sites
+    src/lmm.cpp:1161,1206,1553)."""
+    xs, dfs = [], []
+    for df in (10.0, 194.0, 1408.0, 49998.0, 199998.0, 200004.0, 300000.0, 1000000.0):
+        for x in (1e-8, 0.01, 0.5, 1.0, 3.0, 10.0, 30.0, 60.0, 300.0, 2000.0, df - 0.5, df + 0.5, 5.0 * df):
+            xs.append(x); dfs.append(df)
+    got = ctx.cdf_tails(np.array(xs), np.array(dfs))
+    want = np.array([O.fdist_Q(x, 1.0, d) for x, d in zip(xs, dfs)])
+    big = want > 1e-290
+    assert np.all(np.abs(got[big] - want[big]) <= 1e-9 * want[big] + 1e-17), np.abs(got - want)[big].max()   # 1 - P leaves ~1e-16 absolute
+    assert np.all(got[~big] <= 1e-290)
+    assert np.all(got[(np.array(dfs) > 2e5) & (np.array(xs) == 300.0)] == 0.0)       # the reference's own 1 - P = 0
+    xc = np.array([-1.0, 0.0, 1e-12, 0.3, 1.0, 10.0, 100.0, 1400.0])
+    assert np.allclose(ctx.cdf_tails(xc), [O.chisq1_Q(x) for x in xc], rtol=1e-12, atol=0)

@@ -34,6 +34,28 @@ def test_fdist_and_chisq_tails_match_scipy():
         assert O.chisq1_Q(x) == pytest.approx(scipy.stats.chi2.sf(x, 1) if x > 0 else 1.0, rel=1e-12)
 
 
+def test_fdist_tail_asymptotic_branch_beyond_200k_individuals():
+    """GSL's beta_inc_AXPY switches to A&S 26.5.17 when df/2 > 1e5 (cdf/beta_inc.c; call sites src/lmm.cpp:1161,1206):
+    Q = 1 - gsl_sf_gamma_inc_P(1/2, -N log1p(-u)), N = df/2 - 1/4 -- close to the exact tail where the subtraction has
+    digits left, exactly 0 once P rounds to 1 (the reference prints p = 0 there).  The restatement reproduces both."""
+    import math
+    for df in (200004, 300000, 1000000):
+        r = float(df)
+        for x in (1e-8, 0.01, 0.5, 3.0, 10.0, 30.0, 60.0):
+            u = x / (r + x)
+            N = df / 2.0 + (0.5 - 1.0) / 2.0
+            want = -1.0 * math.erf(math.sqrt(-N * math.log1p(-u))) + 1.0
+            got = O.fdist_Q(x, 1.0, df)
+            assert got == want, (df, x)
+            exact = scipy.special.betaincc(0.5, df / 2.0, u)
+            assert got == pytest.approx(exact, rel=2e-9 if x <= 30 else 1e-4), (df, x)
+        assert O.fdist_Q(300.0, 1.0, df) == 0.0                      # the reference's own underflow of 1 - P
+        # x >= nu2/nu1 keeps the continued fraction (u <= 1/2 is never beyond the peak a/(a+b))
+        assert O.fdist_Q(2.0 * df, 1.0, df) == pytest.approx(scipy.special.betainc(df / 2.0, 0.5, 1.0 / 3.0), rel=1e-8, abs=1e-300)
+    # just below the switch the continued fraction is still used
+    assert O.fdist_Q(300.0, 1.0, 199998) == pytest.approx(scipy.special.betaincc(0.5, 99999.0, 300.0 / 200298.0), rel=1e-9)
+
+
 @pytest.fixture(scope="module")
 def mouse(golden_dir):
     d = os.path.join(golden_dir, "mouse_hs1940")
