@@ -626,16 +626,17 @@ def run_lmm(args):
             # executed FP64 flops (FMA = 2) per individual: hoisted slot = 1 mul + 2(c+2) FMA, + (c+2) products per pass of 5 slots;
             # refinement pass (2 lambdas): nidx products + 2 x (den FMA, reciprocal = 4 FMA, (P-1) mul, P x (1 add + nidx FMA)), P = powers
             f_common = counters["common_slots"] * (1 + 4.0 * (nc + 2)) + (counters["common_slots"] / 5.0) * (nc + 2)
-            f_p2 = counters["order2"] * (nidx + 2 * (2 + 8 + 1 + 2 * (1 + 2 * nidx)))
-            f_p3 = counters["order3"] * (nidx + 2 * (2 + 8 + 2 + 3 * (1 + 2 * nidx)))
+            f_p2 = counters["two_power_passes"] * (nidx + 2 * (2 + 8 + 1 + 2 * (1 + 2 * nidx)))
+            f_p3 = counters["three_power_passes"] * (nidx + 2 * (2 + 8 + 2 + 3 * (1 + 2 * nidx)))
             flops = (f_common + f_p2 + f_p3) * n_c
             ach64 = flops / (lmm_ms * 1e-3) / 1e12
             lmm_roof["fp64"] = {"achieved": ach64, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach64 / fp64_peak,
                                 "peak_source": "measured here: independent DFMA chains on all SMs for 0.5 s (gb200_measure_fp64_fma)",
                                 "passes_per_snp": {"hoisted_lambda_slots": counters["common_slots"] / max(1, counters["snps"]),
-                                                   "two_power_passes": counters["order2"] / max(1, counters["snps"]),
-                                                   "three_power_passes": counters["order3"] / max(1, counters["snps"]),
-                                                   "with_logdet": counters["with_logdet"] / max(1, counters["snps"])},
+                                                   "exact_two_power_passes": counters["two_power_passes"] / max(1, counters["snps"]),
+                                                   "exact_three_power_passes": counters["three_power_passes"] / max(1, counters["snps"]),
+                                                   "exact_with_logdet": counters["with_logdet"] / max(1, counters["snps"])},
+                                "interpolated_refinement": bool(ctx.get_option("lmm_interp")),
                                 "note": "executed flops from the kernel's own pass counters (log / special functions not counted)"}
         except Exception as ex:
             lmm_roof["fp64"] = {"error": repr(ex)[:200]}

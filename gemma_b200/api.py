@@ -187,7 +187,7 @@ class Context:
     def lmm_counters(self, reset=False):
         a = (C.c_ulonglong * 6)()
         self._chk(self.lib.gb200_lmm_counters(self.h, a, int(reset)))
-        return dict(zip(("common_slots", "order1", "order2", "order3", "with_logdet", "snps"), [int(x) for x in a]))
+        return dict(zip(("common_slots", "two_power_passes", "three_power_passes", "with_logdet", "unused", "snps"), [int(x) for x in a]))
 
     def cdf_tails(self, x, nu2=None, nu1=1.0):
         """Device restatement of gsl_cdf_fdist_Q(x, nu1, nu2) (nu2 given) or gsl_cdf_chisq_Q(x, 1) (nu2 None)."""

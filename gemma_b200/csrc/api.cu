@@ -86,7 +86,7 @@ void gb200_destroy(gb200_ctx *c) {
                         &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale,
                         &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles,
                         &c->i8.kin_qbits, &c->i8.kin_y, &c->dWtx, &c->dEnv, &c->dX2, &c->dFlip, &c->dLmW, &c->dLmY,
-                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab};
+                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam};
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
@@ -187,6 +187,15 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "gemm_stages must be 0..8");
     c->gemm_stages = value; return GB200_OK;
   }
+  if (!strcmp(name, "lmm_interp")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "lmm_interp must be 0 or 1");
+    if (value != c->lmm_interp) c->common_ready = false;
+    c->lmm_interp = value; return GB200_OK;
+  }
+  if (!strcmp(name, "eigh_path")) {
+    if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "eigh_path must be 0, 1 or 2");
+    c->eigh_path = value; return GB200_OK;
+  }
   if (!strcmp(name, "lmm_hoist")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "lmm_hoist must be 0 or 1");
     c->lmm_hoist = value; return GB200_OK;
@@ -232,6 +241,7 @@ int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
   if (!strcmp(name, "kin_miss_max_permille")) { *value = (long)(c->kin_miss_max * 1000.0 + 0.5); return GB200_OK; }
   if (!strcmp(name, "lmm_kernel")) { *value = c->lmm_kernel; return GB200_OK; }
   if (!strcmp(name, "lmm_hoist")) { *value = c->lmm_hoist; return GB200_OK; }
+  if (!strcmp(name, "lmm_interp")) { *value = c->lmm_interp; return GB200_OK; }
   if (!strcmp(name, "batch_chunk")) { *value = c->n_c ? (long)lmm_chunk_snps(c) : c->batch_chunk; return GB200_OK; }
   if (!strcmp(name, "stage_mask")) { *value = c->stage_mask; return GB200_OK; }
   if (!strcmp(name, "gemm_groups")) { *value = c->gemm_groups; return GB200_OK; }
@@ -511,7 +521,7 @@ static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
-  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.xcov = nullptr; D.xcov_idx = 0;
+  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.cheb = nullptr; D.cheb_marg = 0.0; D.xcov = nullptr; D.xcov_idx = 0;
   D.cnt = c->count_work ? c->dTicket.as<unsigned long long>() + 4 : nullptr;     // 8 words behind the ticket words
   D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
   D.gen_stride = 0;
@@ -630,16 +640,38 @@ static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu,
   const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
   if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
   if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3 && c->lmm_hoist) {
-    // SNP-independent sums at the lambdas shared by every SNP (once per setup/params pair)
-    const size_t J = (size_t)c->prm.n_region + 3, rec = lmm_common_record_doubles((int)c->n_cvt);
+    // SNP-independent sums at the lambdas shared by every SNP (once per setup/params pair); with lmm_interp also at the
+    // Chebyshev nodes of every grid interval (the per-SNP kernel then serves its Brent / Newton evaluations from interpolants)
+    const size_t J0 = (size_t)c->prm.n_region + 3, rec = lmm_common_record_doubles((int)c->n_cvt);
+    const int M = lmm_cheb_nodes();
+    const double marg = 0.15;
+    size_t n_nodes = c->lmm_interp ? (size_t)c->prm.n_region * (size_t)M : 0;
+    if ((J0 + n_nodes) * c->n_c * sizeof(double) > ((size_t)2 << 30)) n_nodes = 0;        // node rows stay below 2 GB
+    // 20 nodes resolve an interval of one decade (+ margins) to ~1e-14; wider intervals (a coarse -region grid) keep the exact passes
+    if (log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region > 2.4) n_nodes = 0;
+    const size_t J = J0 + n_nodes;
     if (!c->common_ready) {
       GB_CUDA(c, c->dHrows.reserve(J * c->n_c * sizeof(double)));
       GB_CUDA(c, c->dCtab.reserve(J * rec * sizeof(double)));
-      GB_CUDA(c, launch_lmm_common((int)c->n_cvt, D, c->prm, c->dHrows.as<double>(), c->dCtab.as<double>(), c->stream));
+      if (n_nodes) {
+        std::vector<double> lams(n_nodes);
+        const double interval = log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region;
+        for (int g = 0; g < c->prm.n_region; ++g) {
+          const double lo = log(c->prm.l_min) + interval * (double)g - marg, hi = log(c->prm.l_min) + interval * (double)(g + 1) + marg;
+          for (int m = 0; m < M; ++m) lams[(size_t)g * M + m] = exp(0.5 * (lo + hi) + 0.5 * (hi - lo) * cos(M_PI * ((double)m + 0.5) / (double)M));
+        }
+        GB_CUDA(c, c->dNodeLam.reserve(n_nodes * sizeof(double)));
+        GB_CUDA(c, cudaMemcpyAsync(c->dNodeLam.p, lams.data(), n_nodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        GB_CUDA(c, cudaStreamSynchronize(c->stream));      // `lams` goes out of scope
+        GB_CUDA(c, c->dCheb.reserve(lmm_cheb_doubles((int)c->n_cvt, c->prm.n_region) * sizeof(double)));
+      }
+      GB_CUDA(c, launch_lmm_common((int)c->n_cvt, D, c->prm, c->dHrows.as<double>(), c->dCtab.as<double>(), c->dNodeLam.as<double>(),
+                                   (int)n_nodes, c->dCheb.as<double>(), c->stream));
       GB_CUDA(c, cudaStreamSynchronize(c->stream));       // the tests may run on a side stream
       c->common_ready = true;
     }
-    D.Hrows = c->dHrows.as<double>(); D.ctab = c->dCtab.as<double>(); D.n_common = (int)J;
+    D.Hrows = c->dHrows.as<double>(); D.ctab = c->dCtab.as<double>(); D.n_common = (int)J0;
+    if (n_nodes) { D.cheb = c->dCheb.as<double>(); D.cheb_marg = marg; }
   }
   if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3)
     GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));

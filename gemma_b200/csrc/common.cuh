@@ -107,6 +107,7 @@ struct gb200_ctx {
   gb::DevBuf dMvY, dMvNull, dMvOut;      // multivariate LMM: U^T Y rows (2 x n_c), MvNull, per-SNP output rows
   gb::MvConst mvK; bool mv_ready = false, mv_null_ready = false;
   gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
+  gb::DevBuf dCheb, dNodeLam;   // Chebyshev tables / node lambdas of the interpolated refinement
   bool common_ready = false;
   // scratch
   gb::DevBuf dX, dUtXt, dOut, dBed, dMask, dIdx, dTicket, dTmp;
@@ -138,8 +139,10 @@ struct gb200_ctx {
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K; sparse FP64 terms for missing genotypes), 1 = FP64 only
   double kin_miss_max = 0.2;   // chunks with a larger fraction of missing genotypes take the dense FP64 path
   long lmm_kernel = 0;   // 0 auto (v2 when supported), 1 = v1 warp-per-SNP, 2 = v2 lockstep CTA, 3 = any-covariate-count kernel
+  long lmm_interp = 1;   // lockstep kernel: Brent / Newton evaluations served by Chebyshev interpolants over each grid interval (needs lmm_hoist)
   long lmm_hoist = 1;    // lockstep kernel: SNP-independent sums at the shared lambdas computed once per run
   size_t n_c = 0;        // n rounded up to 512 (vector / UtX row padding)
+  long eigh_path = 0;    // 0 auto (cusolverDnXsyevd up to n = 32768, cusolverMgSyevd on this one device beyond), 1 = Xsyevd, 2 = MgSyevd
   size_t eigh_workspace_bytes = 0;   // device workspace of the last eigendecomposition (reported by bench.py)
   gb::I8State i8;
 };
@@ -202,7 +205,10 @@ cudaError_t launch_mv_assoc(int c, const MvConst &K, const MvNull *nm, const dou
                             int num_sms, cudaStream_t st);
 cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double *Wt, const double *y, const double *WtWi, const double *Wty,
                       double yPwy, int test_mode, gb200_sumstat *out, cudaStream_t st);
-cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st);
+cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, const double *node_lams,
+                              int n_nodes, double *cheb, cudaStream_t st);
+int lmm_cheb_nodes();
+size_t lmm_cheb_doubles(int n_cvt, int n_region);
 size_t lmm_common_record_doubles(int n_cvt);
 cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,
                                 int l, gb200_sumstat *out, unsigned int *ticket, int num_sms, cudaStream_t st);

@@ -1,11 +1,13 @@
 // eigh.cu -- once-per-run symmetric eigendecomposition of the (centred) kinship matrix on
 // the device.  Replaces EigenDecomp_Zeroed -> lapack_eigen_symmv -> dsyevr_
-// (src/lapack.cpp:149-291).  The O(n^3) factorisation itself is cuSOLVER's syevd (64-bit
-// API so the workspace may exceed 2^31 elements at n = 50 000); centring, the transpose
+// (src/lapack.cpp:149-291).  The O(n^3) factorisation itself is cuSOLVER's syevd (cusolverDnXsyevd
+// up to n = 32768, where that entry point stops; cusolverMgSyevd on this one device beyond); centring, the transpose
 // that puts eigenvectors in the COLUMNS of row-major U (lapack.cpp:228) and the <1e-10
 // zeroing (lapack.cpp:268-269) are ours.
 #include "common.cuh"
 #include <cusolverDn.h>
+#include <cusolverMg.h>
+#include <dlfcn.h>
 
 namespace gb {
 
@@ -30,9 +32,106 @@ __global__ void zero_small_kernel(double *eval, size_t n, double *stats) {
   }
 }
 
+
+// ---- cusolverMgSyevd on ONE device -----------------------------------------------------------------------------------------
+// cusolverDnXsyevd refuses n > 32768 (CUSOLVER_STATUS_INVALID_VALUE from its bufferSize; probed on CUDA 12.9: n = 40 000, 46 340,
+// 50 000, 65 536 all fail, as do the legacy Dsyevd / Dormtr entry points), and BASELINE config 4 has n = 50 000.  The multi-GPU
+// solver of the same library has no such limit and runs on a 1 x 1 device grid: measured 110 s at n = 50 000 on one B200 (64 GB
+// workspace), eigenvalues equal to Xsyevd's to 2e-15 where both run (scripts/eig_probe.cu).  Loaded with dlopen so that the rest
+// of the library does not depend on libcusolverMg being installed.
+struct MgApi {
+  void *lib = nullptr;
+  cusolverStatus_t (*Create)(cusolverMgHandle_t *) = nullptr;
+  cusolverStatus_t (*Destroy)(cusolverMgHandle_t) = nullptr;
+  cusolverStatus_t (*DeviceSelect)(cusolverMgHandle_t, int, int[]) = nullptr;
+  cusolverStatus_t (*CreateDeviceGrid)(cudaLibMgGrid_t *, int32_t, int32_t, const int32_t[], cusolverMgGridMapping_t) = nullptr;
+  cusolverStatus_t (*DestroyGrid)(cudaLibMgGrid_t) = nullptr;
+  cusolverStatus_t (*CreateMatrixDesc)(cudaLibMgMatrixDesc_t *, int64_t, int64_t, int64_t, int64_t, cudaDataType, const cudaLibMgGrid_t) = nullptr;
+  cusolverStatus_t (*DestroyMatrixDesc)(cudaLibMgMatrixDesc_t) = nullptr;
+  cusolverStatus_t (*Syevd_bufferSize)(cusolverMgHandle_t, cusolverEigMode_t, cublasFillMode_t, int, void *[], int, int, cudaLibMgMatrixDesc_t,
+                                       void *, cudaDataType, cudaDataType, int64_t *) = nullptr;
+  cusolverStatus_t (*Syevd)(cusolverMgHandle_t, cusolverEigMode_t, cublasFillMode_t, int, void *[], int, int, cudaLibMgMatrixDesc_t, void *,
+                            cudaDataType, cudaDataType, void *[], int64_t, int *) = nullptr;
+  bool ok = false;
+};
+static MgApi &mg_api() {
+  static MgApi a;
+  if (a.lib || a.ok) return a;
+  for (const char *name : {"libcusolverMg.so.11", "libcusolverMg.so", "/usr/local/cuda/lib64/libcusolverMg.so.11"}) {
+    a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) return a;
+#define MG_SYM(field, sym) *(void **)(&a.field) = dlsym(a.lib, sym)
+  MG_SYM(Create, "cusolverMgCreate"); MG_SYM(Destroy, "cusolverMgDestroy"); MG_SYM(DeviceSelect, "cusolverMgDeviceSelect");
+  MG_SYM(CreateDeviceGrid, "cusolverMgCreateDeviceGrid"); MG_SYM(DestroyGrid, "cusolverMgDestroyGrid");
+  MG_SYM(CreateMatrixDesc, "cusolverMgCreateMatrixDesc"); MG_SYM(DestroyMatrixDesc, "cusolverMgDestroyMatrixDesc");
+  MG_SYM(Syevd_bufferSize, "cusolverMgSyevd_bufferSize"); MG_SYM(Syevd, "cusolverMgSyevd");
+#undef MG_SYM
+  a.ok = a.Create && a.Destroy && a.DeviceSelect && a.CreateDeviceGrid && a.DestroyGrid && a.CreateMatrixDesc && a.DestroyMatrixDesc &&
+         a.Syevd_bufferSize && a.Syevd;
+  return a;
+}
+
 }  // namespace gb
 
 using namespace gb;
+
+// dA (n x n, ld n, symmetric; destroyed) -> eigenvectors in the ROWS of the row-major view of dA (== columns of the column-major
+// array, like Xsyevd leaves them), eigenvalues ascending in dW.  Blocks the host; uses cuSOLVER's own streams.
+static int eigh_mg(gb200_ctx *ctx, double *dA, size_t n, double *dW) {
+  MgApi &mg = mg_api();
+  if (!mg.ok) return set_err(ctx, GB200_ERR_UNSUPPORTED, "gb200_eigh: n > 32768 needs libcusolverMg (cusolverDnXsyevd stops at 32768), which could not be loaded");
+  const int tile = 256;
+  const size_t ncols = (n + tile - 1) / tile * tile;            // the last column tile is stored in full
+  cusolverMgHandle_t h = nullptr; cudaLibMgGrid_t grid = nullptr; cudaLibMgMatrixDesc_t desc = nullptr;
+  DevBuf dP, dWork;
+  std::vector<double> W(n);
+  auto fail = [&](int code, const std::string &msg) {
+    dP.release(); dWork.release();
+    if (desc) mg.DestroyMatrixDesc(desc);
+    if (grid) mg.DestroyGrid(grid);
+    if (h) mg.Destroy(h);
+    return set_err(ctx, code, msg);
+  };
+#define MG_CALL(call)                                                                                                    \
+  do { cusolverStatus_t _s = (call); if (_s != CUSOLVER_STATUS_SUCCESS) return fail(GB200_ERR_NUMERIC, std::string(#call " failed, cusolver status ") + std::to_string((int)_s)); } while (0)
+#define MG_CUDA(call)                                                                                                    \
+  do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(GB200_ERR_CUDA, std::string(#call " failed: ") + cudaGetErrorString(_e)); } while (0)
+  int dev[1] = {ctx->device};
+  int32_t dev32[1] = {ctx->device};
+  MG_CALL(mg.Create(&h));
+  MG_CALL(mg.DeviceSelect(h, 1, dev));
+  MG_CALL(mg.CreateDeviceGrid(&grid, 1, 1, dev32, CUDALIBMG_GRID_MAPPING_COL_MAJOR));
+  MG_CALL(mg.CreateMatrixDesc(&desc, (int64_t)n, (int64_t)n, (int64_t)n, (int64_t)tile, CUDA_R_64F, grid));
+  double *A = dA;
+  if (ncols != n) {
+    MG_CUDA(dP.reserve(n * ncols * sizeof(double)));
+    MG_CUDA(cudaMemcpyAsync(dP.p, dA, n * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    MG_CUDA(cudaMemsetAsync(dP.as<double>() + n * n, 0, n * (ncols - n) * sizeof(double), ctx->stream));
+    A = dP.as<double>();
+  }
+  MG_CUDA(cudaStreamSynchronize(ctx->stream));
+  void *arrA[1] = {A};
+  int64_t lwork = 0;
+  MG_CALL(mg.Syevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, arrA, 1, 1, desc, W.data(), CUDA_R_64F, CUDA_R_64F, &lwork));
+  ctx->eigh_workspace_bytes = (size_t)lwork * sizeof(double) + (A != dA ? n * ncols * sizeof(double) : 0);
+  MG_CUDA(dWork.reserve((size_t)(lwork > 0 ? lwork : 1) * sizeof(double)));
+  void *arrW[1] = {dWork.p};
+  int info = -1;
+  MG_CALL(mg.Syevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, arrA, 1, 1, desc, W.data(), CUDA_R_64F, CUDA_R_64F, arrW, lwork, &info));
+  MG_CUDA(cudaDeviceSynchronize());
+  if (info != 0) return fail(GB200_ERR_NUMERIC, "gb200_eigh: cusolverMgSyevd did not converge, info=" + std::to_string(info));
+  dWork.release();
+  if (A != dA) MG_CUDA(cudaMemcpyAsync(dA, A, n * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  MG_CUDA(cudaMemcpyAsync(dW, W.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(cudaStreamSynchronize(ctx->stream));
+  dP.release();
+  mg.DestroyMatrixDesc(desc); mg.DestroyGrid(grid); mg.Destroy(h);
+#undef MG_CALL
+#undef MG_CUDA
+  return GB200_OK;
+}
 
 // Device-resident core: dA (n x n, ld n; destroyed) -> dV (n x n, eigenvectors in COLUMNS of the row-major matrix), dW (n + 4 doubles:
 // eigenvalues ascending with the < 1e-10 zeroing applied, then 3 statistics).  The only large temporary is cuSOLVER's workspace.
@@ -73,6 +172,11 @@ static int eigh_device(gb200_ctx *ctx, double *dA, size_t n, int center, double 
       EIGH_CUDA(dRow.reserve((n + 1) * sizeof(double)));
       EIGH_CUDA(launch_center_matrix(dA, n, n, dRow.as<double>(), st));
     }
+    const bool use_mg = ctx->eigh_path == 2 || (ctx->eigh_path == 0 && n > 32768);
+    if (use_mg) {
+      const int rc = eigh_mg(ctx, dA, n, dW);
+      if (rc) { cleanup(); return rc; }
+    } else {
     EIGH_SOLVER(cusolverDnCreate(&h));
     EIGH_SOLVER(cusolverDnSetStream(h, st));
     EIGH_SOLVER(cusolverDnCreateParams(&params));
@@ -97,6 +201,7 @@ static int eigh_device(gb200_ctx *ctx, double *dA, size_t n, int center, double 
       return set_err(ctx, GB200_ERR_NUMERIC, "gb200_eigh: syevd did not converge, info=" + std::to_string(info));
     }
     dWork.release();
+    }
     // cuSOLVER leaves eigenvector j in column j of the column-major array == row j of the
     // row-major view; transpose so that U[i][j] = v_j[i] (eigenvectors in columns).
     EIGH_CUDA(launch_transpose(dA, n, n, n, dV, n, st));

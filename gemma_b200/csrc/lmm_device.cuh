@@ -39,6 +39,10 @@ struct LmmConst {
   const double *Hrows;   // n_common rows of n_c doubles: h_i = 1/(lambda_j delta_i + 1)
   const double *ctab;    // n_common records: SNP-independent sums at lambda_j (v2c_stride doubles each)
   int n_common;
+  // Chebyshev tables of the interpolated root refinement (lmm_v2.cuh): null = off.  Hrows / ctab then hold, after the n_common
+  // shared rows, cheb_M node rows per grid interval; cheb = [cos table (4 M) | per interval: coefficients of the SNP-independent sums]
+  const double *cheb;
+  double cheb_marg;      // half-width added to every interval in log(lambda)
   const double *xcov;    // G x E: covariate column xcov_idx is this per-SNP vector (U^T x) instead of a row of Wt; null otherwise
   int xcov_idx;
   unsigned long long *cnt;  // optional work counters of the lockstep kernel (gb200_lmm_counters); null = off

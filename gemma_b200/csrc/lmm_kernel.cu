@@ -78,14 +78,17 @@ static cudaError_t launch_assoc_v2_nc(const LmmConst &D, const LmmParams &prm, c
 
 // SNP-independent quantities at the lambdas every SNP visits (grid 0..n_region, exactly l_max, l_mle_null): one CTA per
 // lambda writes the h row and the record read by the hoisted passes of lmm_v2.cuh.  Once per (setup, params) pair.
+// Rows j >= n_region + 3 are the Chebyshev nodes of the interpolated refinement: their lambdas come from `node_lams`.
 template <int NC>
-__global__ void __launch_bounds__(256) lmm_common_kernel(LmmConst D, LmmParams prm, double *__restrict__ H, double *__restrict__ ctab) {
+__global__ void __launch_bounds__(256) lmm_common_kernel(LmmConst D, LmmParams prm, double *__restrict__ H, double *__restrict__ ctab,
+                                                         const double *__restrict__ node_lams) {
   constexpr int CN = v2c_nidx(NC), CS = v2c_stride(NC), NVC = NC + 1, NVAL = 3 * CN + 3;
   __shared__ double part[8][NVAL];
   const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_region = prm.n_region;
   const double lambda_interval = log(prm.l_max / prm.l_min) / (double)n_region;
-  const double lam = (j <= n_region) ? prm.l_min * exp(lambda_interval * (double)j) : (j == n_region + 1 ? prm.l_max : prm.l_mle_null);
+  const double lam = (j <= n_region) ? prm.l_min * exp(lambda_interval * (double)j)
+                                     : (j == n_region + 1 ? prm.l_max : (j == n_region + 2 ? prm.l_mle_null : node_lams[j - (n_region + 3)]));
   double acc[NVAL];
 #pragma unroll
   for (int q = 0; q < NVAL; ++q) acc[q] = 0.0;
@@ -126,16 +129,45 @@ __global__ void __launch_bounds__(256) lmm_common_kernel(LmmConst D, LmmParams p
   if (tid == 0) ctab[(size_t)j * CS + 3 * CN + 3] = lam;
 }
 
-cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, cudaStream_t st) {
-  const int J = prm.n_region + 3;
+// Chebyshev coefficients (first-kind nodes, tau_m = cos(pi (m + 1/2) / M)) of the SNP-independent sums over one grid interval:
+// f = S^1 pairs (CN), S^2 pairs (CN), sum h, sum h^2, sum log(l d + 1); block g = interval, thread = (f, k).  Block 0 also
+// writes the cosine table cos(pi j / (2 M)), j < 4 M, used by the per-SNP kernel for its own transforms.
+template <int NC>
+__global__ void __launch_bounds__(512) lmm_cheb_coef_kernel(const double *__restrict__ ctab, int row0, double *__restrict__ cheb) {
+  constexpr int CN = v2c_nidx(NC), CS = v2c_stride(NC), NF = 2 * CN + 3, M = V2_CM;
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (g == 0 && tid < 4 * M) cheb[tid] = cospi((double)tid / (double)(2 * M));
+  if (tid >= NF * M) return;
+  const int f = tid / M, k = tid - f * M;
+  const int off = (f < 2 * CN) ? CN + f : 3 * CN + (f - 2 * CN);        // S^1 | S^2 are contiguous behind S^0; then tr1, tr2, logdet
+  double acc = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double v = ctab[(size_t)(row0 + g * M + m) * CS + off];
+    acc = fma(v, cospi((double)(k * (2 * m + 1)) / (double)(2 * M)), acc);
+  }
+  cheb[4 * M + ((size_t)g * NF + f) * M + k] = acc * (k == 0 ? 1.0 / M : 2.0 / M);
+}
+
+cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, const double *node_lams,
+                              int n_nodes, double *cheb, cudaStream_t st) {
+  const int J0 = prm.n_region + 3, J = J0 + n_nodes;
   switch (n_cvt) {
-    case 1: lmm_common_kernel<1><<<J, 256, 0, st>>>(D, prm, H, ctab); break;
-    case 2: lmm_common_kernel<2><<<J, 256, 0, st>>>(D, prm, H, ctab); break;
-    case 3: lmm_common_kernel<3><<<J, 256, 0, st>>>(D, prm, H, ctab); break;
+    case 1: lmm_common_kernel<1><<<J, 256, 0, st>>>(D, prm, H, ctab, node_lams); break;
+    case 2: lmm_common_kernel<2><<<J, 256, 0, st>>>(D, prm, H, ctab, node_lams); break;
+    case 3: lmm_common_kernel<3><<<J, 256, 0, st>>>(D, prm, H, ctab, node_lams); break;
     default: return cudaErrorInvalidValue;
+  }
+  if (n_nodes > 0) {
+    switch (n_cvt) {
+      case 1: lmm_cheb_coef_kernel<1><<<prm.n_region, 512, 0, st>>>(ctab, J0, cheb); break;
+      case 2: lmm_cheb_coef_kernel<2><<<prm.n_region, 512, 0, st>>>(ctab, J0, cheb); break;
+      case 3: lmm_cheb_coef_kernel<3><<<prm.n_region, 512, 0, st>>>(ctab, J0, cheb); break;
+    }
   }
   return cudaGetLastError();
 }
+int lmm_cheb_nodes() { return V2_CM; }
+size_t lmm_cheb_doubles(int n_cvt, int n_region) { return 4 * (size_t)V2_CM + (size_t)n_region * (2 * (size_t)v2c_nidx(n_cvt) + 3) * V2_CM; }
 size_t lmm_common_record_doubles(int n_cvt) { return (size_t)v2c_stride(n_cvt); }
 
 bool lmm_v2_supported(int n_cvt, int n_region) { return n_cvt >= 1 && n_cvt <= 3 && n_region <= V2_MAX_REGION; }

@@ -41,11 +41,17 @@ constexpr int V2_MAX_REGION = 64;
 constexpr int V2_NSG = 2;              // grid lambdas per pass (register budget: 2 CTAs per SM need <= 128 registers)
 constexpr int V2_NSC = 5;              // common-lambda slots per hoisted pass (h rows staged next to the data rows)
 
+constexpr int V2_CM = 20;              // Chebyshev nodes per grid interval of the interpolated refinement (a multiple of V2_NSC)
+
 __host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS + V2_NSC) * V2_CHUNK; }
+// per warp: Chebyshev coefficients of its SNP's x-sums over the current interval (2 powers x (nc + 2) sums x V2_CM) + one pass of node values
+__host__ __device__ constexpr size_t v2_cheb_warp_doubles(int nc) { return (size_t)(2 * (nc + 2)) * (V2_CM + V2_NSC); }
 // SNP-independent sums at one common lambda: S^k_ab over (w_1..w_c, y) for k = 0,1,2, then sum h, sum h^2, sum log(l d+1), lambda
 __host__ __device__ constexpr int v2c_nidx(int nc) { return (nc + 2) * (nc + 1) / 2; }
 __host__ __device__ constexpr int v2c_stride(int nc) { return 3 * v2c_nidx(nc) + 4; }
-__host__ __device__ constexpr size_t v2_smem_bytes(int nc) { return v2_stage_doubles(nc) * V2_STAGES * sizeof(double) + 64; }
+__host__ __device__ constexpr size_t v2_smem_bytes(int nc) {
+  return v2_stage_doubles(nc) * V2_STAGES * sizeof(double) + 64 + v2_cheb_warp_doubles(nc) * V2_WARPS * sizeof(double);
+}
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -473,14 +479,17 @@ __device__ __forceinline__ void v2fn_init(V2Fn &F) {
 
 // Advance until an evaluation is required (returns req.need) or the interval list is exhausted.
 // `ev_*` carry the result of the evaluation requested by the previous call.
+// `single`: the caller walks the grid intervals itself (v2fn_due / v2fn_begin) and gets control back when the chain returns to
+// the scan state, i.e. when the current interval is finished.
 __device__ __noinline__ void v2fn_advance(V2Fn &F, const double *glam, const double *gd1, int n_region, double l_min,
-                                          double l_max, double ev_d1, double ev_d2, double ev_f, V2Req &req) {
+                                          double l_max, double ev_d1, double ev_d2, double ev_f, V2Req &req, bool single = false) {
   req.need = false;
   const unsigned max_iter = 100;
   for (;;) {
     switch (F.stage) {
       case V2_SCAN: {
         if (F.rs.aborted || F.rs.stopped) { F.stage = V2_DONE; return; }
+        if (single) return;
         while (F.next_g < n_region && !(gd1[F.next_g] * gd1[F.next_g + 1] <= 0)) F.next_g++;
         if (F.next_g >= n_region) { F.stage = V2_DONE; return; }
         const int g = F.next_g++;
@@ -615,6 +624,157 @@ __device__ __forceinline__ void v2_finalize(RootState &R, double f_min, double f
   }
 }
 
+
+// ---- interpolated refinement ---------------------------------------------------------------------------------------
+// After the grid scan every remaining evaluation of CalcLambda (Brent, Newton, the final f) asks for the sums S^k_ab at a
+// lambda INSIDE one grid interval.  As functions of t = log(lambda) they are analytic in the strip |Im t| < pi (the poles sit
+// at t = -log(delta_i) +- i pi), so on an interval of width log(10) + 2 x 0.15 their Chebyshev interpolant through V2_CM = 20
+// nodes is exact to ~1e-14 relative (measured; the geometric rate is 5^-M).  The node lambdas are the same for every SNP, hence
+// "common" rows like the grid lambdas: the x-dependent sums at the nodes cost 4 hoisted passes, the SNP-independent ones are
+// tabulated once per run (lmm_cheb_coef_kernel).  The root searches then run on scalars -- same Brent / Newton control flow,
+// same iterates to ~1e-12 -- instead of ~10 more passes of 62 FP64 operations per individual.  Third powers come from
+// S^3 = S^2 + 1/2 dS^2/dt (dh/dt = h^2 - h).  A lambda outside the padded interval (a diverging Newton step) is served by an
+// exact pass, as before.
+__device__ __forceinline__ bool v2fn_due(const V2Fn &F, const double *gd1, int g) {
+  return F.stage == V2_SCAN && !F.rs.aborted && !F.rs.stopped && (gd1[g] * gd1[g + 1] <= 0);
+}
+__device__ __forceinline__ void v2fn_begin(V2Fn &F, const double *glam, const double *gd1, int g) {
+  const double x_lower = glam[g], x_upper = glam[g + 1], f_lower = gd1[g], f_upper = gd1[g + 1];
+  F.next_g = g + 1;
+  F.a = x_lower; F.fa = f_lower; F.b = x_upper; F.fb = f_upper; F.c = x_upper; F.fc = f_upper;
+  F.d = x_upper - x_lower; F.e = x_upper - x_lower;
+  F.root = 0.5 * (x_lower + x_upper); F.xl = x_lower; F.xu = x_upper;
+  F.status = GB_ST_ERR; F.iter = 0;
+  F.stage = V2_BRENT_PREP;
+}
+
+// Clenshaw: value / tau-derivative of sum_k c_k T_k(tau)
+template <bool GLOBAL>
+__device__ __forceinline__ double v2_cheb_val(const double *c, double tau) {
+  double b1 = 0.0, b2 = 0.0;
+  const double t2 = tau + tau;
+#pragma unroll
+  for (int k = V2_CM - 1; k >= 1; --k) {
+    const double ck = GLOBAL ? __ldg(c + k) : c[k];
+    const double b0 = fma(t2, b1, ck) - b2;
+    b2 = b1; b1 = b0;
+  }
+  return fma(tau, b1, (GLOBAL ? __ldg(c) : c[0])) - b2;
+}
+template <bool GLOBAL>
+__device__ __forceinline__ double v2_cheb_der(const double *c, double tau) {
+  // p' = sum_{j=0}^{M-2} (j + 1) c_{j+1} U_j(tau)
+  double b1 = 0.0, b2 = 0.0;
+  const double t2 = tau + tau;
+#pragma unroll
+  for (int j = V2_CM - 2; j >= 0; --j) {
+    const double dj = (double)(j + 1) * (GLOBAL ? __ldg(c + j + 1) : c[j + 1]);
+    const double b0 = fma(t2, b1, dj) - b2;
+    b2 = b1; b1 = b0;
+  }
+  return b1;
+}
+
+template <int NC>
+__device__ __forceinline__ void v2_assemble_arr(const double (&C)[(NC + 2) * (NC + 1) / 2], const double (&Xq)[NC + 2],
+                                                double (&S)[(NC + 3) * (NC + 2) / 2]) {
+  constexpr int NV = NC + 2;
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int b = a; b < NV; ++b) {
+      double v;
+      if (a == NC) v = (b == NC) ? Xq[NC] : Xq[NC + 1];
+      else if (b == NC) v = Xq[a];
+      else v = C[abidx(a > NC ? NC : a, b > NC ? NC : b, NC + 1)];
+      S[abidx(a, b, NV)] = v;
+    }
+}
+
+// all sums at lambda from the interpolants of interval g; coef = this warp's x-sum coefficients (shared memory)
+template <int NC, int ORD>
+__device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coef, int g, double tau, double dtau_dt, double lam,
+                                            double n, bool want_f, double logdetI, V2Eval &ev) {
+  constexpr int NQ = NC + 2, NIDX = (NC + 3) * (NC + 2) / 2, CN = v2c_nidx(NC), M = V2_CM;
+  const double *gc = D.cheb + 4 * M + (size_t)g * (2 * CN + 3) * M;
+  double X1[NQ], X2[NQ], X3[NQ], C1[CN], C2[CN], C3[CN];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    X1[q] = v2_cheb_val<false>(coef + q * M, tau);
+    X2[q] = v2_cheb_val<false>(coef + (NQ + q) * M, tau);
+    X3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<false>(coef + (NQ + q) * M, tau), X2[q]) : 0.0;
+  }
+#pragma unroll
+  for (int q = 0; q < CN; ++q) {
+    C1[q] = v2_cheb_val<true>(gc + q * M, tau);
+    C2[q] = v2_cheb_val<true>(gc + (CN + q) * M, tau);
+    C3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<true>(gc + (CN + q) * M, tau), C2[q]) : 0.0;
+  }
+  const double tr1 = v2_cheb_val<true>(gc + 2 * CN * M, tau), tr2 = v2_cheb_val<true>(gc + (2 * CN + 1) * M, tau);
+  const double ld = want_f ? v2_cheb_val<true>(gc + (2 * CN + 2) * M, tau) : 0.0;
+  double S1[NIDX], S2[NIDX], S3[NIDX];
+  v2_assemble_arr<NC>(C1, X1, S1);
+  v2_assemble_arr<NC>(C2, X2, S2);
+  if (ORD >= 3) v2_assemble_arr<NC>(C3, X3, S3);
+  v2_derive<NC, ORD>(S1, S2, S3, tr1, tr2, lam, n, want_f, ld, logdetI, ev);
+}
+
+// Runs one chain inside interval g until the interval is finished (returns false) or it asks for a lambda the interpolant does
+// not cover (returns true with `rq` filled; the caller delivers the values through `evv` and calls again).
+template <int NC>
+__device__ __forceinline__ bool v2_drive(const LmmConst &D, V2Fn &F, bool fnR, const double *coef, int g, double lo, double hi,
+                                         const double *glam, const double *gd1, int n_region, double l_min, double l_max,
+                                         double n, double logdetI, double (&evv)[3], V2Req &rq) {
+  const double dtau_dt = 2.0 / (hi - lo);
+  for (;;) {
+    v2fn_advance(F, glam, gd1, n_region, l_min, l_max, evv[0], evv[1], evv[2], rq, true);
+    if (!rq.need) return false;
+    const double tau = (2.0 * log(rq.lam) - (lo + hi)) / (hi - lo);
+    if (!(tau >= -1.0 && tau <= 1.0)) return true;          // also catches NaN
+    V2Eval ev;
+    if (rq.K >= 3) v2_interp_eval<NC, 3>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, ev);
+    else v2_interp_eval<NC, 2>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, ev);
+    evv[0] = fnR ? ev.d1R : ev.d1L; evv[1] = fnR ? ev.d2R : ev.d2L; evv[2] = fnR ? ev.fR : ev.fL;
+    if (fnR && rq.logdet) { F.cache_lam = rq.lam; F.cP_xx = ev.P_xx; F.cP_xy = ev.P_xy; F.cP_yy = ev.P_yy; F.cPx_yy = ev.Px_yy; }
+    rq.need = false;
+  }
+}
+
+// One exact lockstep pass for up to two lambdas per warp (slot 0 = REML chain, slot 1 = ML chain).  Every thread of the CTA calls it.
+template <int NC>
+__device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *const *xrows, double *smem, int nchunks, int pad,
+                                              bool active, const V2Req (&rq)[2], double n, double logdetI, V2Eval (&ev)[2],
+                                              unsigned int &tally2, unsigned int &tally3, unsigned int &tallyld) {
+  constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
+  const int k0 = rq[0].need ? rq[0].K : 0, k1 = rq[1].need ? rq[1].K : 0;
+  const int Kloc = active ? (k0 > k1 ? k0 : k1) : 0;
+  const bool big = Kloc >= 3;     // per warp, like the non-interpolated loop below: both pass shapes walk the same pipeline (same barriers, same copies)
+  const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
+  const bool wl[2] = {rq[0].need && rq[0].logdet, rq[1].need && rq[1].logdet};
+  const bool any_ld = wl[0] || wl[1];
+  if (active) { if (big) tally3++; else tally2++; if (any_ld) tallyld++; }
+  double dummy[NIDX];
+  if (big) {
+    V2Acc<NC, 2, 1, 3> acc;
+    if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
+    else v2_pass<NC, 2, 1, 3, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
+    if (active) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        v2_derive<NC, 3>(acc.S[s][0], acc.S[s][1], acc.S[s][2], acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
+    }
+  } else {
+    V2Acc<NC, 2, 1, 2> acc;
+    if (any_ld) v2_pass<NC, 2, 1, 2, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
+    else v2_pass<NC, 2, 1, 2, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
+    if (active) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        v2_derive<NC, 2>(acc.S[s][0], acc.S[s][1], dummy, acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
+    }
+  }
+}
+
 // One CTA = 8 SNPs.  xrows[w] (shared memory) = U^T x row of warp w or nullptr.
 template <int NC>
 __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmParams &prm, const double *const *xrows,
@@ -632,6 +792,9 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   const bool need_search = needR || needL;
   double dummy[NIDX];
   unsigned int tally2 = 0, tally3 = 0, tallyld = 0, tallyc = 0;   // executed passes of this warp by kind (work counters)
+  // order-1 quantities at exactly l_min / l_max from the hoisted grid passes: the Wald test when the REML estimate is an end point
+  bool have_bound = false;
+  double wminP[4] = {0, 0, 0, 0}, wmaxP[4] = {0, 0, 0, 0};
 
 #if GB_V2_TMA
   const bool hoist = (D.ctab != nullptr);
@@ -677,11 +840,12 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
               V2Eval ev;
               v2_derive<NC, 2>(S1, S2, dummy, tr1, tr2, lamj, n, slot == 0, ldj, logdetI, ev);
               glam[slot] = lamj; gd1R[slot] = ev.d1R; gd1L[slot] = ev.d1L;
-              if (slot == 0) { fRmin = ev.fR; fLmin = ev.fL; }
+              if (slot == 0) { fRmin = ev.fR; fLmin = ev.fL; wminP[0] = ev.P_xx; wminP[1] = ev.P_xy; wminP[2] = ev.P_yy; wminP[3] = ev.Px_yy; }
             } else if (slot < n_grid) {                            // exactly l_max: f only
               V2Eval ev;
               v2_derive<NC, 1>(S1, dummy, dummy, tr1, 0.0, lamj, n, true, ldj, logdetI, ev);
               fRmax = ev.fR; fLmax = ev.fL;
+              wmaxP[0] = ev.P_xx; wmaxP[1] = ev.P_xy; wmaxP[2] = ev.P_yy; wmaxP[3] = ev.Px_yy; have_bound = true;
             } else {                                               // score test at l_mle_null ("3 is before 1")
               Derived<NC, 1> d;
               sweep_tables<NC, 1>(S1, dummy, dummy, d);
@@ -753,6 +917,78 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   if (need_search) {
     double evR[3] = {0, 0, 0}, evL[3] = {0, 0, 0};     // d1, d2, f delivered to each chain
     bool finalized = false, wald_pending = false, wald_done = !needR;
+#if GB_V2_TMA
+    if (hoist && D.cheb != nullptr) {
+      // ---- interpolated refinement: the grid intervals in the reference's order; per interval 4 node passes, then scalars only
+      constexpr int NQ = NC + 2, M = V2_CM;
+      double *coef = smem + v2_stage_doubles(NC) * V2_STAGES + 8 + (size_t)(threadIdx.x >> 5) * v2_cheb_warp_doubles(NC);
+      double *stg = coef + 2 * NQ * M;
+      const int lane = threadIdx.x & 31;
+      const double t0 = log(l_min);
+      for (int g = 0; g < n_region; ++g) {
+        const bool dueR = valid && v2fn_due(FR, gd1R, g), dueL = valid && v2fn_due(FL, gd1L, g);
+        const bool due = dueR || dueL;
+        if (!__syncthreads_or(due ? 1 : 0)) continue;
+        if (due)
+          for (int o = lane; o < 2 * NQ * M; o += 32) coef[o] = 0.0;
+        for (int p0 = 0; p0 < M; p0 += V2_NSC) {
+          int jrow[V2_NSC];
+#pragma unroll
+          for (int s2 = 0; s2 < V2_NSC; ++s2) jrow[s2] = D.n_common + g * M + p0 + s2;
+          V2CAcc<NC> acc;
+          v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc);
+          if (due) {
+            tallyc += V2_NSC;
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int s2 = 0; s2 < V2_NSC; ++s2)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) { stg[(s2 * 2 + 0) * NQ + q] = acc.X[s2][0][q]; stg[(s2 * 2 + 1) * NQ + q] = acc.X[s2][1][q]; }
+            }
+            __syncwarp();
+            // discrete cosine transform of the node values, 5 nodes at a time: c_k += f_m cos(pi k (m + 1/2) / M)
+            for (int o = lane; o < 2 * NQ * M; o += 32) {
+              const int kq = o / M, kk = o - kq * M;
+              double a = coef[o];
+#pragma unroll
+              for (int s2 = 0; s2 < V2_NSC; ++s2)
+                a = fma(stg[s2 * 2 * NQ + kq], __ldg(D.cheb + (kk * (2 * (p0 + s2) + 1)) % (4 * M)), a);
+              coef[o] = a;
+            }
+            __syncwarp();
+          }
+        }
+        if (due) {
+          for (int o = lane; o < 2 * NQ * M; o += 32) coef[o] *= ((o % M) == 0) ? (1.0 / M) : (2.0 / M);
+          __syncwarp();
+          if (dueR) v2fn_begin(FR, glam, gd1R, g);
+          if (dueL) v2fn_begin(FL, glam, gd1L, g);
+        }
+        const double lo = t0 + lambda_interval * (double)g - D.cheb_marg, hi = t0 + lambda_interval * (double)(g + 1) + D.cheb_marg;
+        bool runR = dueR, runL = dueL;
+        for (;;) {
+          bool blkR = false, blkL = false;
+          if (runR) { blkR = v2_drive<NC>(D, FR, true, coef, g, lo, hi, glam, gd1R, n_region, l_min, l_max, n, logdetI, evR, rq[0]); runR = blkR; }
+          if (runL) { blkL = v2_drive<NC>(D, FL, false, coef, g, lo, hi, glam, gd1L, n_region, l_min, l_max, n, logdetI, evL, rq[1]); runL = blkL; }
+          if (!blkR) rq[0].need = false;
+          if (!blkL) rq[1].need = false;
+          const bool blocked = blkR || blkL;
+          if (!__syncthreads_or(blocked ? 1 : 0)) break;
+          V2Eval ev[2];
+          v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, blocked, rq, n, logdetI, ev, tally2, tally3, tallyld);
+          if (blkR) {
+            evR[0] = ev[0].d1R; evR[1] = ev[0].d2R; evR[2] = ev[0].fR;
+            if (rq[0].logdet) { FR.cache_lam = rq[0].lam; FR.cP_xx = ev[0].P_xx; FR.cP_xy = ev[0].P_xy; FR.cP_yy = ev[0].P_yy; FR.cPx_yy = ev[0].Px_yy; }
+          }
+          if (blkL) { evL[0] = ev[1].d1L; evL[1] = ev[1].d2L; evL[2] = ev[1].fL; }
+        }
+      }
+      if (FR.stage == V2_SCAN) FR.stage = V2_DONE;           // interval list exhausted
+      if (FL.stage == V2_SCAN) FL.stage = V2_DONE;
+      rq[0].need = rq[1].need = false;
+    }
+#endif
     for (;;) {
       if (FR.stage != V2_DONE) v2fn_advance(FR, glam, gd1R, n_region, l_min, l_max, evR[0], evR[1], evR[2], rq[0]); else rq[0].need = false;
       if (FL.stage != V2_DONE) v2fn_advance(FL, glam, gd1L, n_region, l_min, l_max, evL[0], evL[1], evL[2], rq[1]); else rq[1].need = false;
@@ -768,6 +1004,11 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
             Derived<NC, 1> d; d.P_xx = FR.cP_xx; d.P_xy = FR.cP_xy; d.P_yy = FR.cP_yy; d.Px_yy = FR.cPx_yy;
             wald_score_from<NC>(d, D.n, false, beta, se, p_wald);
             wald_done = true;
+          } else if (have_bound && (lambda_remle == l_min || lambda_remle == l_max)) {   // end point: tables of the hoisted grid passes
+            const double *w = (lambda_remle == l_min) ? wminP : wmaxP;
+            Derived<NC, 1> d; d.P_xx = w[0]; d.P_xy = w[1]; d.P_yy = w[2]; d.Px_yy = w[3];
+            wald_score_from<NC>(d, D.n, false, beta, se, p_wald);
+            wald_done = true;
           } else wald_pending = true;
         }
       }
@@ -775,31 +1016,9 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       if (want_wald) { rq[0].need = true; rq[0].lam = lambda_remle; rq[0].K = 1; rq[0].logdet = false; }
       const bool active = valid && (rq[0].need || rq[1].need);
       if (!__syncthreads_or(active ? 1 : 0)) break;
-      const int Kmax = (rq[0].need ? rq[0].K : 0) > (rq[1].need ? rq[1].K : 0) ? (rq[0].need ? rq[0].K : 0) : (rq[1].need ? rq[1].K : 0);
       const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
-      const bool wl[2] = {rq[0].need && rq[0].logdet, rq[1].need && rq[1].logdet};
       V2Eval ev[2];
-      const bool any_ld = wl[0] || wl[1];
-      if (active) { if (Kmax >= 3) tally3++; else tally2++; if (any_ld) tallyld++; }
-      if (Kmax >= 3) {
-        V2Acc<NC, 2, 1, 3> acc;
-        if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
-        else v2_pass<NC, 2, 1, 3, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
-        if (active) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            v2_derive<NC, 3>(acc.S[s][0], acc.S[s][1], acc.S[s][2], acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
-        }
-      } else {
-        V2Acc<NC, 2, 1, 2> acc;
-        if (any_ld) v2_pass<NC, 2, 1, 2, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
-        else v2_pass<NC, 2, 1, 2, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
-        if (active) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            v2_derive<NC, 2>(acc.S[s][0], acc.S[s][1], dummy, acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
-        }
-      }
+      v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, active, rq, n, logdetI, ev, tally2, tally3, tallyld);
       if (active) {
         if (want_wald) {
           Derived<NC, 1> d; d.P_xx = ev[0].P_xx; d.P_xy = ev[0].P_xy; d.P_yy = ev[0].P_yy; d.Px_yy = ev[0].Px_yy;

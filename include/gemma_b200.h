@@ -83,9 +83,10 @@ GB200_API int gb200_profile_get(gb200_ctx *ctx, const char *name, double *ms, lo
 /* Measured plain (non-tensor) FP64 FMA rate of this device, TFLOP/s with an FMA counted as 2 flops: independent DFMA chains on every SM
  * for about `seconds` -- the roofline denominator of the per-SNP kernel, which is FP64-issue bound (MEASURED_PEAKS.json has no FP64 figure). */
 GB200_API int gb200_measure_fp64_fma(gb200_ctx *ctx, double seconds, double *tflops, double *ms);
-/* Work counters of the lockstep per-SNP kernel since the last reset: lambda evaluations by kind
- * {0: hoisted common-lambda slots, 1: order-1 (f / Wald), 2: order-2 (Brent), 3: order-3 (Newton), 4: evaluations with log-determinant,
- *  5: SNPs}.  counts may be NULL to reset only.  Used by bench.py to state the kernel's executed FP64 flops. */
+/* Work counters of the lockstep per-SNP kernel since the last reset, summed over SNPs:
+ * {0: lambda slots of hoisted passes (grid, end points, score test, Chebyshev nodes), 1: exact two-lambda passes with powers 1..2,
+ *  2: exact two-lambda passes with powers 1..3, 3: exact passes that also accumulate the log-determinant, 4: unused, 5: SNPs}.
+ * counts may be NULL to reset only.  Used by bench.py to state the kernel's executed FP64 flops. */
 GB200_API int gb200_lmm_counters(gb200_ctx *ctx, unsigned long long counts[6], int reset);
 
 /* The device restatement of the two GSL tails the path calls: out[i] = gsl_cdf_fdist_Q(x[i], nu1, nu2[i]) (call sites

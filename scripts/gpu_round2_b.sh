@@ -10,7 +10,7 @@ echo "pytest rc=$?" >> gpurun_out/b_pytest.log
 ( time timeout 600 python bench.py --workload gk --steps 4 --warmup 3 ) > gpurun_out/b_bench_gk.json 2> gpurun_out/b_bench_gk.err
 ( time timeout 900 python bench.py --workload lmm1 --steps 4 --warmup 3 ) > gpurun_out/b_bench_lmm1.json 2> gpurun_out/b_bench_lmm1.err
 ( time timeout 900 python bench.py --workload mv --steps 3 --warmup 3 ) > gpurun_out/b_bench_mv.json 2> gpurun_out/b_bench_mv.err
-( time timeout 1500 scripts/eig_probe 50000 ) > gpurun_out/b_eig_probe.log 2>&1
+( time timeout 900 scripts/eig_probe 50000 ) > gpurun_out/b_eig_probe.log 2>&1
 timeout 900 ncu --section SpeedOfLight --section ComputeWorkloadAnalysis --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section Occupancy --section SchedulerStats \
   --clock-control none --import-source on -k regex:'lmm_assoc_v2_kernel' -s 4 -c 1 -o gpurun_out/b_prof_lmm \
   python bench.py --u-source qr --batch 8192 --steps 1 --warmup 3 --no-e2e --no-parity --no-cpu-baseline --no-gk > gpurun_out/b_ncu_lmm.log 2>&1

@@ -217,6 +217,24 @@ def test_eigh_matches_lapack_semantics(ctx):
     assert np.allclose(ev2, ev, atol=1e-11)
 
 
+@pytest.mark.parametrize("n", [193, 1100])
+def test_eigh_large_n_solver_agrees_with_the_default_one(ctx, n):
+    """Beyond n = 32768 cusolverDnXsyevd refuses the problem and gb200_eigh switches to cusolverMgSyevd on the same device
+    (csrc/eigh.cu); forced here at small n: same eigenvalues, orthonormal eigenvectors in columns, same spectral reconstruction."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, 2 * n)); K = A @ A.T / (2 * n)
+    U1, ev1, tr1, nz1 = ctx.eigh(K, center=True)
+    ctx.set_option("eigh_path", 2)
+    try:
+        U2, ev2, tr2, nz2 = ctx.eigh(K, center=True)
+    finally:
+        ctx.set_option("eigh_path", 0)
+    assert np.allclose(ev2, ev1, atol=1e-11) and tr2 == pytest.approx(tr1, rel=1e-12) and nz2 == nz1 == 1
+    assert np.allclose(U2.T @ U2, np.eye(n), atol=1e-11)
+    Kc = O.center_matrix(K)
+    assert np.allclose((U2 * ev2) @ U2.T, Kc, atol=1e-10)
+
+
 @pytest.mark.parametrize("k_mode", [1, 2])
 def test_kinship_geno_bed_and_precentred_paths(ctx, k_mode):
     n, l = 211, 500
