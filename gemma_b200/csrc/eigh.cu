@@ -53,13 +53,27 @@ struct MgApi {
   cusolverStatus_t (*Syevd)(cusolverMgHandle_t, cusolverEigMode_t, cublasFillMode_t, int, void *[], int, int, cudaLibMgMatrixDesc_t, void *,
                             cudaDataType, cudaDataType, void *[], int64_t, int *) = nullptr;
   bool ok = false;
+  std::string why;
 };
 static MgApi &mg_api() {
   static MgApi a;
   if (a.lib || a.ok) return a;
-  for (const char *name : {"libcusolverMg.so.11", "libcusolverMg.so", "/usr/local/cuda/lib64/libcusolverMg.so.11"}) {
-    a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+  // First choice: the libcusolverMg that ships NEXT TO the libcusolver this process has loaded (a Python process with torch has
+  // the pip-packaged cuBLAS / cuSOLVER of torch's CUDA minor version in memory; the toolkit's libcusolverMg then fails to bind
+  // against that older libcublas -- "undefined symbol: cublasSetEnvironmentMode").  Then the default search path.
+  std::vector<std::string> names;
+  Dl_info di;
+  if (dladdr((void *)&cusolverDnCreate, &di) && di.dli_fname) {
+    std::string path(di.dli_fname);
+    const size_t slash = path.rfind('/');
+    if (slash != std::string::npos) names.push_back(path.substr(0, slash + 1) + "libcusolverMg.so.11");
+  }
+  names.push_back("libcusolverMg.so.11"); names.push_back("libcusolverMg.so"); names.push_back("/usr/local/cuda/lib64/libcusolverMg.so.11");
+  for (const std::string &name : names) {
+    a.lib = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL);
     if (a.lib) break;
+    const char *e = dlerror();
+    a.why += name + ": " + (e ? e : "?") + "; ";
   }
   if (!a.lib) return a;
 #define MG_SYM(field, sym) *(void **)(&a.field) = dlsym(a.lib, sym)
@@ -81,7 +95,7 @@ using namespace gb;
 // array, like Xsyevd leaves them), eigenvalues ascending in dW.  Blocks the host; uses cuSOLVER's own streams.
 static int eigh_mg(gb200_ctx *ctx, double *dA, size_t n, double *dW) {
   MgApi &mg = mg_api();
-  if (!mg.ok) return set_err(ctx, GB200_ERR_UNSUPPORTED, "gb200_eigh: n > 32768 needs libcusolverMg (cusolverDnXsyevd stops at 32768), which could not be loaded");
+  if (!mg.ok) return set_err(ctx, GB200_ERR_UNSUPPORTED, "gb200_eigh: n > 32768 needs libcusolverMg (cusolverDnXsyevd stops at 32768), which could not be loaded: " + mg.why);
   const int tile = 256;
   const size_t ncols = (n + tile - 1) / tile * tile;            // the last column tile is stored in full
   cusolverMgHandle_t h = nullptr; cudaLibMgGrid_t grid = nullptr; cudaLibMgMatrixDesc_t desc = nullptr;

@@ -834,10 +834,12 @@ bool i8_available(gb200_ctx *) { return get_encode() != nullptr; }
 // carries a relative error of about  colmax_i sqrt(n) / (sqrt(12) * 127.4 * 256^(T-1)).
 //  * i8_default_planes(n): the U-independent worst case (colmax_i = 1, an eigenvector concentrated on one individual):
 //    smallest T with that bound <= 2^-30 -- T = 5 up to n = 3.1e6.  Used when the planes are requested before U is known.
-//  * i8_choose_planes(colmax, n): the same bound evaluated with the MEASURED largest column maximum of this U, target 2^-28
-//    (3.7e-9 on a projected value; the statistics inherit it scaled by 1/|z-score|, two orders below the 1e-6 parity bar for
-//    every SNP with |z| > 0.004).  Eigenvectors of a kinship matrix of unrelated individuals are delocalised (colmax ~ 4.6 / sqrt(n)):
-//    T = 4; family / population structure that concentrates an eigenvector on few individuals raises colmax and with it T.
+//  * i8_choose_planes(colmax, n): the same bound evaluated with the MEASURED largest column maximum of this U, target 2^-29
+//    (1.9e-9 on a projected value; beta inherits it as 1.9e-9 x se, i.e. relative 1.9e-9 / |z-score| -- inside the 1e-6 parity
+//    bar for every SNP with |z| > 0.002 -- and se / p-values at the 1e-9 level).  Eigenvectors of a kinship matrix of unrelated
+//    individuals are delocalised (colmax ~ sqrt(4 ln n / n)): T = 4; family / population structure that concentrates an eigenvector
+//    on few individuals raises colmax and with it T.  Small cohorts (n < 8192), where the projection is a minor cost, never go
+//    below 5 planes.
 int i8_default_planes(size_t n) {
   const double need = sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * 1073741824.0;     // bound * 2^30 at T = 1
   int T = 1 + (int)ceil(log2(need) / 8.0);
@@ -847,9 +849,10 @@ int i8_default_planes(size_t n) {
 }
 int i8_choose_planes(double colmax_max, size_t n) {
   if (!(colmax_max > 0.0) || !isfinite(colmax_max)) return 4;
-  const double need = colmax_max * sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * 268435456.0;   // bound * 2^28 at T = 1
+  const double need = colmax_max * sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * 536870912.0;   // bound * 2^29 at T = 1
   int T = 1 + (int)ceil(log2(need) / 8.0);
   if (T < 4) T = 4;
+  if (n < 8192 && T < 5) T = 5;
   if (T > 8) T = 8;
   return T;
 }

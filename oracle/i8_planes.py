@@ -21,11 +21,12 @@ def default_planes(n):
 
 
 def choose_planes(colmax_max, n):
-    """i8_choose_planes: the same bound with the measured largest column maximum, target 2^-28."""
+    """i8_choose_planes: the same bound with the measured largest column maximum, target 2^-29; at least 5 planes below n = 8192."""
     if not (colmax_max > 0 and math.isfinite(colmax_max)):
         return 4
-    need = colmax_max * math.sqrt(n if n > 1 else 2) / (math.sqrt(12.0) * TOP) * 2.0 ** 28
-    return min(8, max(4, 1 + int(math.ceil(math.log2(need) / 8.0))))
+    need = colmax_max * math.sqrt(n if n > 1 else 2) / (math.sqrt(12.0) * TOP) * 2.0 ** 29
+    T = min(8, max(4, 1 + int(math.ceil(math.log2(need) / 8.0))))
+    return max(T, 5) if n < 8192 else T
 
 
 def slice_planes(U, T):
