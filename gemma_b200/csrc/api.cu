@@ -14,6 +14,7 @@ int i8_prepare(gb200_ctx *ctx);                       // slice U into int8 plane
 int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                    size_t l, size_t bytes_per_snp, double *UtXt_dev);   // UtXt l x n (ld n)
 bool i8_available(gb200_ctx *ctx);
+int i8_project_geno(gb200_ctx *ctx, const double *G_dev, size_t l, size_t ldg, double *UtXt_dev, bool *taken);   // dosage rows as exact digit rows
 int i8_default_planes(size_t n);
 int i8_effective_planes(gb200_ctx *c, int *T_out);
 bool kin_i8_eligible(gb200_ctx *ctx);
@@ -83,7 +84,7 @@ void gb200_destroy(gb200_ctx *c) {
     for (auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   gb::DevBuf *bufs[] = {&c->dK, &c->dU, &c->dEval, &c->dWt, &c->dY, &c->dNull, &c->dX, &c->dUtXt, &c->dOut,
-                        &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale,
+                        &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale, &c->i8.wave_ctr,
                         &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles,
                         &c->i8.kin_qbits, &c->i8.kin_y, &c->dWtx, &c->dEnv, &c->dX2, &c->dFlip, &c->dLmW, &c->dLmY,
                         &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam};
@@ -182,6 +183,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
   if (!strcmp(name, "lmm_kernel")) {
     if (value < 0 || value > 3) return set_err(c, GB200_ERR_ARG, "lmm_kernel must be 0,1,2,3");
     c->lmm_kernel = value; return GB200_OK;
+  }
+  if (!strcmp(name, "gemm_wave_sync")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "gemm_wave_sync must be 0 or 1");
+    c->gemm_wave_sync = value; return GB200_OK;
   }
   if (!strcmp(name, "gemm_stages")) {
     if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "gemm_stages must be 0..8");
@@ -759,12 +764,20 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
   GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream));
   GB_CUDA(c, c->dOut.reserve(l * sizeof(gb200_sumstat)));
   GB_CUDA(c, cudaMemcpy2DAsync(c->dX.p, n * 8, G, ldg * 8, n * 8, l, cudaMemcpyHostToDevice, c->stream));
-  {
-    ProfScope ps(c, "decode");
-    GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+  // dosage rows printed with a few decimals are exact integer digit rows: tensor-core projection (i8gemm_sm100.cu); otherwise FP64
+  bool taken = false;
+  if (c->utx_path != 1 && i8_available(c) && (c->utx_path == 2 || n >= 1024)) {
+    rc = i8_project_geno(c, c->dX.as<double>(), l, n, c->dUtXt.as<double>(), &taken);
+    if (rc) return rc;
   }
-  rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
-  if (rc) return rc;
+  if (!taken) {
+    {
+      ProfScope ps(c, "decode");
+      GB_CUDA(c, launch_lmm_impute(c->dX.as<double>(), l, n, n, c->stream));
+    }
+    rc = project_fp64_snpmajor(c, c->dX.as<double>(), l, c->dUtXt.as<double>());
+    if (rc) return rc;
+  }
   rc = lmm_assoc_dev(c, c->dUtXt.as<double>(), l, c->n_c, c->dOut.as<gb200_sumstat>());
   if (rc) return rc;
   GB_CUDA(c, cudaMemcpyAsync(out, c->dOut.p, l * sizeof(gb200_sumstat), cudaMemcpyDeviceToHost, c->stream));

@@ -46,6 +46,7 @@ struct I8State {
   DevBuf scale;                  // per eigenvector: scale s_i, column maximum, 1 / s_i (3 n doubles)
   DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
   DevBuf miss_mean;              // per-SNP mean + hole count (+ holes per 256-SNP tile)
+  DevBuf wave_ctr;               // wave synchronisation counter of the CTA-pair projection kernel
   DevBuf holeq;                  // l_pad x n_pad int8 hole-indicator rows (second GEMM pass of the mean imputation)
   void *tmap_a = nullptr, *tmap_b = nullptr, *tmap_q = nullptr;   // CUtensorMap storage (host)
   // kinship (K = Z Z^T on the int8 tensor pipe)
@@ -133,8 +134,9 @@ struct gb200_ctx {
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
   long gemm_groups = 1;  // 2: pair kernel with two eigenvector groups per tile (shared genotype tile) and the hole pass on the tensor pipe; 1: one group, FP64 hole fix-up
+  long gemm_wave_sync = 1; // CTA-pair projection: producers start every tile wave together (keeps the K-panels shared through L2)
   long gemm_stages = 0;  // TMA pipeline stages of the CTA-pair projection kernel (0 = as many 32 KB stages as fit, at most 6)
-  long gemm_panel = 0;   // raster panel width of that kernel in 2-group units (0 = default 6)
+  long gemm_panel = 0;   // raster panel width of the projection kernels in eigenvector groups (0 = default: 9 for the CTA-pair kernel; 2-group units, 6, for gemm_groups = 2)
   long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)
   long kin_path = 0;     // 0 auto (int8 tensor cores for centred K; sparse FP64 terms for missing genotypes), 1 = FP64 only
   double kin_miss_max = 0.2;   // chunks with a larger fraction of missing genotypes take the dense FP64 path

@@ -136,16 +136,17 @@ struct I8KernelParams {
   const int *tile_holes;    // mode 2: holes per 256-row tile; tiles without a hole are skipped
   int panel;                // raster panel width in units of NB eigenvector groups
   int stages;               // i8_gemm_pair_kernel: TMA pipeline stages
+  unsigned int *wave_ctr;   // i8_gemm_pair_kernel: wave synchronisation counter (zeroed before the launch) or null
 };
 
-__device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_groups, int &m_blk, int &n_grp) {
+__device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_groups, int panel_w, int &m_blk, int &n_grp) {
   // panels of I8_PANEL eigenvector groups; inside a panel SNP tiles vary slowest so that the ~148
   // concurrently running CTAs cover a ~12 x 12 block of (SNP tile, group) pairs: each A/B K-panel
   // streamed from HBM is shared by ~12 CTAs through L2.
-  const int panel_tiles = I8_PANEL * m_tiles;
+  const int panel_tiles = panel_w * m_tiles;
   const int panel = tile / panel_tiles;
-  const int first = panel * I8_PANEL;
-  const int width = (n_groups - first < I8_PANEL) ? (n_groups - first) : I8_PANEL;
+  const int first = panel * panel_w;
+  const int width = (n_groups - first < panel_w) ? (n_groups - first) : panel_w;
   const int r = tile - panel * panel_tiles;
   m_blk = r / width;
   n_grp = first + r % width;
@@ -153,7 +154,7 @@ __device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_
 
 __device__ __forceinline__ void tile_coords(const I8KernelParams &p, int tile, int &m_blk, int &n_grp) {
   if (p.tiles) { const int2 t = p.tiles[tile]; m_blk = t.x; n_grp = t.y; }
-  else tile_coords_raster(tile, p.m_tiles, p.n_groups, m_blk, n_grp);
+  else tile_coords_raster(tile, p.m_tiles, p.n_groups, p.panel > 0 ? p.panel : I8_PANEL, m_blk, n_grp);
 }
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
@@ -382,8 +383,23 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      unsigned int wave = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++wave) {
         int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
+        if (p.wave_ctr && wave > 0) {
+          // Wave synchronisation: the ~74 tile pairs that run concurrently share their genotype / plane K-panels through L2
+          // only while they walk K in phase (a panel is n bytes long: two tiles half a tile apart are 1 GB of other traffic
+          // apart, and L2 holds 126 MB).  Left alone the pairs drift out of phase within a few waves and DRAM traffic climbs to
+          // 20x the algorithmic bytes; starting every wave together keeps the reads at (a + b) panels per a x b tile block.
+          // Every producer counts in after queueing its last K-block and waits (bounded) for the other CTAs before the next tile.
+          const unsigned int want = gridDim.x * wave;
+          unsigned int seen, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wave_ctr) : "memory");
+            if (seen >= want) break;
+            __nanosleep(200);
+          } while (++spins < 20000u);                      // ~4 ms: never a deadlock if part of the grid is not resident
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);             // local: released by the leader's multicast commit
           const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
@@ -392,6 +408,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tma_load_2d_pair(&tmap_b, full_leader, smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N + (int)rank * halfN);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
+        if (p.wave_ctr) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.wave_ctr) : "memory");
       }
     }
   } else if (warp == 1) {
@@ -940,7 +957,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
   p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : 6; p.stages = I8_STAGES;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : (pair2 ? 6 : (pair ? 9 : I8_PANEL)); p.stages = I8_STAGES; p.wave_ctr = nullptr;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
   const int tiles = p.m_tiles * p.n_groups;
   if (pair2) {
@@ -978,6 +995,11 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     int ns = c->gemm_stages > 0 ? (int)c->gemm_stages : 6;
     while (ns > 2 && 1024 + (size_t)ns * stage_pair + 256 > 227 * 1024) --ns;
     p.stages = ns;
+    if (c->gemm_wave_sync && 2 * pairs == c->num_sms / 2 * 2 && tiles > pairs) {       // whole-chip persistent grid: every CTA is resident
+      GB_CUDA(c, c->i8.wave_ctr.reserve(sizeof(unsigned int)));
+      GB_CUDA(c, cudaMemsetAsync(c->i8.wave_ctr.p, 0, sizeof(unsigned int), c->stream));
+      p.wave_ctr = c->i8.wave_ctr.as<unsigned int>();
+    }
     const size_t smem_pair = 1024 + (size_t)ns * stage_pair + 256;
     ProfScope ps(c, "utx");
     i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
@@ -997,6 +1019,222 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
                                                       nmiss, UtXt_dev, c->n_c);
   GB_CUDA(c, cudaGetLastError());
+  return GB200_OK;
+}
+
+// ==========================================================================================
+// Dosage-valued (BIMBAM mean-genotype) batches on the same tensor-core projection.  The reference hands the parsed doubles to
+// cblas_dgemm (src/lmm.cpp:1590-1618, :1521).  A mean-genotype file prints its values with a few decimals (the mouse example: 0/1/2
+// with an occasional "1.03" or "0.4375"), so every non-missing entry of a SNP row is q / 10^d for an integer q and a small d.  The
+// row is then EXACTLY representable by one to three unsigned base-256 digit rows (q < 256, < 65536, < 2^24), each of which goes
+// through the int8 GEMM like a PLINK genotype row; the epilogue pass recombines  U^T x = (sum_k 256^k U^T q_k) / 10^d  in FP64 and
+// the holes get their  mean * sum_{j missing} U[j][:]  like the PLINK path.  Rows that are plain 0/1/2 cost what a PLINK row costs.
+// A batch that contains a value with more than 6 decimals (or a negative one) is not taken: the caller keeps the FP64 GEMM.
+__global__ void __launch_bounds__(256) geno_classify_kernel(const double *__restrict__ G, int n, size_t ldg, double *__restrict__ mean,
+                                                            int *__restrict__ nmiss, int *__restrict__ dsel, int *__restrict__ nplanes) {
+  __shared__ double sh_sum[8], sh_max[8];
+  __shared__ int sh_miss[8], sh_d[8];
+  const int s = blockIdx.x;
+  const double *g = G + (size_t)s * ldg;
+  double sum = 0.0, xmax = 0.0;
+  int miss = 0, dreq = 0;                       // dreq = 7: not representable with <= 6 decimals
+  for (int p = threadIdx.x; p < n; p += 256) {
+    const double x = g[p];
+    if (isnan(x)) { miss++; continue; }
+    sum += x;
+    if (!(x >= 0.0) || !(x < 16.0)) { dreq = 7; continue; }
+    xmax = fmax(xmax, x);
+    double sc = 1.0;
+    int d = 0;
+    for (; d <= 6; ++d, sc *= 10.0) {
+      const double v = x * sc;
+      if (fabs(v - rint(v)) <= 1e-8) break;
+    }
+    dreq = d > dreq ? d : dreq;
+  }
+  for (int m = 16; m >= 1; m >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, m); xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, m));
+    miss += __shfl_xor_sync(0xffffffffu, miss, m); const int o = __shfl_xor_sync(0xffffffffu, dreq, m); dreq = o > dreq ? o : dreq;
+  }
+  if ((threadIdx.x & 31) == 0) { sh_sum[threadIdx.x >> 5] = sum; sh_max[threadIdx.x >> 5] = xmax; sh_miss[threadIdx.x >> 5] = miss; sh_d[threadIdx.x >> 5] = dreq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tx = 0.0; int tm = 0, td = 0;
+    for (int w = 0; w < 8; ++w) { ts += sh_sum[w]; tx = fmax(tx, sh_max[w]); tm += sh_miss[w]; td = sh_d[w] > td ? sh_d[w] : td; }
+    nmiss[s] = tm;
+    mean[s] = ts / (double)(n - tm);                 // x_mean of src/lmm.cpp:1599-1604 (NaN for an all-missing row, as there)
+    int T = 0;
+    if (td <= 6) {
+      double sc = 1.0; for (int d = 0; d < td; ++d) sc *= 10.0;
+      const double qmax = rint(tx * sc);
+      T = qmax < 256.0 ? 1 : (qmax < 65536.0 ? 2 : (qmax < 16777216.0 ? 3 : 0));
+    }
+    dsel[s] = td; nplanes[s] = T;                    // T == 0: this batch stays on the FP64 path
+  }
+}
+
+// exclusive scan of nplanes over one chunk of SNPs -> digit-row offsets; info = {rows, #rows not representable, all rows plain (d = 0, one plane)}
+__global__ void __launch_bounds__(1024) geno_rowoff_kernel(const int *__restrict__ nplanes, const int *__restrict__ dsel, int l, int *__restrict__ rowoff,
+                                                           int *__restrict__ info) {
+  __shared__ int part[1024];
+  const int per = (l + 1023) / 1024, b0 = threadIdx.x * per;
+  int t = 0, bad = 0, fancy = 0;
+  for (int k = 0; k < per && b0 + k < l; ++k) { const int T = nplanes[b0 + k]; t += T; bad += (T == 0); fancy += (T != 1 || dsel[b0 + k] != 0); }
+  part[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int off = part[threadIdx.x] - t;
+  for (int k = 0; k < per && b0 + k < l; ++k) { rowoff[b0 + k] = off; off += nplanes[b0 + k]; }
+  if (bad) atomicAdd(&info[1], bad);
+  if (fancy) atomicAdd(&info[2], fancy);
+  if (threadIdx.x == 1023) info[0] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) geno_to_planes_kernel(const double *__restrict__ G, int n, size_t ldg, int n_padk, const int *__restrict__ dsel,
+                                                             const int *__restrict__ nplanes, const int *__restrict__ rowoff, uint8_t *__restrict__ A) {
+  const int s = blockIdx.x;
+  const int T = nplanes[s], d = dsel[s];
+  const double *g = G + (size_t)s * ldg;
+  double sc = 1.0;
+  for (int k = 0; k < d; ++k) sc *= 10.0;
+  uint8_t *a0 = A + (size_t)rowoff[s] * n_padk;
+  for (int p = threadIdx.x; p < n_padk; p += 256) {
+    unsigned q = 0u;
+    if (p < n) { const double x = g[p]; if (!isnan(x)) q = (unsigned)rint(x * sc); }      // holes enter as 0; their mean term is added afterwards
+    for (int k = 0; k < T; ++k) a0[(size_t)k * n_padk + p] = (uint8_t)((q >> (8 * k)) & 255u);
+  }
+}
+
+// U^T x = (sum_k 256^k C_k) / 10^d  +  mean * sum_{j missing} U[j][:]      (one CTA per SNP)
+__global__ void __launch_bounds__(256) geno_combine_kernel(const double *__restrict__ G, int n, size_t ldg, const double *__restrict__ Ct, size_t ldc,
+                                                           const int *__restrict__ dsel, const int *__restrict__ nplanes, const int *__restrict__ rowoff,
+                                                           const double *__restrict__ mean, const int *__restrict__ nmiss,
+                                                           const double *__restrict__ U, double *__restrict__ out, size_t ldo, int in_place) {
+  constexpr int CAP = 1024;
+  __shared__ int list[CAP];
+  __shared__ int count;
+  const int s = blockIdx.x;
+  const int T = nplanes[s], d = dsel[s];
+  double p10 = 1.0;
+  for (int k = 0; k < d; ++k) p10 *= 10.0;
+  const double *c0 = Ct + (size_t)rowoff[s] * ldc;
+  double *o = out + (size_t)s * ldo;
+  if (!in_place) {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      double v = c0[(size_t)(T - 1) * ldc + i];
+      for (int k = T - 2; k >= 0; --k) v = fma(v, 256.0, c0[(size_t)k * ldc + i]);
+      o[i] = v / p10;
+    }
+  }
+  if (nmiss[s] == 0) return;
+  const double m = mean[s];
+  const double *g = G + (size_t)s * ldg;
+  for (int base = 0; base < n; base += CAP) {
+    __syncthreads();
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const int hi_p = min(n, base + CAP);
+    for (int p = base + threadIdx.x; p < hi_p; p += 256)
+      if (isnan(g[p])) list[atomicAdd(&count, 1)] = p;
+    __syncthreads();
+    const int cnt = count;
+    if (cnt > 0) {
+      if (threadIdx.x == 0)       // fixed summation order
+        for (int a = 1; a < cnt; ++a) { int key = list[a], b2 = a - 1; while (b2 >= 0 && list[b2] > key) { list[b2 + 1] = list[b2]; --b2; } list[b2 + 1] = key; }
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += 256) {
+        double acc = 0.0;
+        for (int q = 0; q < cnt; ++q) acc += U[(size_t)list[q] * n + i];
+        o[i] += m * acc;
+      }
+    }
+  }
+}
+
+// G_dev: l x n SNP-major doubles (ld ldg), NaN = missing.  *taken = false (and nothing written) when a value is not a short decimal.
+int i8_project_geno(gb200_ctx *c, const double *G_dev, size_t l, size_t ldg, double *UtXt_dev, bool *taken) {
+  *taken = false;
+  int rc = i8_prepare(c);
+  if (rc) return rc;
+  const I8Geom g = make_geom(c->n, c->i8.n_slices);
+  if (!(c->cta_pair != 0 && (g.N % 32 == 0 || g.N == 240))) return GB200_OK;          // only the CTA-pair kernel carries this path
+  const size_t CH = 2048;                                   // SNPs per GEMM launch (bounds the digit-row scratch: <= 3 x 2048 rows)
+  GB_CUDA(c, c->i8.miss_mean.reserve(l * (sizeof(double) + 4 * sizeof(int)) + 64));
+  double *mean = c->i8.miss_mean.as<double>();
+  int *nmiss = reinterpret_cast<int *>(mean + l), *dsel = nmiss + l, *nplanes = dsel + l, *rowoff = nplanes + l, *info = rowoff + l;
+  {
+    ProfScope ps(c, "decode");
+    geno_classify_kernel<<<(unsigned)l, 256, 0, c->stream>>>(G_dev, g.n, ldg, mean, nmiss, dsel, nplanes);
+    GB_CUDA(c, cudaGetLastError());
+  }
+  // representable at all?  (one small read-back per batch)
+  {
+    GB_CUDA(c, cudaMemsetAsync(info, 0, 4 * sizeof(int), c->stream));
+    geno_rowoff_kernel<<<1, 1024, 0, c->stream>>>(nplanes, dsel, (int)l, rowoff, info);
+    int h[4];
+    GB_CUDA(c, cudaMemcpyAsync(h, info, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h[1] != 0) return GB200_OK;
+  }
+  GB_CUDA(c, c->i8.geno.reserve((3 * CH + 256) * (size_t)g.n_padk));
+  GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, (uint64_t)g.n_groups * (uint64_t)g.N, (uint64_t)g.n_padk, (uint32_t)(g.N / 2)))
+    return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the U planes (pair)");
+  c->i8.tmap_b_half = true;
+  for (size_t s0 = 0; s0 < l; s0 += CH) {
+    const size_t lc = l - s0 < CH ? l - s0 : CH;
+    int h[4];
+    GB_CUDA(c, cudaMemsetAsync(info, 0, 4 * sizeof(int), c->stream));
+    geno_rowoff_kernel<<<1, 1024, 0, c->stream>>>(nplanes + s0, dsel + s0, (int)lc, rowoff + s0, info);
+    GB_CUDA(c, cudaMemcpyAsync(h, info, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t R = (size_t)h[0], R_pad = (R + 255) / 256 * 256;
+    const bool plain = (h[2] == 0);                         // every row is 0..255 integers: the GEMM writes U^T x itself
+    {
+      ProfScope ps(c, "decode");
+      GB_CUDA(c, cudaMemsetAsync(c->i8.geno.as<uint8_t>() + R * (size_t)g.n_padk, 0, (R_pad - R) * (size_t)g.n_padk, c->stream));
+      geno_to_planes_kernel<<<(unsigned)lc, 256, 0, c->stream>>>(G_dev + s0 * ldg, g.n, ldg, g.n_padk, dsel + s0, nplanes + s0, rowoff + s0,
+                                                                 c->i8.geno.as<uint8_t>());
+      GB_CUDA(c, cudaGetLastError());
+    }
+    double *Ct = UtXt_dev + s0 * c->n_c;
+    if (!plain) { GB_CUDA(c, c->dTmp.reserve(R_pad * c->n_c * sizeof(double))); Ct = c->dTmp.as<double>(); }
+    if (!make_tmap((CUtensorMap *)c->i8.tmap_a, c->i8.geno.p, R_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
+      return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the dosage digit rows");
+    I8KernelParams p;
+    p.T = g.T; p.NE = g.NE; p.N = g.N; p.n = g.n; p.l = (int)R;
+    p.num_k_blocks = g.n_padk / I8_BK;
+    p.m_tiles = (int)(R_pad / 256); p.n_groups = g.n_groups;
+    p.lbo_units = 1; p.scale = c->i8.scale.as<double>();
+    p.C = Ct; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
+    p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : 9;
+    const size_t stage_pair = (size_t)I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK;
+    int ns = c->gemm_stages > 0 ? (int)c->gemm_stages : 6;
+    while (ns > 2 && 1024 + (size_t)ns * stage_pair + 256 > 227 * 1024) --ns;
+    p.stages = ns; p.wave_ctr = nullptr;
+    const int tiles = p.m_tiles * p.n_groups;
+    int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
+    if (c->gemm_wave_sync && 2 * pairs == c->num_sms / 2 * 2 && tiles > pairs) {
+      GB_CUDA(c, c->i8.wave_ctr.reserve(sizeof(unsigned int)));
+      GB_CUDA(c, cudaMemsetAsync(c->i8.wave_ctr.p, 0, sizeof(unsigned int), c->stream));
+      p.wave_ctr = c->i8.wave_ctr.as<unsigned int>();
+    }
+    {
+      ProfScope ps(c, "utx");
+      i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, 1024 + (size_t)ns * stage_pair + 256, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+      GB_CUDA(c, cudaGetLastError());
+    }
+    ProfScope ps2(c, "fix");
+    geno_combine_kernel<<<(unsigned)lc, 256, 0, c->stream>>>(G_dev + s0 * ldg, g.n, ldg, Ct, c->n_c, dsel + s0, nplanes + s0, rowoff + s0, mean + s0,
+                                                             nmiss + s0, c->dU.as<double>(), UtXt_dev + s0 * c->n_c, c->n_c, plain ? 1 : 0);
+    GB_CUDA(c, cudaGetLastError());
+  }
+  *taken = true;
   return GB200_OK;
 }
 
@@ -1285,7 +1523,7 @@ int kin_i8_flush(gb200_ctx *c) {
   p.lbo_units = 1; p.scale = nullptr;
   p.C = c->dK.as<double>(); p.ldc = n; p.mode = 1;
   p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = 6; p.stages = I8_STAGES;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = I8_PANEL; p.stages = I8_STAGES; p.wave_ctr = nullptr;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
   GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (c->kin_cta_pair != 0) {

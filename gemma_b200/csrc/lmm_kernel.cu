@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(V2_THREADS, (NC <= GB_V2_CTAS2_MAXNC) ? GB_V2_
 #if GB_V2_TMA
   v2_pipeline_init(v2_smem, NC);
 #endif
+  unsigned int pipe_it = 0;            // chunks that went through the stage ring so far (identical in every thread)
   for (;;) {
     if (threadIdx.x == 0) grp_s = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(V2_THREADS, (NC <= GB_V2_CTAS2_MAXNC) ? GB_V2_
     if (lane == 0) xrows[warp] = valid ? UtXt + (size_t)s * ldu : nullptr;
     __syncthreads();
     gb200_sumstat r;
-    v2_analyze_group<NC>(D, prm, xrows, v2_smem, nchunks, pad, valid, r);
+    v2_analyze_group<NC>(D, prm, xrows, v2_smem, nchunks, pad, valid, r, pipe_it);
     if (valid && lane == 0) out[s] = r;
     __syncthreads();
   }

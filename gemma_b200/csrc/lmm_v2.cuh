@@ -86,13 +86,23 @@ __device__ __forceinline__ void v2_bulk_load(void *dst, const void *src, uint32_
                ::"r"(v2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(v2_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint64_t *v2_bars(double *smem, int nc) { return reinterpret_cast<uint64_t *>(smem + v2_stage_doubles(nc) * V2_STAGES); }
+__device__ __forceinline__ void v2_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(v2_smem_u32(bar)) : "memory");
+}
+// The stages form ONE ring for the whole kernel: chunk number k (counted across passes, identical in every thread) lives in stage
+// k % V2_STAGES, its arrival is phase k / V2_STAGES of full[stage], and it may be overwritten once all V2_WARPS warps have arrived on
+// empty[stage] for it.  No CTA-wide barrier inside or between passes: thread 0 issues chunk k + 2 as soon as chunk k - 1 has been
+// released by every warp, each warp consumes at its own pace (at most V2_STAGES - 1 chunks apart), and the first chunks of the next
+// pass are in flight while slower warps still finish the previous one.
+__device__ __forceinline__ void v2_acquire_stage(uint64_t *empty, unsigned int k) {
+  if (k >= (unsigned int)V2_STAGES) v2_mbar_wait(&empty[k % V2_STAGES], ((k / V2_STAGES) - 1u) & 1u);
+}
 
 // once per kernel, before the first pass
 __device__ __forceinline__ void v2_pipeline_init(double *smem, int nc) {
   if (threadIdx.x == 0) {
     uint64_t *bars = v2_bars(smem, nc);
-    for (int s = 0; s < V2_STAGES; ++s) v2_mbar_init(&bars[s], 1);
-    *reinterpret_cast<unsigned int *>(&bars[V2_STAGES]) = 0u;        // passes completed so far
+    for (int s = 0; s < V2_STAGES; ++s) { v2_mbar_init(&bars[s], 1); v2_mbar_init(&bars[V2_STAGES + s], V2_WARPS); }   // full[] (TMA bytes), empty[] (one arrival per warp)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -209,7 +219,7 @@ __device__ __forceinline__ void v2_chunk(const double *__restrict__ st, int warp
 // whether this warp does arithmetic.  want_ld[s] adds sum log|lambda*delta+1| for slot s.
 template <int NC, int NS, int KLO, int KHI, bool LD>
 __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
-                                        int pad, bool active, const double (&lam)[NS], V2Acc<NC, NS, KLO, KHI> &acc) {
+                                        int pad, bool active, const double (&lam)[NS], V2Acc<NC, NS, KLO, KHI> &acc, unsigned int &pipe_it) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   constexpr int NK = KHI - KLO + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -225,35 +235,34 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
     }
   }
 #if GB_V2_TMA
-  uint64_t *bars = v2_bars(smem, NC);
-  const unsigned int npass = *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]);     // identical in every thread
-  // fills of stage s per pass (every pass walks the same nchunks): phase parity = (passes * fills + fill index) & 1
-  unsigned int base_par[V2_STAGES];
-#pragma unroll
-  for (int s = 0; s < V2_STAGES; ++s) {
-    const unsigned int fills = (s < nchunks) ? (unsigned int)((nchunks - s + V2_STAGES - 1) / V2_STAGES) : 0u;
-    base_par[s] = npass * fills;
-  }
+  uint64_t *full = v2_bars(smem, NC), *empty = full + V2_STAGES;
+  const unsigned int it0 = pipe_it;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int c = 0; c < V2_STAGES - 1; ++c)
-      if (c < nchunks) v2_issue_tma<NC>(D, xrows, smem + (size_t)c * stage_d, c, &bars[c]);
+      if (c < nchunks) {
+        const unsigned int k = it0 + (unsigned int)c;
+        v2_acquire_stage(empty, k);
+        v2_issue_tma<NC>(D, xrows, smem + (size_t)(k % V2_STAGES) * stage_d, c, &full[k % V2_STAGES]);
+      }
   }
   for (int c = 0; c < nchunks; ++c) {
-    __syncthreads();                                      // everyone is done with chunk c-1: its stage may be refilled
     if (threadIdx.x == 0) {
       const int cn = c + V2_STAGES - 1;
-      if (cn < nchunks) v2_issue_tma<NC>(D, xrows, smem + (size_t)(cn % V2_STAGES) * stage_d, cn, &bars[cn % V2_STAGES]);
+      if (cn < nchunks) {
+        const unsigned int kn = it0 + (unsigned int)cn;
+        v2_acquire_stage(empty, kn);
+        v2_issue_tma<NC>(D, xrows, smem + (size_t)(kn % V2_STAGES) * stage_d, cn, &full[kn % V2_STAGES]);
+      }
     }
-    {
-      const int sidx = c % V2_STAGES;
-      const unsigned int par = (sidx == 0 ? base_par[0] : sidx == 1 ? base_par[1] : base_par[V2_STAGES - 1]) + (unsigned int)(c / V2_STAGES);
-      v2_mbar_wait(&bars[sidx], par & 1u);                // chunk c has landed
-    }
-    if (active) v2_chunk<NC, NS, KLO, KHI, LD>(smem + (size_t)(c % V2_STAGES) * stage_d, warp, lane, lam, acc);
+    const unsigned int k = it0 + (unsigned int)c;
+    const int sidx = (int)(k % V2_STAGES);
+    v2_mbar_wait(&full[sidx], (k / V2_STAGES) & 1u);        // chunk c has landed
+    if (active) v2_chunk<NC, NS, KLO, KHI, LD>(smem + (size_t)sidx * stage_d, warp, lane, lam, acc);
+    __syncwarp();
+    if (lane == 0) v2_mbar_arrive(&empty[sidx]);            // this warp is done with the stage
   }
-  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]) = npass + 1u;
-  __syncthreads();                                        // stages are free for the next pass; the counter is visible
+  pipe_it = it0 + (unsigned int)nchunks;
 #else
   // prologue: stages 0 .. STAGES-2
 #pragma unroll
@@ -323,7 +332,7 @@ __device__ __forceinline__ void v2_issue_common(const LmmConst &D, const double 
 
 template <int NC, bool WITH_I>
 __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
-                                               bool active, const int (&jrow)[V2_NSC], V2CAcc<NC> &acc) {
+                                               bool active, const int (&jrow)[V2_NSC], V2CAcc<NC> &acc, unsigned int &pipe_it) {
   constexpr int NQ = NC + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t stage_d = v2_stage_doubles(NC);
@@ -333,32 +342,31 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
 #pragma unroll
     for (int s = 0; s < V2_NSC; ++s) { acc.X[s][0][q] = 0.0; acc.X[s][1][q] = 0.0; }
   }
-  uint64_t *bars = v2_bars(smem, NC);
-  const unsigned int npass = *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]);
-  unsigned int base_par[V2_STAGES];
-#pragma unroll
-  for (int s = 0; s < V2_STAGES; ++s) {
-    const unsigned int fills = (s < nchunks) ? (unsigned int)((nchunks - s + V2_STAGES - 1) / V2_STAGES) : 0u;
-    base_par[s] = npass * fills;
-  }
+  uint64_t *full = v2_bars(smem, NC), *empty = full + V2_STAGES;
+  const unsigned int it0 = pipe_it;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int c = 0; c < V2_STAGES - 1; ++c)
-      if (c < nchunks) v2_issue_common<NC>(D, xrows, smem + (size_t)c * stage_d, c, &bars[c], jrow);
+      if (c < nchunks) {
+        const unsigned int k = it0 + (unsigned int)c;
+        v2_acquire_stage(empty, k);
+        v2_issue_common<NC>(D, xrows, smem + (size_t)(k % V2_STAGES) * stage_d, c, &full[k % V2_STAGES], jrow);
+      }
   }
   for (int c = 0; c < nchunks; ++c) {
-    __syncthreads();
     if (threadIdx.x == 0) {
       const int cn = c + V2_STAGES - 1;
-      if (cn < nchunks) v2_issue_common<NC>(D, xrows, smem + (size_t)(cn % V2_STAGES) * stage_d, cn, &bars[cn % V2_STAGES], jrow);
+      if (cn < nchunks) {
+        const unsigned int kn = it0 + (unsigned int)cn;
+        v2_acquire_stage(empty, kn);
+        v2_issue_common<NC>(D, xrows, smem + (size_t)(kn % V2_STAGES) * stage_d, cn, &full[kn % V2_STAGES], jrow);
+      }
     }
-    {
-      const int sidx = c % V2_STAGES;
-      const unsigned int par = (sidx == 0 ? base_par[0] : sidx == 1 ? base_par[1] : base_par[V2_STAGES - 1]) + (unsigned int)(c / V2_STAGES);
-      v2_mbar_wait(&bars[sidx], par & 1u);
-    }
+    const unsigned int k = it0 + (unsigned int)c;
+    const int sidx = (int)(k % V2_STAGES);
+    v2_mbar_wait(&full[sidx], (k / V2_STAGES) & 1u);
     if (active) {
-      const double *st = smem + (size_t)(c % V2_STAGES) * stage_d;
+      const double *st = smem + (size_t)sidx * stage_d;
       const double *sl = st + lane;
       const double *xl = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK + lane;
       const double *hl = st + (NC + 2 + V2_WARPS) * V2_CHUNK + lane;
@@ -387,9 +395,10 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) v2_mbar_arrive(&empty[sidx]);
   }
-  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned int *>(&bars[V2_STAGES]) = npass + 1u;
-  __syncthreads();
+  pipe_it = it0 + (unsigned int)nchunks;
   if (active) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -744,7 +753,7 @@ __device__ __forceinline__ bool v2_drive(const LmmConst &D, V2Fn &F, bool fnR, c
 template <int NC>
 __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *const *xrows, double *smem, int nchunks, int pad,
                                               bool active, const V2Req (&rq)[2], double n, double logdetI, V2Eval (&ev)[2],
-                                              unsigned int &tally2, unsigned int &tally3, unsigned int &tallyld) {
+                                              unsigned int &tally2, unsigned int &tally3, unsigned int &tallyld, unsigned int &pipe_it) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   const int k0 = rq[0].need ? rq[0].K : 0, k1 = rq[1].need ? rq[1].K : 0;
   const int Kloc = active ? (k0 > k1 ? k0 : k1) : 0;
@@ -756,8 +765,8 @@ __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *cons
   double dummy[NIDX];
   if (big) {
     V2Acc<NC, 2, 1, 3> acc;
-    if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
-    else v2_pass<NC, 2, 1, 3, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
+    if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
+    else v2_pass<NC, 2, 1, 3, false>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
     if (active) {
 #pragma unroll
       for (int s = 0; s < 2; ++s)
@@ -765,8 +774,8 @@ __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *cons
     }
   } else {
     V2Acc<NC, 2, 1, 2> acc;
-    if (any_ld) v2_pass<NC, 2, 1, 2, true>(D, xrows, smem, nchunks, pad, active, lam, acc);
-    else v2_pass<NC, 2, 1, 2, false>(D, xrows, smem, nchunks, pad, active, lam, acc);
+    if (any_ld) v2_pass<NC, 2, 1, 2, true>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
+    else v2_pass<NC, 2, 1, 2, false>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
     if (active) {
 #pragma unroll
       for (int s = 0; s < 2; ++s)
@@ -778,7 +787,7 @@ __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *cons
 // One CTA = 8 SNPs.  xrows[w] (shared memory) = U^T x row of warp w or nullptr.
 template <int NC>
 __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmParams &prm, const double *const *xrows,
-                                                 double *smem, int nchunks, int pad, bool valid, gb200_sumstat &out) {
+                                                 double *smem, int nchunks, int pad, bool valid, gb200_sumstat &out, unsigned int &pipe_it) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   const int mode = prm.a_mode;
   const bool needR = (mode == 1 || mode == 4), needL = (mode == 2 || mode == 4 || mode == 9);
@@ -818,8 +827,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       }
       V2CAcc<NC> acc;
       const bool with_I = (s0 == 0) && need_search;
-      if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc);
-      else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc);
+      if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it);
+      else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it);
       if (valid) {
         tallyc += V2_NSC;
         if (with_I) {
@@ -862,7 +871,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
     {
       V2Acc<NC, 1, 0, 2> acc;
       const double lam[1] = {l_min * exp(lambda_interval * 0.0)};
-      v2_pass<NC, 1, 0, 2, true>(D, xrows, smem, nchunks, pad, valid, lam, acc);
+      v2_pass<NC, 1, 0, 2, true>(D, xrows, smem, nchunks, pad, valid, lam, acc, pipe_it);
       if (valid) {
         Derived<NC, 1> dI;
         sweep_tables<NC, 1>(acc.S[0][0], dummy, dummy, dI);
@@ -878,7 +887,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       double lam[V2_NSG];
 #pragma unroll
       for (int s = 0; s < V2_NSG; ++s) lam[s] = (g0 + s <= n_region) ? l_min * exp(lambda_interval * (double)(g0 + s)) : 1.0;
-      v2_pass<NC, V2_NSG, 1, 2, false>(D, xrows, smem, nchunks, pad, valid, lam, acc);
+      v2_pass<NC, V2_NSG, 1, 2, false>(D, xrows, smem, nchunks, pad, valid, lam, acc, pipe_it);
       if (valid) {
 #pragma unroll
         for (int s = 0; s < V2_NSG; ++s) {
@@ -895,7 +904,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   if (need_search || needS) {
     V2Acc<NC, 2, 1, 1> acc;
     const double lam[2] = {l_max, needS ? prm.l_mle_null : 1.0};
-    v2_pass<NC, 2, 1, 1, true>(D, xrows, smem, nchunks, pad, valid, lam, acc);
+    v2_pass<NC, 2, 1, 1, true>(D, xrows, smem, nchunks, pad, valid, lam, acc, pipe_it);
     if (valid) {
       V2Eval ev;
       v2_derive<NC, 1>(acc.S[0][0], dummy, dummy, acc.tr[0][0], 0.0, lam[0], n, true, acc.ld[0], logdetI, ev);
@@ -936,7 +945,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
 #pragma unroll
           for (int s2 = 0; s2 < V2_NSC; ++s2) jrow[s2] = D.n_common + g * M + p0 + s2;
           V2CAcc<NC> acc;
-          v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc);
+          v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it);
           if (due) {
             tallyc += V2_NSC;
             __syncwarp();
@@ -976,7 +985,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
           const bool blocked = blkR || blkL;
           if (!__syncthreads_or(blocked ? 1 : 0)) break;
           V2Eval ev[2];
-          v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, blocked, rq, n, logdetI, ev, tally2, tally3, tallyld);
+          v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, blocked, rq, n, logdetI, ev, tally2, tally3, tallyld, pipe_it);
           if (blkR) {
             evR[0] = ev[0].d1R; evR[1] = ev[0].d2R; evR[2] = ev[0].fR;
             if (rq[0].logdet) { FR.cache_lam = rq[0].lam; FR.cP_xx = ev[0].P_xx; FR.cP_xy = ev[0].P_xy; FR.cP_yy = ev[0].P_yy; FR.cPx_yy = ev[0].Px_yy; }
@@ -1018,7 +1027,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       if (!__syncthreads_or(active ? 1 : 0)) break;
       const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
       V2Eval ev[2];
-      v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, active, rq, n, logdetI, ev, tally2, tally3, tallyld);
+      v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, active, rq, n, logdetI, ev, tally2, tally3, tallyld, pipe_it);
       if (active) {
         if (want_wald) {
           Derived<NC, 1> d; d.P_xx = ev[0].P_xx; d.P_xy = ev[0].P_xy; d.P_yy = ev[0].P_yy; d.Px_yy = ev[0].Px_yy;

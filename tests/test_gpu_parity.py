@@ -1141,3 +1141,47 @@ def test_device_tails_match_the_restated_gsl_tails_including_the_asymptotic_bran
     assert np.all(got[(np.array(dfs) > 2e5) & (np.array(xs) == 300.0)] == 0.0)       # the reference's own 1 - P = 0
     xc = np.array([-1.0, 0.0, 1e-12, 0.3, 1.0, 10.0, 100.0, 1400.0])
     assert np.allclose(ctx.cdf_tails(xc), [O.chisq1_Q(x) for x in xc], rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_dosage_rows_take_the_tensor_core_projection_as_exact_digit_rows(ctx):
+    """BIMBAM mean genotypes (src/lmm.cpp:1590-1618, dgemm at :1521): values printed with up to 6 decimals are integers over a power
+    of ten, so each SNP row goes through the int8 GEMM as 1-3 exact base-256 digit rows (i8gemm_sm100.cu, i8_project_geno).  Same
+    statistics as the FP64 projection and as the oracle; a batch with a long decimal stays on the FP64 GEMM."""
+    n, l = 1300, 96
+    rng = np.random.default_rng(77)
+    pb = random_problem(n, 1, 4, 78)
+    f = rng.uniform(0.05, 0.5, l)
+    G = rng.binomial(2, f[:, None], size=(l, n)).astype(np.float64)              # SNP-major, plain 0/1/2 rows ...
+    for s, dec in ((3, 1), (7, 2), (8, 3), (20, 4), (21, 5), (40, 6), (41, 3)):      # ... and dosage rows with 1..6 decimals
+        G[s] = np.round(np.clip(G[s] + rng.normal(0, 0.3, n), 0, 2), dec)
+    G[50] = np.round(rng.uniform(0, 2, n), 2)
+    G[rng.random(G.shape) < 0.01] = np.nan                                       # missing entries: mean-imputed (lmm.cpp:1611-1618)
+    X = O.lmm_impute(G)
+    y = pb["y"] + 0.5 * (X[:, 8] - X[:, 8].mean())
+    ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], y)
+    nm = ctx.lmm_null(pb["trace_G"])
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ref = O.lmm_analyze_utx(pb["ev"], pb["U"].T @ pb["W"], pb["U"].T @ y, pb["U"].T @ X, 4,
+                            l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ctx.set_option("utx_path", 1)
+    fp = ctx.lmm_batch_geno(G)
+    ctx.set_option("utx_path", 0)
+    ctx.profile_enable(True); ctx.profile_reset()
+    got = ctx.lmm_batch_geno(G)
+    assert ctx.profile_get("fix")[1] >= 1                     # the digit-row path ran (its recombination pass is profiled as "fix")
+    check_sumstat(got, ref, 4)
+    check_sumstat(fp, ref, 4)
+    for k in ("beta", "se", "p_wald", "p_lrt", "p_score"):
+        m = ~np.isnan(fp[k])
+        assert np.allclose(got[k][m], fp[k][m], rtol=1e-7, atol=1e-300), k
+    # one value with nine decimals: the batch is not representable, the FP64 GEMM takes it (same answers)
+    G2 = G.copy(); G2[5, 11] = 0.123456789
+    ctx.profile_reset()
+    got2 = ctx.lmm_batch_geno(G2)
+    assert ctx.profile_get("fix")[1] == 0
+    ctx.profile_enable(False)
+    X2 = O.lmm_impute(G2)
+    ref2 = O.lmm_analyze_utx(pb["ev"], pb["U"].T @ pb["W"], pb["U"].T @ y, pb["U"].T @ X2, 4,
+                             l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    check_sumstat(got2, ref2, 4)
