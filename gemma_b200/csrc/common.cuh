@@ -134,6 +134,7 @@ struct gb200_ctx {
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
   long gemm_groups = 1;  // 2: pair kernel with two eigenvector groups per tile (shared genotype tile) and the hole pass on the tensor pipe; 1: one group, FP64 hole fix-up
+  long hole_gemm = 1;      // CTA-pair projection: batches with many missing genotypes add mean * U^T q by a second GEMM pass over the hole-indicator rows (decided on the device); 0 = always the gather kernel
   long gemm_wave_sync = 1; // CTA-pair projection: producers start every tile wave together (keeps the K-panels shared through L2)
   long gemm_stages = 0;  // TMA pipeline stages of the CTA-pair projection kernel (0 = as many 32 KB stages as fit, at most 6)
   long gemm_panel = 0;   // raster panel width of the projection kernels in eigenvector groups (0 = default: 9 for the CTA-pair kernel; 2-group units, 6, for gemm_groups = 2)

@@ -134,6 +134,7 @@ struct I8KernelParams {
   // i8_gemm_pair2_kernel only
   const double *row_mean;   // mode 2: C[s][:] += row_mean[s] * (A . planes) * scale   (A = hole indicator rows)
   const int *tile_holes;    // mode 2: holes per 256-row tile; tiles without a hole are skipped
+  const int *hole_switch;   // mode 2 (pair kernel): [0] = 1 when the batch's holes go through this GEMM pass, 0 = the sparse gather kernel has them
   int panel;                // raster panel width in units of NB eigenvector groups
   int stages;               // i8_gemm_pair_kernel: TMA pipeline stages
   unsigned int *wave_ctr;   // i8_gemm_pair_kernel: wave synchronisation counter (zeroed before the launch) or null
@@ -358,7 +359,9 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const bool leader = (rank == 0);
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int num_tiles = p.tiles ? p.num_tiles : p.m_tiles * p.n_groups;    // m_tiles counts 256-row tiles here
+  int num_tiles = p.tiles ? p.num_tiles : p.m_tiles * p.n_groups;          // m_tiles counts 256-row tiles here
+  if (p.mode == 2 && p.hole_switch && __ldg(p.hole_switch) == 0) num_tiles = 0;   // the gather kernel handles this batch's holes (uniform over the grid)
+  auto skip = [&](int m_blk) -> bool { return p.mode == 2 && __ldg(p.tile_holes + m_blk) == 0; };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -386,6 +389,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       unsigned int wave = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++wave) {
         int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
+        if (skip(m_blk)) continue;
         if (p.wave_ctr && wave > 0) {
           // Wave synchronisation: the ~74 tile pairs that run concurrently share their genotype / plane K-panels through L2
           // only while they walk K in phase (a panel is n bytes long: two tiles half a tile apart are 1 GB of other traffic
@@ -418,6 +422,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        if (p.mode == 2) { int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp); if (skip(m_blk)) continue; }
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * I8_ACC_COLS);
@@ -444,9 +449,11 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const double w256 = 256.0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
+      if (skip(m_blk)) continue;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int s = m_blk * 256 + (int)rank * I8_BM + ew * 32 + lane;
+      const double rm = (p.mode == 2 && s < p.l) ? __ldg(p.row_mean + s) : 0.0;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * I8_ACC_COLS);
       const int i0 = n_grp * p.NE;
       if (p.mode == 1) {
@@ -483,7 +490,10 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int i = i0 + e0 + q;
-              if (i < p.n) crow[i] = v[q] * __ldg(p.scale + i);
+              if (i < p.n) {
+                const double val = v[q] * __ldg(p.scale + i);
+                if (p.mode == 2) crow[i] = fma(rm, val, crow[i]); else crow[i] = val;     // mode 2: + mean * U^T q (hole indicator rows)
+              }
             }
           }
         }
@@ -773,16 +783,32 @@ __global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__r
   }
 }
 
+// Holes either way: few holes -> gather the rows of U at the holes (miss_fix_kernel: holes x n x 8 B of reads, 400 KB per hole at
+// n = 50 000); many holes -> a second pass of the projection GEMM over the hole-indicator rows (mode 2: C += mean * U^T q, same
+// cost as the main pass, independent of the hole count).  The gather costs holes x 8 n B / 6.5 TB/s, the GEMM pass about
+// 2 T n^2 l / 3e15 s: the switch sits where the gather would take longer.  Decided on the device (no read-back).
+__global__ void hole_switch_kernel(const int *__restrict__ tile_holes, int n_tiles, double holes_max, int *__restrict__ sw) {
+  __shared__ double part[8];
+  double t = 0.0;
+  for (int k = threadIdx.x; k < n_tiles; k += 256) t += (double)tile_holes[k];
+  for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) t += part[w]; sw[0] = (t > holes_max) ? 1 : 0; }
+}
+
 // U^T x += mean * sum_{j in holes} U[j][:]   for SNPs with missing genotypes
 __global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__restrict__ bed, size_t bytes_per_snp,
                                                        const int *__restrict__ idx, int n,
                                                        const double *__restrict__ U, const double *__restrict__ mean,
-                                                       const int *__restrict__ nmiss, double *__restrict__ C, size_t ldc) {
+                                                       const int *__restrict__ nmiss, double *__restrict__ C, size_t ldc,
+                                                       const int *__restrict__ hole_switch) {
   constexpr int CAP = 2048;
   __shared__ int list[CAP];
   __shared__ int count;
   const int s = blockIdx.x;
   if (nmiss[s] == 0) return;
+  if (hole_switch && __ldg(hole_switch) != 0) return;       // dense holes: the tensor-core hole pass has them
   const unsigned char *row = bed + (size_t)s * bytes_per_snp;
   const double m = mean[s];
   double *c = C + (size_t)s * ldc;
@@ -933,19 +959,21 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   const size_t m_rows = pair ? 256 : I8_BM;
   const size_t l_pad = (l + m_rows - 1) / m_rows * m_rows;
   GB_CUDA(c, c->i8.geno.reserve(l_pad * (size_t)g.n_padk));
-  GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int)) + (l_pad / 256 + 1) * sizeof(int)));
+  GB_CUDA(c, c->i8.miss_mean.reserve(l_pad * (sizeof(double) + sizeof(int)) + (l_pad / 256 + 2) * sizeof(int)));
   double *mean = c->i8.miss_mean.as<double>();
   int *nmiss = reinterpret_cast<int *>(mean + l_pad);
   int *tile_holes = nmiss + l_pad;
-  if (pair2) {
+  const bool hole_gemm = pair && !pair2 && c->hole_gemm != 0;   // hybrid: gather when holes are few, tensor-core hole pass when they are many
+  if (pair2 || hole_gemm) {
     GB_CUDA(c, c->i8.holeq.reserve(l_pad * (size_t)g.n_padk));
-    GB_CUDA(c, cudaMemsetAsync(tile_holes, 0, (l_pad / 256 + 1) * sizeof(int), c->stream));
+    GB_CUDA(c, cudaMemsetAsync(tile_holes, 0, (l_pad / 256 + 2) * sizeof(int), c->stream));
   }
   {
   ProfScope ps(c, "decode");
   bed_to_i8_kernel<<<(unsigned)l_pad, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, g.n_padk, (int)l,
                                                            c->i8.geno.as<int8_t>(), mean, nmiss,
-                                                           pair2 ? c->i8.holeq.as<int8_t>() : nullptr, pair2 ? tile_holes : nullptr);
+                                                           (pair2 || hole_gemm) ? c->i8.holeq.as<int8_t>() : nullptr,
+                                                           (pair2 || hole_gemm) ? tile_holes : nullptr);
   GB_CUDA(c, cudaGetLastError());
   }
   if (!make_tmap((CUtensorMap *)c->i8.tmap_a, c->i8.geno.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
@@ -957,7 +985,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
   p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : (pair2 ? 6 : (pair ? 9 : I8_PANEL)); p.stages = I8_STAGES; p.wave_ctr = nullptr;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : (pair2 ? 6 : (pair ? 9 : I8_PANEL)); p.stages = I8_STAGES; p.wave_ctr = nullptr; p.hole_switch = nullptr;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
   const int tiles = p.m_tiles * p.n_groups;
   if (pair2) {
@@ -1001,9 +1029,29 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
       p.wave_ctr = c->i8.wave_ctr.as<unsigned int>();
     }
     const size_t smem_pair = 1024 + (size_t)ns * stage_pair + 256;
-    ProfScope ps(c, "utx");
-    i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
-    GB_CUDA(c, cudaGetLastError());
+    {
+      ProfScope ps(c, "utx");
+      i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
+      GB_CUDA(c, cudaGetLastError());
+    }
+    if (hole_gemm) {
+      int *sw = tile_holes + (l_pad / 256 + 1);
+      // gather: holes * 8 n bytes at ~5 TB/s;  hole pass: the main pass again, ~2 T n^2 l_pad / 2.8e15 s
+      const double t_gemm = 2.0 * (double)g.T * (double)g.n * (double)g.n * (double)l_pad / 2.8e15;
+      const double holes_max = t_gemm * 5.0e12 / (8.0 * (double)g.n);
+      hole_switch_kernel<<<1, 256, 0, c->stream>>>(tile_holes, (int)(l_pad / 256), holes_max, sw);
+      if (!c->i8.tmap_q) c->i8.tmap_q = aligned_alloc(64, sizeof(CUtensorMap));
+      if (!make_tmap((CUtensorMap *)c->i8.tmap_q, c->i8.holeq.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
+        return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the hole-indicator tile");
+      I8KernelParams ph = p;
+      ph.mode = 2; ph.row_mean = mean; ph.tile_holes = tile_holes; ph.hole_switch = sw; ph.wave_ctr = nullptr;
+      ProfScope ps(c, "fix");
+      i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_q, *(CUtensorMap *)c->i8.tmap_b, ph);
+      GB_CUDA(c, cudaGetLastError());
+      miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean, nmiss, UtXt_dev, c->n_c, sw);
+      GB_CUDA(c, cudaGetLastError());
+      return GB200_OK;
+    }
   } else {
     if (c->i8.tmap_b_half) {
       if (!make_tmap((CUtensorMap *)c->i8.tmap_b, c->i8.slices.p, (uint64_t)g.n_groups * (uint64_t)g.N, (uint64_t)g.n_padk, (uint32_t)g.N))
@@ -1017,7 +1065,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   }
   ProfScope ps2(c, "fix");
   miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
-                                                      nmiss, UtXt_dev, c->n_c);
+                                                      nmiss, UtXt_dev, c->n_c, nullptr);
   GB_CUDA(c, cudaGetLastError());
   return GB200_OK;
 }
@@ -1216,7 +1264,7 @@ int i8_project_geno(gb200_ctx *c, const double *G_dev, size_t l, size_t ldg, dou
     const size_t stage_pair = (size_t)I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK;
     int ns = c->gemm_stages > 0 ? (int)c->gemm_stages : 6;
     while (ns > 2 && 1024 + (size_t)ns * stage_pair + 256 > 227 * 1024) --ns;
-    p.stages = ns; p.wave_ctr = nullptr;
+    p.stages = ns; p.wave_ctr = nullptr; p.hole_switch = nullptr;
     const int tiles = p.m_tiles * p.n_groups;
     int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
     if (c->gemm_wave_sync && 2 * pairs == c->num_sms / 2 * 2 && tiles > pairs) {
@@ -1523,7 +1571,7 @@ int kin_i8_flush(gb200_ctx *c) {
   p.lbo_units = 1; p.scale = nullptr;
   p.C = c->dK.as<double>(); p.ldc = n; p.mode = 1;
   p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = I8_PANEL; p.stages = I8_STAGES; p.wave_ctr = nullptr;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = I8_PANEL; p.stages = I8_STAGES; p.wave_ctr = nullptr; p.hole_switch = nullptr;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
   GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (c->kin_cta_pair != 0) {
