@@ -94,15 +94,17 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16=1400.0, bf16_burst=1590.0, source="fallback (B200_PROFILING.md)")
 
 
-def committed_traffic(kernel, n, batch):
-    """Per-launch DRAM bytes of `kernel` from the committed ncu capture of this configuration (profiles/r02_traffic.json)."""
+def committed_traffic(kernel, n, snps_per_launch):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu capture of this n (profiles/r02_traffic.json, written by
+    scripts/ncu_extract.py), scaled by SNPs per launch when the run's launches differ from the captured 8192-SNP launch (both
+    kernels stream per SNP; the capture itself is one launch)."""
     p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p)).get(kernel)
-    if not t or t.get("n") != n or t.get("snps_per_launch") != batch:
+    if not t or t.get("n") != n:
         return None
-    return t["dram_read_bytes"] + t["dram_write_bytes"]
+    return (t["dram_read_bytes"] + t["dram_write_bytes"]) * float(snps_per_launch) / float(t["snps_per_launch"])
 
 
 class ClockSampler:
@@ -602,7 +604,7 @@ def run_lmm(args):
         ach = 2.0 * n * n * snps_per_launch / (utx_ms / utx_n * 1e-3) / 1e12            # 2 n^2 flop per SNP
         roof = {"kernel": "i8_gemm_pair_kernel (U^T X projection, tcgen05 int8)" if i8 else "dgemm_kernel (FP64 U^T X)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": ach / peaks["bf16"],
-                "traffic": committed_traffic("i8_gemm_pair_kernel", n, int(snps_per_launch)) if i8 else None,
+                "traffic": committed_traffic("i8_gemm_pair_kernel", n, snps_per_launch) if i8 else None,
                 "algorithmic_bytes_per_launch": T * n * n + snps_per_launch * (n + 8.0 * n) if i8 else None,
                 "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                 "note": "algorithmic FP64-equivalent flops 2*n^2 per SNP; the int8 path executes n_slices x as many integer MACs",
@@ -616,7 +618,7 @@ def run_lmm(args):
         a = by / (lmm_ms / lmm_n * 1e-3) / 1e9
         lmm_roof = {"kernel": "lmm_assoc_v2_kernel (fused per-SNP tests)", "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "share_of_step": lmm_ms / ms_compute, "avg_launch_ms": lmm_ms / lmm_n,
-                    "snps_per_launch": snps_per_launch, "traffic": committed_traffic("lmm_assoc_v2_kernel", n, int(snps_per_launch)),
+                    "snps_per_launch": snps_per_launch, "traffic": committed_traffic("lmm_assoc_v2_kernel", n, snps_per_launch),
                     "note": "algorithmic bytes 8n+64 per SNP (SURVEY 8d); the kernel is FP64-issue bound by construction, see `fp64`"}
         try:
             fp64_peak, _ = ctx.measure_fp64_fma(0.5)

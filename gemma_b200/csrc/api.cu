@@ -87,7 +87,7 @@ void gb200_destroy(gb200_ctx *c) {
                         &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale, &c->i8.wave_ctr,
                         &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles,
                         &c->i8.kin_qbits, &c->i8.kin_y, &c->dWtx, &c->dEnv, &c->dX2, &c->dFlip, &c->dLmW, &c->dLmY,
-                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam};
+                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam, &c->dVnull, &c->i8.xex};
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
@@ -187,6 +187,11 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
   if (!strcmp(name, "gemm_wave_sync")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "gemm_wave_sync must be 0 or 1");
     c->gemm_wave_sync = value; return GB200_OK;
+  }
+  if (!strcmp(name, "x_exact")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "x_exact must be 0 or 1");
+    if (value != c->x_exact) c->common_ready = false;
+    c->x_exact = value; return GB200_OK;
   }
   if (!strcmp(name, "hole_gemm")) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "hole_gemm must be 0 or 1");
@@ -530,7 +535,7 @@ static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
-  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.cheb = nullptr; D.cheb_marg = 0.0; D.xcov = nullptr; D.xcov_idx = 0;
+  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.cheb = nullptr; D.cheb_marg = 0.0; D.xex = nullptr; D.xcov = nullptr; D.xcov_idx = 0;
   D.cnt = c->count_work ? c->dTicket.as<unsigned long long>() + 4 : nullptr;     // 8 words behind the ticket words
   D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
   D.gen_stride = 0;
@@ -638,6 +643,56 @@ static int lmm_check_ready(gb200_ctx *c, const char *who) {
   return GB200_OK;
 }
 
+// Run-constant tables of the lockstep per-SNP kernel, built once per (setup, params) pair: SNP-independent sums and h rows at the
+// lambdas every SNP visits; with lmm_interp also at the Chebyshev nodes of every grid interval (the kernel then serves its Brent /
+// Newton evaluations from interpolants); with x_exact the vectors v_q = U (h(l_mle_null) (.) q) behind LmmConst::xex.
+struct CommonInfo { size_t J0 = 0, n_nodes = 0; double marg = 0.15; bool on = false; };
+static int lmm_ensure_common(gb200_ctx *c, CommonInfo &ci) {
+  ci.on = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && c->lmm_kernel != 1 && c->lmm_kernel != 3 && c->lmm_hoist;
+  if (!ci.on) return GB200_OK;
+  LmmConst D = make_const(c);
+  const size_t J0 = (size_t)c->prm.n_region + 3, rec = lmm_common_record_doubles((int)c->n_cvt);
+  const int M = lmm_cheb_nodes();
+  size_t n_nodes = c->lmm_interp ? (size_t)c->prm.n_region * (size_t)M : 0;
+  if ((J0 + n_nodes) * c->n_c * sizeof(double) > ((size_t)2 << 30)) n_nodes = 0;        // node rows stay below 2 GB
+  // 20 nodes resolve an interval of one decade (+ margins) to ~1e-14; wider intervals (a coarse -region grid) keep the exact passes
+  if (log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region > 2.4) n_nodes = 0;
+  ci.J0 = J0; ci.n_nodes = n_nodes;
+  if (c->common_ready) return GB200_OK;
+  const size_t J = J0 + n_nodes;
+  GB_CUDA(c, c->dHrows.reserve(J * c->n_c * sizeof(double)));
+  GB_CUDA(c, c->dCtab.reserve(J * rec * sizeof(double)));
+  if (n_nodes) {
+    std::vector<double> lams(n_nodes);
+    const double interval = log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region;
+    for (int g = 0; g < c->prm.n_region; ++g) {
+      const double lo = log(c->prm.l_min) + interval * (double)g - ci.marg, hi = log(c->prm.l_min) + interval * (double)(g + 1) + ci.marg;
+      for (int m = 0; m < M; ++m) lams[(size_t)g * M + m] = exp(0.5 * (lo + hi) + 0.5 * (hi - lo) * cos(M_PI * ((double)m + 0.5) / (double)M));
+    }
+    GB_CUDA(c, c->dNodeLam.reserve(n_nodes * sizeof(double)));
+    GB_CUDA(c, cudaMemcpyAsync(c->dNodeLam.p, lams.data(), n_nodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));      // `lams` goes out of scope
+    GB_CUDA(c, c->dCheb.reserve(lmm_cheb_doubles((int)c->n_cvt, c->prm.n_region) * sizeof(double)));
+  }
+  GB_CUDA(c, launch_lmm_common((int)c->n_cvt, D, c->prm, c->dHrows.as<double>(), c->dCtab.as<double>(), c->dNodeLam.as<double>(),
+                               (int)n_nodes, c->dCheb.as<double>(), c->stream));
+  c->vnull_ready = false;
+  if (c->x_exact && c->prm.l_mle_null > 0.0 && c->dU.p && !c->overlap) {
+    gb::DevBuf scratch;
+    const size_t by = (c->n_cvt + 1) * c->n_c * sizeof(double);
+    GB_CUDA(c, scratch.reserve(by));
+    GB_CUDA(c, c->dVnull.reserve(by));
+    GB_CUDA(c, cudaMemsetAsync(c->dVnull.p, 0, by, c->stream));
+    GB_CUDA(c, launch_lmm_vnull((int)c->n_cvt, D, c->prm.l_mle_null, c->dU.as<double>(), scratch.as<double>(), c->dVnull.as<double>(), c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    scratch.release();
+    c->vnull_ready = true;
+  }
+  GB_CUDA(c, cudaStreamSynchronize(c->stream));       // the tests may run on a side stream
+  c->common_ready = true;
+  return GB200_OK;
+}
+
 // association kernel on a device-resident rotated batch
 static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev,
                          bool plink_rule = false, cudaStream_t st = nullptr, unsigned int *ticket = nullptr) {
@@ -645,43 +700,21 @@ static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu,
   c->prm.plink_rule = plink_rule ? 1 : 0;
   if (!st) st = c->stream;
   if (!ticket) ticket = c->dTicket.as<unsigned int>();
-  ProfScope ps(c, "lmm", 1, st);
   const bool v2_ok = lmm_v2_supported((int)c->n_cvt, c->prm.n_region) && ldu == c->n_c;
   if (c->lmm_kernel == 2 && !v2_ok) return set_err(c, GB200_ERR_UNSUPPORTED, "lmm_kernel=2 (lockstep CTA kernel) needs n_cvt <= 3 and n_region <= 64");
-  if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3 && c->lmm_hoist) {
-    // SNP-independent sums at the lambdas shared by every SNP (once per setup/params pair); with lmm_interp also at the
-    // Chebyshev nodes of every grid interval (the per-SNP kernel then serves its Brent / Newton evaluations from interpolants)
-    const size_t J0 = (size_t)c->prm.n_region + 3, rec = lmm_common_record_doubles((int)c->n_cvt);
-    const int M = lmm_cheb_nodes();
-    const double marg = 0.15;
-    size_t n_nodes = c->lmm_interp ? (size_t)c->prm.n_region * (size_t)M : 0;
-    if ((J0 + n_nodes) * c->n_c * sizeof(double) > ((size_t)2 << 30)) n_nodes = 0;        // node rows stay below 2 GB
-    // 20 nodes resolve an interval of one decade (+ margins) to ~1e-14; wider intervals (a coarse -region grid) keep the exact passes
-    if (log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region > 2.4) n_nodes = 0;
-    const size_t J = J0 + n_nodes;
-    if (!c->common_ready) {
-      GB_CUDA(c, c->dHrows.reserve(J * c->n_c * sizeof(double)));
-      GB_CUDA(c, c->dCtab.reserve(J * rec * sizeof(double)));
-      if (n_nodes) {
-        std::vector<double> lams(n_nodes);
-        const double interval = log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region;
-        for (int g = 0; g < c->prm.n_region; ++g) {
-          const double lo = log(c->prm.l_min) + interval * (double)g - marg, hi = log(c->prm.l_min) + interval * (double)(g + 1) + marg;
-          for (int m = 0; m < M; ++m) lams[(size_t)g * M + m] = exp(0.5 * (lo + hi) + 0.5 * (hi - lo) * cos(M_PI * ((double)m + 0.5) / (double)M));
-        }
-        GB_CUDA(c, c->dNodeLam.reserve(n_nodes * sizeof(double)));
-        GB_CUDA(c, cudaMemcpyAsync(c->dNodeLam.p, lams.data(), n_nodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        GB_CUDA(c, cudaStreamSynchronize(c->stream));      // `lams` goes out of scope
-        GB_CUDA(c, c->dCheb.reserve(lmm_cheb_doubles((int)c->n_cvt, c->prm.n_region) * sizeof(double)));
-      }
-      GB_CUDA(c, launch_lmm_common((int)c->n_cvt, D, c->prm, c->dHrows.as<double>(), c->dCtab.as<double>(), c->dNodeLam.as<double>(),
-                                   (int)n_nodes, c->dCheb.as<double>(), c->stream));
-      GB_CUDA(c, cudaStreamSynchronize(c->stream));       // the tests may run on a side stream
-      c->common_ready = true;
+  if (v2_ok) {
+    CommonInfo ci;
+    const int rc = lmm_ensure_common(c, ci);
+    if (rc) return rc;
+    if (ci.on) {
+      D.Hrows = c->dHrows.as<double>(); D.ctab = c->dCtab.as<double>(); D.n_common = (int)ci.J0;
+      if (ci.n_nodes) { D.cheb = c->dCheb.as<double>(); D.cheb_marg = ci.marg; }
+      // exact x-sums of the batch the int8 projection has just written into this very buffer
+      if (c->i8.xex_valid && c->i8.xex_for == UtXt && c->i8.xex_l == l) D.xex = c->i8.xex.as<double>();
     }
-    D.Hrows = c->dHrows.as<double>(); D.ctab = c->dCtab.as<double>(); D.n_common = (int)J0;
-    if (n_nodes) { D.cheb = c->dCheb.as<double>(); D.cheb_marg = marg; }
   }
+  c->i8.xex_valid = false;
+  ProfScope ps(c, "lmm", 1, st);
   if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3)
     GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));
   else
@@ -794,6 +827,7 @@ int gb200_lmm_batch_geno(gb200_ctx *c, const double *G, size_t l, size_t ldg, gb
 static int project_bed_dev(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                            size_t l, size_t bytes_per_snp, double *dst = nullptr) {
   const size_t n = c->n;
+  if (c->prm_ready) { CommonInfo ci; const int rc0 = lmm_ensure_common(c, ci); if (rc0) return rc0; }   // v_q of LmmConst::xex before the first batch
   if (!dst) { GB_CUDA(c, reserve_zeroed(c->dUtXt, l * c->n_c * 8, c->stream)); dst = c->dUtXt.as<double>(); }
   bool use_i8 = false;
   if (c->utx_path == 2) {

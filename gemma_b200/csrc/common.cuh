@@ -46,6 +46,9 @@ struct I8State {
   DevBuf scale;                  // per eigenvector: scale s_i, column maximum, 1 / s_i (3 n doubles)
   DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
   DevBuf miss_mean;              // per-SNP mean + hole count (+ holes per 256-SNP tile)
+  DevBuf xex;                    // exact order-1 x-sums of the batch last projected by i8_project_bed (l x (n_cvt + 1)); valid flag below
+  bool xex_valid = false;
+  const double *xex_for = nullptr; size_t xex_l = 0;   // the U^T X buffer / row count those sums belong to
   DevBuf wave_ctr;               // wave synchronisation counter of the CTA-pair projection kernel
   DevBuf holeq;                  // l_pad x n_pad int8 hole-indicator rows (second GEMM pass of the mean imputation)
   void *tmap_a = nullptr, *tmap_b = nullptr, *tmap_q = nullptr;   // CUtensorMap storage (host)
@@ -108,6 +111,8 @@ struct gb200_ctx {
   gb::DevBuf dMvY, dMvNull, dMvOut;      // multivariate LMM: U^T Y rows (2 x n_c), MvNull, per-SNP output rows
   gb::MvConst mvK; bool mv_ready = false, mv_null_ready = false;
   gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
+  gb::DevBuf dVnull;            // v_q = U (h(l_mle_null) (.) q), q over (w, y): exact x-sums of int8-projected batches (LmmConst::xex)
+  bool vnull_ready = false;
   gb::DevBuf dCheb, dNodeLam;   // Chebyshev tables / node lambdas of the interpolated refinement
   bool common_ready = false;
   // scratch
@@ -134,6 +139,7 @@ struct gb200_ctx {
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
   long gemm_groups = 1;  // 2: pair kernel with two eigenvector groups per tile (shared genotype tile) and the hole pass on the tensor pipe; 1: one group, FP64 hole fix-up
+  long x_exact = 1;        // int8-projected PLINK batches: exact x-sums at l_mle_null computed in genotype space (LmmConst::xex)
   long hole_gemm = 1;      // CTA-pair projection: batches with many missing genotypes add mean * U^T q by a second GEMM pass over the hole-indicator rows (decided on the device); 0 = always the gather kernel
   long gemm_wave_sync = 1; // CTA-pair projection: producers start every tile wave together (keeps the K-panels shared through L2)
   long gemm_stages = 0;  // TMA pipeline stages of the CTA-pair projection kernel (0 = as many 32 KB stages as fit, at most 6)
@@ -210,6 +216,7 @@ cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double 
                       double yPwy, int test_mode, gb200_sumstat *out, cudaStream_t st);
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, const double *node_lams,
                               int n_nodes, double *cheb, cudaStream_t st);
+cudaError_t launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const double *U, double *scratch, double *v, cudaStream_t st);
 int lmm_cheb_nodes();
 size_t lmm_cheb_doubles(int n_cvt, int n_region);
 size_t lmm_common_record_doubles(int n_cvt);

@@ -747,8 +747,12 @@ __global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__r
                                                         const int *__restrict__ idx, int n, int n_padk, int l,
                                                         int8_t *__restrict__ G, double *__restrict__ mean,
                                                         int *__restrict__ nmiss, int8_t *__restrict__ Q,
-                                                        int *__restrict__ tile_holes) {
+                                                        int *__restrict__ tile_holes,
+                                                        const double *__restrict__ vnull, int nq, int ldv, double *__restrict__ xex) {
   __shared__ int sh_sum[8], sh_miss[8];
+  __shared__ double sh_x[8][2 * 4];
+  // exact x-sums (LmmConst::xex): x . v_q over the observed genotypes and sum of v_q over the holes (the mean joins at the end)
+  double ex[4] = {0.0, 0.0, 0.0, 0.0}, eh[4] = {0.0, 0.0, 0.0, 0.0};
   const int s = blockIdx.x;
   int8_t *g = G + (size_t)s * n_padk;
   int8_t *qr = Q ? Q + (size_t)s * n_padk : nullptr;     // hole-indicator row (second GEMM pass of the mean imputation)
@@ -767,9 +771,22 @@ __global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__r
       if (lo == 0) v = hi == 0 ? 2 : 1;
       else if (hi == 0) { miss++; hq = 1; }
       sum += v;
+      if (vnull && (v | hq)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq) { const double t = __ldg(vnull + (size_t)q * ldv + p); if (hq) eh[q] += t; else ex[q] = fma((double)v, t, ex[q]); }
+      }
     }
     g[p] = v;
     if (qr) qr[p] = hq;
+  }
+  if (vnull) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double a = ex[q], b = eh[q];
+      for (int m = 16; m >= 1; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); b += __shfl_xor_sync(0xffffffffu, b, m); }
+      if ((threadIdx.x & 31) == 0) { sh_x[threadIdx.x >> 5][2 * q] = a; sh_x[threadIdx.x >> 5][2 * q + 1] = b; }
+    }
   }
   for (int m = 16; m >= 1; m >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, m); miss += __shfl_xor_sync(0xffffffffu, miss, m); }
   if ((threadIdx.x & 31) == 0) { sh_sum[threadIdx.x >> 5] = sum; sh_miss[threadIdx.x >> 5] = miss; }
@@ -780,6 +797,14 @@ __global__ void __launch_bounds__(256) bed_to_i8_kernel(const unsigned char *__r
     nmiss[s] = tm;
     mean[s] = (double)ts / (double)(n - tm);          // x_mean of src/lmm.cpp:1819
     if (tile_holes && tm) atomicAdd(tile_holes + (s >> 8), tm);
+    if (vnull) {
+      const double mu = (double)ts / (double)(n - tm);
+      for (int q = 0; q < nq && q < 4; ++q) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh_x[w][2 * q]; b += sh_x[w][2 * q + 1]; }
+        xex[(size_t)s * nq + q] = fma(mu, b, a);
+      }
+    }
   }
 }
 
@@ -832,7 +857,15 @@ __global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__re
       __syncthreads();
       for (int i = threadIdx.x; i < n; i += 256) {
         double acc = 0.0;
-        for (int q = 0; q < cnt; ++q) acc += U[(size_t)list[q] * n + i];
+        int q = 0;
+        for (; q + 8 <= cnt; q += 8) {                       // 8 independent row loads in flight per thread (the rows are 8 n bytes apart)
+          double v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(U + (size_t)list[q + k] * n + i);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc += v[k];           // same left-to-right order as the scalar loop
+        }
+        for (; q < cnt; ++q) acc += __ldg(U + (size_t)list[q] * n + i);
         c[i] += m * acc;
       }
     }
@@ -968,14 +1001,21 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     GB_CUDA(c, c->i8.holeq.reserve(l_pad * (size_t)g.n_padk));
     GB_CUDA(c, cudaMemsetAsync(tile_holes, 0, (l_pad / 256 + 2) * sizeof(int), c->stream));
   }
+  const int nq = (int)c->n_cvt + 1;
+  const bool want_xex = c->vnull_ready && c->x_exact && nq <= 4 && !c->overlap;
+  c->i8.xex_valid = false;
+  if (want_xex) GB_CUDA(c, c->i8.xex.reserve(l_pad * (size_t)nq * sizeof(double)));
   {
   ProfScope ps(c, "decode");
   bed_to_i8_kernel<<<(unsigned)l_pad, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, g.n_padk, (int)l,
                                                            c->i8.geno.as<int8_t>(), mean, nmiss,
                                                            (pair2 || hole_gemm) ? c->i8.holeq.as<int8_t>() : nullptr,
-                                                           (pair2 || hole_gemm) ? tile_holes : nullptr);
+                                                           (pair2 || hole_gemm) ? tile_holes : nullptr,
+                                                           want_xex ? c->dVnull.as<double>() : nullptr, nq, (int)c->n_c,
+                                                           want_xex ? c->i8.xex.as<double>() : nullptr);
   GB_CUDA(c, cudaGetLastError());
   }
+  if (want_xex) { c->i8.xex_valid = true; c->i8.xex_for = UtXt_dev; c->i8.xex_l = l; }
   if (!make_tmap((CUtensorMap *)c->i8.tmap_a, c->i8.geno.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))
     return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the genotype tile");
   I8KernelParams p;
@@ -1036,9 +1076,9 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     }
     if (hole_gemm) {
       int *sw = tile_holes + (l_pad / 256 + 1);
-      // gather: holes * 8 n bytes at ~5 TB/s;  hole pass: the main pass again, ~2 T n^2 l_pad / 2.8e15 s
+      // gather: holes * 8 n bytes at ~4 TB/s;  hole pass: the main pass again, ~2 T n^2 l_pad / 2.8e15 s
       const double t_gemm = 2.0 * (double)g.T * (double)g.n * (double)g.n * (double)l_pad / 2.8e15;
-      const double holes_max = t_gemm * 5.0e12 / (8.0 * (double)g.n);
+      const double holes_max = t_gemm * 4.0e12 / (8.0 * (double)g.n);
       hole_switch_kernel<<<1, 256, 0, c->stream>>>(tile_holes, (int)(l_pad / 256), holes_max, sw);
       if (!c->i8.tmap_q) c->i8.tmap_q = aligned_alloc(64, sizeof(CUtensorMap));
       if (!make_tmap((CUtensorMap *)c->i8.tmap_q, c->i8.holeq.p, l_pad, (uint64_t)g.n_padk, (uint32_t)I8_BM))

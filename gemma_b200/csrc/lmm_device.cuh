@@ -43,6 +43,11 @@ struct LmmConst {
   // shared rows, cheb_M node rows per grid interval; cheb = [cos table (4 M) | per interval: coefficients of the SNP-independent sums]
   const double *cheb;
   double cheb_marg;      // half-width added to every interval in log(lambda)
+  // Exact x-sums at lambda* = l_mle_null for this batch (int8 projection only; null = off): xex[s * (n_cvt + 1) + q] =
+  // sum_i h_i(lambda*) (U^T x_s)_i q_i for q over (w_1..w_c, y), formed in GENOTYPE space as x_s . v_q with v_q = U (h (.) q) -- an
+  // FP64 dot product with no digit-plane rounding.  The lockstep kernel adds (exact - projected) to the order-1 x-sums of the score
+  // test and of the final f / Wald evaluation: the plane rounding of U^T x then reaches beta only in second order.
+  const double *xex;
   const double *xcov;    // G x E: covariate column xcov_idx is this per-SNP vector (U^T x) instead of a row of Wt; null otherwise
   int xcov_idx;
   unsigned long long *cnt;  // optional work counters of the lockstep kernel (gb200_lmm_counters); null = off

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(V2_THREADS, (NC <= GB_V2_CTAS2_MAXNC) ? GB_V2_
     if (lane == 0) xrows[warp] = valid ? UtXt + (size_t)s * ldu : nullptr;
     __syncthreads();
     gb200_sumstat r;
-    v2_analyze_group<NC>(D, prm, xrows, v2_smem, nchunks, pad, valid, r, pipe_it);
+    v2_analyze_group<NC>(D, prm, xrows, v2_smem, nchunks, pad, valid, r, pipe_it,
+                         (D.xex && valid) ? D.xex + (size_t)s * (NC + 1) : nullptr);
     if (valid && lane == 0) out[s] = r;
     __syncthreads();
   }
@@ -434,4 +435,41 @@ extern "C" int gb200_cdf_tails(gb200_ctx *c, int kind, const double *x, double n
   GB_CUDA(c, cudaStreamSynchronize(c->stream));
   dx.release(); dn.release(); dout.release();
   return GB200_OK;
+}
+
+// ---- exact x-sums at l_mle_null (LmmConst::xex): the SNP-independent vectors v_q = U (h (.) q), q over (w_1..w_c, y) ------------
+namespace gb {
+__global__ void __launch_bounds__(256) lmm_hq_kernel(LmmConst D, int n_cvt, double lam, double *__restrict__ a) {
+  // a[q][i] = q_i / (lam * delta_i + 1), rows of n_c doubles, zero in the padding
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= D.n_c) return;
+  const bool in = i < D.n;
+  const double h = in ? 1.0 / fma(lam, __ldg(D.delta + i), 1.0) : 0.0;
+  for (int q = 0; q < n_cvt; ++q) a[(size_t)q * D.n_c + i] = in ? h * __ldg(D.Wt + (size_t)q * D.ldv + i) : 0.0;
+  a[(size_t)n_cvt * D.n_c + i] = in ? h * __ldg(D.y + i) : 0.0;
+}
+// one warp per individual j: v[q][j] = sum_i U[j][i] a[q][i]
+__global__ void __launch_bounds__(256) lmm_vnull_kernel(const double *__restrict__ U, int n, int n_c, int nq, const double *__restrict__ a,
+                                                        double *__restrict__ v) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const double *u = U + (size_t)j * n;
+  double acc[GB200_MAX_CVT + 1];
+  for (int q = 0; q < nq; ++q) acc[q] = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const double x = __ldg(u + i);
+    for (int q = 0; q < nq; ++q) acc[q] = fma(x, __ldg(a + (size_t)q * n_c + i), acc[q]);
+  }
+  for (int q = 0; q < nq; ++q) {
+    const double t = warp_allsum(acc[q]);
+    if (lane == 0) v[(size_t)q * n_c + j] = t;
+  }
+}
+}  // namespace gb
+
+// v: (n_cvt + 1) rows of n_c doubles; scratch: same size
+cudaError_t gb::launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const double *U, double *scratch, double *v, cudaStream_t st) {
+  lmm_hq_kernel<<<(D.n_c + 255) / 256, 256, 0, st>>>(D, n_cvt, lam, scratch);
+  lmm_vnull_kernel<<<(D.n + 7) / 8, 256, 0, st>>>(U, D.n, D.n_c, n_cvt + 1, scratch, v);
+  return cudaGetLastError();
 }

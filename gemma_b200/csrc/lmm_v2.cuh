@@ -91,7 +91,7 @@ __device__ __forceinline__ void v2_mbar_arrive(uint64_t *bar) {
 }
 // The stages form ONE ring for the whole kernel: chunk number k (counted across passes, identical in every thread) lives in stage
 // k % V2_STAGES, its arrival is phase k / V2_STAGES of full[stage], and it may be overwritten once all V2_WARPS warps have arrived on
-// empty[stage] for it.  No CTA-wide barrier inside or between passes: thread 0 issues chunk k + 2 as soon as chunk k - 1 has been
+// empty[stage] for it.  No CTA-wide barrier inside or between passes: chunk k + 2 is queued (by lane 0 of warp (k + 2) % V2_WARPS) as soon as chunk k - 1 has been
 // released by every warp, each warp consumes at its own pace (at most V2_STAGES - 1 chunks apart), and the first chunks of the next
 // pass are in flight while slower warps still finish the previous one.
 __device__ __forceinline__ void v2_acquire_stage(uint64_t *empty, unsigned int k) {
@@ -237,20 +237,22 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
 #if GB_V2_TMA
   uint64_t *full = v2_bars(smem, NC), *empty = full + V2_STAGES;
   const unsigned int it0 = pipe_it;
-  if (threadIdx.x == 0) {
+  // the producer duty rotates over the warps (chunk k is queued by lane 0 of warp k % V2_WARPS): a fixed producer thread made its
+  // warp ~40 % slower than the other seven and the whole ring ran at that warp's pace
 #pragma unroll
-    for (int c = 0; c < V2_STAGES - 1; ++c)
-      if (c < nchunks) {
-        const unsigned int k = it0 + (unsigned int)c;
+  for (int c = 0; c < V2_STAGES - 1; ++c)
+    if (c < nchunks) {
+      const unsigned int k = it0 + (unsigned int)c;
+      if (lane == 0 && warp == (int)(k % V2_WARPS)) {
         v2_acquire_stage(empty, k);
         v2_issue_tma<NC>(D, xrows, smem + (size_t)(k % V2_STAGES) * stage_d, c, &full[k % V2_STAGES]);
       }
-  }
+    }
   for (int c = 0; c < nchunks; ++c) {
-    if (threadIdx.x == 0) {
+    {
       const int cn = c + V2_STAGES - 1;
-      if (cn < nchunks) {
-        const unsigned int kn = it0 + (unsigned int)cn;
+      const unsigned int kn = it0 + (unsigned int)cn;
+      if (cn < nchunks && lane == 0 && warp == (int)(kn % V2_WARPS)) {
         v2_acquire_stage(empty, kn);
         v2_issue_tma<NC>(D, xrows, smem + (size_t)(kn % V2_STAGES) * stage_d, cn, &full[kn % V2_STAGES]);
       }
@@ -344,20 +346,20 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
   }
   uint64_t *full = v2_bars(smem, NC), *empty = full + V2_STAGES;
   const unsigned int it0 = pipe_it;
-  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int c = 0; c < V2_STAGES - 1; ++c)
-      if (c < nchunks) {
-        const unsigned int k = it0 + (unsigned int)c;
+  for (int c = 0; c < V2_STAGES - 1; ++c)
+    if (c < nchunks) {
+      const unsigned int k = it0 + (unsigned int)c;
+      if (lane == 0 && warp == (int)(k % V2_WARPS)) {         // rotating producer, see v2_pass
         v2_acquire_stage(empty, k);
         v2_issue_common<NC>(D, xrows, smem + (size_t)(k % V2_STAGES) * stage_d, c, &full[k % V2_STAGES], jrow);
       }
-  }
+    }
   for (int c = 0; c < nchunks; ++c) {
-    if (threadIdx.x == 0) {
+    {
       const int cn = c + V2_STAGES - 1;
-      if (cn < nchunks) {
-        const unsigned int kn = it0 + (unsigned int)cn;
+      const unsigned int kn = it0 + (unsigned int)cn;
+      if (cn < nchunks && lane == 0 && warp == (int)(kn % V2_WARPS)) {
         v2_acquire_stage(empty, kn);
         v2_issue_common<NC>(D, xrows, smem + (size_t)(kn % V2_STAGES) * stage_d, cn, &full[kn % V2_STAGES], jrow);
       }
@@ -703,7 +705,7 @@ __device__ __forceinline__ void v2_assemble_arr(const double (&C)[(NC + 2) * (NC
 // all sums at lambda from the interpolants of interval g; coef = this warp's x-sum coefficients (shared memory)
 template <int NC, int ORD>
 __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coef, int g, double tau, double dtau_dt, double lam,
-                                            double n, bool want_f, double logdetI, V2Eval &ev) {
+                                            double n, bool want_f, double logdetI, const double *dlt, V2Eval &ev) {
   constexpr int NQ = NC + 2, NIDX = (NC + 3) * (NC + 2) / 2, CN = v2c_nidx(NC), M = V2_CM;
   const double *gc = D.cheb + 4 * M + (size_t)g * (2 * CN + 3) * M;
   double X1[NQ], X2[NQ], X3[NQ], C1[CN], C2[CN], C3[CN];
@@ -712,6 +714,11 @@ __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coe
     X1[q] = v2_cheb_val<false>(coef + q * M, tau);
     X2[q] = v2_cheb_val<false>(coef + (NQ + q) * M, tau);
     X3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<false>(coef + (NQ + q) * M, tau), X2[q]) : 0.0;
+  }
+  if (dlt && want_f) {           // final f / Wald tables: exact-minus-projected x-sums (LmmConst::xex), order 1 only
+#pragma unroll
+    for (int a = 0; a < NC; ++a) X1[a] += dlt[a];
+    X1[NC + 1] += dlt[NC];
   }
 #pragma unroll
   for (int q = 0; q < CN; ++q) {
@@ -733,7 +740,7 @@ __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coe
 template <int NC>
 __device__ __forceinline__ bool v2_drive(const LmmConst &D, V2Fn &F, bool fnR, const double *coef, int g, double lo, double hi,
                                          const double *glam, const double *gd1, int n_region, double l_min, double l_max,
-                                         double n, double logdetI, double (&evv)[3], V2Req &rq) {
+                                         double n, double logdetI, const double *dlt, double (&evv)[3], V2Req &rq) {
   const double dtau_dt = 2.0 / (hi - lo);
   for (;;) {
     v2fn_advance(F, glam, gd1, n_region, l_min, l_max, evv[0], evv[1], evv[2], rq, true);
@@ -741,8 +748,8 @@ __device__ __forceinline__ bool v2_drive(const LmmConst &D, V2Fn &F, bool fnR, c
     const double tau = (2.0 * log(rq.lam) - (lo + hi)) / (hi - lo);
     if (!(tau >= -1.0 && tau <= 1.0)) return true;          // also catches NaN
     V2Eval ev;
-    if (rq.K >= 3) v2_interp_eval<NC, 3>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, ev);
-    else v2_interp_eval<NC, 2>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, ev);
+    if (rq.K >= 3) v2_interp_eval<NC, 3>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, dlt, ev);
+    else v2_interp_eval<NC, 2>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, dlt, ev);
     evv[0] = fnR ? ev.d1R : ev.d1L; evv[1] = fnR ? ev.d2R : ev.d2L; evv[2] = fnR ? ev.fR : ev.fL;
     if (fnR && rq.logdet) { F.cache_lam = rq.lam; F.cP_xx = ev.P_xx; F.cP_xy = ev.P_xy; F.cP_yy = ev.P_yy; F.cPx_yy = ev.Px_yy; }
     rq.need = false;
@@ -787,7 +794,8 @@ __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *cons
 // One CTA = 8 SNPs.  xrows[w] (shared memory) = U^T x row of warp w or nullptr.
 template <int NC>
 __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmParams &prm, const double *const *xrows,
-                                                 double *smem, int nchunks, int pad, bool valid, gb200_sumstat &out, unsigned int &pipe_it) {
+                                                 double *smem, int nchunks, int pad, bool valid, gb200_sumstat &out, unsigned int &pipe_it,
+                                                 const double *xe = nullptr) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   const int mode = prm.a_mode;
   const bool needR = (mode == 1 || mode == 4), needL = (mode == 2 || mode == 4 || mode == 9);
@@ -804,6 +812,11 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   // order-1 quantities at exactly l_min / l_max from the hoisted grid passes: the Wald test when the REML estimate is an end point
   bool have_bound = false;
   double wminP[4] = {0, 0, 0, 0}, wmaxP[4] = {0, 0, 0, 0};
+  // exact-minus-projected order-1 x-sums at l_mle_null (LmmConst::xex), over (w_1..w_c, y)
+  bool have_dlt = false;
+  double dlt[NC + 1];
+#pragma unroll
+  for (int a = 0; a <= NC; ++a) dlt[a] = 0.0;
 
 #if GB_V2_TMA
   const bool hoist = (D.ctab != nullptr);
@@ -815,7 +828,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
     // ---- hoisted passes: every lambda shared by all SNPs (grid 0..n_region, exactly l_max, l_mle_null), V2_NSC at a time
     constexpr int CS = v2c_stride(NC), CN = v2c_nidx(NC);
     const int n_grid = need_search ? n_region + 2 : 0;
-    const int nslots = n_grid + (needS ? 1 : 0);
+    const bool comp = (xe != nullptr) && prm.l_mle_null > 0.0;       // the slot at l_mle_null also serves the exact-sum correction
+    const int nslots = n_grid + ((needS || comp) ? 1 : 0);
     const int j_score = n_region + 2;
     double S1[NIDX], S2[NIDX];
     for (int s0 = 0; s0 < nslots; s0 += V2_NSC) {
@@ -855,10 +869,19 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
               v2_derive<NC, 1>(S1, dummy, dummy, tr1, 0.0, lamj, n, true, ldj, logdetI, ev);
               fRmax = ev.fR; fLmax = ev.fL;
               wmaxP[0] = ev.P_xx; wmaxP[1] = ev.P_xy; wmaxP[2] = ev.P_yy; wmaxP[3] = ev.Px_yy; have_bound = true;
-            } else {                                               // score test at l_mle_null ("3 is before 1")
-              Derived<NC, 1> d;
-              sweep_tables<NC, 1>(S1, dummy, dummy, d);
-              wald_score_from<NC>(d, D.n, true, beta, se, p_score);
+            } else {                                               // the slot at l_mle_null
+              if (comp) {
+#pragma unroll
+                for (int a = 0; a < NC; ++a) { const double e = __ldg(xe + a); dlt[a] = e - acc.X[s][0][a]; S1[abidx(a, NC, NC + 2)] = e; }
+                const double ey = __ldg(xe + NC);
+                dlt[NC] = ey - acc.X[s][0][NC + 1]; S1[abidx(NC, NC + 1, NC + 2)] = ey;
+                have_dlt = true;
+              }
+              if (needS) {                                         // score test ("3 is before 1")
+                Derived<NC, 1> d;
+                sweep_tables<NC, 1>(S1, dummy, dummy, d);
+                wald_score_from<NC>(d, D.n, true, beta, se, p_score);
+              }
             }
           }
         }
@@ -978,8 +1001,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         bool runR = dueR, runL = dueL;
         for (;;) {
           bool blkR = false, blkL = false;
-          if (runR) { blkR = v2_drive<NC>(D, FR, true, coef, g, lo, hi, glam, gd1R, n_region, l_min, l_max, n, logdetI, evR, rq[0]); runR = blkR; }
-          if (runL) { blkL = v2_drive<NC>(D, FL, false, coef, g, lo, hi, glam, gd1L, n_region, l_min, l_max, n, logdetI, evL, rq[1]); runL = blkL; }
+          if (runR) { blkR = v2_drive<NC>(D, FR, true, coef, g, lo, hi, glam, gd1R, n_region, l_min, l_max, n, logdetI, have_dlt ? dlt : nullptr, evR, rq[0]); runR = blkR; }
+          if (runL) { blkL = v2_drive<NC>(D, FL, false, coef, g, lo, hi, glam, gd1L, n_region, l_min, l_max, n, logdetI, have_dlt ? dlt : nullptr, evL, rq[1]); runL = blkL; }
           if (!blkR) rq[0].need = false;
           if (!blkL) rq[1].need = false;
           const bool blocked = blkR || blkL;

@@ -948,8 +948,12 @@ def test_cta_pair_projection_and_kinship_match_single_cta():
         c.set_option("cta_pair", 0)
         single = c.lmm_project_bed(bed, n)
         c.set_option("cta_pair", 1)
+        c.set_option("hole_gemm", 0)                                # holes by the gather kernel, like the single-CTA kernel
         pair = c.lmm_project_bed(bed, n)
         assert np.array_equal(single, pair), T                      # exact integer accumulation: bit-identical
+        c.set_option("hole_gemm", 1)                                # holes by a second tensor-core pass when they are many (device-side switch):
+        pair_h = c.lmm_project_bed(bed, n)                          # mean * U^T q then carries the plane rounding of U as well
+        assert np.abs(pair_h - pair).max() / np.abs(ref).max() < (1e-6 if T == 4 else 1e-11), T
     assert np.abs(pair - ref).max() / np.abs(ref).max() < 1e-6
     bedk, Gk = synth.make_bed(n, 900, seed=77)
     Xc = O.kin_transform(Gk, 1)
