@@ -3,7 +3,7 @@
 # has a second, usually empty, hole-pass launch of the same kernel: -s counts both).
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-( time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale_parity.py -q -x -k "cta_pair or assoc or i8 or properties or n50000 or subbatch or nan_rule" ) > gpurun_out/g_pytest.log 2>&1
+( time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale_parity.py -q -x -k "cta_pair or assoc or i8 or properties or n50000 or n10000 or subbatch or nan_rule or exact_x or dosage or cuda_path or mouse_hs1940_gk or bxd" ) > gpurun_out/g_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/g_pytest.log
 ( time timeout 600 python bench.py --u-source qr --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-gk ) > gpurun_out/g_bench_lmm_qr.json 2> gpurun_out/g_bench_lmm_qr.err
 ( time timeout 600 python bench.py --u-source qr --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-gk --no-parity --miss 0.001 ) > gpurun_out/g_bench_lmm_qr_miss01pct.json 2> gpurun_out/g_bench_lmm_qr_miss01pct.err

@@ -1189,3 +1189,33 @@ def test_dosage_rows_take_the_tensor_core_projection_as_exact_digit_rows(ctx):
     ref2 = O.lmm_analyze_utx(pb["ev"], pb["U"].T @ pb["W"], pb["U"].T @ y, pb["U"].T @ X2, 4,
                              l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
     check_sumstat(got2, ref2, 4)
+
+
+@pytest.mark.gpu
+def test_exact_x_sums_remove_the_plane_rounding_from_beta(ctx):
+    """Four digit planes leave ~1e-9 of rounding noise on every projected value; beta = P_xy / P_xx inherits it divided by the
+    SNP's |z-score|.  The bed entry points therefore also form x . v_q, v_q = U (h(l_mle_null) (.) q), in genotype space (an FP64
+    dot product, no planes) and the per-SNP kernel replaces the projected order-1 x-sums of the score test / final Wald tables by
+    exact + (interpolated - projected at l_mle_null) (LmmConst::xex): the noise reaches beta only in second order."""
+    n, l = 1536, 400
+    pb = random_problem(n, 1, 4, 191)
+    bed, G = synth.make_bed(n, l, seed=192, miss_rate=0.01)
+    X = O.lmm_impute(np.where(G < 0, np.nan, G))
+    y = pb["y"] + 0.5 * (X[:, 7] - X[:, 7].mean())
+    ctx.lmm_setup(pb["U"], pb["ev"], pb["W"], y)
+    nm = ctx.lmm_null(pb["trace_G"])
+    ctx.lmm_params(4, l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ref = O.lmm_analyze_utx(pb["ev"], pb["U"].T @ pb["W"], pb["U"].T @ y, pb["U"].T @ X, 4,
+                            l_mle_null=nm["l_mle_null"], logl_mle_H0=nm["logl_mle_H0"])
+    ctx.set_option("utx_path", 2); ctx.set_option("n_slices", 4)
+    errs = {}
+    try:
+        for xe in (0, 1):
+            ctx.set_option("x_exact", xe)
+            got = ctx.lmm_batch_bed(bed, n)
+            errs[xe] = {k: float(np.nanmax(np.abs(got[k] - ref[k]) / np.maximum(np.abs(ref[k]), 1e-300))) for k in ("beta", "se", "p_wald", "p_lrt", "p_score")}
+    finally:
+        ctx.set_option("x_exact", 1); ctx.set_option("utx_path", 0); ctx.set_option("n_slices", 0)
+    assert errs[1]["beta"] < 1e-9 and errs[1]["beta"] < errs[0]["beta"] / 10, errs
+    for k in ("se", "p_wald", "p_lrt", "p_score"):
+        assert errs[1][k] < 1e-7, errs
