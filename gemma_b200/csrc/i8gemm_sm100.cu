@@ -830,6 +830,7 @@ __global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__re
                                                        const int *__restrict__ hole_switch) {
   constexpr int CAP = 2048;
   __shared__ int list[CAP];
+  __shared__ int wcount[8];
   __shared__ int count;
   const int s = blockIdx.x;
   if (nmiss[s] == 0) return;
@@ -837,39 +838,52 @@ __global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__re
   const unsigned char *row = bed + (size_t)s * bytes_per_snp;
   const double m = mean[s];
   double *c = C + (size_t)s * ldc;
-  for (int base = 0; base < n; base += CAP) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // The holes of the SNP are collected in ascending order (ballot compaction: the summation order below is fixed) up to CAP at a
+  // time -- in practice all of them: the gather only serves batches with few holes -- and the rows of U at the holes are then summed
+  // in ONE sweep over the eigenvectors, 8 independent row loads in flight per thread.
+  int start = 0;
+  while (start < n) {
     if (threadIdx.x == 0) count = 0;
     __syncthreads();
-    const int hi_p = min(n, base + CAP);
-    for (int p = base + threadIdx.x; p < hi_p; p += 256) {
-      const size_t j = idx ? (size_t)idx[p] : (size_t)p;
-      const unsigned b = (unsigned)row[j >> 2] >> (2 * (j & 3));
-      if ((b & 3u) == 1u) list[atomicAdd(&count, 1)] = p;      // low=1, high=0 -> missing
+    int p0 = start;
+    for (; p0 < n; p0 += 256) {
+      if (count + 256 > CAP) break;                          // uniform: `count` only changes between the barriers below
+      const int p = p0 + threadIdx.x;
+      bool hole = false;
+      if (p < n) {
+        const size_t j = idx ? (size_t)idx[p] : (size_t)p;
+        const unsigned b = (unsigned)row[j >> 2] >> (2 * (j & 3));
+        hole = (b & 3u) == 1u;                               // low = 1, high = 0 -> missing
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hole);
+      if (lane == 0) wcount[warp] = __popc(bal);
+      __syncthreads();
+      int off = count;
+      for (int w = 0; w < warp; ++w) off += wcount[w];
+      if (hole) list[off + __popc(bal & ((1u << lane) - 1u))] = p;
+      __syncthreads();
+      if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += wcount[w]; count += t; }
+      __syncthreads();
     }
-    __syncthreads();
     const int cnt = count;
     if (cnt > 0) {
-      // deterministic order: sort-free but order-independent result is NOT guaranteed for FP adds,
-      // so order the short list (cnt is small) before summing
-      if (threadIdx.x == 0) {
-        for (int a = 1; a < cnt; ++a) { int key = list[a], b2 = a - 1; while (b2 >= 0 && list[b2] > key) { list[b2 + 1] = list[b2]; --b2; } list[b2 + 1] = key; }
-      }
-      __syncthreads();
       for (int i = threadIdx.x; i < n; i += 256) {
         double acc = 0.0;
         int q = 0;
-        for (; q + 8 <= cnt; q += 8) {                       // 8 independent row loads in flight per thread (the rows are 8 n bytes apart)
+        for (; q + 8 <= cnt; q += 8) {
           double v[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = __ldg(U + (size_t)list[q + k] * n + i);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc += v[k];           // same left-to-right order as the scalar loop
+          for (int k = 0; k < 8; ++k) acc += v[k];           // left to right: the order of the holes
         }
         for (; q < cnt; ++q) acc += __ldg(U + (size_t)list[q] * n + i);
         c[i] += m * acc;
       }
     }
     __syncthreads();
+    start = p0;
   }
 }
 
