@@ -37,6 +37,14 @@ constexpr int V2_WARPS = GB_V2_WARPS;
 constexpr int V2_THREADS = V2_WARPS * 32;
 constexpr int V2_CHUNK = 256;          // individuals per pipeline stage
 constexpr int V2_STAGES = 3;
+#ifndef GB_V2_AHEAD
+#define GB_V2_AHEAD 1
+#endif
+// chunks queued ahead of the one being consumed.  With V2_STAGES - 1 the producing lane has to wait until EVERY warp has released the
+// chunk just before its own (source-level ncu: 27 % of the kernel's stall samples sat in those waits -- the ring degenerated into a
+// per-chunk barrier); with one chunk less the other warps may trail by two chunks before a producer blocks, and one 2.9 us chunk of
+// lead is still several memory latencies.
+constexpr int V2_AHEAD = GB_V2_AHEAD;
 constexpr int V2_MAX_REGION = 64;
 constexpr int V2_NSG = 2;              // grid lambdas per pass (register budget: 2 CTAs per SM need <= 128 registers)
 constexpr int V2_NSC = 5;              // common-lambda slots per hoisted pass (h rows staged next to the data rows)
@@ -77,8 +85,8 @@ __device__ __forceinline__ void v2_mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = v2_smem_u32(bar);
   uint32_t done;
   do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(1000u) : "memory");      // suspend-time hint (ns): the ring waits were 14 % of all issued instructions as bare spins
   } while (!done);
 }
 __device__ __forceinline__ void v2_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -240,7 +248,7 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
   // the producer duty rotates over the warps (chunk k is queued by lane 0 of warp k % V2_WARPS): a fixed producer thread made its
   // warp ~40 % slower than the other seven and the whole ring ran at that warp's pace
 #pragma unroll
-  for (int c = 0; c < V2_STAGES - 1; ++c)
+  for (int c = 0; c < V2_AHEAD; ++c)
     if (c < nchunks) {
       const unsigned int k = it0 + (unsigned int)c;
       if (lane == 0 && warp == (int)(k % V2_WARPS)) {
@@ -250,7 +258,7 @@ __device__ __forceinline__ void v2_pass(const LmmConst &D, const double *const *
     }
   for (int c = 0; c < nchunks; ++c) {
     {
-      const int cn = c + V2_STAGES - 1;
+      const int cn = c + V2_AHEAD;
       const unsigned int kn = it0 + (unsigned int)cn;
       if (cn < nchunks && lane == 0 && warp == (int)(kn % V2_WARPS)) {
         v2_acquire_stage(empty, kn);
@@ -347,7 +355,7 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
   uint64_t *full = v2_bars(smem, NC), *empty = full + V2_STAGES;
   const unsigned int it0 = pipe_it;
 #pragma unroll
-  for (int c = 0; c < V2_STAGES - 1; ++c)
+  for (int c = 0; c < V2_AHEAD; ++c)
     if (c < nchunks) {
       const unsigned int k = it0 + (unsigned int)c;
       if (lane == 0 && warp == (int)(k % V2_WARPS)) {         // rotating producer, see v2_pass
@@ -357,7 +365,7 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
     }
   for (int c = 0; c < nchunks; ++c) {
     {
-      const int cn = c + V2_STAGES - 1;
+      const int cn = c + V2_AHEAD;
       const unsigned int kn = it0 + (unsigned int)cn;
       if (cn < nchunks && lane == 0 && warp == (int)(kn % V2_WARPS)) {
         v2_acquire_stage(empty, kn);
@@ -372,28 +380,51 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
       const double *sl = st + lane;
       const double *xl = st + (NC + 2) * V2_CHUNK + warp * V2_CHUNK + lane;
       const double *hl = st + (NC + 2 + V2_WARPS) * V2_CHUNK + lane;
+      // register double buffer: the 8 + NC shared-memory values of individual u + 1 are requested before the 38 FP64 operations of
+      // individual u (the h loads sat directly in front of their first use: `short scoreboard` was 17 % of the stall samples)
+      double cx, cw[NC], cy, ch[V2_NSC];
+      cx = xl[0]; cy = sl[(NC + 1) * V2_CHUNK];
+#pragma unroll
+      for (int a = 0; a < NC; ++a) cw[a] = sl[(a + 1) * V2_CHUNK];
+#pragma unroll
+      for (int s = 0; s < V2_NSC; ++s) ch[s] = hl[s * V2_CHUNK];
 #pragma unroll
       for (int u = 0; u < V2_CHUNK / 32; ++u) {
-        const int j = u * 32;
-        const double x = xl[j];
+        double nx = 0.0, nw[NC], ny = 0.0, nh[V2_NSC];
+        if (u + 1 < V2_CHUNK / 32) {
+          const int j = (u + 1) * 32;
+          nx = xl[j]; ny = sl[(NC + 1) * V2_CHUNK + j];
+#pragma unroll
+          for (int a = 0; a < NC; ++a) nw[a] = sl[(a + 1) * V2_CHUNK + j];
+#pragma unroll
+          for (int s = 0; s < V2_NSC; ++s) nh[s] = hl[s * V2_CHUNK + j];
+        }
+        const double x = cx;
         double px[NQ];
 #pragma unroll
-        for (int a = 0; a < NC; ++a) px[a] = sl[(a + 1) * V2_CHUNK + j] * x;
+        for (int a = 0; a < NC; ++a) px[a] = cw[a] * x;
         px[NC] = x * x;
-        px[NC + 1] = x * sl[(NC + 1) * V2_CHUNK + j];
+        px[NC + 1] = x * cy;
         if (WITH_I) {
 #pragma unroll
           for (int q = 0; q < NQ; ++q) acc.I[q] += px[q];
         }
 #pragma unroll
         for (int s = 0; s < V2_NSC; ++s) {
-          const double h = hl[s * V2_CHUNK + j];
+          const double h = ch[s];
           const double h2 = h * h;
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             acc.X[s][0][q] = fma(h, px[q], acc.X[s][0][q]);
             acc.X[s][1][q] = fma(h2, px[q], acc.X[s][1][q]);
           }
+        }
+        if (u + 1 < V2_CHUNK / 32) {
+          cx = nx; cy = ny;
+#pragma unroll
+          for (int a = 0; a < NC; ++a) cw[a] = nw[a];
+#pragma unroll
+          for (int s = 0; s < V2_NSC; ++s) ch[s] = nh[s];
         }
       }
     }
