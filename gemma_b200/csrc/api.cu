@@ -652,8 +652,8 @@ static int lmm_ensure_common(gb200_ctx *c, CommonInfo &ci) {
   if (!ci.on) return GB200_OK;
   LmmConst D = make_const(c);
   const size_t J0 = (size_t)c->prm.n_region + 3, rec = lmm_common_record_doubles((int)c->n_cvt);
-  const int M = lmm_cheb_nodes();
-  size_t n_nodes = c->lmm_interp ? (size_t)c->prm.n_region * (size_t)M : 0;
+  const int M = lmm_cheb_nodes(), XM = lmm_cheb_xnodes();      // per interval: M nodes for the SNP-independent tables, then XM for the x-sums
+  size_t n_nodes = c->lmm_interp ? (size_t)c->prm.n_region * (size_t)(M + XM) : 0;
   if ((J0 + n_nodes) * c->n_c * sizeof(double) > ((size_t)2 << 30)) n_nodes = 0;        // node rows stay below 2 GB
   // 20 nodes resolve an interval of one decade (+ margins) to ~1e-14; wider intervals (a coarse -region grid) keep the exact passes
   if (log(c->prm.l_max / c->prm.l_min) / (double)c->prm.n_region > 2.4) n_nodes = 0;
@@ -668,6 +668,8 @@ static int lmm_ensure_common(gb200_ctx *c, CommonInfo &ci) {
     for (int g = 0; g < c->prm.n_region; ++g) {
       const double lo = log(c->prm.l_min) + interval * (double)g - ci.marg, hi = log(c->prm.l_min) + interval * (double)(g + 1) + ci.marg;
       for (int m = 0; m < M; ++m) lams[(size_t)g * M + m] = exp(0.5 * (lo + hi) + 0.5 * (hi - lo) * cos(M_PI * ((double)m + 0.5) / (double)M));
+      for (int m = 0; m < XM; ++m)
+        lams[(size_t)c->prm.n_region * M + (size_t)g * XM + m] = exp(0.5 * (lo + hi) + 0.5 * (hi - lo) * cos(M_PI * ((double)m + 0.5) / (double)XM));
     }
     GB_CUDA(c, c->dNodeLam.reserve(n_nodes * sizeof(double)));
     GB_CUDA(c, cudaMemcpyAsync(c->dNodeLam.p, lams.data(), n_nodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));

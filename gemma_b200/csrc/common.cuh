@@ -218,6 +218,7 @@ cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm
                               int n_nodes, double *cheb, cudaStream_t st);
 cudaError_t launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const double *U, double *scratch, double *v, cudaStream_t st);
 int lmm_cheb_nodes();
+int lmm_cheb_xnodes();
 size_t lmm_cheb_doubles(int n_cvt, int n_region);
 size_t lmm_common_record_doubles(int n_cvt);
 cudaError_t launch_lmm_assoc_v2(int n_cvt, const LmmConst &D, const LmmParams &prm, const double *UtXt, size_t ldu,

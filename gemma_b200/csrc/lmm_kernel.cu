@@ -169,6 +169,7 @@ cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm
   return cudaGetLastError();
 }
 int lmm_cheb_nodes() { return V2_CM; }
+int lmm_cheb_xnodes() { return V2_XM; }
 size_t lmm_cheb_doubles(int n_cvt, int n_region) { return 4 * (size_t)V2_CM + (size_t)n_region * (2 * (size_t)v2c_nidx(n_cvt) + 3) * V2_CM; }
 size_t lmm_common_record_doubles(int n_cvt) { return (size_t)v2c_stride(n_cvt); }
 

@@ -49,11 +49,15 @@ constexpr int V2_MAX_REGION = 64;
 constexpr int V2_NSG = 2;              // grid lambdas per pass (register budget: 2 CTAs per SM need <= 128 registers)
 constexpr int V2_NSC = 5;              // common-lambda slots per hoisted pass (h rows staged next to the data rows)
 
-constexpr int V2_CM = 20;              // Chebyshev nodes per grid interval of the interpolated refinement (a multiple of V2_NSC)
+constexpr int V2_CM = 20;              // Chebyshev nodes per grid interval for the SNP-independent sums (tabulated once per run: free)
+constexpr int V2_XM = 10;              // Chebyshev nodes per grid interval for the x-sums of a SNP (a multiple of V2_NSC): they enter the
+                                       // derivatives with weight O(z^2 / n) (sweep of x) or through one O(1) pivot ratio against a trace
+                                       // of order n, so 5^-10 ~ 1e-7 moves a root by ~1e-12 relative; f(lambda_hat) and the Wald
+                                       // tables are NOT taken from these interpolants but from one exact pass at the end
 
 __host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS + V2_NSC) * V2_CHUNK; }
 // per warp: Chebyshev coefficients of its SNP's x-sums over the current interval (2 powers x (nc + 2) sums x V2_CM) + one pass of node values
-__host__ __device__ constexpr size_t v2_cheb_warp_doubles(int nc) { return (size_t)(2 * (nc + 2)) * (V2_CM + V2_NSC); }
+__host__ __device__ constexpr size_t v2_cheb_warp_doubles(int nc) { return (size_t)(2 * (nc + 2)) * (V2_XM + V2_NSC); }
 // SNP-independent sums at one common lambda: S^k_ab over (w_1..w_c, y) for k = 0,1,2, then sum h, sum h^2, sum log(l d+1), lambda
 __host__ __device__ constexpr int v2c_nidx(int nc) { return (nc + 2) * (nc + 1) / 2; }
 __host__ __device__ constexpr int v2c_stride(int nc) { return 3 * v2c_nidx(nc) + 4; }
@@ -510,7 +514,7 @@ struct V2Fn {
   double cache_lam, cP_xx, cP_xy, cP_yy, cPx_yy;
 };
 
-struct V2Req { bool need; double lam; int K; bool logdet; };
+struct V2Req { bool need; double lam; int K; bool logdet; bool ext; double ld_ext; };   // ext: f wanted with sum log(l d + 1) supplied (ld_ext, from the run's table) instead of accumulated
 
 __device__ __forceinline__ void v2fn_init(V2Fn &F) {
   F.stage = V2_SCAN; F.next_g = 0; F.status = GB_ST_ERR; F.iter = F.iter2 = 0;
@@ -525,7 +529,7 @@ __device__ __forceinline__ void v2fn_init(V2Fn &F) {
 // the scan state, i.e. when the current interval is finished.
 __device__ __noinline__ void v2fn_advance(V2Fn &F, const double *glam, const double *gd1, int n_region, double l_min,
                                           double l_max, double ev_d1, double ev_d2, double ev_f, V2Req &req, bool single = false) {
-  req.need = false;
+  req.need = false; req.ext = false; req.ld_ext = 0.0;
   const unsigned max_iter = 100;
   for (;;) {
     switch (F.stage) {
@@ -691,25 +695,25 @@ __device__ __forceinline__ void v2fn_begin(V2Fn &F, const double *glam, const do
 }
 
 // Clenshaw: value / tau-derivative of sum_k c_k T_k(tau)
-template <bool GLOBAL>
+template <bool GLOBAL, int M>
 __device__ __forceinline__ double v2_cheb_val(const double *c, double tau) {
   double b1 = 0.0, b2 = 0.0;
   const double t2 = tau + tau;
 #pragma unroll
-  for (int k = V2_CM - 1; k >= 1; --k) {
+  for (int k = M - 1; k >= 1; --k) {
     const double ck = GLOBAL ? __ldg(c + k) : c[k];
     const double b0 = fma(t2, b1, ck) - b2;
     b2 = b1; b1 = b0;
   }
   return fma(tau, b1, (GLOBAL ? __ldg(c) : c[0])) - b2;
 }
-template <bool GLOBAL>
+template <bool GLOBAL, int M>
 __device__ __forceinline__ double v2_cheb_der(const double *c, double tau) {
   // p' = sum_{j=0}^{M-2} (j + 1) c_{j+1} U_j(tau)
   double b1 = 0.0, b2 = 0.0;
   const double t2 = tau + tau;
 #pragma unroll
-  for (int j = V2_CM - 2; j >= 0; --j) {
+  for (int j = M - 2; j >= 0; --j) {
     const double dj = (double)(j + 1) * (GLOBAL ? __ldg(c + j + 1) : c[j + 1]);
     const double b0 = fma(t2, b1, dj) - b2;
     b2 = b1; b1 = b0;
@@ -737,14 +741,14 @@ __device__ __forceinline__ void v2_assemble_arr(const double (&C)[(NC + 2) * (NC
 template <int NC, int ORD>
 __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coef, int g, double tau, double dtau_dt, double lam,
                                             double n, bool want_f, double logdetI, const double *dlt, V2Eval &ev) {
-  constexpr int NQ = NC + 2, NIDX = (NC + 3) * (NC + 2) / 2, CN = v2c_nidx(NC), M = V2_CM;
+  constexpr int NQ = NC + 2, NIDX = (NC + 3) * (NC + 2) / 2, CN = v2c_nidx(NC), M = V2_CM, XM = V2_XM;
   const double *gc = D.cheb + 4 * M + (size_t)g * (2 * CN + 3) * M;
   double X1[NQ], X2[NQ], X3[NQ], C1[CN], C2[CN], C3[CN];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    X1[q] = v2_cheb_val<false>(coef + q * M, tau);
-    X2[q] = v2_cheb_val<false>(coef + (NQ + q) * M, tau);
-    X3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<false>(coef + (NQ + q) * M, tau), X2[q]) : 0.0;
+    X1[q] = v2_cheb_val<false, XM>(coef + q * XM, tau);
+    X2[q] = v2_cheb_val<false, XM>(coef + (NQ + q) * XM, tau);
+    X3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<false, XM>(coef + (NQ + q) * XM, tau), X2[q]) : 0.0;
   }
   if (dlt && want_f) {           // final f / Wald tables: exact-minus-projected x-sums (LmmConst::xex), order 1 only
 #pragma unroll
@@ -753,12 +757,12 @@ __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coe
   }
 #pragma unroll
   for (int q = 0; q < CN; ++q) {
-    C1[q] = v2_cheb_val<true>(gc + q * M, tau);
-    C2[q] = v2_cheb_val<true>(gc + (CN + q) * M, tau);
-    C3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<true>(gc + (CN + q) * M, tau), C2[q]) : 0.0;
+    C1[q] = v2_cheb_val<true, M>(gc + q * M, tau);
+    C2[q] = v2_cheb_val<true, M>(gc + (CN + q) * M, tau);
+    C3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<true, M>(gc + (CN + q) * M, tau), C2[q]) : 0.0;
   }
-  const double tr1 = v2_cheb_val<true>(gc + 2 * CN * M, tau), tr2 = v2_cheb_val<true>(gc + (2 * CN + 1) * M, tau);
-  const double ld = want_f ? v2_cheb_val<true>(gc + (2 * CN + 2) * M, tau) : 0.0;
+  const double tr1 = v2_cheb_val<true, M>(gc + 2 * CN * M, tau), tr2 = v2_cheb_val<true, M>(gc + (2 * CN + 1) * M, tau);
+  const double ld = want_f ? v2_cheb_val<true, M>(gc + (2 * CN + 2) * M, tau) : 0.0;
   double S1[NIDX], S2[NIDX], S3[NIDX];
   v2_assemble_arr<NC>(C1, X1, S1);
   v2_assemble_arr<NC>(C2, X2, S2);
@@ -788,38 +792,75 @@ __device__ __forceinline__ bool v2_drive(const LmmConst &D, V2Fn &F, bool fnR, c
 }
 
 // One exact lockstep pass for up to two lambdas per warp (slot 0 = REML chain, slot 1 = ML chain).  Every thread of the CTA calls it.
+// `dlt` (or null): exact-minus-projected order-1 x-sums (LmmConst::xex), added for requests flagged `ext` (the final evaluations).
 template <int NC>
 __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *const *xrows, double *smem, int nchunks, int pad,
                                               bool active, const V2Req (&rq)[2], double n, double logdetI, V2Eval (&ev)[2],
-                                              unsigned int &tally2, unsigned int &tally3, unsigned int &tallyld, unsigned int &pipe_it) {
-  constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
+                                              unsigned int &tally2, unsigned int &tally3, unsigned int &tallyld, unsigned int &pipe_it,
+                                              const double *dlt = nullptr) {
+  constexpr int NIDX = (NC + 3) * (NC + 2) / 2, NV = NC + 2;
   const int k0 = rq[0].need ? rq[0].K : 0, k1 = rq[1].need ? rq[1].K : 0;
   const int Kloc = active ? (k0 > k1 ? k0 : k1) : 0;
-  const bool big = Kloc >= 3;     // per warp, like the non-interpolated loop below: both pass shapes walk the same pipeline (same barriers, same copies)
+  // per warp, like the passes themselves: all shapes walk the same stage ring (same rows, same chunk count)
   const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
-  const bool wl[2] = {rq[0].need && rq[0].logdet, rq[1].need && rq[1].logdet};
-  const bool any_ld = wl[0] || wl[1];
-  if (active) { if (big) tally3++; else tally2++; if (any_ld) tallyld++; }
+  const bool wf[2] = {rq[0].need && (rq[0].logdet || rq[0].ext), rq[1].need && (rq[1].logdet || rq[1].ext)};     // f wanted
+  const bool any_ld = (rq[0].need && rq[0].logdet && !rq[0].ext) || (rq[1].need && rq[1].logdet && !rq[1].ext);   // log accumulated in the pass
+  if (active) { if (Kloc >= 3) tally3++; else tally2++; if (any_ld) tallyld++; }
   double dummy[NIDX];
-  if (big) {
+  auto fix = [&](double (&S1)[NIDX], int s2) {            // exact x-sums for the final evaluations
+    if (dlt && rq[s2].ext) {
+#pragma unroll
+      for (int a = 0; a < NC; ++a) S1[abidx(a, NC, NV)] += dlt[a];
+      S1[abidx(NC, NC + 1, NV)] += dlt[NC];
+    }
+  };
+  if (Kloc >= 3) {
     V2Acc<NC, 2, 1, 3> acc;
     if (any_ld) v2_pass<NC, 2, 1, 3, true>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
     else v2_pass<NC, 2, 1, 3, false>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
     if (active) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
-        v2_derive<NC, 3>(acc.S[s][0], acc.S[s][1], acc.S[s][2], acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        fix(acc.S[s2][0], s2);
+        v2_derive<NC, 3>(acc.S[s2][0], acc.S[s2][1], acc.S[s2][2], acc.tr[s2][0], acc.tr[s2][1], lam[s2], n, wf[s2],
+                         rq[s2].ext ? rq[s2].ld_ext : acc.ld[s2], logdetI, ev[s2]);
+      }
     }
-  } else {
+  } else if (Kloc == 2 || any_ld) {
     V2Acc<NC, 2, 1, 2> acc;
     if (any_ld) v2_pass<NC, 2, 1, 2, true>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
     else v2_pass<NC, 2, 1, 2, false>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
     if (active) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
-        v2_derive<NC, 2>(acc.S[s][0], acc.S[s][1], dummy, acc.tr[s][0], acc.tr[s][1], lam[s], n, wl[s], acc.ld[s], logdetI, ev[s]);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        fix(acc.S[s2][0], s2);
+        v2_derive<NC, 2>(acc.S[s2][0], acc.S[s2][1], dummy, acc.tr[s2][0], acc.tr[s2][1], lam[s2], n, wf[s2],
+                         rq[s2].ext ? rq[s2].ld_ext : acc.ld[s2], logdetI, ev[s2]);
+      }
+    }
+  } else {                                                 // order-1 tables only (final f / Wald evaluations; idle warps of such a pass)
+    V2Acc<NC, 2, 1, 1> acc;
+    v2_pass<NC, 2, 1, 1, false>(D, xrows, smem, nchunks, pad, active, lam, acc, pipe_it);
+    if (active) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        fix(acc.S[s2][0], s2);
+        v2_derive<NC, 1>(acc.S[s2][0], dummy, dummy, acc.tr[s2][0], 0.0, lam[s2], n, wf[s2], rq[s2].ext ? rq[s2].ld_ext : 0.0, logdetI, ev[s2]);
+      }
     }
   }
+}
+
+// sum_i log(lambda delta_i + 1) from the run's Chebyshev table of the grid interval that contains lambda
+template <int NC>
+__device__ __forceinline__ double v2_table_logdet(const LmmConst &D, double lam, double l_min, double interval, int n_region) {
+  constexpr int CN = v2c_nidx(NC), M = V2_CM;
+  const double t = log(lam), t0 = log(l_min);
+  int g = (int)floor((t - t0) / interval);
+  g = g < 0 ? 0 : (g >= n_region ? n_region - 1 : g);
+  const double lo = t0 + interval * (double)g - D.cheb_marg, hi = t0 + interval * (double)(g + 1) + D.cheb_marg;
+  const double tau = (2.0 * t - (lo + hi)) / (hi - lo);
+  return v2_cheb_val<true, M>(D.cheb + 4 * M + ((size_t)g * (2 * CN + 3) + (2 * CN + 2)) * M, tau);
 }
 
 // One CTA = 8 SNPs.  xrows[w] (shared memory) = U^T x row of warp w or nullptr.
@@ -976,14 +1017,14 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
   v2fn_init(FR); v2fn_init(FL);
   if (!needR || !valid) FR.stage = V2_DONE;
   if (!needL || !valid) FL.stage = V2_DONE;
-  V2Req rq[2]; rq[0].need = rq[1].need = false;
+  V2Req rq[2]; rq[0].need = rq[1].need = false; rq[0].ext = rq[1].ext = false; rq[0].ld_ext = rq[1].ld_ext = 0.0;
   if (need_search) {
     double evR[3] = {0, 0, 0}, evL[3] = {0, 0, 0};     // d1, d2, f delivered to each chain
     bool finalized = false, wald_pending = false, wald_done = !needR;
 #if GB_V2_TMA
     if (hoist && D.cheb != nullptr) {
       // ---- interpolated refinement: the grid intervals in the reference's order; per interval 4 node passes, then scalars only
-      constexpr int NQ = NC + 2, M = V2_CM;
+      constexpr int NQ = NC + 2, M = V2_XM;                // x-sum nodes; the SNP-independent tables have V2_CM nodes per interval
       double *coef = smem + v2_stage_doubles(NC) * V2_STAGES + 8 + (size_t)(threadIdx.x >> 5) * v2_cheb_warp_doubles(NC);
       double *stg = coef + 2 * NQ * M;
       const int lane = threadIdx.x & 31;
@@ -997,7 +1038,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         for (int p0 = 0; p0 < M; p0 += V2_NSC) {
           int jrow[V2_NSC];
 #pragma unroll
-          for (int s2 = 0; s2 < V2_NSC; ++s2) jrow[s2] = D.n_common + g * M + p0 + s2;
+          for (int s2 = 0; s2 < V2_NSC; ++s2) jrow[s2] = D.n_common + n_region * V2_CM + g * M + p0 + s2;   // x-node rows follow the table-node rows
           V2CAcc<NC> acc;
           v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it);
           if (due) {
@@ -1016,7 +1057,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
               double a = coef[o];
 #pragma unroll
               for (int s2 = 0; s2 < V2_NSC; ++s2)
-                a = fma(stg[s2 * 2 * NQ + kq], __ldg(D.cheb + (kk * (2 * (p0 + s2) + 1)) % (4 * M)), a);
+                a = fma(stg[s2 * 2 * NQ + kq], __ldg(D.cheb + (V2_CM / M) * ((kk * (2 * (p0 + s2) + 1)) % (4 * M))), a);   // cos(pi j / (2 M)) from the table of cos(pi j / (2 V2_CM))
               coef[o] = a;
             }
             __syncwarp();
@@ -1050,6 +1091,24 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       if (FR.stage == V2_SCAN) FR.stage = V2_DONE;           // interval list exhausted
       if (FL.stage == V2_SCAN) FL.stage = V2_DONE;
       rq[0].need = rq[1].need = false;
+      // ---- final evaluations: f and the order-1 tables at the estimates the searches ended on, by ONE exact pass (the x-sum
+      // interpolants only steered the searches).  An end-point estimate already has exact values from the grid passes.
+      {
+        bool exR = false, exL = false;
+        if (valid && needR && FR.rs.have && !FR.rs.aborted) { RootState t = FR.rs; v2_finalize(t, fRmin, fRmax, l_min, l_max); exR = (t.lambda == FR.rs.lambda) && isfinite(t.lambda); }
+        if (valid && needL && FL.rs.have && !FL.rs.aborted) { RootState t = FL.rs; v2_finalize(t, fLmin, fLmax, l_min, l_max); exL = (t.lambda == FL.rs.lambda) && isfinite(t.lambda); }
+        if (__syncthreads_or((exR || exL) ? 1 : 0)) {
+          rq[0].need = exR; rq[0].lam = exR ? FR.rs.lambda : 1.0; rq[0].K = 1; rq[0].logdet = false; rq[0].ext = exR;
+          rq[0].ld_ext = exR ? v2_table_logdet<NC>(D, FR.rs.lambda, l_min, lambda_interval, n_region) : 0.0;
+          rq[1].need = exL; rq[1].lam = exL ? FL.rs.lambda : 1.0; rq[1].K = 1; rq[1].logdet = false; rq[1].ext = exL;
+          rq[1].ld_ext = exL ? v2_table_logdet<NC>(D, FL.rs.lambda, l_min, lambda_interval, n_region) : 0.0;
+          V2Eval ev[2];
+          v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, exR || exL, rq, n, logdetI, ev, tally2, tally3, tallyld, pipe_it, have_dlt ? dlt : nullptr);
+          if (exR) { FR.rs.logf = ev[0].fR; FR.cache_lam = FR.rs.lambda; FR.cP_xx = ev[0].P_xx; FR.cP_xy = ev[0].P_xy; FR.cP_yy = ev[0].P_yy; FR.cPx_yy = ev[0].Px_yy; }
+          if (exL) FL.rs.logf = ev[1].fL;
+          rq[0].need = rq[1].need = false; rq[0].ext = rq[1].ext = false;
+        }
+      }
     }
 #endif
     for (;;) {
@@ -1076,7 +1135,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
         }
       }
       const bool want_wald = valid && finalized && wald_pending && !wald_done;
-      if (want_wald) { rq[0].need = true; rq[0].lam = lambda_remle; rq[0].K = 1; rq[0].logdet = false; }
+      if (want_wald) { rq[0].need = true; rq[0].lam = lambda_remle; rq[0].K = 1; rq[0].logdet = false; rq[0].ext = false; }
       const bool active = valid && (rq[0].need || rq[1].need);
       if (!__syncthreads_or(active ? 1 : 0)) break;
       const double lam[2] = {rq[0].need ? rq[0].lam : 1.0, rq[1].need ? rq[1].lam : 1.0};
