@@ -133,12 +133,13 @@ __global__ void __launch_bounds__(256) lmm_common_kernel(LmmConst D, LmmParams p
 
 // Chebyshev coefficients (first-kind nodes, tau_m = cos(pi (m + 1/2) / M)) of the SNP-independent sums over one grid interval:
 // f = S^1 pairs (CN), S^2 pairs (CN), sum h, sum h^2, sum log(l d + 1); block g = interval, thread = (f, k).  Block 0 also
-// writes the cosine table cos(pi j / (2 M)), j < 4 M, used by the per-SNP kernel for its own transforms.
+// writes the cosine tables cos(pi j / (2 M)), j < 4 M, for M = V2_CM and V2_XM (the per-SNP kernel's own transform uses the second).
 template <int NC>
 __global__ void __launch_bounds__(512) lmm_cheb_coef_kernel(const double *__restrict__ ctab, int row0, double *__restrict__ cheb) {
   constexpr int CN = v2c_nidx(NC), CS = v2c_stride(NC), NF = 2 * CN + 3, M = V2_CM;
   const int g = blockIdx.x, tid = threadIdx.x;
   if (g == 0 && tid < 4 * M) cheb[tid] = cospi((double)tid / (double)(2 * M));
+  if (g == 0 && tid < 4 * V2_XM) cheb[4 * M + tid] = cospi((double)tid / (double)(2 * V2_XM));
   if (tid >= NF * M) return;
   const int f = tid / M, k = tid - f * M;
   const int off = (f < 2 * CN) ? CN + f : 3 * CN + (f - 2 * CN);        // S^1 | S^2 are contiguous behind S^0; then tr1, tr2, logdet
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(512) lmm_cheb_coef_kernel(const double *__rest
     const double v = ctab[(size_t)(row0 + g * M + m) * CS + off];
     acc = fma(v, cospi((double)(k * (2 * m + 1)) / (double)(2 * M)), acc);
   }
-  cheb[4 * M + ((size_t)g * NF + f) * M + k] = acc * (k == 0 ? 1.0 / M : 2.0 / M);
+  cheb[V2_CHEB_BASE + ((size_t)g * NF + f) * M + k] = acc * (k == 0 ? 1.0 / M : 2.0 / M);
 }
 
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, const double *node_lams,
@@ -170,7 +171,7 @@ cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm
 }
 int lmm_cheb_nodes() { return V2_CM; }
 int lmm_cheb_xnodes() { return V2_XM; }
-size_t lmm_cheb_doubles(int n_cvt, int n_region) { return 4 * (size_t)V2_CM + (size_t)n_region * (2 * (size_t)v2c_nidx(n_cvt) + 3) * V2_CM; }
+size_t lmm_cheb_doubles(int n_cvt, int n_region) { return (size_t)V2_CHEB_BASE + (size_t)n_region * (2 * (size_t)v2c_nidx(n_cvt) + 3) * V2_CM; }
 size_t lmm_common_record_doubles(int n_cvt) { return (size_t)v2c_stride(n_cvt); }
 
 bool lmm_v2_supported(int n_cvt, int n_region) { return n_cvt >= 1 && n_cvt <= 3 && n_region <= V2_MAX_REGION; }

@@ -50,10 +50,14 @@ constexpr int V2_NSG = 2;              // grid lambdas per pass (register budget
 constexpr int V2_NSC = 5;              // common-lambda slots per hoisted pass (h rows staged next to the data rows)
 
 constexpr int V2_CM = 20;              // Chebyshev nodes per grid interval for the SNP-independent sums (tabulated once per run: free)
-constexpr int V2_XM = 10;              // Chebyshev nodes per grid interval for the x-sums of a SNP (a multiple of V2_NSC): they enter the
-                                       // derivatives with weight O(z^2 / n) (sweep of x) or through one O(1) pivot ratio against a trace
-                                       // of order n, so 5^-10 ~ 1e-7 moves a root by ~1e-12 relative; f(lambda_hat) and the Wald
-                                       // tables are NOT taken from these interpolants but from one exact pass at the end
+constexpr int V2_XM = 15;              // Chebyshev nodes per grid interval for the x-sums of a SNP (a multiple of V2_NSC).  The x-sums enter the
+                                       // derivatives with weight O(z^2 / n) (sweep of x) or through one O(1) pivot ratio against a trace of
+                                       // order n, but the iterates must still be reproduced to ~1e-11: the reference reports the PREVIOUS
+                                       // Newton iterate once |l_k - l_{k-1}| < 1e-5 l_k (src/lmm.cpp:2096), so an evaluation error eps flips
+                                       // the iteration count -- and moves the reported lambda by ~1e-5 -- for a fraction eps / 1e-5 of the
+                                       // SNPs (10 nodes, 1e-7: one SNP in a hundred, measured; 15 nodes, 3e-11 x weight: < 1e-6).
+                                       // f(lambda_hat) and the Wald tables are NOT taken from these interpolants but from one exact pass.
+constexpr int V2_CHEB_BASE = 4 * (V2_CM + V2_XM);   // LmmConst::cheb: cos(pi j / (2 V2_CM)), j < 4 V2_CM | cos(pi j / (2 V2_XM)), j < 4 V2_XM | coefficients
 
 __host__ __device__ constexpr size_t v2_stage_doubles(int nc) { return (size_t)(nc + 2 + V2_WARPS + V2_NSC) * V2_CHUNK; }
 // per warp: Chebyshev coefficients of its SNP's x-sums over the current interval (2 powers x (nc + 2) sums x V2_CM) + one pass of node values
@@ -742,7 +746,7 @@ template <int NC, int ORD>
 __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coef, int g, double tau, double dtau_dt, double lam,
                                             double n, bool want_f, double logdetI, const double *dlt, V2Eval &ev) {
   constexpr int NQ = NC + 2, NIDX = (NC + 3) * (NC + 2) / 2, CN = v2c_nidx(NC), M = V2_CM, XM = V2_XM;
-  const double *gc = D.cheb + 4 * M + (size_t)g * (2 * CN + 3) * M;
+  const double *gc = D.cheb + V2_CHEB_BASE + (size_t)g * (2 * CN + 3) * M;
   double X1[NQ], X2[NQ], X3[NQ], C1[CN], C2[CN], C3[CN];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
@@ -860,7 +864,7 @@ __device__ __forceinline__ double v2_table_logdet(const LmmConst &D, double lam,
   g = g < 0 ? 0 : (g >= n_region ? n_region - 1 : g);
   const double lo = t0 + interval * (double)g - D.cheb_marg, hi = t0 + interval * (double)(g + 1) + D.cheb_marg;
   const double tau = (2.0 * t - (lo + hi)) / (hi - lo);
-  return v2_cheb_val<true, M>(D.cheb + 4 * M + ((size_t)g * (2 * CN + 3) + (2 * CN + 2)) * M, tau);
+  return v2_cheb_val<true, M>(D.cheb + V2_CHEB_BASE + ((size_t)g * (2 * CN + 3) + (2 * CN + 2)) * M, tau);
 }
 
 // One CTA = 8 SNPs.  xrows[w] (shared memory) = U^T x row of warp w or nullptr.
@@ -1057,7 +1061,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
               double a = coef[o];
 #pragma unroll
               for (int s2 = 0; s2 < V2_NSC; ++s2)
-                a = fma(stg[s2 * 2 * NQ + kq], __ldg(D.cheb + (V2_CM / M) * ((kk * (2 * (p0 + s2) + 1)) % (4 * M))), a);   // cos(pi j / (2 M)) from the table of cos(pi j / (2 V2_CM))
+                a = fma(stg[s2 * 2 * NQ + kq], __ldg(D.cheb + 4 * V2_CM + (kk * (2 * (p0 + s2) + 1)) % (4 * M)), a);   // cos(pi j / (2 V2_XM))
               coef[o] = a;
             }
             __syncwarp();
