@@ -197,6 +197,10 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "hole_gemm must be 0 or 1");
     c->hole_gemm = value; return GB200_OK;
   }
+  if (!strcmp(name, "gemm_l2hint")) {
+    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "gemm_l2hint must be 0 or 1");
+    c->gemm_l2hint = value; return GB200_OK;
+  }
   if (!strcmp(name, "gemm_stages")) {
     if (value < 0 || value > 8) return set_err(c, GB200_ERR_ARG, "gemm_stages must be 0..8");
     c->gemm_stages = value; return GB200_OK;

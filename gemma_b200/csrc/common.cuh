@@ -142,6 +142,7 @@ struct gb200_ctx {
   long x_exact = 1;        // int8-projected PLINK batches: exact x-sums at l_mle_null computed in genotype space (LmmConst::xex)
   long hole_gemm = 1;      // CTA-pair projection: batches with many missing genotypes add mean * U^T q by a second GEMM pass over the hole-indicator rows (decided on the device); 0 = always the gather kernel
   long gemm_wave_sync = 1; // CTA-pair projection: producers start every tile wave together (keeps the K-panels shared through L2)
+  long gemm_l2hint = 0;  // CTA-pair projection: L2 eviction hints on the TMA loads (A/B measurement)
   long gemm_stages = 0;  // TMA pipeline stages of the CTA-pair projection kernel (0 = as many 32 KB stages as fit, at most 6)
   long gemm_panel = 0;   // raster panel width of the projection kernels in eigenvector groups (0 = default: 9 for the CTA-pair kernel; 2-group units, 6, for gemm_groups = 2)
   long kin_cta_pair = 0; // kinship kernel as CTA pairs (no gain measured on the short kinship launches)

@@ -138,6 +138,7 @@ struct I8KernelParams {
   int panel;                // raster panel width in units of NB eigenvector groups
   int stages;               // i8_gemm_pair_kernel: TMA pipeline stages
   unsigned int *wave_ctr;   // i8_gemm_pair_kernel: wave synchronisation counter (zeroed before the launch) or null
+  int l2_hint;              // i8_gemm_pair_kernel: L2 eviction hints on the TMA loads (genotype panels evict_first, plane panels evict_last)
 };
 
 __device__ __forceinline__ void tile_coords_raster(int tile, int m_tiles, int n_groups, int panel_w, int &m_blk, int &n_grp) {
@@ -324,6 +325,19 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *tmap, uint32
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy): the genotype panels of a wave are read once per wave (evict_first), the
+// plane panels of a raster panel are re-read by the following waves (evict_last)
+__device__ __forceinline__ void tma_load_2d_pair_hint(const CUtensorMap *tmap, uint32_t bar_cluster_addr, void *dst, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 __device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -387,6 +401,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       unsigned int wave = 0;
+      const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++wave) {
         int m_blk, n_grp; tile_coords(p, tile, m_blk, n_grp);
         if (skip(m_blk)) continue;
@@ -408,8 +423,13 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty[stage], phase ^ 1);             // local: released by the leader's multicast commit
           const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
           if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * (a_bytes + b_bytes)));
-          tma_load_2d_pair(&tmap_a, full_leader, smem_a + stage * a_bytes, kb * I8_BK, m_blk * 256 + (int)rank * I8_BM);
-          tma_load_2d_pair(&tmap_b, full_leader, smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N + (int)rank * halfN);
+          if (p.l2_hint) {
+            tma_load_2d_pair_hint(&tmap_a, full_leader, smem_a + stage * a_bytes, kb * I8_BK, m_blk * 256 + (int)rank * I8_BM, pol_a);
+            tma_load_2d_pair_hint(&tmap_b, full_leader, smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N + (int)rank * halfN, pol_b);
+          } else {
+            tma_load_2d_pair(&tmap_a, full_leader, smem_a + stage * a_bytes, kb * I8_BK, m_blk * 256 + (int)rank * I8_BM);
+            tma_load_2d_pair(&tmap_b, full_leader, smem_b + stage * b_bytes, kb * I8_BK, n_grp * p.N + (int)rank * halfN);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         if (p.wave_ctr) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.wave_ctr) : "memory");
@@ -1039,7 +1059,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   p.lbo_units = 1;
   p.scale = c->i8.scale.as<double>();
   p.C = UtXt_dev; p.ldc = c->n_c; p.mode = 0; p.tiles = nullptr; p.num_tiles = 0;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : (pair2 ? 6 : (pair ? 9 : I8_PANEL)); p.stages = I8_STAGES; p.wave_ctr = nullptr; p.hole_switch = nullptr;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = c->gemm_panel > 0 ? (int)c->gemm_panel : (pair2 ? 6 : (pair ? 9 : I8_PANEL)); p.stages = I8_STAGES; p.wave_ctr = nullptr; p.hole_switch = nullptr; p.l2_hint = 0;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)g.N * I8_BK) + 256;
   const int tiles = p.m_tiles * p.n_groups;
   if (pair2) {
@@ -1076,7 +1096,7 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     const size_t stage_pair = (size_t)I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK;                            // A + half of B per stage
     int ns = c->gemm_stages > 0 ? (int)c->gemm_stages : 6;
     while (ns > 2 && 1024 + (size_t)ns * stage_pair + 256 > 227 * 1024) --ns;
-    p.stages = ns;
+    p.stages = ns; p.l2_hint = (int)c->gemm_l2hint;
     if (c->gemm_wave_sync && 2 * pairs == c->num_sms / 2 * 2 && tiles > pairs) {       // whole-chip persistent grid: every CTA is resident
       GB_CUDA(c, c->i8.wave_ctr.reserve(sizeof(unsigned int)));
       GB_CUDA(c, cudaMemsetAsync(c->i8.wave_ctr.p, 0, sizeof(unsigned int), c->stream));
@@ -1318,7 +1338,7 @@ int i8_project_geno(gb200_ctx *c, const double *G_dev, size_t l, size_t ldg, dou
     const size_t stage_pair = (size_t)I8_BM * I8_BK + (size_t)(g.N / 2) * I8_BK;
     int ns = c->gemm_stages > 0 ? (int)c->gemm_stages : 6;
     while (ns > 2 && 1024 + (size_t)ns * stage_pair + 256 > 227 * 1024) --ns;
-    p.stages = ns; p.wave_ctr = nullptr; p.hole_switch = nullptr;
+    p.stages = ns; p.wave_ctr = nullptr; p.hole_switch = nullptr; p.l2_hint = 0;
     const int tiles = p.m_tiles * p.n_groups;
     int pairs = c->num_sms / 2; if (pairs > tiles) pairs = tiles; if (pairs < 1) pairs = 1;
     if (c->gemm_wave_sync && 2 * pairs == c->num_sms / 2 * 2 && tiles > pairs) {
@@ -1625,7 +1645,7 @@ int kin_i8_flush(gb200_ctx *c) {
   p.lbo_units = 1; p.scale = nullptr;
   p.C = c->dK.as<double>(); p.ldc = n; p.mode = 1;
   p.tiles = S.kin_tiles.as<int2>(); p.num_tiles = S.kin_num_tiles;
-  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = I8_PANEL; p.stages = I8_STAGES; p.wave_ctr = nullptr; p.hole_switch = nullptr;
+  p.row_mean = nullptr; p.tile_holes = nullptr; p.panel = I8_PANEL; p.stages = I8_STAGES; p.wave_ctr = nullptr; p.hole_switch = nullptr; p.l2_hint = 0;
   const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + (size_t)256 * I8_BK) + 256;
   GB_CUDA(c, cudaFuncSetAttribute(i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (c->kin_cta_pair != 0) {
