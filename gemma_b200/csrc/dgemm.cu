@@ -3,8 +3,8 @@
 // (non-integer) genotypes, for U^T W / U^T y, and as the generic kinship accumulator;
 // integer genotypes take the tensor-core path in i8gemm_sm100.cu.
 //
-// 128x128x16 CTA tile, 8 warps x (8x4) DMMA m8n8k4 tiles on the FP64 tensor pipe, operands staged in shared
-// memory k-major.  Element strides are arbitrary (covers N/T on either operand and gsl_matrix sub-views with
+// 128x128x16 CTA tile, 8 warps x (8x4) DMMA m8n8k4 tiles on the FP64 tensor pipe, operands staged in two shared-memory
+// stages k-major (register prefetch of the next k-step).  Element strides are arbitrary (covers N/T on either operand and gsl_matrix sub-views with
 // tda != size2).
 #include "common.cuh"
 
@@ -28,8 +28,12 @@ __global__ void __launch_bounds__(256) dgemm_kernel(size_t M, size_t N, size_t K
                                                     const double *__restrict__ A, size_t sam, size_t sak,
                                                     const double *__restrict__ B, size_t sbk, size_t sbn,
                                                     double beta, double *__restrict__ C, size_t ldc) {
-  __shared__ __align__(16) double As[BK][PITCH];
-  __shared__ __align__(16) double Bs[BK][PITCH];
+  // two stages of (A tile | B tile), k-major: the global loads of k-step t + 1 are issued into registers before the 128 DMMAs of
+  // k-step t and stored into the other stage afterwards -- one barrier per k-step, global latency behind the tensor work
+  // (round 1: synchronous loads, two barriers per k-step, 20 TFLOP/s)
+  extern __shared__ __align__(16) double dg_smem[];
+  double (*As)[BK][PITCH] = reinterpret_cast<double (*)[BK][PITCH]>(dg_smem);
+  double (*Bs)[BK][PITCH] = reinterpret_cast<double (*)[BK][PITCH]>(dg_smem + 2 * BK * PITCH);
   const size_t m0 = (size_t)blockIdx.y * BM, n0 = (size_t)blockIdx.x * BN;
   if (LOWER_ONLY && n0 > m0 + BM - 1) return;     // tile entirely above the diagonal
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -43,41 +47,64 @@ __global__ void __launch_bounds__(256) dgemm_kernel(size_t M, size_t N, size_t K
 
   const bool a_kfast = (sak == 1);
   const bool b_nfast = (sbn == 1);
-  for (size_t k0 = 0; k0 < K; k0 += BK) {
+  constexpr int RA = (BM * BK) / 256, RB = (BN * BK) / 256;
+  double ra[RA], rb[RB];
+  auto gload = [&](size_t k0) {
 #pragma unroll
-    for (int r = 0; r < (BM * BK) / 256; ++r) {
+    for (int r = 0; r < RA; ++r) {
       int mm, kk;
       if (a_kfast) { kk = tid % BK; mm = tid / BK + r * (256 / BK); }
       else { mm = tid % BM; kk = tid / BM + r * (256 / BM); }
       const size_t gm = m0 + mm, gk = k0 + kk;
-      double v = 0.0;
-      if (gm < M && gk < K) v = A[gm * sam + gk * sak];
-      As[kk][mm] = v;
+      ra[r] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.0;
     }
 #pragma unroll
-    for (int r = 0; r < (BN * BK) / 256; ++r) {
+    for (int r = 0; r < RB; ++r) {
       int nn, kk;
       if (b_nfast) { nn = tid % BN; kk = tid / BN + r * (256 / BN); }
       else { kk = tid % BK; nn = tid / BK + r * (256 / BK); }
       const size_t gn = n0 + nn, gk = k0 + kk;
-      double v = 0.0;
-      if (gn < N && gk < K) v = B[gk * sbk + gn * sbn];
-      Bs[kk][nn] = v;
+      rb[r] = (gn < N && gk < K) ? B[gk * sbk + gn * sbn] : 0.0;
     }
-    __syncthreads();
+  };
+  auto sstore = [&](int st) {
+#pragma unroll
+    for (int r = 0; r < RA; ++r) {
+      int mm, kk;
+      if (a_kfast) { kk = tid % BK; mm = tid / BK + r * (256 / BK); }
+      else { mm = tid % BM; kk = tid / BM + r * (256 / BM); }
+      As[st][kk][mm] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      int nn, kk;
+      if (b_nfast) { nn = tid % BN; kk = tid / BN + r * (256 / BN); }
+      else { kk = tid % BK; nn = tid / BK + r * (256 / BK); }
+      Bs[st][kk][nn] = rb[r];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int cur = 0;
+  for (size_t k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) gload(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = As[kk + fk][wm + i * 8 + fr];
+      for (int i = 0; i < 8; ++i) a[i] = As[cur][kk + fk][wm + i * 8 + fr];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk + fk][wn + j * 8 + fr];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[cur][kk + fk][wn + j * 8 + fr];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    if (more) sstore(cur ^ 1);      // the other stage was last read one k-step ago, before the previous barrier
     __syncthreads();
+    cur ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -103,10 +130,17 @@ cudaError_t launch_dgemm(size_t M, size_t N, size_t K, double alpha, const doubl
                          bool lower_only, cudaStream_t st) {
   if (M == 0 || N == 0) return cudaSuccess;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-  if (lower_only)
-    dgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
-  else
-    dgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  constexpr size_t smem = 4 * (size_t)BK * PITCH * sizeof(double);         // 2 stages x (A | B) = 66 KB
+  cudaError_t e;
+  if (lower_only) {
+    e = cudaFuncSetAttribute(dgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dgemm_kernel<true><<<grid, 256, smem, st>>>(M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  } else {
+    e = cudaFuncSetAttribute(dgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dgemm_kernel<false><<<grid, 256, smem, st>>>(M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  }
   return cudaGetLastError();
 }
 

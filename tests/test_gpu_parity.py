@@ -1194,13 +1194,14 @@ def test_dosage_rows_take_the_tensor_core_projection_as_exact_digit_rows(ctx):
 
 
 @pytest.mark.gpu
-def test_exact_x_sums_remove_the_plane_rounding_from_beta(ctx):
+@pytest.mark.parametrize("c", [1, 3])
+def test_exact_x_sums_remove_the_plane_rounding_from_beta(ctx, c):
     """Four digit planes leave ~1e-9 of rounding noise on every projected value; beta = P_xy / P_xx inherits it divided by the
     SNP's |z-score|.  The bed entry points therefore also form x . v_q, v_q = U (h(l_mle_null) (.) q), in genotype space (an FP64
     dot product, no planes) and the per-SNP kernel replaces the projected order-1 x-sums of the score test / final Wald tables by
     exact + (interpolated - projected at l_mle_null) (LmmConst::xex): the noise reaches beta only in second order."""
     n, l = 1536, 400
-    pb = random_problem(n, 1, 4, 191)
+    pb = random_problem(n, c, 4, 191 + c)
     bed, G = synth.make_bed(n, l, seed=192, miss_rate=0.01)
     X = O.lmm_impute(np.where(G < 0, np.nan, G))
     y = pb["y"] + 0.5 * (X[:, 7] - X[:, 7].mean())
