@@ -228,9 +228,11 @@ class Context:
     def kin_add_bed_dev(self, dev_ptr, l, bytes_per_snp):
         self._chk(self.lib.gb200_kin_add_bed_dev(self.h, dev_ptr, l, bytes_per_snp))
 
-    def kin_finish(self):
+    def kin_finish(self, out=None):
+        """out: optional preallocated n x n float64 C-contiguous array (e.g. a view of pinned memory) that receives K."""
         n = self._kin_n
-        K = np.empty((n, n))
+        K = np.empty((n, n)) if out is None else out
+        assert K.shape == (n, n) and K.dtype == np.float64 and K.flags.c_contiguous
         ns = _sz()
         self._chk(self.lib.gb200_kin_finish(self.h, _ptr(K), n, C.byref(ns)))
         return K, ns.value
