@@ -564,6 +564,12 @@ def run_lmm(args):
                "ms_per_step": ms2 / K, "note": "gb200_lmm_batch_bed: pinned host rows, double-buffered H2D on a copy stream under the kernels"}
         del hb, hb_np
 
+    # ---- -gk at N > 1 (BASELINE metric: "-gk K = XX^T TFLOP/s at 1/2/4/8 B200"): every rank accumulates K over its own SNP range, one
+    # all-reduce combines them; a short side measurement inside the default line so that the driver's scaling runs carry it
+    gk_multi = None
+    if not args.no_gk and world > 1 and args.workload == "lmm":
+        gk_multi = measure_gk_sharded(env, 10000, 131072, 4, 2)
+
     if rank != 0:
         env.finish()
         return
@@ -674,7 +680,7 @@ def run_lmm(args):
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": make_config(args, world),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "timed_s": ms * 1e-3,
-            "roofline": roof, "roofline_lmm": lmm_roof, "parity": parity, "cpu_baseline": cpu, "gk": gk,
+            "roofline": roof, "roofline_lmm": lmm_roof, "parity": parity, "cpu_baseline": cpu, "gk": gk if gk is not None else gk_multi,
             "setup": setup, "eigh_s": setup.get("eigh_s"),
             "digit_planes": T, "internal_sub_batch": chunk,
             "kernel_ms": {k: {"ms": v[0], "launches": v[1]} for k, v in prof.items()},
@@ -742,6 +748,52 @@ def measure_gk(env, n, B, K, Wm, ctx=None, cta_pair=-1, miss=0.0):
                          "peak_source": peaks["source"] + ", bf16 sustained", "launches": kin_n, "kernel_ms": kin_ms, "decode_ms": dec_ms,
                          "share_of_step": kin_ms / ms if kin_n else None,
                          "note": "exact int8 MACs: the int8 tensor rate is 2x the bf16 rate, so frac may reach 2.0 against the bf16 denominator"}}
+
+
+def measure_gk_sharded(env, n, B, K, Wm):
+    """-gk 1 on `world` GPUs: rank r accumulates K over its own B SNPs per step (gb200_kin_*), shard.combine_partial_kinship rescales
+    and all-reduces the n^2 doubles.  Every rank calls this; returns the dict on every rank.  A rank that fails before the first
+    collective is reported through a MIN all-reduce of a success flag, so that no rank waits in a collective the others never reach."""
+    torch, dist = env.torch, env.dist
+    from gemma_b200 import synth, shard
+    bps = (n + 3) // 4
+    ok, err, ctxg, beds = 1.0, "", None, None
+
+    def local(k):
+        ctxg.kin_begin(n, 1)
+        for s0 in range(0, B, 32768):
+            ctxg.kin_add_bed_dev(beds[k % 2].data_ptr() + s0 * bps, min(32768, B - s0), bps)
+        return ctxg.kin_finish_dev()
+
+    try:
+        ctxg = env.gb.Context(env.local, stream=env.stream.cuda_stream)
+        beds = [synth.make_bed_torch(n, B, env.dev, seed=SEED, snp_offset=K_SNP_OFFSET + (env.rank * 2 + k) * B) for k in range(2)]
+        local(0)
+        torch.cuda.synchronize()
+    except Exception as ex:
+        ok, err = 0.0, str(ex)[:200]
+    flag = torch.tensor([ok], dtype=torch.float64, device=env.dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if flag.item() < 1.0:
+        return {"error": "a rank failed before the first collective: " + err}
+    for k in range(Wm):
+        ptr, ns = local(k)
+        shard.combine_partial_kinship(shard.device_tensor(ptr, (n, n)), ns)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(env.stream)
+    for k in range(K):
+        ptr, ns = local(Wm + k)
+        Kt, ns_tot = shard.combine_partial_kinship(shard.device_tensor(ptr, (n, n)), ns)
+    e1.record(env.stream)
+    torch.cuda.synchronize()
+    ms = env.max_over_ranks(e0.elapsed_time(e1))
+    tr = float(torch.diagonal(Kt).mean().item())
+    ctxg.close()
+    return {"value": float(n) * (n + 1) * env.world * K * B / (ms * 1e-3) / 1e12, "unit": METRIC["gk"][1], "n_gpus": env.world,
+            "config": "-gk 1 centred kinship, n=%d individuals, %d SNPs per step per GPU (PLINK 2-bit), SNP ranges per rank + one all-reduce of K" % (n, B),
+            "ms_per_step": ms / K, "steps": K, "all_reduce_bytes_per_step": int(n * n * 8), "ns_total": ns_tot, "trace_over_n": tr,
+            "note": "short side measurement of the default line at N > 1; BASELINE config 2 proper is `bench.py --workload gk --gpus N`"}
 
 
 def run_gk(args):
