@@ -14,6 +14,7 @@ int i8_prepare(gb200_ctx *ctx);                       // slice U into int8 plane
 int i8_project_bed(gb200_ctx *ctx, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total,
                    size_t l, size_t bytes_per_snp, double *UtXt_dev);   // UtXt l x n (ld n)
 bool i8_available(gb200_ctx *ctx);
+int i8_xsum_prepare(gb200_ctx *ctx, int ncol);            // digit planes of the exact-sum vectors (c->i8.xs_V)
 int i8_project_geno(gb200_ctx *ctx, const double *G_dev, size_t l, size_t ldg, double *UtXt_dev, bool *taken);   // dosage rows as exact digit rows
 int i8_default_planes(size_t n);
 int i8_effective_planes(gb200_ctx *c, int *T_out);
@@ -49,6 +50,7 @@ static size_t lmm_chunk_snps(const gb200_ctx *c) {
 }
 
 extern "C" {
+static int lmm_ensure_common_public(gb200_ctx *c);
 
 int gb200_abi_version(void) { return GB200_ABI_VERSION; }
 
@@ -87,7 +89,7 @@ void gb200_destroy(gb200_ctx *c) {
                         &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale, &c->i8.wave_ctr,
                         &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles,
                         &c->i8.kin_qbits, &c->i8.kin_y, &c->dWtx, &c->dEnv, &c->dX2, &c->dFlip, &c->dLmW, &c->dLmY,
-                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam, &c->dVnull, &c->i8.xex};
+                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam, &c->dVnull, &c->i8.xex, &c->i8.xs_V, &c->i8.xs_planes, &c->i8.xs_scale, &c->i8.xs_out};
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
@@ -189,7 +191,7 @@ int gb200_set_option(gb200_ctx *c, const char *name, long value) {
     c->gemm_wave_sync = value; return GB200_OK;
   }
   if (!strcmp(name, "x_exact")) {
-    if (value < 0 || value > 1) return set_err(c, GB200_ERR_ARG, "x_exact must be 0 or 1");
+    if (value < 0 || value > 2) return set_err(c, GB200_ERR_ARG, "x_exact must be 0, 1 or 2");
     if (value != c->x_exact) c->common_ready = false;
     c->x_exact = value; return GB200_OK;
   }
@@ -246,6 +248,7 @@ int gb200_get_option(gb200_ctx *c, const char *name, long *value) {
   if (!c) return GB200_ERR_ARG;
   if (!name || !value) return set_err(c, GB200_ERR_ARG, "gb200_get_option: null argument");
   if (!strcmp(name, "n_slices")) {      // effective: the forced count, else the count chosen from this U's column maxima (i8gemm_sm100.cu)
+    if (c->lmm_ready && c->prm_ready) { const int rc0 = lmm_ensure_common_public(c); if (rc0) return rc0; }   // whether the exact linear sums are on decides it
     int T = 0;
     const int rc = i8_effective_planes(c, &T);
     if (rc) return rc;
@@ -442,7 +445,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
   if (n_cvt > GB200_MAX_CVT)
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->common_ready = false; c->gxe_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->i8.xs_ready = false; c->common_ready = false; c->gxe_ready = false;
   c->mask_host.clear();                           // the cached gather index belongs to the previous n
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
   c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
@@ -515,7 +518,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
     return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated_dev: bad argument");
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->common_ready = false; c->gxe_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->i8.xs_ready = false; c->common_ready = false; c->gxe_ready = false;
   c->mask_host.clear();
   const size_t n_c = round_up(n, 512);
   c->dUtXt.release(); c->dUtXt2.release();
@@ -539,7 +542,7 @@ static LmmConst make_const(gb200_ctx *c) {
   LmmConst D;
   D.n = (int)c->n; D.n_c = (int)c->n_c; D.ldv = (int)c->n_c;
   D.delta = c->dEval.as<double>(); D.Wt = c->dWt.as<double>(); D.y = c->dY.as<double>();
-  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.cheb = nullptr; D.cheb_marg = 0.0; D.xex = nullptr; D.xcov = nullptr; D.xcov_idx = 0;
+  D.Hrows = nullptr; D.ctab = nullptr; D.n_common = 0; D.cheb = nullptr; D.cheb_marg = 0.0; D.xex = nullptr; D.xsum = nullptr; D.xsum_ld = 0; D.xsum_nblocks = 0; D.xsum_nblocks_skip = 0; D.xcov = nullptr; D.xcov_idx = 0;
   D.cnt = c->count_work ? c->dTicket.as<unsigned long long>() + 4 : nullptr;     // 8 words behind the ticket words
   D.nc_gen = (c->lmm_kernel == 3) ? 1 : 0;      // > 0 forces the any-covariate-count kernel (the launchers fill the real values)
   D.gen_stride = 0;
@@ -694,10 +697,31 @@ static int lmm_ensure_common(gb200_ctx *c, CommonInfo &ci) {
     scratch.release();
     c->vnull_ready = true;
   }
+  // exact LINEAR x-sums at every hoisted lambda (LmmConst::xsum): V = U A, A's columns h_b^k (.) q over the shared rows and the x-node rows
+  c->i8.xs_ready = false; c->i8.xs_valid = false;
+  if (c->x_exact == 2 && n_nodes && c->dU.p && !c->overlap && !c->mv_ready && c->n >= 1024 && c->utx_path != 1) {
+    const int M = lmm_cheb_nodes(), XM = lmm_cheb_xnodes();
+    const int nq = (int)c->n_cvt + 1, nblocks = (int)J0 + c->prm.n_region * XM, x0 = (int)J0 + c->prm.n_region * M;
+    const int ncol = nblocks * 2 * nq + nq;
+    gb::DevBuf dA;
+    GB_CUDA(c, dA.reserve(c->n * (size_t)ncol * sizeof(double)));
+    GB_CUDA(c, c->i8.xs_V.reserve(c->n * (size_t)ncol * sizeof(double)));
+    GB_CUDA(c, launch_lmm_acols((int)c->n_cvt, D, c->dHrows.as<double>(), (int)J0, x0, nblocks, dA.as<double>(), ncol, c->stream));
+    GB_CUDA(c, launch_dgemm(c->n, (size_t)ncol, c->n, 1.0, c->dU.as<double>(), c->n, 1, dA.as<double>(), (size_t)ncol, 1, 0.0,
+                            c->i8.xs_V.as<double>(), (size_t)ncol, false, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dA.release();
+    const int rc = i8_xsum_prepare(c, ncol);
+    if (rc) return rc;
+    c->xs_nblocks = nblocks; c->xs_skip = c->prm.n_region * M;
+  }
+  c->i8.auto_T = 0; c->i8.ready = false;             // the plane count depends on whether the exact linear sums are on
   GB_CUDA(c, cudaStreamSynchronize(c->stream));       // the tests may run on a side stream
   c->common_ready = true;
   return GB200_OK;
 }
+
+static int lmm_ensure_common_public(gb200_ctx *c) { CommonInfo ci; return lmm_ensure_common(c, ci); }
 
 // association kernel on a device-resident rotated batch
 static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu, gb200_sumstat *out_dev,
@@ -717,9 +741,12 @@ static int lmm_assoc_dev(gb200_ctx *c, const double *UtXt, size_t l, size_t ldu,
       if (ci.n_nodes) { D.cheb = c->dCheb.as<double>(); D.cheb_marg = ci.marg; }
       // exact x-sums of the batch the int8 projection has just written into this very buffer
       if (c->i8.xex_valid && c->i8.xex_for == UtXt && c->i8.xex_l == l) D.xex = c->i8.xex.as<double>();
+      if (c->i8.xs_valid && c->i8.xs_for == UtXt && c->i8.xs_l == l && ci.n_nodes) {
+        D.xsum = c->i8.xs_out.as<double>(); D.xsum_ld = (int)c->i8.xs_ld; D.xsum_nblocks = c->xs_nblocks; D.xsum_nblocks_skip = c->xs_skip;
+      }
     }
   }
-  c->i8.xex_valid = false;
+  c->i8.xex_valid = false; c->i8.xs_valid = false;
   ProfScope ps(c, "lmm", 1, st);
   if (v2_ok && c->lmm_kernel != 1 && c->lmm_kernel != 3)
     GB_CUDA(c, launch_lmm_assoc_v2((int)c->n_cvt, D, c->prm, UtXt, ldu, (int)l, out_dev, ticket, c->num_sms, st));

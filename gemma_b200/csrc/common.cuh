@@ -46,6 +46,13 @@ struct I8State {
   DevBuf scale;                  // per eigenvector: scale s_i, column maximum, 1 / s_i (3 n doubles)
   DevBuf geno;                   // l_pad x n_pad int8 genotype tile source
   DevBuf miss_mean;              // per-SNP mean + hole count (+ holes per 256-SNP tile)
+  // exact linear x-sums at every hoisted lambda (LmmConst::xsum): V = U A (n x xs_ncol) in individual space, its digit planes, the result of the last batch
+  DevBuf xs_V, xs_planes, xs_scale, xs_out;
+  void *tmap_v = nullptr;
+  int xs_ncol = 0, xs_T = 0, xs_NE = 0, xs_groups = 0;
+  size_t xs_ld = 0;
+  bool xs_ready = false, xs_valid = false;
+  const double *xs_for = nullptr; size_t xs_l = 0;
   DevBuf xex;                    // exact order-1 x-sums of the batch last projected by i8_project_bed (l x (n_cvt + 1)); valid flag below
   bool xex_valid = false;
   const double *xex_for = nullptr; size_t xex_l = 0;   // the U^T X buffer / row count those sums belong to
@@ -113,6 +120,7 @@ struct gb200_ctx {
   gb::DevBuf dHrows, dCtab;     // common-lambda h rows / records of the lockstep kernel (lmm_v2.cuh hoisted passes)
   gb::DevBuf dVnull;            // v_q = U (h(l_mle_null) (.) q), q over (w, y): exact x-sums of int8-projected batches (LmmConst::xex)
   bool vnull_ready = false;
+  int xs_nblocks = 0, xs_skip = 0;   // LmmConst::xsum layout of the current common tables
   gb::DevBuf dCheb, dNodeLam;   // Chebyshev tables / node lambdas of the interpolated refinement
   bool common_ready = false;
   // scratch
@@ -139,7 +147,8 @@ struct gb200_ctx {
   long n_slices = 0;     // 0 = default
   long cta_pair = 1;     // projection kernel as CTA pairs (tcgen05 cta_group::2): -25% time at n = 50 000
   long gemm_groups = 1;  // 2: pair kernel with two eigenvector groups per tile (shared genotype tile) and the hole pass on the tensor pipe; 1: one group, FP64 hole fix-up
-  long x_exact = 1;        // int8-projected PLINK batches: exact x-sums at l_mle_null computed in genotype space (LmmConst::xex)
+  long x_exact = 2;        // int8-projected PLINK batches: 2 = exact LINEAR x-sums at every hoisted lambda from a side GEMM in genotype space
+                           // (LmmConst::xsum; lets the projection run on 3 digit planes), 1 = exact sums at l_mle_null only (LmmConst::xex), 0 = off
   long hole_gemm = 1;      // CTA-pair projection: batches with many missing genotypes add mean * U^T q by a second GEMM pass over the hole-indicator rows (decided on the device); 0 = always the gather kernel
   long gemm_wave_sync = 1; // CTA-pair projection: producers start every tile wave together (keeps the K-panels shared through L2)
   long gemm_l2hint = 0;  // CTA-pair projection: L2 eviction hints on the TMA loads (A/B measurement)
@@ -218,6 +227,7 @@ cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double 
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, const double *node_lams,
                               int n_nodes, double *cheb, cudaStream_t st);
 cudaError_t launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const double *U, double *scratch, double *v, cudaStream_t st);
+cudaError_t launch_lmm_acols(int n_cvt, const LmmConst &D, const double *H, int J0, int x0, int nblocks, double *A, int ncol, cudaStream_t st);
 int lmm_cheb_nodes();
 int lmm_cheb_xnodes();
 size_t lmm_cheb_doubles(int n_cvt, int n_region);

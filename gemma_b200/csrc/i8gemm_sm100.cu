@@ -702,11 +702,13 @@ i8_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
 // ------------------------------------------------------------------------------------------
 // U -> int8 digit planes
-__global__ void col_absmax_kernel(const double *__restrict__ U, int n, double *__restrict__ colmax) {
+// column maxima of a row-major matrix with n rows (individuals), ncols columns, leading dimension ld
+__global__ void col_absmax_kernel(const double *__restrict__ U, int n, double *__restrict__ colmax, int ncols = -1, size_t ld = 0) {
+  if (ncols < 0) { ncols = n; ld = (size_t)n; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= ncols) return;
   double m = 0.0;
-  for (int j = 0; j < n; ++j) m = fmax(m, fabs(U[(size_t)j * n + i]));
+  for (int j = 0; j < n; ++j) m = fmax(m, fabs(U[(size_t)j * ld + i]));
   colmax[i] = m;
 }
 
@@ -736,20 +738,21 @@ __global__ void __launch_bounds__(256) vec_max_kernel(const double *__restrict__
 
 // one 32x32 tile of U per block: read U[j][i] coalesced in i, write planes coalesced in j
 __global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ U, int n, const double *__restrict__ mult,
-                                                    int T, int NE, int n_padk, int8_t *__restrict__ planes) {
+                                                    int T, int NE, int n_padk, int8_t *__restrict__ planes, int ncols = -1, size_t ld = 0) {
+  if (ncols < 0) { ncols = n; ld = (size_t)n; }               // square U by default; rectangular (n individuals x ncols) for the exact-sum vectors
   __shared__ long long q[32][33];
   const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   for (int r = ty; r < 32; r += 8) {
     const int j = j0 + r, i = i0 + tx;
     long long v = 0;
-    if (j < n && i < n) v = llrint(U[(size_t)j * n + i] * mult[i]);
+    if (j < n && i < ncols) v = llrint(U[(size_t)j * ld + i] * mult[i]);
     q[r][tx] = v;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
-    const int i = i0 + r, j = j0 + tx;      // thread writes eigenvector i, individual j
-    if (i >= n || j >= n) continue;
+    const int i = i0 + r, j = j0 + tx;      // thread writes column (eigenvector) i, individual j
+    if (i >= ncols || j >= n) continue;
     long long Q = q[tx][r];
     const int g = i / NE, e = i - g * NE;
     const size_t row0 = (size_t)g * (size_t)(T * NE) + (size_t)e;
@@ -847,7 +850,8 @@ __global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__re
                                                        const int *__restrict__ idx, int n,
                                                        const double *__restrict__ U, const double *__restrict__ mean,
                                                        const int *__restrict__ nmiss, double *__restrict__ C, size_t ldc,
-                                                       const int *__restrict__ hole_switch) {
+                                                       const int *__restrict__ hole_switch, int ncols = -1, size_t ldu = 0) {
+  if (ncols < 0) { ncols = n; ldu = (size_t)n; }             // rows of U (n columns) by default; rows of the exact-sum vectors V (ncols) otherwise
   constexpr int CAP = 2048;
   __shared__ int list[CAP];
   __shared__ int wcount[8];
@@ -888,17 +892,17 @@ __global__ void __launch_bounds__(256) miss_fix_kernel(const unsigned char *__re
     }
     const int cnt = count;
     if (cnt > 0) {
-      for (int i = threadIdx.x; i < n; i += 256) {
+      for (int i = threadIdx.x; i < ncols; i += 256) {
         double acc = 0.0;
         int q = 0;
         for (; q + 8 <= cnt; q += 8) {
           double v[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = __ldg(U + (size_t)list[q + k] * n + i);
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(U + (size_t)list[q + k] * ldu + i);
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc += v[k];           // left to right: the order of the holes
         }
-        for (; q < cnt; ++q) acc += __ldg(U + (size_t)list[q] * n + i);
+        for (; q < cnt; ++q) acc += __ldg(U + (size_t)list[q] * ldu + i);
         c[i] += m * acc;
       }
     }
@@ -957,11 +961,15 @@ int i8_default_planes(size_t n) {
   if (T > 8) T = 8;
   return T;
 }
-int i8_choose_planes(double colmax_max, size_t n) {
+int i8_choose_planes(double colmax_max, size_t n, bool linear_sums_exact = false) {
   if (!(colmax_max > 0.0) || !isfinite(colmax_max)) return 4;
-  const double need = colmax_max * sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * 536870912.0;   // bound * 2^29 at T = 1
+  // with the exact linear x-sums (LmmConst::xsum) the projected U^T x only feeds sums QUADRATIC in x, where independent rounding noise
+  // eps averages to eps / sqrt(n): the target relaxes from 2^-29 to 2^-21 and delocalised eigenvectors get by with 3 planes
+  const double target = linear_sums_exact ? 2097152.0 : 536870912.0;                                      // 2^21 | 2^29
+  const double need = colmax_max * sqrt((double)(n > 1 ? n : 2)) / (sqrt(12.0) * 127.4) * target;        // bound / target at T = 1
   int T = 1 + (int)ceil(log2(need) / 8.0);
-  if (T < 4) T = 4;
+  const int Tmin = linear_sums_exact ? 3 : 4;
+  if (T < Tmin) T = Tmin;
   if (n < 8192 && T < 5) T = 5;
   if (T > 8) T = 8;
   return T;
@@ -981,7 +989,7 @@ int i8_effective_planes(gb200_ctx *c, int *T_out) {
     GB_CUDA(c, cudaStreamSynchronize(c->stream));
     tmp.release();
     c->i8.colmax_max = m;
-    c->i8.auto_T = i8_choose_planes(m, c->n);
+    c->i8.auto_T = i8_choose_planes(m, c->n, c->i8.xs_ready && c->x_exact == 2);
   }
   *T_out = c->i8.auto_T;
   return GB200_OK;
@@ -1015,6 +1023,32 @@ int i8_prepare(gb200_ctx *c) {
   return GB200_OK;
 }
 
+// Digit planes (6) and tensor map of the exact-sum vectors V (n individuals x ncol, row-major in c->i8.xs_V): the side GEMM G . V of
+// every int8-projected batch gives the sums linear in x at all hoisted lambdas (LmmConst::xsum).
+int i8_xsum_prepare(gb200_ctx *c, int ncol) {
+  I8State &S = c->i8;
+  S.xs_ready = false;
+  const int T = 6, NE = 40, N = T * NE;                       // same tile shape as the 6-plane projection (N = 240)
+  const int n = (int)c->n, n_padk = (int)((c->n + I8_BK - 1) / I8_BK * I8_BK);
+  const int groups = (ncol + NE - 1) / NE;
+  const size_t rows = (size_t)groups * N, bytes = rows * (size_t)n_padk;
+  GB_CUDA(c, S.xs_planes.reserve(bytes));
+  GB_CUDA(c, S.xs_scale.reserve((size_t)ncol * 3 * sizeof(double)));
+  GB_CUDA(c, cudaMemsetAsync(S.xs_planes.p, 0, bytes, c->stream));
+  double *scale = S.xs_scale.as<double>(), *colmax = scale + ncol, *mult = colmax + ncol;
+  col_absmax_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(S.xs_V.as<double>(), n, colmax, ncol, (size_t)ncol);
+  col_scale_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(colmax, ncol, T, scale, mult);
+  dim3 grid((ncol + 31) / 32, (n + 31) / 32);
+  slice_kernel<<<grid, 256, 0, c->stream>>>(S.xs_V.as<double>(), n, mult, T, NE, n_padk, S.xs_planes.as<int8_t>(), ncol, (size_t)ncol);
+  GB_CUDA(c, cudaGetLastError());
+  if (!S.tmap_v) S.tmap_v = aligned_alloc(64, sizeof(CUtensorMap));
+  if (!make_tmap((CUtensorMap *)S.tmap_v, S.xs_planes.p, rows, (uint64_t)n_padk, (uint32_t)(N / 2)))
+    return set_err(c, GB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the exact-sum planes");
+  S.xs_ncol = ncol; S.xs_T = T; S.xs_NE = NE; S.xs_groups = groups; S.xs_ld = (size_t)((ncol + 7) / 8 * 8);
+  S.xs_ready = true;
+  return GB200_OK;
+}
+
 int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_dev, size_t ni_total, size_t l,
                    size_t bytes_per_snp, double *UtXt_dev) {
   (void)ni_total;
@@ -1036,7 +1070,9 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
     GB_CUDA(c, cudaMemsetAsync(tile_holes, 0, (l_pad / 256 + 2) * sizeof(int), c->stream));
   }
   const int nq = (int)c->n_cvt + 1;
-  const bool want_xex = c->vnull_ready && c->x_exact && nq <= 4 && !c->overlap;
+  const bool want_xsum = c->i8.xs_ready && c->x_exact == 2 && pair && !pair2 && !c->overlap;
+  const bool want_xex = !want_xsum && c->vnull_ready && c->x_exact && nq <= 4 && !c->overlap;
+  c->i8.xs_valid = false;
   c->i8.xex_valid = false;
   if (want_xex) GB_CUDA(c, c->i8.xex.reserve(l_pad * (size_t)nq * sizeof(double)));
   {
@@ -1107,6 +1143,28 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
       ProfScope ps(c, "utx");
       i8_gemm_pair_kernel<<<2 * pairs, I8_THREADS, smem_pair, c->stream>>>(*(CUtensorMap *)c->i8.tmap_a, *(CUtensorMap *)c->i8.tmap_b, p);
       GB_CUDA(c, cudaGetLastError());
+    }
+    if (want_xsum) {
+      // side GEMM: the same genotype tiles against the 6 planes of the exact-sum vectors, then mean * (sum of V rows at the holes)
+      I8State &S = c->i8;
+      GB_CUDA(c, S.xs_out.reserve(l_pad * S.xs_ld * sizeof(double)));
+      I8KernelParams q = p;
+      q.T = S.xs_T; q.NE = S.xs_NE; q.N = S.xs_T * S.xs_NE; q.n = S.xs_ncol; q.n_groups = S.xs_groups;
+      q.scale = S.xs_scale.as<double>(); q.C = S.xs_out.as<double>(); q.ldc = S.xs_ld; q.mode = 0; q.wave_ctr = nullptr; q.panel = 4;
+      const size_t stage_v = (size_t)I8_BM * I8_BK + (size_t)(q.N / 2) * I8_BK;
+      int nsv = 6; while (nsv > 2 && 1024 + (size_t)nsv * stage_v + 256 > 227 * 1024) --nsv;
+      q.stages = nsv;
+      const int tiles_v = q.m_tiles * q.n_groups;
+      int pairs_v = c->num_sms / 2; if (pairs_v > tiles_v) pairs_v = tiles_v; if (pairs_v < 1) pairs_v = 1;
+      {
+        ProfScope ps(c, "xsum");
+        i8_gemm_pair_kernel<<<2 * pairs_v, I8_THREADS, 1024 + (size_t)nsv * stage_v + 256, c->stream>>>(*(CUtensorMap *)S.tmap_a, *(CUtensorMap *)S.tmap_v, q);
+        GB_CUDA(c, cudaGetLastError());
+        miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, S.xs_V.as<double>(), mean, nmiss, S.xs_out.as<double>(),
+                                                            S.xs_ld, nullptr, S.xs_ncol, (size_t)S.xs_ncol);
+        GB_CUDA(c, cudaGetLastError());
+      }
+      S.xs_valid = true; S.xs_for = UtXt_dev; S.xs_l = l;
     }
     if (hole_gemm) {
       int *sw = tile_holes + (l_pad / 256 + 1);

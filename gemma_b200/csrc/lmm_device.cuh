@@ -48,6 +48,14 @@ struct LmmConst {
   // FP64 dot product with no digit-plane rounding.  The lockstep kernel adds (exact - projected) to the order-1 x-sums of the score
   // test and of the final f / Wald evaluation: the plane rounding of U^T x then reaches beta only in second order.
   const double *xex;
+  // Exact LINEAR x-sums of this batch at every hoisted lambda (null = off): row s holds, for block b (the shared rows 0..n_common-1,
+  // then the x-node rows) and power k = 1, 2: sum_i h_i^k (U^T x)_i q_i for q over (w_1..w_c, y) at [(b * 2 + (k - 1)) * (c + 1) + q],
+  // and behind the last block the unit-weight sums.  Formed as x . v with v = U (h^k (.) q) by a side GEMM in genotype space (int8
+  // digit planes of the few hundred v's): independent of the rounding of the projected U^T x, which then only feeds the sums
+  // quadratic in x -- where independent rounding noise averages out -- so that the projection itself can run on 3 planes.
+  const double *xsum;
+  int xsum_ld, xsum_nblocks;   // row stride in doubles; number of (lambda) blocks
+  int xsum_nblocks_skip;       // rows between the shared rows and the x-node rows (the table-node rows, which carry no x-sums)
   const double *xcov;    // G x E: covariate column xcov_idx is this per-SNP vector (U^T x) instead of a row of Wt; null otherwise
   int xcov_idx;
   unsigned long long *cnt;  // optional work counters of the lockstep kernel (gb200_lmm_counters); null = off

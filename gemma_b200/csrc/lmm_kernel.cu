@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(V2_THREADS, (NC <= GB_V2_CTAS2_MAXNC) ? GB_V2_
     __syncthreads();
     gb200_sumstat r;
     v2_analyze_group<NC>(D, prm, xrows, v2_smem, nchunks, pad, valid, r, pipe_it,
-                         (D.xex && valid) ? D.xex + (size_t)s * (NC + 1) : nullptr);
+                         (D.xex && valid) ? D.xex + (size_t)s * (NC + 1) : nullptr,
+                         (D.xsum && valid) ? D.xsum + (size_t)s * D.xsum_ld : nullptr);
     if (valid && lane == 0) out[s] = r;
     __syncthreads();
   }
@@ -473,5 +474,33 @@ __global__ void __launch_bounds__(256) lmm_vnull_kernel(const double *__restrict
 cudaError_t gb::launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const double *U, double *scratch, double *v, cudaStream_t st) {
   lmm_hq_kernel<<<(D.n_c + 255) / 256, 256, 0, st>>>(D, n_cvt, lam, scratch);
   lmm_vnull_kernel<<<(D.n + 7) / 8, 256, 0, st>>>(U, D.n, D.n_c, n_cvt + 1, scratch, v);
+  return cudaGetLastError();
+}
+
+// ---- exact linear x-sums (LmmConst::xsum): the columns a_{b,k,q} = h_b^k (.) q of A (n x ncol, row-major), q over (w_1..w_c, y);
+// block b: the shared rows 0..J0-1 of Hrows, then the x-node rows (which start at row x0); last block: unit weights.
+namespace gb {
+__global__ void __launch_bounds__(256) lmm_acols_kernel(LmmConst D, int n_cvt, const double *__restrict__ H, int J0, int x0, int nblocks,
+                                                        double *__restrict__ A, int ncol) {
+  const int i = blockIdx.x * 256 + threadIdx.x;            // individual (eigen-coordinate)
+  const int b = blockIdx.y;                                // block; b == nblocks: unit weights
+  if (i >= D.n) return;
+  const int nq = n_cvt + 1;
+  double q[GB200_MAX_CVT + 1];
+  for (int a = 0; a < n_cvt; ++a) q[a] = __ldg(D.Wt + (size_t)a * D.ldv + i);
+  q[n_cvt] = __ldg(D.y + i);
+  double *row = A + (size_t)i * ncol;
+  if (b == nblocks) {
+    for (int a = 0; a < nq; ++a) row[(size_t)nblocks * 2 * nq + a] = q[a];
+    return;
+  }
+  const int r = b < J0 ? b : x0 + (b - J0);
+  const double h = __ldg(H + (size_t)r * D.n_c + i);
+  for (int a = 0; a < nq; ++a) { row[((size_t)b * 2) * nq + a] = h * q[a]; row[((size_t)b * 2 + 1) * nq + a] = h * h * q[a]; }
+}
+}  // namespace gb
+cudaError_t gb::launch_lmm_acols(int n_cvt, const LmmConst &D, const double *H, int J0, int x0, int nblocks, double *A, int ncol, cudaStream_t st) {
+  dim3 grid((D.n + 255) / 256, nblocks + 1);
+  lmm_acols_kernel<<<grid, 256, 0, st>>>(D, n_cvt, H, J0, x0, nblocks, A, ncol);
   return cudaGetLastError();
 }

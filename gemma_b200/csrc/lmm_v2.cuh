@@ -325,6 +325,7 @@ template <int NC>
 struct V2CAcc {
   double X[V2_NSC][2][NC + 2];     // sum h^k v_q x  for q over (w_1..w_c, x, y), k = 1, 2
   double I[NC + 2];                // unit-weight sums (the Iab table of LogRL_f)
+  double dl[NC + 1];               // exact minus projected order-1 sums at the l_mle_null row (when the exact linear sums are on)
 };
 
 template <int NC>
@@ -350,7 +351,8 @@ __device__ __forceinline__ void v2_issue_common(const LmmConst &D, const double 
 
 template <int NC, bool WITH_I>
 __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
-                                               bool active, const int (&jrow)[V2_NSC], V2CAcc<NC> &acc, unsigned int &pipe_it) {
+                                               bool active, const int (&jrow)[V2_NSC], V2CAcc<NC> &acc, unsigned int &pipe_it,
+                                               const double *xs = nullptr, int jscore = -1) {
   constexpr int NQ = NC + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t stage_d = v2_stage_doubles(NC);
@@ -446,6 +448,31 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
       if (WITH_I) acc.I[q] = warp_allsum(acc.I[q]);
 #pragma unroll
       for (int s = 0; s < V2_NSC; ++s) { acc.X[s][0][q] = warp_allsum(acc.X[s][0][q]); acc.X[s][1][q] = warp_allsum(acc.X[s][1][q]); }
+    }
+    if (xs) {
+      // the sums LINEAR in x come from the side GEMM in genotype space (LmmConst::xsum); the pass keeps its own value only for x'x
+#pragma unroll
+      for (int s = 0; s < V2_NSC; ++s) {
+        const int b = jrow[s] < D.n_common ? jrow[s] : jrow[s] - (D.xsum_nblocks_skip);
+        const double *e = xs + (size_t)b * 2 * (NC + 1);
+        if (jrow[s] == jscore) {
+#pragma unroll
+          for (int a = 0; a < NC; ++a) acc.dl[a] = __ldg(e + a) - acc.X[s][0][a];
+          acc.dl[NC] = __ldg(e + NC) - acc.X[s][0][NC + 1];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int a = 0; a < NC; ++a) acc.X[s][k][a] = __ldg(e + k * (NC + 1) + a);
+          acc.X[s][k][NC + 1] = __ldg(e + k * (NC + 1) + NC);
+        }
+      }
+      if (WITH_I) {
+        const double *e = xs + (size_t)D.xsum_nblocks * 2 * (NC + 1);
+#pragma unroll
+        for (int a = 0; a < NC; ++a) acc.I[a] = __ldg(e + a);
+        acc.I[NC + 1] = __ldg(e + NC);
+      }
     }
   }
 }
@@ -871,7 +898,7 @@ __device__ __forceinline__ double v2_table_logdet(const LmmConst &D, double lam,
 template <int NC>
 __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmParams &prm, const double *const *xrows,
                                                  double *smem, int nchunks, int pad, bool valid, gb200_sumstat &out, unsigned int &pipe_it,
-                                                 const double *xe = nullptr) {
+                                                 const double *xe = nullptr, const double *xs = nullptr) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2;
   const int mode = prm.a_mode;
   const bool needR = (mode == 1 || mode == 4), needL = (mode == 2 || mode == 4 || mode == 9);
@@ -904,7 +931,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
     // ---- hoisted passes: every lambda shared by all SNPs (grid 0..n_region, exactly l_max, l_mle_null), V2_NSC at a time
     constexpr int CS = v2c_stride(NC), CN = v2c_nidx(NC);
     const int n_grid = need_search ? n_region + 2 : 0;
-    const bool comp = (xe != nullptr) && prm.l_mle_null > 0.0;       // the slot at l_mle_null also serves the exact-sum correction
+    const bool comp = (xe != nullptr || xs != nullptr) && prm.l_mle_null > 0.0;       // the slot at l_mle_null also serves the exact-sum correction
     const int nslots = n_grid + ((needS || comp) ? 1 : 0);
     const int j_score = n_region + 2;
     double S1[NIDX], S2[NIDX];
@@ -917,8 +944,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       }
       V2CAcc<NC> acc;
       const bool with_I = (s0 == 0) && need_search;
-      if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it);
-      else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it);
+      if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score);
+      else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score);
       if (valid) {
         tallyc += V2_NSC;
         if (with_I) {
@@ -946,7 +973,11 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
               fRmax = ev.fR; fLmax = ev.fL;
               wmaxP[0] = ev.P_xx; wmaxP[1] = ev.P_xy; wmaxP[2] = ev.P_yy; wmaxP[3] = ev.Px_yy; have_bound = true;
             } else {                                               // the slot at l_mle_null
-              if (comp) {
+              if (comp && xs) {                                   // the pass has already put the exact sums in place and kept the difference
+#pragma unroll
+                for (int a = 0; a <= NC; ++a) dlt[a] = acc.dl[a];
+                have_dlt = true;
+              } else if (comp) {
 #pragma unroll
                 for (int a = 0; a < NC; ++a) { const double e = __ldg(xe + a); dlt[a] = e - acc.X[s][0][a]; S1[abidx(a, NC, NC + 2)] = e; }
                 const double ey = __ldg(xe + NC);
@@ -1044,7 +1075,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
 #pragma unroll
           for (int s2 = 0; s2 < V2_NSC; ++s2) jrow[s2] = D.n_common + n_region * V2_CM + g * M + p0 + s2;   // x-node rows follow the table-node rows
           V2CAcc<NC> acc;
-          v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it);
+          v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it, xs, -1);
           if (due) {
             tallyc += V2_NSC;
             __syncwarp();
