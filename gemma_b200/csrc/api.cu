@@ -89,7 +89,7 @@ void gb200_destroy(gb200_ctx *c) {
                         &c->dBed, &c->dMask, &c->dIdx, &c->dTicket, &c->dTmp, &c->i8.slices, &c->i8.scale, &c->i8.wave_ctr,
                         &c->i8.geno, &c->i8.miss_mean, &c->i8.kin_zt, &c->i8.kin_stats, &c->i8.kin_a, &c->i8.kin_tiles,
                         &c->i8.kin_qbits, &c->i8.kin_y, &c->dWtx, &c->dEnv, &c->dX2, &c->dFlip, &c->dLmW, &c->dLmY,
-                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam, &c->dVnull, &c->i8.xex, &c->i8.xs_V, &c->i8.xs_planes, &c->i8.xs_scale, &c->i8.xs_out};
+                        &c->dLmSmall, &c->dMvY, &c->dMvNull, &c->dMvOut, &c->dHrows, &c->dCtab, &c->dCheb, &c->dNodeLam, &c->dVnull, &c->i8.xex, &c->i8.xs_V, &c->i8.xs_planes, &c->i8.xs_scale, &c->i8.xs_out, &c->i8.xs_patch_idx};
   for (auto b : bufs) b->release();
   if (c->i8.tmap_a) free(c->i8.tmap_a);
   if (c->i8.tmap_b) free(c->i8.tmap_b);
@@ -702,11 +702,27 @@ static int lmm_ensure_common(gb200_ctx *c, CommonInfo &ci) {
   if (c->x_exact == 2 && n_nodes && c->dU.p && !c->overlap && !c->mv_ready && c->n >= 1024 && c->utx_path != 1) {
     const int M = lmm_cheb_nodes(), XM = lmm_cheb_xnodes();
     const int nq = (int)c->n_cvt + 1, nblocks = (int)J0 + c->prm.n_region * XM, x0 = (int)J0 + c->prm.n_region * M;
-    const int ncol = nblocks * 2 * nq + nq;
+    // eigenvectors with a coherent plane rounding: the null ones (constant vector of a centred K) and the 32 leading ones (population
+    // structure: near piecewise-constant); their U^T x entries come exactly from the side GEMM as well
+    std::vector<double> ev(c->n);
+    GB_CUDA(c, cudaMemcpyAsync(ev.data(), c->dEval.p, c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<int> pidx;
+    for (size_t i = 0; i < c->n && ev[i] == 0.0; ++i) pidx.push_back((int)i);
+    const bool too_many_null = pidx.size() > 64;
+    for (size_t k = 0; k < 32 && k < c->n; ++k) { const int i = (int)(c->n - 1 - k); if (ev[i] != 0.0) pidx.push_back(i); }
+    const int npatch = (int)pidx.size(), patch0 = nblocks * 2 * nq + nq;
+    const int ncol = patch0 + npatch;
+    if (!too_many_null) {
+    GB_CUDA(c, c->i8.xs_patch_idx.reserve(npatch * sizeof(int)));
+    GB_CUDA(c, cudaMemcpyAsync(c->i8.xs_patch_idx.p, pidx.data(), npatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    GB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->i8.xs_npatch = npatch; c->i8.xs_patch0 = patch0;
     gb::DevBuf dA;
     GB_CUDA(c, dA.reserve(c->n * (size_t)ncol * sizeof(double)));
     GB_CUDA(c, c->i8.xs_V.reserve(c->n * (size_t)ncol * sizeof(double)));
-    GB_CUDA(c, launch_lmm_acols((int)c->n_cvt, D, c->dHrows.as<double>(), (int)J0, x0, nblocks, dA.as<double>(), ncol, c->stream));
+    GB_CUDA(c, launch_lmm_acols((int)c->n_cvt, D, c->dHrows.as<double>(), (int)J0, x0, nblocks, dA.as<double>(), ncol,
+                                c->i8.xs_patch_idx.as<int>(), npatch, patch0, c->stream));
     GB_CUDA(c, launch_dgemm(c->n, (size_t)ncol, c->n, 1.0, c->dU.as<double>(), c->n, 1, dA.as<double>(), (size_t)ncol, 1, 0.0,
                             c->i8.xs_V.as<double>(), (size_t)ncol, false, c->stream));
     GB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -714,6 +730,7 @@ static int lmm_ensure_common(gb200_ctx *c, CommonInfo &ci) {
     const int rc = i8_xsum_prepare(c, ncol);
     if (rc) return rc;
     c->xs_nblocks = nblocks; c->xs_skip = c->prm.n_region * M;
+    }
   }
   c->i8.auto_T = 0; c->i8.ready = false;             // the plane count depends on whether the exact linear sums are on
   GB_CUDA(c, cudaStreamSynchronize(c->stream));       // the tests may run on a side stream

@@ -50,6 +50,7 @@ struct I8State {
   DevBuf xs_V, xs_planes, xs_scale, xs_out;
   void *tmap_v = nullptr;
   int xs_ncol = 0, xs_T = 0, xs_NE = 0, xs_groups = 0;
+  DevBuf xs_patch_idx; int xs_npatch = 0, xs_patch0 = 0;   // eigenvector indices whose U^T x entries are overwritten by exact values (columns xs_patch0.. of the side GEMM)
   size_t xs_ld = 0;
   bool xs_ready = false, xs_valid = false;
   const double *xs_for = nullptr; size_t xs_l = 0;
@@ -227,7 +228,8 @@ cudaError_t launch_lm(const double *X, size_t l, int n, int n_cvt, const double 
 cudaError_t launch_lmm_common(int n_cvt, const LmmConst &D, const LmmParams &prm, double *H, double *ctab, const double *node_lams,
                               int n_nodes, double *cheb, cudaStream_t st);
 cudaError_t launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const double *U, double *scratch, double *v, cudaStream_t st);
-cudaError_t launch_lmm_acols(int n_cvt, const LmmConst &D, const double *H, int J0, int x0, int nblocks, double *A, int ncol, cudaStream_t st);
+cudaError_t launch_lmm_acols(int n_cvt, const LmmConst &D, const double *H, int J0, int x0, int nblocks, double *A, int ncol,
+                             const int *patch_idx, int npatch, int patch0, cudaStream_t st);
 int lmm_cheb_nodes();
 int lmm_cheb_xnodes();
 size_t lmm_cheb_doubles(int n_cvt, int n_region);

@@ -1023,6 +1023,15 @@ int i8_prepare(gb200_ctx *c) {
   return GB200_OK;
 }
 
+// U^T x entries of the eigenvectors listed in idx <- their exact values from the side GEMM (columns col0.. of xs)
+__global__ void xs_patch_kernel(const double *__restrict__ xs, size_t ld, int col0, const int *__restrict__ idx, int npatch, int l,
+                                double *__restrict__ UtXt, size_t ldu) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= l * npatch) return;
+  const int s = t / npatch, k = t - s * npatch;
+  UtXt[(size_t)s * ldu + (size_t)__ldg(idx + k)] = xs[(size_t)s * ld + col0 + k];
+}
+
 // Digit planes (6) and tensor map of the exact-sum vectors V (n individuals x ncol, row-major in c->i8.xs_V): the side GEMM G . V of
 // every int8-projected batch gives the sums linear in x at all hoisted lambdas (LmmConst::xsum).
 int i8_xsum_prepare(gb200_ctx *c, int ncol) {
@@ -1182,6 +1191,11 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
       GB_CUDA(c, cudaGetLastError());
       miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean, nmiss, UtXt_dev, c->n_c, sw);
       GB_CUDA(c, cudaGetLastError());
+      if (want_xsum && c->i8.xs_npatch > 0) {
+        xs_patch_kernel<<<(unsigned)((l * (size_t)c->i8.xs_npatch + 255) / 256), 256, 0, c->stream>>>(c->i8.xs_out.as<double>(), c->i8.xs_ld, c->i8.xs_patch0,
+            c->i8.xs_patch_idx.as<int>(), c->i8.xs_npatch, (int)l, UtXt_dev, c->n_c);
+        GB_CUDA(c, cudaGetLastError());
+      }
       return GB200_OK;
     }
   } else {
@@ -1199,6 +1213,11 @@ int i8_project_bed(gb200_ctx *c, const unsigned char *bed_dev, const int *idx_de
   miss_fix_kernel<<<(unsigned)l, 256, 0, c->stream>>>(bed_dev, bytes_per_snp, idx_dev, g.n, c->dU.as<double>(), mean,
                                                       nmiss, UtXt_dev, c->n_c, nullptr);
   GB_CUDA(c, cudaGetLastError());
+  if (want_xsum && c->i8.xs_npatch > 0) {
+    xs_patch_kernel<<<(unsigned)((l * (size_t)c->i8.xs_npatch + 255) / 256), 256, 0, c->stream>>>(c->i8.xs_out.as<double>(), c->i8.xs_ld, c->i8.xs_patch0,
+        c->i8.xs_patch_idx.as<int>(), c->i8.xs_npatch, (int)l, UtXt_dev, c->n_c);
+    GB_CUDA(c, cudaGetLastError());
+  }
   return GB200_OK;
 }
 

@@ -481,11 +481,17 @@ cudaError_t gb::launch_lmm_vnull(int n_cvt, const LmmConst &D, double lam, const
 // block b: the shared rows 0..J0-1 of Hrows, then the x-node rows (which start at row x0); last block: unit weights.
 namespace gb {
 __global__ void __launch_bounds__(256) lmm_acols_kernel(LmmConst D, int n_cvt, const double *__restrict__ H, int J0, int x0, int nblocks,
-                                                        double *__restrict__ A, int ncol) {
+                                                        double *__restrict__ A, int ncol, const int *__restrict__ patch_idx, int npatch, int patch0) {
   const int i = blockIdx.x * 256 + threadIdx.x;            // individual (eigen-coordinate)
-  const int b = blockIdx.y;                                // block; b == nblocks: unit weights
+  const int b = blockIdx.y;                                // block; b == nblocks: unit weights (+ the one-hot columns of the patched eigenvectors)
   if (i >= D.n) return;
   const int nq = n_cvt + 1;
+  if (b == nblocks) {
+    // columns [patch0, patch0 + npatch): e_{idx}: V = U A then carries eigenvector idx itself -> exact U^T x entries for the null and
+    // the leading eigenvectors (their digit-plane rounding is coherent across individuals: constant / piecewise-constant vectors)
+    double *r0 = A + (size_t)i * ncol;
+    for (int k = 0; k < npatch; ++k) r0[patch0 + k] = (__ldg(patch_idx + k) == i) ? 1.0 : 0.0;
+  }
   double q[GB200_MAX_CVT + 1];
   for (int a = 0; a < n_cvt; ++a) q[a] = __ldg(D.Wt + (size_t)a * D.ldv + i);
   q[n_cvt] = __ldg(D.y + i);
@@ -499,8 +505,9 @@ __global__ void __launch_bounds__(256) lmm_acols_kernel(LmmConst D, int n_cvt, c
   for (int a = 0; a < nq; ++a) { row[((size_t)b * 2) * nq + a] = h * q[a]; row[((size_t)b * 2 + 1) * nq + a] = h * h * q[a]; }
 }
 }  // namespace gb
-cudaError_t gb::launch_lmm_acols(int n_cvt, const LmmConst &D, const double *H, int J0, int x0, int nblocks, double *A, int ncol, cudaStream_t st) {
+cudaError_t gb::launch_lmm_acols(int n_cvt, const LmmConst &D, const double *H, int J0, int x0, int nblocks, double *A, int ncol,
+                                 const int *patch_idx, int npatch, int patch0, cudaStream_t st) {
   dim3 grid((D.n + 255) / 256, nblocks + 1);
-  lmm_acols_kernel<<<grid, 256, 0, st>>>(D, n_cvt, H, J0, x0, nblocks, A, ncol);
+  lmm_acols_kernel<<<grid, 256, 0, st>>>(D, n_cvt, H, J0, x0, nblocks, A, ncol, patch_idx, npatch, patch0);
   return cudaGetLastError();
 }
