@@ -445,7 +445,7 @@ static int lmm_upload_common(gb200_ctx *c, size_t n, size_t n_cvt, const double 
   if (n_cvt > GB200_MAX_CVT)
     return set_err(c, GB200_ERR_UNSUPPORTED, "gb200_lmm_setup: n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup: need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->i8.xs_ready = false; c->common_ready = false; c->gxe_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->i8.xs_ready = false; c->i8.no_xsum_consumer = false; c->common_ready = false; c->gxe_ready = false;
   c->mask_host.clear();                           // the cached gather index belongs to the previous n
   const size_t n_c = round_up(n, 512);            // vectors and U^T x rows are zero-padded to the pipeline chunk
   c->dUtXt.release(); c->dUtXt2.release();        // row pitch changes with n: force fresh zeroed buffers
@@ -518,7 +518,7 @@ int gb200_lmm_setup_rotated_dev(gb200_ctx *c, size_t n, size_t n_cvt, const doub
     return set_err(c, GB200_ERR_ARG, "gb200_lmm_setup_rotated_dev: bad argument");
   if (n_cvt > GB200_MAX_CVT) return set_err(c, GB200_ERR_UNSUPPORTED, "n_cvt exceeds GB200_MAX_CVT");
   if (n_cvt + 1 >= n) return set_err(c, GB200_ERR_ARG, "need n > n_cvt + 1");
-  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->i8.xs_ready = false; c->common_ready = false; c->gxe_ready = false;
+  c->lmm_ready = false; c->i8.ready = false; c->i8.auto_T = 0; c->i8.xs_ready = false; c->i8.no_xsum_consumer = false; c->common_ready = false; c->gxe_ready = false;
   c->mask_host.clear();
   const size_t n_c = round_up(n, 512);
   c->dUtXt.release(); c->dUtXt2.release();

@@ -53,6 +53,7 @@ struct I8State {
   DevBuf xs_patch_idx; int xs_npatch = 0, xs_patch0 = 0;   // eigenvector indices whose U^T x entries are overwritten by exact values (columns xs_patch0.. of the side GEMM)
   size_t xs_ld = 0;
   bool xs_ready = false, xs_valid = false;
+  bool no_xsum_consumer = false;   // set by a projection that does not produce the exact sums (dosage rows): the plane count then stays >= 4
   const double *xs_for = nullptr; size_t xs_l = 0;
   DevBuf xex;                    // exact order-1 x-sums of the batch last projected by i8_project_bed (l x (n_cvt + 1)); valid flag below
   bool xex_valid = false;

@@ -992,6 +992,7 @@ int i8_effective_planes(gb200_ctx *c, int *T_out) {
     c->i8.auto_T = i8_choose_planes(m, c->n, c->i8.xs_ready && c->x_exact == 2);
   }
   *T_out = c->i8.auto_T;
+  if (c->i8.no_xsum_consumer && *T_out < 4) *T_out = 4;     // a consumer without the exact linear sums (dosage rows) has used this context
   return GB200_OK;
 }
 
@@ -1358,6 +1359,7 @@ __global__ void __launch_bounds__(256) geno_combine_kernel(const double *__restr
 // G_dev: l x n SNP-major doubles (ld ldg), NaN = missing.  *taken = false (and nothing written) when a value is not a short decimal.
 int i8_project_geno(gb200_ctx *c, const double *G_dev, size_t l, size_t ldg, double *UtXt_dev, bool *taken) {
   *taken = false;
+  c->i8.no_xsum_consumer = true;      // these rows get no exact linear sums from the side GEMM: at least 4 planes from now on
   int rc = i8_prepare(c);
   if (rc) return rc;
   const I8Geom g = make_geom(c->n, c->i8.n_slices);

@@ -20,12 +20,14 @@ def default_planes(n):
     return min(8, max(4, 1 + int(math.ceil(math.log2(need) / 8.0))))
 
 
-def choose_planes(colmax_max, n):
-    """i8_choose_planes: the same bound with the measured largest column maximum, target 2^-29; at least 5 planes below n = 8192."""
+def choose_planes(colmax_max, n, linear_sums_exact=False):
+    """i8_choose_planes: the same bound with the measured largest column maximum, target 2^-29; at least 5 planes below n = 8192.
+    With the exact linear x-sums of the side GEMM (LmmConst::xsum) the projected values only feed sums quadratic in x: target 2^-21,
+    at least 3 planes."""
     if not (colmax_max > 0 and math.isfinite(colmax_max)):
         return 4
-    need = colmax_max * math.sqrt(n if n > 1 else 2) / (math.sqrt(12.0) * TOP) * 2.0 ** 29
-    T = min(8, max(4, 1 + int(math.ceil(math.log2(need) / 8.0))))
+    need = colmax_max * math.sqrt(n if n > 1 else 2) / (math.sqrt(12.0) * TOP) * 2.0 ** (21 if linear_sums_exact else 29)
+    T = min(8, max(3 if linear_sums_exact else 4, 1 + int(math.ceil(math.log2(need) / 8.0))))
     return max(T, 5) if n < 8192 else T
 
 

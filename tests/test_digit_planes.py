@@ -26,6 +26,11 @@ def test_plane_count_rules():
         assert P.choose_planes(np.sqrt(4 * np.log(n) / n), n) == 4
         assert P.choose_planes(13.5 / np.sqrt(n), n) == 4 and P.choose_planes(14.2 / np.sqrt(n), n) == 5
         assert P.choose_planes(1.0, n) == 5
+    # with the exact linear x-sums (side GEMM) the projection only feeds sums quadratic in x: 3 planes for delocalised eigenvectors
+    for n in (10000, 50000):
+        assert P.choose_planes(np.sqrt(4 * np.log(n) / n), n, linear_sums_exact=True) == 3
+        assert P.choose_planes(1.0, n, linear_sums_exact=True) == 4
+    assert P.choose_planes(0.05, 4000, linear_sums_exact=True) == 5
     q = _orthogonal(400, 1)
     assert P.choose_planes(np.abs(q).max(), 400) == 5 and P.choose_planes(np.abs(q).max() * np.sqrt(400 / 8192), 8192) == 4
     assert P.choose_planes(0.0, 400) == 4
