@@ -349,7 +349,9 @@ __device__ __forceinline__ void v2_issue_common(const LmmConst &D, const double 
   for (int s = 0; s < V2_NSC; ++s) v2_bulk_load(hs + s * V2_CHUNK, D.Hrows + (size_t)jrow[s] * D.n_c + off0, ROW, bar);
 }
 
-template <int NC, bool WITH_I>
+// XONLY: the sums linear in x come from the side GEMM (LmmConst::xsum), the pass only accumulates x'x per lambda and power
+// (3 FP64 operations per individual and slot instead of 7; no covariate / phenotype operands)
+template <int NC, bool WITH_I, bool XONLY = false>
 __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *const *xrows, double *smem, int nchunks,
                                                bool active, const int (&jrow)[V2_NSC], V2CAcc<NC> &acc, unsigned int &pipe_it,
                                                const double *xs = nullptr, int jscore = -1) {
@@ -392,10 +394,13 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
       const double *hl = st + (NC + 2 + V2_WARPS) * V2_CHUNK + lane;
       // register double buffer: the 8 + NC shared-memory values of individual u + 1 are requested before the 38 FP64 operations of
       // individual u (the h loads sat directly in front of their first use: `short scoreboard` was 17 % of the stall samples)
-      double cx, cw[NC], cy, ch[V2_NSC];
-      cx = xl[0]; cy = sl[(NC + 1) * V2_CHUNK];
+      double cx, cw[NC], cy = 0.0, ch[V2_NSC];
+      cx = xl[0];
+      if (!XONLY) {
+        cy = sl[(NC + 1) * V2_CHUNK];
 #pragma unroll
-      for (int a = 0; a < NC; ++a) cw[a] = sl[(a + 1) * V2_CHUNK];
+        for (int a = 0; a < NC; ++a) cw[a] = sl[(a + 1) * V2_CHUNK];
+      }
 #pragma unroll
       for (int s = 0; s < V2_NSC; ++s) ch[s] = hl[s * V2_CHUNK];
 #pragma unroll
@@ -403,36 +408,54 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
         double nx = 0.0, nw[NC], ny = 0.0, nh[V2_NSC];
         if (u + 1 < V2_CHUNK / 32) {
           const int j = (u + 1) * 32;
-          nx = xl[j]; ny = sl[(NC + 1) * V2_CHUNK + j];
+          nx = xl[j];
+          if (!XONLY) {
+            ny = sl[(NC + 1) * V2_CHUNK + j];
 #pragma unroll
-          for (int a = 0; a < NC; ++a) nw[a] = sl[(a + 1) * V2_CHUNK + j];
+            for (int a = 0; a < NC; ++a) nw[a] = sl[(a + 1) * V2_CHUNK + j];
+          }
 #pragma unroll
           for (int s = 0; s < V2_NSC; ++s) nh[s] = hl[s * V2_CHUNK + j];
         }
         const double x = cx;
-        double px[NQ];
+        if (XONLY) {
+          const double xx = x * x;
+          if (WITH_I) acc.I[NC] += xx;
 #pragma unroll
-        for (int a = 0; a < NC; ++a) px[a] = cw[a] * x;
-        px[NC] = x * x;
-        px[NC + 1] = x * cy;
-        if (WITH_I) {
+          for (int s = 0; s < V2_NSC; ++s) {
+            const double h = ch[s];
+            const double hx = h * xx;
+            acc.X[s][0][NC] += hx;
+            acc.X[s][1][NC] = fma(h, hx, acc.X[s][1][NC]);
+          }
+        } else {
+          double px[NQ];
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) acc.I[q] += px[q];
-        }
+          for (int a = 0; a < NC; ++a) px[a] = cw[a] * x;
+          px[NC] = x * x;
+          px[NC + 1] = x * cy;
+          if (WITH_I) {
 #pragma unroll
-        for (int s = 0; s < V2_NSC; ++s) {
-          const double h = ch[s];
-          const double h2 = h * h;
+            for (int q = 0; q < NQ; ++q) acc.I[q] += px[q];
+          }
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) {
-            acc.X[s][0][q] = fma(h, px[q], acc.X[s][0][q]);
-            acc.X[s][1][q] = fma(h2, px[q], acc.X[s][1][q]);
+          for (int s = 0; s < V2_NSC; ++s) {
+            const double h = ch[s];
+            const double h2 = h * h;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              acc.X[s][0][q] = fma(h, px[q], acc.X[s][0][q]);
+              acc.X[s][1][q] = fma(h2, px[q], acc.X[s][1][q]);
+            }
           }
         }
         if (u + 1 < V2_CHUNK / 32) {
-          cx = nx; cy = ny;
+          cx = nx;
+          if (!XONLY) {
+            cy = ny;
 #pragma unroll
-          for (int a = 0; a < NC; ++a) cw[a] = nw[a];
+            for (int a = 0; a < NC; ++a) cw[a] = nw[a];
+          }
 #pragma unroll
           for (int s = 0; s < V2_NSC; ++s) ch[s] = nh[s];
         }
@@ -445,6 +468,7 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
   if (active) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
+      if (XONLY && q != NC) continue;                       // only x'x was accumulated; the linear sums are filled in below
       if (WITH_I) acc.I[q] = warp_allsum(acc.I[q]);
 #pragma unroll
       for (int s = 0; s < V2_NSC; ++s) { acc.X[s][0][q] = warp_allsum(acc.X[s][0][q]); acc.X[s][1][q] = warp_allsum(acc.X[s][1][q]); }
@@ -455,11 +479,6 @@ __device__ __forceinline__ void v2_pass_common(const LmmConst &D, const double *
       for (int s = 0; s < V2_NSC; ++s) {
         const int b = jrow[s] < D.n_common ? jrow[s] : jrow[s] - (D.xsum_nblocks_skip);
         const double *e = xs + (size_t)b * 2 * (NC + 1);
-        if (jrow[s] == jscore) {
-#pragma unroll
-          for (int a = 0; a < NC; ++a) acc.dl[a] = __ldg(e + a) - acc.X[s][0][a];
-          acc.dl[NC] = __ldg(e + NC) - acc.X[s][0][NC + 1];
-        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
 #pragma unroll
@@ -543,6 +562,9 @@ struct V2Fn {
   RootState rs;
   // f-evaluation cache for the Wald test
   double cache_lam, cP_xx, cP_xy, cP_yy, cPx_yy;
+  // order-1 sums linear in x (w_1 x .. w_c x, x y) at the last f-evaluation (cX) and at the estimate kept so far (bX), taken from the
+  // interpolants of the EXACT node values when LmmConst::xsum is on: the final exact pass uses them instead of its own projected sums
+  double cX[4], bX[4];
 };
 
 struct V2Req { bool need; double lam; int K; bool logdet; bool ext; double ld_ext; };   // ext: f wanted with sum log(l d + 1) supplied (ld_ext, from the run's table) instead of accumulated
@@ -552,6 +574,8 @@ __device__ __forceinline__ void v2fn_init(V2Fn &F) {
   F.rs.l = F.rs.l_temp = 0.0; F.rs.lambda = nan(""); F.rs.logf = nan("");
   F.rs.have = F.rs.aborted = F.rs.stopped = false;
   F.cache_lam = nan("");
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { F.cX[a] = nan(""); F.bX[a] = nan(""); }
 }
 
 // Advance until an evaluation is required (returns req.need) or the interval list is exhausted.
@@ -771,7 +795,7 @@ __device__ __forceinline__ void v2_assemble_arr(const double (&C)[(NC + 2) * (NC
 // all sums at lambda from the interpolants of interval g; coef = this warp's x-sum coefficients (shared memory)
 template <int NC, int ORD>
 __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coef, int g, double tau, double dtau_dt, double lam,
-                                            double n, bool want_f, double logdetI, const double *dlt, V2Eval &ev) {
+                                            double n, bool want_f, double logdetI, const double *dlt, V2Eval &ev, double *xlin = nullptr) {
   constexpr int NQ = NC + 2, NIDX = (NC + 3) * (NC + 2) / 2, CN = v2c_nidx(NC), M = V2_CM, XM = V2_XM;
   const double *gc = D.cheb + V2_CHEB_BASE + (size_t)g * (2 * CN + 3) * M;
   double X1[NQ], X2[NQ], X3[NQ], C1[CN], C2[CN], C3[CN];
@@ -780,6 +804,11 @@ __device__ __noinline__ void v2_interp_eval(const LmmConst &D, const double *coe
     X1[q] = v2_cheb_val<false, XM>(coef + q * XM, tau);
     X2[q] = v2_cheb_val<false, XM>(coef + (NQ + q) * XM, tau);
     X3[q] = (ORD >= 3) ? fma(0.5 * dtau_dt, v2_cheb_der<false, XM>(coef + (NQ + q) * XM, tau), X2[q]) : 0.0;
+  }
+  if (xlin) {
+#pragma unroll
+    for (int a = 0; a < NC; ++a) xlin[a] = X1[a];
+    xlin[NC] = X1[NC + 1];
   }
   if (dlt && want_f) {           // final f / Wald tables: exact-minus-projected x-sums (LmmConst::xex), order 1 only
 #pragma unroll
@@ -809,13 +838,18 @@ __device__ __forceinline__ bool v2_drive(const LmmConst &D, V2Fn &F, bool fnR, c
                                          double n, double logdetI, const double *dlt, double (&evv)[3], V2Req &rq) {
   const double dtau_dt = 2.0 / (hi - lo);
   for (;;) {
+    const double prev_lambda = F.rs.lambda; const bool prev_have = F.rs.have;
     v2fn_advance(F, glam, gd1, n_region, l_min, l_max, evv[0], evv[1], evv[2], rq, true);
+    if (F.rs.have && (!prev_have || F.rs.lambda != prev_lambda)) {      // the candidate of the last f-evaluation is the estimate kept so far
+#pragma unroll
+      for (int a = 0; a < 4; ++a) F.bX[a] = F.cX[a];
+    }
     if (!rq.need) return false;
     const double tau = (2.0 * log(rq.lam) - (lo + hi)) / (hi - lo);
     if (!(tau >= -1.0 && tau <= 1.0)) return true;          // also catches NaN
     V2Eval ev;
-    if (rq.K >= 3) v2_interp_eval<NC, 3>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, dlt, ev);
-    else v2_interp_eval<NC, 2>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, dlt, ev);
+    if (rq.K >= 3) v2_interp_eval<NC, 3>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, dlt, ev, rq.logdet ? F.cX : nullptr);
+    else v2_interp_eval<NC, 2>(D, coef, g, tau, dtau_dt, rq.lam, n, rq.logdet, logdetI, dlt, ev, rq.logdet ? F.cX : nullptr);
     evv[0] = fnR ? ev.d1R : ev.d1L; evv[1] = fnR ? ev.d2R : ev.d2L; evv[2] = fnR ? ev.fR : ev.fL;
     if (fnR && rq.logdet) { F.cache_lam = rq.lam; F.cP_xx = ev.P_xx; F.cP_xy = ev.P_xy; F.cP_yy = ev.P_yy; F.cPx_yy = ev.Px_yy; }
     rq.need = false;
@@ -828,7 +862,7 @@ template <int NC>
 __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *const *xrows, double *smem, int nchunks, int pad,
                                               bool active, const V2Req (&rq)[2], double n, double logdetI, V2Eval (&ev)[2],
                                               unsigned int &tally2, unsigned int &tally3, unsigned int &tallyld, unsigned int &pipe_it,
-                                              const double *dlt = nullptr) {
+                                              const double *dlt = nullptr, const double *xl0 = nullptr, const double *xl1 = nullptr) {
   constexpr int NIDX = (NC + 3) * (NC + 2) / 2, NV = NC + 2;
   const int k0 = rq[0].need ? rq[0].K : 0, k1 = rq[1].need ? rq[1].K : 0;
   const int Kloc = active ? (k0 > k1 ? k0 : k1) : 0;
@@ -839,7 +873,12 @@ __device__ __noinline__ void v2_exact_pair(const LmmConst &D, const double *cons
   if (active) { if (Kloc >= 3) tally3++; else tally2++; if (any_ld) tallyld++; }
   double dummy[NIDX];
   auto fix = [&](double (&S1)[NIDX], int s2) {            // exact x-sums for the final evaluations
-    if (dlt && rq[s2].ext) {
+    const double *xl = s2 == 0 ? xl0 : xl1;
+    if (xl && rq[s2].ext) {                                // interpolated from the exact node values (LmmConst::xsum)
+#pragma unroll
+      for (int a = 0; a < NC; ++a) S1[abidx(a, NC, NV)] = xl[a];
+      S1[abidx(NC, NC + 1, NV)] = xl[NC];
+    } else if (dlt && rq[s2].ext) {
 #pragma unroll
       for (int a = 0; a < NC; ++a) S1[abidx(a, NC, NV)] += dlt[a];
       S1[abidx(NC, NC + 1, NV)] += dlt[NC];
@@ -931,7 +970,7 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
     // ---- hoisted passes: every lambda shared by all SNPs (grid 0..n_region, exactly l_max, l_mle_null), V2_NSC at a time
     constexpr int CS = v2c_stride(NC), CN = v2c_nidx(NC);
     const int n_grid = need_search ? n_region + 2 : 0;
-    const bool comp = (xe != nullptr || xs != nullptr) && prm.l_mle_null > 0.0;       // the slot at l_mle_null also serves the exact-sum correction
+    const bool comp = (xe != nullptr) && (xs == nullptr) && prm.l_mle_null > 0.0;     // the slot at l_mle_null also serves the exact-sum correction (x_exact = 1)
     const int nslots = n_grid + ((needS || comp) ? 1 : 0);
     const int j_score = n_region + 2;
     double S1[NIDX], S2[NIDX];
@@ -944,8 +983,12 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
       }
       V2CAcc<NC> acc;
       const bool with_I = (s0 == 0) && need_search;
-      if (with_I) v2_pass_common<NC, true>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score);
-      else v2_pass_common<NC, false>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score);
+      // with the exact linear sums on (CTA-uniform: D.xsum) the hoisted passes accumulate x'x only
+      const bool xonly = (D.xsum != nullptr);
+      if (with_I) { if (xonly) v2_pass_common<NC, true, true>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score);
+                    else v2_pass_common<NC, true, false>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score); }
+      else { if (xonly) v2_pass_common<NC, false, true>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score);
+             else v2_pass_common<NC, false, false>(D, xrows, smem, nchunks, valid, jrow, acc, pipe_it, xs, j_score); }
       if (valid) {
         tallyc += V2_NSC;
         if (with_I) {
@@ -973,10 +1016,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
               fRmax = ev.fR; fLmax = ev.fL;
               wmaxP[0] = ev.P_xx; wmaxP[1] = ev.P_xy; wmaxP[2] = ev.P_yy; wmaxP[3] = ev.Px_yy; have_bound = true;
             } else {                                               // the slot at l_mle_null
-              if (comp && xs) {                                   // the pass has already put the exact sums in place and kept the difference
-#pragma unroll
-                for (int a = 0; a <= NC; ++a) dlt[a] = acc.dl[a];
-                have_dlt = true;
+              if (comp && xs) {
+                // the pass has already put the exact sums in place; the final exact pass takes its linear sums from the interpolants
               } else if (comp) {
 #pragma unroll
                 for (int a = 0; a < NC; ++a) { const double e = __ldg(xe + a); dlt[a] = e - acc.X[s][0][a]; S1[abidx(a, NC, NC + 2)] = e; }
@@ -1075,7 +1116,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
 #pragma unroll
           for (int s2 = 0; s2 < V2_NSC; ++s2) jrow[s2] = D.n_common + n_region * V2_CM + g * M + p0 + s2;   // x-node rows follow the table-node rows
           V2CAcc<NC> acc;
-          v2_pass_common<NC, false>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it, xs, -1);
+          if (D.xsum != nullptr) v2_pass_common<NC, false, true>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it, xs, -1);
+          else v2_pass_common<NC, false, false>(D, xrows, smem, nchunks, due, jrow, acc, pipe_it, xs, -1);
           if (due) {
             tallyc += V2_NSC;
             __syncwarp();
@@ -1116,6 +1158,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
           if (!__syncthreads_or(blocked ? 1 : 0)) break;
           V2Eval ev[2];
           v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, blocked, rq, n, logdetI, ev, tally2, tally3, tallyld, pipe_it);
+          if (blkR && rq[0].logdet) FR.cX[0] = nan("");       // this f-evaluation did not come from the exact interpolants
+          if (blkL && rq[1].logdet) FL.cX[0] = nan("");
           if (blkR) {
             evR[0] = ev[0].d1R; evR[1] = ev[0].d2R; evR[2] = ev[0].fR;
             if (rq[0].logdet) { FR.cache_lam = rq[0].lam; FR.cP_xx = ev[0].P_xx; FR.cP_xy = ev[0].P_xy; FR.cP_yy = ev[0].P_yy; FR.cPx_yy = ev[0].Px_yy; }
@@ -1138,7 +1182,8 @@ __device__ __forceinline__ void v2_analyze_group(const LmmConst &D, const LmmPar
           rq[1].need = exL; rq[1].lam = exL ? FL.rs.lambda : 1.0; rq[1].K = 1; rq[1].logdet = false; rq[1].ext = exL;
           rq[1].ld_ext = exL ? v2_table_logdet<NC>(D, FL.rs.lambda, l_min, lambda_interval, n_region) : 0.0;
           V2Eval ev[2];
-          v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, exR || exL, rq, n, logdetI, ev, tally2, tally3, tallyld, pipe_it, have_dlt ? dlt : nullptr);
+          v2_exact_pair<NC>(D, xrows, smem, nchunks, pad, exR || exL, rq, n, logdetI, ev, tally2, tally3, tallyld, pipe_it, have_dlt ? dlt : nullptr,
+                            (xs && exR && isfinite(FR.bX[0])) ? FR.bX : nullptr, (xs && exL && isfinite(FL.bX[0])) ? FL.bX : nullptr);
           if (exR) { FR.rs.logf = ev[0].fR; FR.cache_lam = FR.rs.lambda; FR.cP_xx = ev[0].P_xx; FR.cP_xy = ev[0].P_xy; FR.cP_yy = ev[0].P_yy; FR.cPx_yy = ev[0].Px_yy; }
           if (exL) FL.rs.logf = ev[1].fL;
           rq[0].need = rq[1].need = false; rq[0].ext = rq[1].ext = false;
