@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lmm", choices=["lmm", "lmm4", "lmm1", "gk", "mv"])
-    ap.add_argument("--n", type=int, default=0, help="analysed individuals (0 = the workload's BASELINE size)")
+    ap.add_argument("--n", "--individuals", dest="n", type=int, default=0,
+                    help="analysed individuals (0 = the workload's BASELINE size); spell it --individuals under torch.distributed.run, whose own parser trips over --n")
     ap.add_argument("--batch", type=int, default=0, help="SNPs per step per GPU (0 = the workload's default)")
     ap.add_argument("--mode", type=int, default=0, help="-lmm mode (0 = the workload's: 4 for lmm, 1 for lmm1 / mv)")
     ap.add_argument("--cvt", type=int, default=1, help="covariates incl. intercept (BASELINE configs: 1); extra columns are synthetic N(0,1)")
