@@ -136,6 +136,8 @@ struct Run {
   Params P;
   vector<vector<double>> pheno; vector<vector<int>> ind_pheno;
   vector<vector<double>> cvt; vector<int> ind_cvt; size_t n_cvt = 1;
+  bool cvt_from_file = false;                       // ind_cvt still is the covariate file's indicator (not the all-ones default)
+  bool cvt_cleared = false;                         // the covariate file held constant columns only: CheckCvt emptied indicator_cvt
   vector<double> gxe; vector<int> ind_gxe;          // -gxe: ReadFile_column(file_gxe, indicator_gxe, gxe, 1), src/param.cpp:236-240
   vector<int> indicator_idv; size_t ni_total = 0, ni_test = 0;
   std::map<string, std::tuple<string, long, double>> anno;
@@ -282,24 +284,48 @@ static void process_cvt_phen(Run &R) {                 // ProcessCvtPhen + Check
       for (size_t r : rows) { mn = std::min(mn, R.cvt[r][j]); mx = std::max(mx, R.cvt[r][j]); }
       if (mn == mx) n_const++;
     }
-    if (n_const == R.n_cvt) { R.ind_cvt.clear(); R.cvt.clear(); R.n_cvt = 1; }
+    if (n_const == R.n_cvt) { R.ind_cvt.clear(); R.cvt.clear(); R.n_cvt = 1; R.cvt_cleared = true; }
     else if (n_const == 0) {
       std::cout << "no intercept term is found in the cvt file: a column of 1s is added" << std::endl;
       for (size_t r : rows) R.cvt[r].push_back(1.0);
       R.n_cvt++;
     }
   }
+  R.cvt_from_file = !R.ind_cvt.empty();
   if (R.ind_cvt.empty()) { R.cvt.assign(R.ni_total, vector<double>(1, 1.0)); R.ind_cvt.assign(R.ni_total, 1); R.n_cvt = 1; }
 }
 
-// -nind (BIMBAM only; the PLINK branch rebuilds indicator_idv afterwards, src/param.cpp:247-274): trim_individuals,
-// src/param.cpp:74-90, applied after ProcessCvtPhen (:315-316).  The vector is cut to the NUMBER of set flags seen
-// when the scan stops, i.e. the first min(#set, nind) individuals of the file, and ni_total / ni_test follow
-// (CheckData, src/param.cpp:1033-1041).
-static void trim_individuals(Run &R) {
-  if (R.P.nind <= 0 || !R.P.file_bfile.empty()) return;
+// Size trim_individuals (src/param.cpp:74-90) leaves a flag vector of `size` entries with: the NUMBER of set flags seen when the scan
+// stops (not the index it stopped at), i.e. min(#set, nind).
+static size_t trim_count(const vector<int> &v, size_t size, size_t ni_max) {
   size_t count = 0;
-  for (int v : R.indicator_idv) { if (v) count++; if (count >= (size_t)R.P.nind) break; }
+  for (size_t i = 0; i < size; ++i) { if (v[i]) count++; if (count >= ni_max) break; }
+  return count;
+}
+
+// -nind: the reference trims indicator_cvt right after reading the covariates (src/param.cpp:234), indicator_idv and indicator_cvt
+// again after ProcessCvtPhen on the BIMBAM branch only (:315-316; the PLINK branch rebuilds indicator_idv from the .fam and never
+// trims it), never indicator_gxe, and then CheckData (:1001-1014) refuses the run when the sizes disagree.  Without a covariate
+// file indicator_cvt is the all-ones vector ProcessCvtPhen builds (:2085-2092), trimmed like the rest.  Consequences reproduced here:
+// PLINK input ignores -nind unless a covariate file is given, in which case the run is refused; BIMBAM input is refused when a kept
+// covariate row is missing (the second trim shrinks the vector again) or when -nind exceeds the number of usable individuals while
+// some are unusable.  Otherwise the first min(#set, nind) individuals of the file stay and ni_total / ni_test follow (:1033-1041).
+static void trim_individuals(Run &R) {
+  if (R.P.nind <= 0) return;
+  const size_t ni_max = (size_t)R.P.nind;
+  const string cvt_msg = "number of rows in the covariates file do not match the number of individuals. ";
+  size_t cvt_size = R.ind_cvt.size();                                                  // all ones unless it came from the file
+  if (R.cvt_from_file) cvt_size = trim_count(R.ind_cvt, cvt_size, ni_max);            // :234
+  if (!R.P.file_bfile.empty()) {
+    if (R.cvt_from_file && cvt_size != R.indicator_idv.size()) die(cvt_msg + std::to_string(cvt_size));
+    return;
+  }
+  const size_t count = trim_count(R.indicator_idv, R.indicator_idv.size(), ni_max);   // :315
+  if (!R.cvt_cleared) {
+    cvt_size = trim_count(R.ind_cvt, cvt_size, ni_max);                                // :316
+    if (cvt_size != count) die(cvt_msg + std::to_string(cvt_size));
+  }
+  if (!R.ind_gxe.empty() && R.ind_gxe.size() != count) die("number of rows in the gxe file do not match the number of individuals. ");
   if (count == R.indicator_idv.size()) return;
   R.indicator_idv.resize(count); R.ni_total = count;
   R.ni_test = 0; for (int v : R.indicator_idv) R.ni_test += v;

@@ -6,6 +6,7 @@ the analysed SNPs with n_miss and af; `gemma-b200 -qc-only` must select the same
 CPU only."""
 import gzip
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -69,6 +70,12 @@ def _make_case(d, seed, plink, n=60, l=120):
     return ["-bfile", os.path.join(d, "pl")]
 
 
+def _first_error(txt):
+    m = re.findall(r"(?:error!|ERROR:)[^\n]*", txt)
+    assert m, txt[-400:]
+    return m[0].replace("ERROR: Enforce failed for ", "").split(" in /root")[0].replace("error! ", "").strip()
+
+
 def _count(txt, key):
     for ln in txt.splitlines():
         if key in ln:
@@ -77,7 +84,8 @@ def _count(txt, key):
 
 
 VARIANTS = [[], ["cvt"], ["-maf", "0.05"], ["-miss", "0.03"], ["-hwe", "0.5"], ["cvt", "-r2", "0.3"], ["-maf", "0", "-miss", "0.2"],
-            ["-notsnp"], ["cvt", "-hwe", "0.9", "-maf", "0.1"], ["-n", "2"]]
+            ["-notsnp"], ["cvt", "-hwe", "0.9", "-maf", "0.1"], ["-n", "2"],
+            ["-nind", "7"], ["-nind", "40"], ["-nind", "1000"], ["cvt", "-nind", "45"], ["cvt", "-nind", "1000"]]
 
 
 @pytest.mark.parametrize("plink", [False, True], ids=["bimbam", "plink"])
@@ -88,6 +96,7 @@ def test_qc_selection_matches_the_reference_cli(tmp_path, seed, plink):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "gemma_b200", "host")])
     d = str(tmp_path)
     base = _make_case(d, seed, plink)
+    n_refused = 0
     for k, v in enumerate(VARIANTS):
         args = base + (["-c", os.path.join(d, "cvt.txt")] if "cvt" in v else []) + [x for x in v if x != "cvt"]
         mine = subprocess.run([CLI] + args + ["-lm", "1", "-qc-only", "-o", "mine%d" % k, "-outdir", os.path.join(d, "output")],
@@ -95,9 +104,11 @@ def test_qc_selection_matches_the_reference_cli(tmp_path, seed, plink):
         try:
             out_ref = REF.run_cli(args + ["-lm", "1", "-o", "ref%d" % k], d)
         except RuntimeError as e:
-            # the reference refuses this input (a .fam file has one phenotype column: -n 2): same refusal, same message
-            assert plink and "-n" in v and mine.returncode != 0, (v, str(e)[-400:])
-            assert "phenotypes do not match geno file" in str(e) and "phenotypes do not match geno file" in mine.stdout + mine.stderr
+            # the reference refuses this input (a .fam file has one phenotype column: -n 2; -nind against covariate rows, see
+            # trim_individuals in gemma_cli.cpp): same refusal, same message
+            assert mine.returncode != 0, (v, str(e)[-400:])
+            assert _first_error(str(e)) == _first_error(mine.stdout + mine.stderr), (v, str(e)[-400:], mine.stdout[-400:])
+            n_refused += 1
             continue
         assert mine.returncode == 0, (v, mine.stdout + mine.stderr)
         for key in COUNT_KEYS:
@@ -107,4 +118,5 @@ def test_qc_selection_matches_the_reference_cli(tmp_path, seed, plink):
         assert [r[1] for r in ref_rows] == [m[0] for m in kept], v                                 # same SNPs, same order
         assert [r[3] for r in ref_rows] == [m[2] for m in kept], v                                 # n_miss
         assert [r[7] for r in ref_rows] == ["%.3f" % float(m[3]) for m in kept], v               # af as the reference prints it
-        assert len(kept) >= 10                                                                     # the case is not degenerate
+        assert len(kept) >= (10 if "-nind" not in v else 1)                                                                     # the case is not degenerate
+    assert n_refused >= 1                                  # the refusal branch is exercised (-nind 1000 with unusable individuals)
