@@ -1189,7 +1189,8 @@ int main(int argc, char **argv) {
   if (P.qc_only) {
     std::ofstream out(out_path(R, "qc"));
     for (size_t i = 0; i < R.snpInfo.size(); ++i)
-      out << R.snpInfo[i].rs << "\t" << R.indicator_snp[i] << "\t" << R.snpInfo[i].n_miss << "\t" << std::setprecision(17) << R.snpInfo[i].maf << "\n";
+      out << R.snpInfo[i].rs << "\t" << R.indicator_snp[i] << "\t" << R.snpInfo[i].n_miss << "\t" << std::setprecision(17) << R.snpInfo[i].maf
+          << "\t" << R.snpInfo[i].chr << "\t" << R.snpInfo[i].bp << "\t" << R.snpInfo[i].a_minor << "\t" << R.snpInfo[i].a_major << "\n";
     if (old) std::cout.rdbuf(old);
     return 0;
   }

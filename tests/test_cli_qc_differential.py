@@ -1,6 +1,6 @@
 """Differential test of the host side of the CLI (readers + individual / SNP QC) against the reference's
 OWN CLI (oracle/_ref/gemma_ref, the unmodified src/*.cpp) on randomised BIMBAM and PLINK inputs with the awkward cases mixed in:
-NA phenotypes / covariates, monomorphic SNPs, dosage-valued genotypes, mixed separators, SNPs collinear with a covariate, and the
+NA phenotypes / covariates, monomorphic SNPs, dosage-valued genotypes, mixed separators, a shuffled and incomplete annotation file, SNPs collinear with a covariate, and the
 -miss / -maf / -hwe / -r2 / -notsnp / -n switches.  The reference runs `-lm 1` (cheap, no kinship needed) and its assoc file lists
 the analysed SNPs with n_miss and af; `gemma-b200 -qc-only` must select the same SNPs / individuals and print the same counts.
 CPU only."""
@@ -44,8 +44,11 @@ def _make_case(d, seed, plink, n=60, l=120):
         for i in range(n):
             fo.write("1\t" + ("NA" if cvna[i] else "%.4f" % cv[i, 0]) + "\t%.4f\n" % cv[i, 1])
     with open(os.path.join(d, "anno.txt"), "w") as fo:
-        for s in range(l):
-            fo.write("rs%d, %d, %d\n" % (s, 1000 + 10 * s, 1 + s % 3))
+        for s in rng.permutation(l):                                       # shuffled, incomplete, mixed separators, non-numeric chr
+            if s % 11 == 7:
+                continue
+            sep = [", ", "\t", " ", ","][s % 4]
+            fo.write(sep.join(["rs%d" % s, "%d" % (1000 + 10 * s), ["1", "2", "X", "19"][s % 4]]) + ("" if s % 5 else sep + "0.5") + "\n")
     if not plink:
         with gzip.open(os.path.join(d, "geno.txt.gz"), "wt") as fo:
             for s in range(l):
@@ -116,6 +119,7 @@ def test_qc_selection_matches_the_reference_cli(tmp_path, seed, plink):
         ref_rows = [ln.split("\t") for ln in open(os.path.join(d, "output", "ref%d.assoc.txt" % k)).read().splitlines()[1:]]
         kept = [m for m in (ln.rstrip("\n").split("\t") for ln in open(os.path.join(d, "output", "mine%d.qc.txt" % k))) if m[1] == "1"]
         assert [r[1] for r in ref_rows] == [m[0] for m in kept], v                                 # same SNPs, same order
+        assert [[r[0], r[2], r[5], r[6]] for r in ref_rows] == [m[4:8] for m in kept], v           # chr, ps, allele1, allele0 (annotation / .bim)
         assert [r[3] for r in ref_rows] == [m[2] for m in kept], v                                 # n_miss
         assert [r[7] for r in ref_rows] == ["%.3f" % float(m[3]) for m in kept], v               # af as the reference prints it
         assert len(kept) >= (10 if "-nind" not in v else 1)                                                                     # the case is not degenerate
