@@ -1148,7 +1148,6 @@ int main(int argc, char **argv) {
         (P.a_mode >= 51 && P.a_mode <= 54)) && !P.qc_only)
     die("analysis mode not supported by gemma-b200 (only -gk 1/2, -eigen, -lmm 1/2/3/4/9, -lm 1/2/3/4)");
   if (P.p_column.empty()) P.p_column.push_back(1);                                 // src/param.cpp:635-636
-  if (P.a_mode >= 51 && (!P.file_gxe.empty() || !P.loco.empty())) die("-lm does not take -gxe / -loco");
   if (P.p_column.size() > 1 && (P.a_mode < 20 || P.a_mode >= 51) && !P.qc_only) {
     if (!(P.a_mode >= 1 && P.a_mode <= 4 && P.p_column.size() == 2)) die("multivariate analysis: only -lmm 1/2/3/4 with two phenotypes (-n a b) is supported");
     if (!P.file_gxe.empty()) die("multivariate G x E is not supported");
@@ -1161,23 +1160,26 @@ int main(int argc, char **argv) {
   mkdir(P.path_out.c_str(), 0755);                                                 // src/main.cpp:59-66
   const double t_start = now_s();
 
+  if (!P.loco.empty()) {                                                           // CheckParam, src/param.cpp:923-933
+    if (!((P.a_mode >= 1 && P.a_mode <= 4) || P.a_mode == 9 || P.a_mode == 21 || P.a_mode == 22 || (P.qc_only && P.a_mode == 0)))
+      die("LOCO only works with LMM and K");
+    if (!P.file_gxe.empty()) die("LOCO does not support GXE (yet)");
+    if (P.file_anno.empty()) die("LOCO requires annotation file (-a switch)");
+    if (!P.file_ksnps.empty()) die("LOCO does not allow -ksnps switch");
+    if (!P.file_gwasnps.empty()) die("LOCO does not allow -gwasnps switch");
+    if (!P.file_bfile.empty()) die("LOCO with PLINK input mis-aligns rows in the reference (its own tests are disabled); use BIMBAM input");
+  }
   std::cout << "Reading Files ... " << std::endl;
   if (!P.file_snps.empty()) read_snp_set(P.file_snps, R.setSnps);
   if (!P.file_ksnps.empty()) read_snp_set(P.file_ksnps, R.setKSnps);
   if (!P.file_gwasnps.empty()) read_snp_set(P.file_gwasnps, R.setGWASnps);
   if (!P.file_anno.empty()) read_anno(R);
-  if (!P.loco.empty()) {                                                           // src/param.cpp:923-933, 52-66, 497-500
-    if (P.file_anno.empty()) die("LOCO requires annotation file (-a switch)");
-    if (!P.file_ksnps.empty()) die("LOCO does not allow -ksnps switch");
-    if (!P.file_gwasnps.empty()) die("LOCO does not allow -gwasnps switch");
-    if (!P.file_bfile.empty()) die("LOCO with PLINK input mis-aligns rows in the reference (its own tests are disabled); use BIMBAM input");
+  if (!P.loco.empty())                                                             // src/param.cpp:52-66, 497-500
     for (const auto &kv : R.anno) (std::get<0>(kv.second) != P.loco ? R.setKSnps : R.setGWASnps).insert(kv.first);
-  }
   if (!P.file_bfile.empty()) { read_bim(R); read_fam(R); if (!P.file_pheno.empty()) { R.pheno.clear(); R.ind_pheno.clear(); read_pheno(R); } }
   else read_pheno(R);
   if (!P.file_cvt.empty()) read_cvt(R);
   if (!P.file_gxe.empty()) {
-    if (!P.loco.empty()) die("LOCO does not support GXE (yet)");                    // src/param.cpp:927
     read_gxe(R);
   }
   process_cvt_phen(R);

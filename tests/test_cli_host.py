@@ -80,7 +80,8 @@ def test_cli_rejects_unknown_flags_and_missing_inputs():
     # flag combinations the reference refuses (src/gemma.cpp:1125-1131, src/param.cpp:923-933) or that are outside this framework
     for argv, msg in ((["-g", "x", "-p", "y", "-gk", "-lmm", "1"], "only one of"),
                       (["-g", "x", "-p", "y", "-k", "k", "-lmm", "7"], "not supported"),
-                      (["-g", "x", "-p", "y", "-lm", "1", "-gxe", "e"], "-lm does not take"),
+                      (["-g", "x", "-p", "y", "-a", "a", "-lm", "1", "-loco", "1"], "LOCO only works with LMM and K"),
+                      (["-g", "x", "-p", "y", "-a", "a", "-k", "k", "-lmm", "1", "-loco", "1", "-gxe", "e"], "LOCO does not support GXE"),
                       (["-g", "x", "-p", "y", "-k", "k", "-n", "1", "2", "3", "-lmm", "1"], "two phenotypes"),
                       (["-g", "x", "-p", "y", "-k", "k", "-n", "1", "2", "-lmm", "1", "-gxe", "e"], "multivariate G x E"),
                       (["-p", "y", "-gk"], "need -g and -p")):
