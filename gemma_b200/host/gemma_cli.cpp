@@ -1193,6 +1193,11 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < R.snpInfo.size(); ++i)
       out << R.snpInfo[i].rs << "\t" << R.indicator_snp[i] << "\t" << R.snpInfo[i].n_miss << "\t" << std::setprecision(17) << R.snpInfo[i].maf
           << "\t" << R.snpInfo[i].chr << "\t" << R.snpInfo[i].bp << "\t" << R.snpInfo[i].a_minor << "\t" << R.snpInfo[i].a_major << "\n";
+    if (!P.file_kin.empty()) {                       // the kinship matrix of the analysed individuals exactly as read_kin hands it on
+      vector<double> G;
+      read_kin(R, G);
+      write_bin(out_path(R, "kin") + ".bin", G.data(), R.ni_test, R.ni_test);
+    }
     if (old) std::cout.rdbuf(old);
     return 0;
   }

@@ -59,6 +59,8 @@ def lib():
                                             _dp, C.c_size_t]
         L.ref_bimbam_kin.restype = C.c_int
         L.ref_bimbam_kin.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_size_t, C.c_int, C.c_size_t, _dp]
+        L.ref_read_kin.restype = C.c_int
+        L.ref_read_kin.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_char_p), C.c_int, _dp, C.c_size_t]
         L.ref_center_matrix.restype = None
         L.ref_center_matrix.argtypes = [_dp, C.c_size_t]
         _LIB = L
@@ -177,6 +179,19 @@ def bimbam_kin(path, indicator_snp, k_mode, ni_total):
     rc = lib().ref_bimbam_kin(path.encode(), isnp.ctypes.data_as(C.POINTER(C.c_int)), len(isnp), k_mode, ni_total, _p(K))
     assert rc == 0
     return K
+
+
+def read_kin(path, indicator_idv, k_mode=1, ids=None):
+    """ReadFile_kin: the kinship matrix of the analysed individuals as the reference reads it from a -km 1 / -km 2 file."""
+    idv = np.ascontiguousarray(indicator_idv, dtype=np.int32)
+    n = int(idv.sum())
+    G = np.zeros((n, n))
+    arr = None
+    if ids is not None:
+        arr = (C.c_char_p * len(ids))(*[s.encode() for s in ids])
+    rc = lib().ref_read_kin(path.encode(), idv.ctypes.data_as(C.POINTER(C.c_int)), len(idv), arr, k_mode, _p(G), n)
+    assert rc == 0
+    return G
 
 
 def center_matrix(G):

@@ -234,4 +234,19 @@ void ref_center_matrix(double *G, size_t n) {
   CenterMatrix(&v.matrix);
 }
 
+// ReadFile_kin (src/gemma_io.cpp:1186-1294): -km 1 matrix or -km 2 "id1 id2 value" list -> G (ni_test x ni_test); ids (or NULL) fill
+// mapID2num the way ReadFile_fam does (individual id -> row of the .fam file)
+int ref_read_kin(const char *file_kin, const int *indicator_idv, size_t ni_total, const char *const *ids, int k_mode, double *G, size_t ni_test) {
+  Quiet q;
+  vector<int> idv(indicator_idv, indicator_idv + ni_total);
+  map<string, int> id2num;
+  if (ids) for (size_t i = 0; i < ni_total; ++i) id2num[string(ids[i])] = (int)i;
+  gsl_matrix *mG = gsl_matrix_alloc(ni_test, ni_test);
+  bool error = false;
+  ReadFile_kin(string(file_kin), idv, id2num, (size_t)k_mode, error, mG);
+  for (size_t i = 0; i < ni_test; ++i) for (size_t j = 0; j < ni_test; ++j) G[i * ni_test + j] = gsl_matrix_get(mG, i, j);
+  gsl_matrix_free(mG);
+  return error ? -1 : 0;
+}
+
 }  // extern "C"
