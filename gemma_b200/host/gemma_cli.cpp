@@ -1197,6 +1197,14 @@ int main(int argc, char **argv) {
       vector<double> G;
       read_kin(R, G);
       write_bin(out_path(R, "kin") + ".bin", G.data(), R.ni_test, R.ni_test);
+      write_matrix(R, G.data(), R.ni_test, R.ni_test, "kin");            // and through the production text writer (WriteMatrix)
+    }
+    if (!P.file_ku.empty() && !P.file_kd.empty()) {   // -u / -d: ReadFile_eigenU / ReadFile_eigenD, then the production writers
+      vector<double> U(R.ni_test * R.ni_test), D(R.ni_test);
+      read_dense_rows(P.file_ku, U.data(), R.ni_test, R.ni_test, "U");
+      read_dense_rows(P.file_kd, D.data(), R.ni_test, 1, "D");
+      write_matrix(R, U.data(), R.ni_test, R.ni_test, "eigU");
+      write_vector(R, D.data(), R.ni_test, "eigD");
     }
     if (old) std::cout.rdbuf(old);
     return 0;

@@ -101,3 +101,28 @@ def test_kinship_readers_match_the_reference(tmp_path, seed):
     assert np.array_equal(got2, want2)
     keep = idv == 1
     assert np.allclose(want2, K[np.ix_(keep, keep)], rtol=1e-9, atol=1e-12)   # and it is the matrix that was written
+
+
+def test_matrix_and_vector_writers_are_byte_identical_to_the_reference(tmp_path):
+    """SURVEY 8 row a5 (WriteMatrix / WriteVector, src/param.cpp:1886-1935).  The reference's CLI writes .cXX.txt / .sXX.txt (-gk 1/2)
+    and .eigenU.txt / .eigenD.txt (-eigen) for a small cohort; gemma-b200 reads each file with its production readers and writes it
+    back with its production writers: the 10-significant-digit text has to come back byte for byte (reader and formatter both exact)."""
+    if not REF.available():
+        pytest.skip("compiled reference not available")
+    d = str(tmp_path)
+    n, l = 41, 150
+    base, ids, _ = _plink_case(d, n, l, 9)
+    with open(base + ".fam", "w") as f:                                      # every individual has a phenotype: complete matrices
+        for i in range(n):
+            f.write("fam%d %s 0 0 1 %.4f\n" % (i, ids[i], np.sin(i)))
+    for k_mode, suffix in ((1, "cXX"), (2, "sXX")):
+        REF.run_cli(["-bfile", base, "-gk", str(k_mode), "-o", "ref"], d)
+        ref_file = os.path.join(d, "output", "ref.%s.txt" % suffix)
+        _run(["-bfile", base, "-k", ref_file], os.path.join(d, "output"), "mine%d" % k_mode)
+        assert open(os.path.join(d, "output", "mine%d.kin.txt" % k_mode), "rb").read() == open(ref_file, "rb").read()
+    REF.run_cli(["-bfile", base, "-k", os.path.join(d, "output", "ref.cXX.txt"), "-eigen", "-o", "ref"], d)
+    fu, fd = os.path.join(d, "output", "ref.eigenU.txt"), os.path.join(d, "output", "ref.eigenD.txt")
+    _run(["-bfile", base, "-k", os.path.join(d, "output", "ref.cXX.txt"), "-u", fu, "-d", fd], os.path.join(d, "output"), "mine_e")
+    assert open(os.path.join(d, "output", "mine_e.eigU.txt"), "rb").read() == open(fu, "rb").read()
+    assert open(os.path.join(d, "output", "mine_e.eigD.txt"), "rb").read() == open(fd, "rb").read()
+    assert os.path.getsize(fu) > n * n * 5 and os.path.getsize(fd) > n * 5
