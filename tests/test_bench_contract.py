@@ -34,8 +34,12 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_under_torchrun_only_rank0_works():
     """Launched like the driver does for N > 1: rank 0 prints the line with all host threads (torch.distributed.run exports
     OMP_NUM_THREADS=1, which the arm overrides), the other rank exits 0 without output."""
+    import socket
+    with socket.socket() as sk:                                     # a port nobody holds right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29653", os.path.join(ROOT, "bench.py"), "--gpus", "2"] + ARGS
+           "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2"] + ARGS
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     d = _check_line(r.stdout, 2)
