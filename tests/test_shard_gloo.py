@@ -11,6 +11,13 @@ from gemma_b200 import shard
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return str(sk.getsockname()[1])
+
+
 def test_snp_ranges_partition_in_order():
     for n, w in ((10, 3), (0, 2), (5, 8), (5000000, 8), (17, 1)):
         r = [shard.snp_range(n, k, w) for k in range(w)]
@@ -43,7 +50,7 @@ def test_two_rank_gloo_gather_preserves_snp_order(tmp_path):
     """ % ROOT))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", _free_port(), str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert "GATHER_OK" in r.stdout, r.stdout + r.stderr
 
@@ -69,6 +76,6 @@ def test_two_rank_gloo_partial_kinship_reduce(tmp_path):
     """ % ROOT))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29572", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", _free_port(), str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert "KIN_OK" in r.stdout, r.stdout + r.stderr
