@@ -49,7 +49,7 @@ struct SnpInfo {   // SNPINFO, src/param.h:37-51
 };
 
 struct Params {
-  string file_geno, file_pheno, file_anno, file_cvt, file_bfile, file_kin, file_ku, file_kd, file_snps, file_ksnps, file_gwasnps, loco, file_gxe;
+  string file_geno, file_pheno, file_anno, file_cvt, file_bfile, file_kin, file_ku, file_kd, file_snps, file_ksnps, file_gwasnps, loco, file_gxe, file_weight;
   string path_out = "./output/", file_out = "result";
   vector<size_t> p_column;
   int a_mode = 0;            // 21/22 -gk, 31 -eigen, 1/2/3/4/9 -lmm
@@ -138,6 +138,7 @@ struct Run {
   vector<vector<double>> cvt; vector<int> ind_cvt; size_t n_cvt = 1;
   bool cvt_from_file = false;                       // ind_cvt still is the covariate file's indicator (not the all-ones default)
   bool cvt_cleared = false;                         // the covariate file held constant columns only: CheckCvt emptied indicator_cvt
+  vector<double> weight; vector<int> ind_weight;    // -widv: ReadFile_column(file_weight, indicator_weight, weight, 1), src/param.cpp:241-245
   vector<double> gxe; vector<int> ind_gxe;          // -gxe: ReadFile_column(file_gxe, indicator_gxe, gxe, 1), src/param.cpp:236-240
   vector<int> indicator_idv; size_t ni_total = 0, ni_test = 0;
   std::map<string, std::tuple<string, long, double>> anno;
@@ -187,17 +188,19 @@ static void read_cvt(Run &R) {                         // ReadFile_cvt, src/gemm
   }
 }
 
-static void read_gxe(Run &R) {                         // ReadFile_column(.., 1), src/gemma_io.cpp:344-383
-  LineReader in(R.P.file_gxe);
-  if (!in.ok()) die("fail to open phenotype file: " + R.P.file_gxe);
+static void read_column(const string &file, vector<int> &ind, vector<double> &val) {   // ReadFile_column(.., 1), src/gemma_io.cpp:344-383
+  LineReader in(file);
+  if (!in.ok()) die("fail to open phenotype file: " + file);
   string line;
   while (in.next(line)) {
     char *p = tok(&line[0]);
     if (!p) die("Problem reading PHENO column");
-    if (strcmp(p, "NA") == 0) { R.ind_gxe.push_back(0); R.gxe.push_back(-9); }
-    else { R.ind_gxe.push_back(1); R.gxe.push_back(atof(p)); }
+    if (strcmp(p, "NA") == 0) { ind.push_back(0); val.push_back(-9); }
+    else { ind.push_back(1); val.push_back(atof(p)); }
   }
 }
+static void read_gxe(Run &R) { read_column(R.P.file_gxe, R.ind_gxe, R.gxe); }
+static void read_weight(Run &R) { read_column(R.P.file_weight, R.ind_weight, R.weight); }
 
 static void read_anno(Run &R) {                        // ReadFile_anno, src/gemma_io.cpp:280-341
   LineReader in(R.P.file_anno);
@@ -274,6 +277,10 @@ static void process_cvt_phen(Run &R) {                 // ProcessCvtPhen + Check
     if (R.ind_gxe.size() != R.ni_total) die("number of rows in the gxe file do not match the number of individuals. ");
     for (size_t i = 0; i < R.ni_total; ++i) R.indicator_idv[i] *= R.ind_gxe[i];
   }
+  if (!R.ind_weight.empty()) {                         // residual weights, src/param.cpp:1015-1021, 2023-2027
+    if (R.ind_weight.size() != R.ni_total) die("number of rows in the weight file do not match the number of individuals. ");
+    for (size_t i = 0; i < R.ni_total; ++i) R.indicator_idv[i] *= R.ind_weight[i];
+  }
   R.ni_test = 0; for (int v : R.indicator_idv) R.ni_test += v;
   if (R.ni_test == 0) die("number of analyzed individuals equals 0. ");
   if (!R.ind_cvt.empty()) {
@@ -326,6 +333,7 @@ static void trim_individuals(Run &R) {
     if (cvt_size != count) die(cvt_msg + std::to_string(cvt_size));
   }
   if (!R.ind_gxe.empty() && R.ind_gxe.size() != count) die("number of rows in the gxe file do not match the number of individuals. ");
+  if (!R.ind_weight.empty() && R.ind_weight.size() != count) die("number of rows in the weight file do not match the number of individuals. ");
   if (count == R.indicator_idv.size()) return;
   R.indicator_idv.resize(count); R.ni_total = count;
   R.ni_test = 0; for (int v : R.indicator_idv) R.ni_test += v;
@@ -856,6 +864,42 @@ static void run_mvlmm(Run &R, gb200_ctx *ctx, const vector<double> &U, const vec
   }
 }
 
+// CenterMatrix (src/mathfunc.cpp:147-177) on the host, only for the -widv route (the default route centres on the device):
+// G <- G - (Gw 1' + 1 Gw')/n + (1'Gw)/n^2, upper triangle mirrored down.
+static void center_matrix_host(vector<double> &G, size_t n) {
+  vector<double> Gw(n, 0.0);
+  for (size_t i = 0; i < n; ++i) { double a = 0.0; for (size_t j = 0; j < n; ++j) a += G[i * n + j]; Gw[i] = a; }
+  double d = 0.0; for (size_t i = 0; i < n; ++i) d += Gw[i];
+  const double inv = 1.0 / (double)n, dd = d / ((double)n * (double)n);
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = i; j < n; ++j) {
+      const double v = G[i * n + j] - inv * (Gw[i] + Gw[j]) + dd;
+      G[i * n + j] = v; G[j * n + i] = v;
+    }
+}
+static double safe_sqrt_cli(double d) {              // src/mathfunc.cpp:122-131 (every d < 0.001 becomes |d|)
+  if (d < 0.001) d = std::fabs(d);
+  return std::sqrt(d);
+}
+
+// -widv residual weights (src/gemma.cpp:2594-2644): G (ni_test x ni_test, as read) is centred and G_ij /= sqrt(w_i w_j) (0 where a weight
+// is not positive); the caller eigendecomposes WITHOUT centring again and scales row i of U by sqrt(w_i).  Returns the weights of the
+// analysed individuals (CopyWeight, src/param.cpp:2130-2142).  Host loops, O(n^2).
+static vector<double> weighted_kinship(const Run &R, vector<double> &G) {
+  const size_t n = R.ni_test;
+  vector<double> w; w.reserve(n);
+  for (size_t i = 0; i < R.ni_total; ++i) if (R.indicator_idv[i] && R.ind_weight[i]) w.push_back(R.weight[i]);
+  if (w.size() != n) die("internal: weights of the analysed individuals");
+  center_matrix_host(G, n);
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = i; j < n; ++j) {
+      double d = G[i * n + j];
+      d = (w[i] <= 0 || w[j] <= 0) ? 0.0 : d / safe_sqrt_cli(w[i] * w[j]);
+      G[i * n + j] = d; G[j * n + i] = d;
+    }
+  return w;
+}
+
 // LMM branch of BatchRun (src/gemma.cpp:2556-2871) incl. -eigen
 static void run_lmm(Run &R, gb200_ctx *ctx) {
   const size_t n = R.ni_test;
@@ -866,7 +910,16 @@ static void run_lmm(Run &R, gb200_ctx *ctx) {
     vector<double> G; read_kin(R, G);
     std::cout << "Start Eigen-Decomposition..." << std::endl;
     int n_zero = 0, n_neg = 0;
-    GB(gb200_eigh(ctx, G.data(), n, n, /*center=*/1, U.data(), n, eval.data(), &R.trace_G, &n_zero, &n_neg));
+    if (R.weight.empty()) {
+      GB(gb200_eigh(ctx, G.data(), n, n, /*center=*/1, U.data(), n, eval.data(), &R.trace_G, &n_zero, &n_neg));
+    } else {
+      const vector<double> w = weighted_kinship(R, G);
+      GB(gb200_eigh(ctx, G.data(), n, n, /*center=*/0, U.data(), n, eval.data(), &R.trace_G, &n_zero, &n_neg));
+      for (size_t i = 0; i < n; ++i) {
+        const double wi = w[i] <= 0 ? 0.0 : safe_sqrt_cli(w[i]);
+        for (size_t j = 0; j < n; ++j) U[i * n + j] *= wi;
+      }
+    }
     if (n_zero > 1) std::cout << "**** WARNING: Matrix G has " << n_zero << " eigenvalues close to zero" << std::endl;
   } else {
     read_dense_rows(R.P.file_ku, U.data(), n, n, "U");
@@ -1091,7 +1144,7 @@ static void usage() {
   std::cout << "gemma-b200: GEMMA-compatible -gk / -eigen / -lmm on a B200\n"
                " -g/-p/-a/-c files (BIMBAM)  |  -bfile prefix (PLINK)   -n col...   -o prefix  -outdir dir\n"
                " -gk [1|2]   -eigen   -lmm [1|2|3|4|9]   -lm [1|2|3|4]   -k K.txt [-km 1|2]   -d D.txt -u U.txt\n"
-               " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -gwasnps file -loco chr -gxe file -lmin x -lmax x -region n -nind n -silence\n"
+               " -miss x -maf x -hwe x -r2 x -notsnp -snps file -ksnps file -gwasnps file -loco chr -gxe file -widv file -lmin x -lmax x -region n -nind n -silence\n"
                " -bin  also write K / U / D as <file>.bin (exact doubles); -k/-u/-d accept such .bin files\n";
 }
 
@@ -1130,6 +1183,7 @@ int main(int argc, char **argv) {
     else if (a == "-lmax") P.l_max = atof(need(i));
     else if (a == "-region") P.n_region = (size_t)atoi(need(i));
     else if (a == "-nind") P.nind = atol(need(i));
+    else if (a == "-widv") P.file_weight = need(i);                              // src/gemma.cpp:819-826
     else if (a == "-device") P.device = atoi(need(i));
     else if (a == "-gk") { P.a_mode = 20 + optnum(i, 1); n_modes++; }            // src/gemma.cpp:1124-1139
     else if (a == "-eigen") { P.a_mode = 31; n_modes++; }
@@ -1179,9 +1233,8 @@ int main(int argc, char **argv) {
   if (!P.file_bfile.empty()) { read_bim(R); read_fam(R); if (!P.file_pheno.empty()) { R.pheno.clear(); R.ind_pheno.clear(); read_pheno(R); } }
   else read_pheno(R);
   if (!P.file_cvt.empty()) read_cvt(R);
-  if (!P.file_gxe.empty()) {
-    read_gxe(R);
-  }
+  if (!P.file_gxe.empty()) read_gxe(R);
+  if (!P.file_weight.empty()) read_weight(R);
   process_cvt_phen(R);
   trim_individuals(R);
   gb200_ctx *ctx = nullptr;
@@ -1198,6 +1251,11 @@ int main(int argc, char **argv) {
       read_kin(R, G);
       write_bin(out_path(R, "kin") + ".bin", G.data(), R.ni_test, R.ni_test);
       write_matrix(R, G.data(), R.ni_test, R.ni_test, "kin");            // and through the production text writer (WriteMatrix)
+      if (!R.weight.empty()) {                        // -widv: the matrix that goes to the eigensolver (centred, weighted) and the weights
+        const vector<double> w = weighted_kinship(R, G);
+        write_bin(out_path(R, "wkin") + ".bin", G.data(), R.ni_test, R.ni_test);
+        write_bin(out_path(R, "widv") + ".bin", w.data(), R.ni_test, 1);
+      }
     }
     if (!P.file_ku.empty() && !P.file_kd.empty()) {   // -u / -d: ReadFile_eigenU / ReadFile_eigenD, then the production writers
       vector<double> U(R.ni_test * R.ni_test), D(R.ni_test);

@@ -1,7 +1,7 @@
 """Differential test of the host side of the CLI (readers + individual / SNP QC) against the reference's
 OWN CLI (oracle/_ref/gemma_ref, the unmodified src/*.cpp) on randomised BIMBAM and PLINK inputs with the awkward cases mixed in:
 NA phenotypes / covariates, monomorphic SNPs, dosage-valued genotypes, mixed separators, a shuffled and incomplete annotation file, SNPs collinear with a covariate, and the
--miss / -maf / -hwe / -r2 / -notsnp / -n / -nind / -gxe / -loco switches (refusals included).  The reference runs `-lm 1` (cheap, no kinship needed) and its assoc file lists
+-miss / -maf / -hwe / -r2 / -notsnp / -n / -nind / -gxe / -widv / -loco switches (refusals included).  The reference runs `-lm 1` (cheap, no kinship needed) and its assoc file lists
 the analysed SNPs with n_miss and af; `gemma-b200 -qc-only` must select the same SNPs / individuals and print the same counts.
 CPU only."""
 import gzip
@@ -46,6 +46,9 @@ def _make_case(d, seed, plink, n=60, l=120):
     with open(os.path.join(d, "gxe.txt"), "w") as fo:                      # -gxe with -lm: only drops the individuals without a value
         for i in range(n):
             fo.write(("NA" if rng.random() < 0.08 else "%.3f" % rng.normal()) + "\n")
+    with open(os.path.join(d, "w.txt"), "w") as fo:                        # -widv: individuals without a weight are dropped
+        for i in range(n):
+            fo.write(("NA" if rng.random() < 0.07 else "%.3f" % rng.uniform(0.2, 3.0)) + "\n")
     with open(os.path.join(d, "anno.txt"), "w") as fo:
         for s in rng.permutation(l):                                       # shuffled, incomplete, mixed separators, non-numeric chr
             if s % 11 == 7:
@@ -92,6 +95,7 @@ def _count(txt, key):
 VARIANTS = [[], ["cvt"], ["-maf", "0.05"], ["-miss", "0.03"], ["-hwe", "0.5"], ["cvt", "-r2", "0.3"], ["-maf", "0", "-miss", "0.2"],
             ["-notsnp"], ["cvt", "-hwe", "0.9", "-maf", "0.1"], ["-n", "2"],
             ["-gxe", "GXE"], ["cvt", "-gxe", "GXE", "-maf", "0.05"], ["-gxe", "GXE", "-nind", "30"], ["-loco", "1"],
+            ["-widv", "WIDV"], ["cvt", "-widv", "WIDV", "-gxe", "GXE"], ["-widv", "WIDV", "-nind", "30"],
             ["-nind", "7"], ["-nind", "40"], ["-nind", "1000"], ["cvt", "-nind", "45"], ["cvt", "-nind", "1000"]]
 
 
@@ -105,7 +109,7 @@ def test_qc_selection_matches_the_reference_cli(tmp_path, seed, plink):
     base = _make_case(d, seed, plink)
     n_refused = 0
     for k, v in enumerate(VARIANTS):
-        args = base + (["-c", os.path.join(d, "cvt.txt")] if "cvt" in v else []) + [os.path.join(d, "gxe.txt") if x == "GXE" else x for x in v if x != "cvt"]
+        args = base + (["-c", os.path.join(d, "cvt.txt")] if "cvt" in v else []) + [{"GXE": os.path.join(d, "gxe.txt"), "WIDV": os.path.join(d, "w.txt")}.get(x, x) for x in v if x != "cvt"]
         mine = subprocess.run([CLI] + args + ["-lm", "1", "-qc-only", "-o", "mine%d" % k, "-outdir", os.path.join(d, "output")],
                               capture_output=True, text=True)
         try:
