@@ -1189,10 +1189,14 @@ int main(int argc, char **argv) {
     else if (a == "-eigen") { P.a_mode = 31; n_modes++; }
     else if (a == "-lmm") { P.a_mode = optnum(i, 1); n_modes++; }                 // src/gemma.cpp:1299-1314
     else if (a == "-lm") { P.a_mode = 50 + optnum(i, 1); n_modes++; }             // src/gemma.cpp:1283-1298
-    else if (a == "-silence") P.silence = true;
+    else if (a == "-silence" || a == "--quiet") P.silence = true;                // src/gemma.cpp:777
     else if (a == "-qc-only") P.qc_only = true;
     else if (a == "-bin") P.bin = true;
-    else if (a == "-no-check" || a == "-check" || a == "-debug" || a == "-strict" || a == "-legacy" || a == "-nocheck") {}
+    else if (a == "-no-check" || a == "-check" || a == "-debug" || a == "-strict" || a == "-legacy" || a == "-nocheck" ||
+             a == "-no-fpe-check" || a == "-debug-data" || a == "-debug-dump") {}   // debug / checking switches of the reference: no effect here
+    else if (a == "-pace" || a == "-seed" || a == "-issue") {                      // accepted like the reference (progress pace, RNG seed of the
+      if (i + 1 < argc && argv[i + 1][0] != '-') ++i;                              // sampling modes, test hook): nothing on this path uses them
+    }
     else if (a == "-h" || a == "-help") { usage(); return 0; }
     else die("unrecognized option " + a);                                          // src/gemma.cpp:1626-1629
   }
