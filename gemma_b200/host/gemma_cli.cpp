@@ -520,6 +520,7 @@ static void print_counts(const Run &R) {               // CheckData, src/param.c
   std::cout << "## number of total SNPs/var        = " << std::setw(8) << R.ns_total << std::endl;
   if (!R.setSnps.empty()) std::cout << "## number of considered SNPS       = " << std::setw(8) << R.setSnps.size() << std::endl;
   if (!R.setKSnps.empty()) std::cout << "## number of SNPS for K            = " << std::setw(8) << R.setKSnps.size() << std::endl;
+  if (!R.setGWASnps.empty()) std::cout << "## number of SNPS for GWAS         = " << std::setw(8) << R.setGWASnps.size() << std::endl;
   std::cout << "## number of analyzed SNPs         = " << std::setw(8) << R.ns_test << std::endl;
 }
 
